@@ -1,0 +1,47 @@
+"""Constructor kwargs of the hot path, as the reference's YAML gives them.
+
+Values restate /root/reference/config/MEAD_emo_video_aug_delta_4_crop_random_crop.yaml:26-52
+(generator_params + common_params; identical in all four shipped configs).  ``TINY_CONFIG`` is a
+shrunken instance of the same architecture used by fast parity tests and the committed golden
+fixtures (full tensors fit in a few hundred KB).
+"""
+import copy
+
+FULL_CONFIG = {
+    "num_channels": 3,
+    "num_kp": 10,
+    "estimate_jacobian": True,
+    "block_expansion": 64,
+    "max_features": 512,
+    "num_down_blocks": 2,
+    "num_bottleneck_blocks": 6,
+    "estimate_occlusion_map": True,
+    "dense_motion_params": {
+        "block_expansion": 64,
+        "max_features": 1024,
+        "num_blocks": 5,
+        "scale_factor": 0.25,
+    },
+}
+
+# Same topology, fewer channels / blocks; image size is chosen by the caller (64x64 in tests).
+TINY_CONFIG = {
+    "num_channels": 3,
+    "num_kp": 3,
+    "estimate_jacobian": True,
+    "block_expansion": 16,
+    "max_features": 64,
+    "num_down_blocks": 2,
+    "num_bottleneck_blocks": 2,
+    "estimate_occlusion_map": True,
+    "dense_motion_params": {
+        "block_expansion": 16,
+        "max_features": 64,
+        "num_blocks": 3,
+        "scale_factor": 0.25,
+    },
+}
+
+
+def get_config(name="full"):
+    return copy.deepcopy({"full": FULL_CONFIG, "tiny": TINY_CONFIG}[name])

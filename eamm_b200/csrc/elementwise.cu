@@ -1,0 +1,434 @@
+// HBM-bound kernels of the EAMM generation path: anti-alias downsample, keypoint stage,
+// flow combine, feature warp x occlusion, image warp, layout conversion.
+// Reference semantics cited per kernel; arithmetic is fp32 throughout (north_star: "fp32 warp").
+#include "common.cuh"
+
+namespace eamm {
+
+// =============================================================================================
+// a3  AntiAliasInterpolation2d  (util.py:1044-1052)
+//   out[c][i][j] = sum_{u,v} k2[u][v] * src[c][step*i+u-6][step*j+v-6],  k2 = outer(g1,g1) (sum 1)
+// Block = (batch item, TR output rows).  Phase 1: horizontal 13-tap filter at the subsampled
+// columns for every needed input row (global reads, L1 absorbs the 13/step overlap); phase 2:
+// vertical 13-tap filter from shared memory; one float4 (R,G,B,0) store per output pixel.
+// =============================================================================================
+constexpr int AA_TAPS = 13;
+constexpr int AA_PAD = 6;
+constexpr int AA_TR = 4;  // output rows per block
+
+__global__ void __launch_bounds__(256)
+aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, float4* __restrict__ dst,
+                     int H, int W, int Ho, int Wo, int step, const float* __restrict__ g1) {
+  extern __shared__ float tmp[];  // [3][rows][Wo]
+  __shared__ float g[AA_TAPS];
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * AA_TR;
+  const int rows = (AA_TR - 1) * step + AA_TAPS;
+  if (threadIdx.x < AA_TAPS) g[threadIdx.x] = g1[threadIdx.x];
+  __syncthreads();
+  const float* img = src + (long long)n * src_n_stride;
+  const int in_row0 = r0 * step - AA_PAD;
+  for (int idx = threadIdx.x; idx < 3 * rows * Wo; idx += blockDim.x) {
+    int j = idx % Wo;
+    int rr = (idx / Wo) % rows;
+    int c = idx / (Wo * rows);
+    int y = in_row0 + rr;
+    float acc = 0.f;
+    if (y >= 0 && y < H) {
+      const float* rowp = img + ((long long)c * H + y) * W;
+      int x0 = j * step - AA_PAD;
+#pragma unroll
+      for (int v = 0; v < AA_TAPS; ++v) {
+        int x = x0 + v;
+        float s = (x >= 0 && x < W) ? __ldg(rowp + x) : 0.f;
+        acc = fmaf(g[v], s, acc);
+      }
+    }
+    tmp[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < AA_TR * Wo; idx += blockDim.x) {
+    int j = idx % Wo;
+    int i = idx / Wo;
+    if (r0 + i >= Ho) continue;
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int u = 0; u < AA_TAPS; ++u) acc = fmaf(g[u], tmp[(c * rows + i * step + u) * Wo + j], acc);
+      o[c] = acc;
+    }
+    dst[((long long)n * Ho + (r0 + i)) * Wo + j] = make_float4(o[0], o[1], o[2], 0.f);
+  }
+}
+
+// =============================================================================================
+// a4+a5+a6  keypoint stage  (dense_motion.py:32-79, util.py:815-855)
+// For every pixel z of the h x w grid and every k in [0,K]:
+//   H_k   = exp(-0.5|z-kp_d,k|^2/var) - exp(-0.5|z-kp_s,k|^2/var)          (H_0 = 0)
+//   z'_k  = J_k (z - kp_d,k) + kp_s,k,  J_k = J_s,k inv(J_d,k)             (z'_0 = z)
+//   S_k   = bilinear sample (zeros padding, align_corners=False) of the small source at z'_k
+// Writes [H_k, S_k.R, S_k.G, S_k.B] into channels 4k..4k+3 of the hourglass input (NHWC) and
+// S_k into sparse_deformed [n,K+1,3,h,w].  Block = one image row; sparse_deformed goes through
+// shared memory so both outputs are written coalesced.
+// =============================================================================================
+constexpr int KP_MAX = 32;
+
+struct KpDev {
+  const float* value; const float* jac; long long vs, js;
+};
+
+__global__ void __launch_bounds__(256)
+kp_stage_kernel(const float4* __restrict__ small_img, long long small_n_stride, KpDev kd, KpDev ks,
+                int K, float kp_var, ActView hg, float* __restrict__ sdef, int* __restrict__ status) {
+  extern __shared__ float s_sd[];  // [(K+1)*3][w]
+  __shared__ float s_kd[KP_MAX * 2], s_ks[KP_MAX * 2], s_J[KP_MAX * 4];
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int h = hg.h, w = hg.w, K1 = K + 1;
+  if (threadIdx.x < K) {
+    int k = threadIdx.x;
+    const float* vd = kd.value + (long long)n * kd.vs + k * 2;
+    const float* vs = ks.value + (long long)n * ks.vs + k * 2;
+    s_kd[2 * k] = vd[0]; s_kd[2 * k + 1] = vd[1];
+    s_ks[2 * k] = vs[0]; s_ks[2 * k + 1] = vs[1];
+    float J[4] = {1.f, 0.f, 0.f, 1.f};
+    if (kd.jac != nullptr) {
+      bool ok = kp_affine(kd.jac + (long long)n * kd.js + k * 4, ks.jac + (long long)n * ks.js + k * 4, J);
+      if (!ok && status != nullptr && y == 0) atomicOr(status, 1);
+    }
+    s_J[4 * k] = J[0]; s_J[4 * k + 1] = J[1]; s_J[4 * k + 2] = J[2]; s_J[4 * k + 3] = J[3];
+  }
+  __syncthreads();
+  const float4* img = small_img + ((long long)n * small_n_stride) / 4;   // stride is in floats
+  const float zy = grid_coord(y, h);
+  for (int idx = threadIdx.x; idx < w * K1; idx += blockDim.x) {
+    int k = idx % K1, x = idx / K1;
+    float zx = grid_coord(x, w);
+    float hm = 0.f, gx = zx, gy = zy;
+    if (k > 0) {
+      int kk = k - 1;
+      float ddx = zx - s_kd[2 * kk], ddy = zy - s_kd[2 * kk + 1];
+      float dsx = zx - s_ks[2 * kk], dsy = zy - s_ks[2 * kk + 1];
+      hm = expf(-0.5f * (ddx * ddx + ddy * ddy) / kp_var) - expf(-0.5f * (dsx * dsx + dsy * dsy) / kp_var);
+      float mx = ddx, my = ddy;
+      if (kd.jac != nullptr) {
+        mx = s_J[4 * kk] * ddx + s_J[4 * kk + 1] * ddy;
+        my = s_J[4 * kk + 2] * ddx + s_J[4 * kk + 3] * ddy;
+      }
+      gx = mx + s_ks[2 * kk];
+      gy = my + s_ks[2 * kk + 1];
+    }
+    Bilinear b = bilinear_setup(gx, gy, w, h);
+    float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    bool xin0 = b.x0 >= 0 && b.x0 < w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < w;
+    bool yin0 = b.y0 >= 0 && b.y0 < h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < h;
+    if (yin0 && xin0) { float4 t = __ldg(img + b.y0 * w + b.x0); float q = wy0 * wx0; r += t.x * q; g += t.y * q; bl += t.z * q; }
+    if (yin0 && xin1) { float4 t = __ldg(img + b.y0 * w + b.x0 + 1); float q = wy0 * b.wx1; r += t.x * q; g += t.y * q; bl += t.z * q; }
+    if (yin1 && xin0) { float4 t = __ldg(img + (b.y0 + 1) * w + b.x0); float q = b.wy1 * wx0; r += t.x * q; g += t.y * q; bl += t.z * q; }
+    if (yin1 && xin1) { float4 t = __ldg(img + (b.y0 + 1) * w + b.x0 + 1); float q = b.wy1 * b.wx1; r += t.x * q; g += t.y * q; bl += t.z * q; }
+    act_store4(hg, act_offset(hg, n, y, x, 4 * k), make_float4(hm, r, g, bl));
+    s_sd[(k * 3 + 0) * w + x] = r;
+    s_sd[(k * 3 + 1) * w + x] = g;
+    s_sd[(k * 3 + 2) * w + x] = bl;
+  }
+  // zero the padding channels of the view (weights there are zero too, but keep NaNs out)
+  const int pad4 = (hg.c - 4 * K1) / 4;
+  for (int idx = threadIdx.x; idx < w * pad4; idx += blockDim.x) {
+    int p = idx % pad4, x = idx / pad4;
+    act_store4(hg, act_offset(hg, n, y, x, 4 * K1 + 4 * p), make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  __syncthreads();
+  if (sdef != nullptr) {
+    for (int idx = threadIdx.x; idx < K1 * 3 * w; idx += blockDim.x) {
+      int x = idx % w, kc = idx / w;
+      sdef[(((long long)n * K1 * 3 + kc) * h + y) * w + x] = s_sd[kc * w + x];
+    }
+  }
+}
+
+// =============================================================================================
+// a8 epilogue  softmax(mask logits) -> mask; deformation = sum_k mask_k * z'_k; occlusion = sigmoid
+// (dense_motion.py:98-111).  One thread per pixel; z'_k recomputed from the keypoints.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+flow_combine_kernel(const float* __restrict__ logits, int ldl, KpDev kd, KpDev ks, int K, int has_occ,
+                    int h, int w, float* __restrict__ mask, float2* __restrict__ deform,
+                    float* __restrict__ occ) {
+  __shared__ float s_kd[KP_MAX * 2], s_ks[KP_MAX * 2], s_J[KP_MAX * 4];
+  const int n = blockIdx.y;
+  const int K1 = K + 1;
+  if (threadIdx.x < K) {
+    int k = threadIdx.x;
+    const float* vd = kd.value + (long long)n * kd.vs + k * 2;
+    const float* vs = ks.value + (long long)n * ks.vs + k * 2;
+    s_kd[2 * k] = vd[0]; s_kd[2 * k + 1] = vd[1];
+    s_ks[2 * k] = vs[0]; s_ks[2 * k + 1] = vs[1];
+    float J[4] = {1.f, 0.f, 0.f, 1.f};
+    if (kd.jac != nullptr) kp_affine(kd.jac + (long long)n * kd.js + k * 4, ks.jac + (long long)n * ks.js + k * 4, J);
+    s_J[4 * k] = J[0]; s_J[4 * k + 1] = J[1]; s_J[4 * k + 2] = J[2]; s_J[4 * k + 3] = J[3];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  const int y = p / w, x = p % w;
+  const float* lp = logits + ((long long)n * h * w + p) * ldl;
+  float l[KP_MAX + 1];
+  float m = -INFINITY;
+  for (int k = 0; k < K1; ++k) { l[k] = __ldg(lp + k); m = fmaxf(m, l[k]); }
+  float sum = 0.f;
+  for (int k = 0; k < K1; ++k) { l[k] = expf(l[k] - m); sum += l[k]; }
+  const float zx = grid_coord(x, w), zy = grid_coord(y, h);
+  float dx = 0.f, dy = 0.f;
+  for (int k = 0; k < K1; ++k) {
+    float mk = l[k] / sum;
+    mask[(((long long)n * K1 + k) * h + y) * w + x] = mk;
+    float gx = zx, gy = zy;
+    if (k > 0) {
+      int kk = k - 1;
+      float ddx = zx - s_kd[2 * kk], ddy = zy - s_kd[2 * kk + 1];
+      float mx = ddx, my = ddy;
+      if (kd.jac != nullptr) {
+        mx = s_J[4 * kk] * ddx + s_J[4 * kk + 1] * ddy;
+        my = s_J[4 * kk + 2] * ddx + s_J[4 * kk + 3] * ddy;
+      }
+      gx = mx + s_ks[2 * kk];
+      gy = my + s_ks[2 * kk + 1];
+    }
+    dx += gx * mk;
+    dy += gy * mk;
+  }
+  deform[(long long)n * h * w + p] = make_float2(dx, dy);
+  if (has_occ) occ[(long long)n * h * w + p] = 1.f / (1.f + expf(-__ldg(lp + K1)));
+}
+
+// =============================================================================================
+// a9-i  out = grid_sample(feat, deformation) * occlusion   (generator.py:57,79-84)
+//       out2 = relu(out*scale2 + shift2)                    (next ResBlock2d norm1+relu, util.py:873-874)
+// NHWC: each thread owns 4 channels of one pixel, so the 4 bilinear taps are four fully
+// coalesced channel-vector reads.  Algorithmic traffic: one read + one (or two) writes of the map.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
+                    ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
+                    const float* __restrict__ shift2, long long total) {
+  const int c4 = feat.c >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(idx % c4);
+    long long pix = idx / c4;
+    int x = (int)(pix % feat.w);
+    int y = (int)((pix / feat.w) % feat.h);
+    int n = (int)(pix / ((long long)feat.w * feat.h));
+    float2 d = __ldg(deform + pix);
+    Bilinear b = bilinear_setup(d.x, d.y, feat.w, feat.h);
+    float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
+    bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
+    bool yin0 = b.y0 >= 0 && b.y0 < feat.h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < feat.h;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yin0 && xin0) { float4 t = act_load4(feat, act_offset(feat, n, b.y0, b.x0, 4 * cg)); float q = wy0 * wx0; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
+    if (yin0 && xin1) { float4 t = act_load4(feat, act_offset(feat, n, b.y0, b.x0 + 1, 4 * cg)); float q = wy0 * b.wx1; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
+    if (yin1 && xin0) { float4 t = act_load4(feat, act_offset(feat, n, b.y0 + 1, b.x0, 4 * cg)); float q = b.wy1 * wx0; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
+    if (yin1 && xin1) { float4 t = act_load4(feat, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 4 * cg)); float q = b.wy1 * b.wx1; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
+    if (occ != nullptr) {
+      float o = __ldg(occ + pix);
+      acc.x *= o; acc.y *= o; acc.z *= o; acc.w *= o;
+    }
+    act_store4(out, act_offset(out, n, y, x, 4 * cg), acc);
+    if (has_out2) {
+      float4 s = __ldg(reinterpret_cast<const float4*>(scale2) + cg);
+      float4 t = __ldg(reinterpret_cast<const float4*>(shift2) + cg);
+      float4 r;
+      r.x = fmaxf(fmaf(acc.x, s.x, t.x), 0.f);
+      r.y = fmaxf(fmaf(acc.y, s.y, t.y), 0.f);
+      r.z = fmaxf(fmaf(acc.z, s.z, t.z), 0.f);
+      r.w = fmaxf(fmaf(acc.w, s.w, t.w), 0.f);
+      act_store4(out2, act_offset(out2, n, y, x, 4 * cg), r);
+    }
+  }
+}
+
+// =============================================================================================
+// a9-ii  deformed = grid_sample(source, interpolate(deformation, (H,W), bilinear))  (generator.py:50-57,86)
+// The flow upsample (align_corners=False: src = (dst+0.5)*h/H - 0.5, clamped at 0, upper tap
+// clamped to h-1) is evaluated on the fly; source and output stay NCHW fp32 (API tensors).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+warp_image_kernel(const float* __restrict__ src, long long src_n_stride, const float2* __restrict__ deform,
+                  float* __restrict__ dst, int C, int H, int W, int h, int w) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  float gx, gy;
+  if (h == H && w == W) {
+    float2 d = __ldg(deform + ((long long)n * h + y) * w + x);
+    gx = d.x; gy = d.y;
+  } else {
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    float fy = sy * ((float)y + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
+    float fx = sx * ((float)x + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
+    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float2* dp = deform + (long long)n * h * w;
+    float2 d00 = __ldg(dp + y0 * w + x0), d01 = __ldg(dp + y0 * w + x1);
+    float2 d10 = __ldg(dp + y1 * w + x0), d11 = __ldg(dp + y1 * w + x1);
+    gx = ly0 * (lx0 * d00.x + lx1 * d01.x) + ly1 * (lx0 * d10.x + lx1 * d11.x);
+    gy = ly0 * (lx0 * d00.y + lx1 * d01.y) + ly1 * (lx0 * d10.y + lx1 * d11.y);
+  }
+  Bilinear b = bilinear_setup(gx, gy, W, H);
+  float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
+  bool xin0 = b.x0 >= 0 && b.x0 < W, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < W;
+  bool yin0 = b.y0 >= 0 && b.y0 < H, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < H;
+  const float* img = src + (long long)n * src_n_stride;
+  for (int c = 0; c < C; ++c) {
+    const float* pl = img + (long long)c * H * W;
+    float acc = 0.f;
+    if (yin0 && xin0) acc += __ldg(pl + b.y0 * W + b.x0) * (wy0 * wx0);
+    if (yin0 && xin1) acc += __ldg(pl + b.y0 * W + b.x0 + 1) * (wy0 * b.wx1);
+    if (yin1 && xin0) acc += __ldg(pl + (b.y0 + 1) * W + b.x0) * (b.wy1 * wx0);
+    if (yin1 && xin1) acc += __ldg(pl + (b.y0 + 1) * W + b.x0 + 1) * (b.wy1 * b.wx1);
+    dst[(((long long)n * C + c) * H + y) * W + x] = acc;
+  }
+}
+
+// =============================================================================================
+// source image NCHW fp32 -> NHWC activation view (zero-filled up to the view's channel count)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+nchw_to_act_kernel(const float* __restrict__ src, int C, ActView dst, long long total) {
+  const int c4 = dst.c >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long pix = idx;
+    int x = (int)(pix % dst.w);
+    int y = (int)((pix / dst.w) % dst.h);
+    int n = (int)(pix / ((long long)dst.w * dst.h));
+    for (int g = 0; g < c4; ++g) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int c = 4 * g + i;
+        v[i] = c < C ? __ldg(src + (((long long)n * C + c) * dst.h + y) * dst.w + x) : 0.f;
+      }
+      act_store4(dst, act_offset(dst, n, y, x, 4 * g), make_float4(v[0], v[1], v[2], v[3]));
+    }
+  }
+}
+
+static inline KpDev to_dev(const eamm_kp* k) {
+  KpDev d; d.value = k->value; d.jac = k->jacobian; d.vs = k->value_stride; d.js = k->jacobian_stride;
+  return d;
+}
+
+}  // namespace eamm
+
+using namespace eamm;
+
+extern "C" int eamm_abi_version(void) { return EAMM_ABI_VERSION; }
+
+extern "C" int eamm_device_ok(int device) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+extern "C" int eamm_aa_downsample(const float* src, int64_t src_n_stride, float* dst, int n, int H, int W,
+                                  int step, const float* g1, void* stream) {
+  if (!src || !dst || !g1 || n <= 0 || H <= 0 || W <= 0 || step <= 0) return EAMM_ERR_ARG;
+  if (H % step || W % step) return EAMM_ERR_SHAPE;
+  if ((uintptr_t)dst % 16) return EAMM_ERR_ALIGN;
+  int Ho = H / step, Wo = W / step;
+  int rows = (AA_TR - 1) * step + AA_TAPS;
+  size_t smem = (size_t)3 * rows * Wo * sizeof(float);
+  if (smem > 200 * 1024) return EAMM_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(aa_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((Ho + AA_TR - 1) / AA_TR, n);
+  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, (float4*)dst, H, W, Ho, Wo, step, g1);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_kp_stage(const float* small_img, int64_t small_n_stride, const eamm_kp* kp_driving,
+                             const eamm_kp* kp_source, int num_kp, float kp_variance, const eamm_act* hg_in,
+                             float* sparse_deformed, int32_t* status, void* stream) {
+  if (!small_img || !kp_driving || !kp_source || !kp_driving->value || !kp_source->value) return EAMM_ERR_ARG;
+  int rc = check_view(hg_in);
+  if (rc) return rc;
+  if (num_kp <= 0 || num_kp > KP_MAX) return EAMM_ERR_UNSUPPORTED;
+  if (hg_in->c < 4 * (num_kp + 1)) return EAMM_ERR_SHAPE;
+  if ((kp_driving->jacobian == nullptr) != (kp_source->jacobian == nullptr)) return EAMM_ERR_ARG;
+  if (hg_in->h < 2 || hg_in->w < 2) return EAMM_ERR_SHAPE;
+  ActView hg = make_view(hg_in);
+  size_t smem = (size_t)(num_kp + 1) * 3 * hg.w * sizeof(float);
+  if (smem > 48 * 1024) return EAMM_ERR_UNSUPPORTED;
+  dim3 grid(hg.h, hg.n);
+  kp_stage_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const float4*)small_img, small_n_stride,
+      to_dev(kp_driving), to_dev(kp_source), num_kp, kp_variance, hg, sparse_deformed, status);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_flow_combine(const float* logits, int ldl, const eamm_kp* kp_driving, const eamm_kp* kp_source,
+                                 int num_kp, int has_occ, int n, int h, int w, float* mask, float* deformation,
+                                 float* occlusion, void* stream) {
+  if (!logits || !kp_driving || !kp_source || !mask || !deformation || n <= 0 || h < 2 || w < 2) return EAMM_ERR_ARG;
+  if (has_occ && !occlusion) return EAMM_ERR_ARG;
+  if (num_kp <= 0 || num_kp > KP_MAX) return EAMM_ERR_UNSUPPORTED;
+  if (ldl < num_kp + 1 + (has_occ ? 1 : 0)) return EAMM_ERR_SHAPE;
+  dim3 grid((h * w + 127) / 128, n);
+  flow_combine_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, ldl, to_dev(kp_driving), to_dev(kp_source),
+      num_kp, has_occ, h, w, mask, (float2*)deformation, occlusion);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
+                                 const eamm_act* out, const eamm_act* out2, const float* scale2,
+                                 const float* shift2, void* stream) {
+  int rc = check_view(feat); if (rc) return rc;
+  rc = check_view(out); if (rc) return rc;
+  if (!deformation) return EAMM_ERR_ARG;
+  if (out->n != feat->n || out->h != feat->h || out->w != feat->w || out->c != feat->c) return EAMM_ERR_SHAPE;
+  ActView f = make_view(feat), o = make_view(out), o2 = o;
+  int has2 = 0;
+  if (out2) {
+    rc = check_view(out2); if (rc) return rc;
+    if (!scale2 || !shift2) return EAMM_ERR_ARG;
+    if (out2->n != feat->n || out2->h != feat->h || out2->w != feat->w || out2->c != feat->c) return EAMM_ERR_SHAPE;
+    o2 = make_view(out2); has2 = 1;
+  }
+  long long total = (long long)f.n * f.h * f.w * (f.c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  warp_occlude_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2, has2,
+                                                               scale2, shift2, total);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_warp_image(const float* src, int64_t src_n_stride, const float* deformation, float* dst,
+                               int n, int C, int H, int W, int h, int w, void* stream) {
+  if (!src || !deformation || !dst || n <= 0 || C <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return EAMM_ERR_ARG;
+  dim3 grid((W + 255) / 256, H, n);
+  warp_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_n_stride, (const float2*)deformation, dst, C, H, W, h, w);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, const eamm_act* dst, void* stream) {
+  if (!src || n <= 0 || C <= 0) return EAMM_ERR_ARG;
+  int rc = check_view(dst); if (rc) return rc;
+  if (dst->n != n || dst->h != H || dst->w != W || dst->c < C) return EAMM_ERR_SHAPE;
+  ActView d = make_view(dst);
+  long long total = (long long)n * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  nchw_to_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, d, total);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,505 @@
+"""Host-side executor of the generation hot path: weight packing, workspace and kernel sequencing.
+
+Everything numeric happens in libeamm_b200.so (C ABI, include/eamm_b200.h); PyTorch is used for
+device memory, streams and the one-off weight repacking (BatchNorm folding etc.).  Call order
+follows /root/reference/modules/generator.py:59-97 and dense_motion.py:81-113.
+
+Precision modes (``precision`` attribute of the drop-in modules):
+  "fp32_simt" fp32 activations, fp32 CUDA-core convs              -- exact-fp32 parity path
+  "fp32"      bf16 hi/lo planes (16 mantissa bits) + 3-pass bf16 tensor-core convs, fp32 accumulate
+  "bf16"      single bf16 plane, 1-pass tensor-core convs, fp32 accumulate; warp/flow math fp32
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-5  # /root/reference/sync_batchnorm/batchnorm.py:39
+
+PRECISIONS = ("fp32_simt", "fp32", "bf16")
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ActBuf:
+    """A zero-initialised NHWC activation buffer [n, h, w, planes*c_buf] and its eamm_act views."""
+
+    def __init__(self, n, h, w, c_buf, mode, device):
+        self.n, self.h, self.w, self.c_buf = n, h, w, c_buf
+        self.planes = 2 if mode == "bf16x2" else 1
+        self.dtype = L.EAMM_F32 if mode == "f32" else L.EAMM_BF16
+        tdt = torch.float32 if mode == "f32" else torch.bfloat16
+        self.t = torch.zeros(n, h, w, self.planes * c_buf, dtype=tdt, device=device)
+
+    def act(self, c_off=0, c=None, n=None, broadcast=False):
+        a = L.Act()
+        a.data = self.t.data_ptr()
+        a.dtype = self.dtype
+        a.n = self.n if n is None else n
+        a.h, a.w = self.h, self.w
+        a.c = self.c_buf - c_off if c is None else c
+        a.c_off, a.c_buf, a.planes = c_off, self.c_buf, self.planes
+        a.n_stride = 0 if broadcast else self.h * self.w * self.planes * self.c_buf
+        return a
+
+    def to_float(self, c_off=0, c=None):
+        """Debug/test helper: the view as an fp32 NCHW tensor (sums the planes)."""
+        c = self.c_buf - c_off if c is None else c
+        t = self.t.view(self.n, self.h, self.w, self.planes, self.c_buf).float().sum(3)
+        return t[..., c_off:c_off + c].permute(0, 3, 1, 2).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# weight packing
+# --------------------------------------------------------------------------------------------
+def fold_bn(w, b, bn):
+    """conv -> eval BatchNorm  ==  conv with w*s, (b-mean)*s+beta   (batchnorm.py:50-53)."""
+    s = bn["weight"] / torch.sqrt(bn["running_var"] + BN_EPS)
+    return w * s.view(-1, 1, 1, 1), (b - bn["running_mean"]) * s + bn["bias"]
+
+
+def bn_affine(bn):
+    s = bn["weight"] / torch.sqrt(bn["running_var"] + BN_EPS)
+    return s, bn["bias"] - bn["running_mean"] * s
+
+
+def up2_parity_weights(w):
+    """nearest-x2 followed by 3x3/pad-1 == four 2x2 convs on the low-res input (util.py:895-897).
+
+    For output pixel (2i+a, 2j+b) the three taps along an axis collapse onto two source pixels:
+    parity 0 -> offsets (-1: w0, 0: w1+w2); parity 1 -> offsets (0: w0+w1, +1: w2).
+    Returns [4 classes (a*2+b)][4 taps (ty*2+tx)][cout][cin]; tap (ty,tx) reads source offset
+    (a-1+ty, b-1+tx).
+    """
+    def collapse(t, axis, parity):
+        a0, a1, a2 = t.select(axis, 0), t.select(axis, 1), t.select(axis, 2)
+        return (a0, a1 + a2) if parity == 0 else (a0 + a1, a2)
+
+    classes = []
+    for a in (0, 1):
+        rows = collapse(w, 2, a)                      # each [cout, cin, 3(kx)]
+        for b in (0, 1):
+            taps = []
+            for r in rows:
+                taps.extend(collapse(r, 2, b))        # each [cout, cin]
+            classes.append(torch.stack(taps, 0))
+    return torch.stack(classes, 0)
+
+
+class ConvLayer:
+    """One packed convolution: kind/flags + device tensors in the layout of the chosen kernel."""
+
+    def __init__(self, name, kind, flags, w, b, cin_slot, nalign, impl, scale2=None, shift2=None):
+        cout, cin = w.shape[0], w.shape[1]
+        self.name, self.kind, self.flags, self.impl = name, kind, flags, impl
+        self.cin, self.cout_valid = cin_slot, cout
+        self.cout = _round_up(cout, nalign)
+        dev = w.device
+        if kind == L.CONV_UP2_3X3:
+            wt = up2_parity_weights(w)                                  # [4][4][cout][cin]
+            wt = wt.reshape(16, cout, cin)
+        else:
+            k = w.shape[2]
+            wt = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)        # [taps][cout][cin]
+        taps = wt.shape[0]
+        full = torch.zeros(taps, self.cout, cin_slot, dtype=torch.float32, device=dev)
+        full[:, :cout, :cin] = wt
+        self.w_ref = full                                               # [taps][cout][cin] fp32
+        self.bias = torch.zeros(self.cout, dtype=torch.float32, device=dev)
+        self.bias[:cout] = b
+        if impl == "simt":
+            self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
+        else:
+            raise ValueError(impl)
+        self.scale2 = self.shift2 = None
+        if scale2 is not None:
+            self.scale2 = torch.ones(self.cout, dtype=torch.float32, device=dev)
+            self.shift2 = torch.zeros(self.cout, dtype=torch.float32, device=dev)
+            self.scale2[:cout] = scale2
+            self.shift2[:cout] = shift2
+
+    def launch(self, lib, stream, inp, out=None, out2=None, residual=None, out_nchw=None, out_nchw_c=0,
+               out_nhwc_f32=None):
+        a = L.ConvArgs()
+        a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
+        a.inp = C.pointer(inp)
+        a.weight = self.weight.data_ptr()
+        a.bias = self.bias.data_ptr()
+        if residual is not None:
+            a.residual = C.pointer(residual)
+        if out is not None:
+            a.out = C.pointer(out)
+        if out2 is not None:
+            a.out2 = C.pointer(out2)
+            a.scale2 = self.scale2.data_ptr()
+            a.shift2 = self.shift2.data_ptr()
+        if out_nchw is not None:
+            a.out_nchw = out_nchw.data_ptr()
+            a.out_nchw_c = out_nchw_c
+        if out_nhwc_f32 is not None:
+            a.out_nhwc_f32 = out_nhwc_f32.data_ptr()
+        fn = lib.eamm_conv_simt
+        L.check(fn(C.byref(a), stream), "conv %s" % self.name)
+
+
+def _kp_struct(kp, batch, num_kp, device):
+    """eamm_kp from the caller's dict ({'value': [B,K,2], 'jacobian': [B,K,2,2]}, dense_motion.py:55).
+
+    A leading dimension of 1 (or an expanded, stride-0 batch) is broadcast over the batch.
+    Returns (struct, tensors-to-keep-alive).
+    """
+    def prep(t, tail, what):
+        if not torch.is_tensor(t) or t.device != device or t.dtype != torch.float32:
+            raise RuntimeError("eamm_b200: kp[%r] must be an fp32 tensor on %s" % (what, device))
+        if tuple(t.shape[1:]) != tail or t.shape[0] not in (1, batch):
+            raise RuntimeError("eamm_b200: kp[%r] must be [B,%s]" % (what, ",".join(map(str, tail))))
+        if t.stride(0) == 0:
+            t = t[:1]
+        t = t.contiguous()
+        stride = 0 if t.shape[0] == 1 else math.prod(tail)
+        return t, stride
+
+    s = L.Kp()
+    v, s.value_stride = prep(kp["value"], (num_kp, 2), "value")
+    s.value = v.data_ptr()
+    keep = [v]
+    if "jacobian" in kp and kp["jacobian"] is not None:
+        j, s.jacobian_stride = prep(kp["jacobian"], (num_kp, 2, 2), "jacobian")
+        s.jacobian = j.data_ptr()
+        keep.append(j)
+    return s, keep
+
+
+class DenseMotionEngine:
+    """Executor for DenseMotionNetwork.forward (dense_motion.py:81-113)."""
+
+    def __init__(self, module, precision):
+        self.m = module
+        self.precision = precision
+        self.lib = L.load()
+        self.impl = "simt"
+        self.mode = {"fp32_simt": "f32", "fp32": "bf16x2", "bf16": "bf16"}[precision]
+        self.calign = 4 if self.impl == "simt" else 64
+        self.nalign = 4 if self.impl == "simt" else 16
+        self.ws = {}
+        self._pack()
+
+    # ---- weights
+    def _pack(self):
+        m = self.m
+        dev = m.mask.weight.device
+        self.device = dev
+        nb = len(m.hourglass.encoder.down_blocks)
+        self.nb = nb
+        K1 = m.num_kp + 1
+        cin0 = K1 * (m.num_channels + 1)
+        enc = m.hourglass.encoder.down_blocks
+        dec = m.hourglass.decoder.up_blocks
+        ca = self.calign
+        self.enc_ch = [cin0] + [blk.conv.out_channels for blk in enc]       # e_0 .. e_nb
+        self.dec_ch = [blk.conv.out_channels for blk in dec]                # up_j output channels
+        self.enc_layers, self.dec_layers = [], []
+        for i, blk in enumerate(enc):
+            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
+            self.enc_layers.append(ConvLayer("hg.enc%d" % i, L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
+                                             _round_up(self.enc_ch[i], ca), self.nalign, self.impl))
+        for j, blk in enumerate(dec):
+            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
+            # input of up_block j: e_nb for j == 0, else cat(up_{j-1} out, e_{nb-j}) with padded slots
+            if j == 0:
+                cin_slot = _round_up(self.enc_ch[nb], ca)
+                wp = w
+            else:
+                c_up, c_sk = self.dec_ch[j - 1], self.enc_ch[nb - j]
+                s_up, s_sk = _round_up(c_up, ca), _round_up(c_sk, ca)
+                cin_slot = s_up + s_sk
+                wp = torch.zeros(w.shape[0], cin_slot, 3, 3, dtype=w.dtype, device=dev)
+                wp[:, :c_up] = w[:, :c_up]
+                wp[:, s_up:s_up + c_sk] = w[:, c_up:]
+            self.dec_layers.append(ConvLayer("hg.dec%d" % j, L.CONV_UP2_3X3, L.EPI_RELU, wp, b, cin_slot,
+                                             self.nalign, self.impl))
+        # mask (+ occlusion) merged into one 7x7 conv over cat(up_{nb-1} out, e_0)
+        c_up, c_sk = self.dec_ch[nb - 1], cin0
+        s_up, s_sk = _round_up(c_up, ca), _round_up(c_sk, ca)
+        wm, bm = m.mask.weight.detach().float(), m.mask.bias.detach().float()
+        self.has_occ = m.occlusion is not None
+        if self.has_occ:
+            wm = torch.cat([wm, m.occlusion.weight.detach().float()], 0)
+            bm = torch.cat([bm, m.occlusion.bias.detach().float()], 0)
+        wp = torch.zeros(wm.shape[0], s_up + s_sk, 7, 7, dtype=wm.dtype, device=dev)
+        wp[:, :c_up] = wm[:, :c_up]
+        wp[:, s_up:s_up + c_sk] = wm[:, c_up:]
+        self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, s_up + s_sk, self.nalign, self.impl)
+        # 1-D factor of the anti-alias kernel: k2 = outer(g1, g1) with sum 1 (util.py:1012-1033)
+        self.step = 1
+        self.g1 = None
+        if m.scale_factor != 1:
+            self.step = int(1 / m.scale_factor)
+            k2 = m.down.weight.detach().float()[0, 0]
+            if k2.shape != (13, 13):
+                raise RuntimeError("eamm_b200: anti-alias kernel must be 13x13 (sigma 1.5, util.py:1012)")
+            g1 = k2.sum(1)                    # rows of an outer product with total sum 1
+            self.g1 = (g1 / g1.sum()).contiguous()
+
+    # ---- workspace for a batch size / image size
+    def workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self.ws.get(key)
+        if ws is not None:
+            return ws
+        dev, ca, nb = self.device, self.calign, self.nb
+        h, w = H // self.step, W // self.step
+        if h >> nb < 1 or w >> nb < 1 or (h % (1 << nb)) or (w % (1 << nb)):
+            raise RuntimeError("eamm_b200: %dx%d motion grid cannot be halved %d times" % (h, w, nb))
+        ws = type("WS", (), {})()
+        ws.h, ws.w = h, w
+        ws.small = torch.zeros(B, h, w, 4, dtype=torch.float32, device=dev)
+        # cat_L = [up_{nb-1-L} out | e_L] at spatial (h>>L, w>>L), L = 0..nb-1; e_nb standalone
+        ws.cat = []
+        for lvl in range(nb):
+            s_up = _round_up(self.dec_ch[nb - 1 - lvl], ca)
+            s_sk = _round_up(self.enc_ch[lvl], ca)
+            buf = ActBuf(B, h >> lvl, w >> lvl, s_up + s_sk, self.mode, dev)
+            buf.s_up, buf.s_sk = s_up, s_sk
+            ws.cat.append(buf)
+        ws.bott = ActBuf(B, h >> nb, w >> nb, _round_up(self.enc_ch[nb], ca), self.mode, dev)
+        K1 = self.m.num_kp + 1
+        ws.logits = torch.empty(B, h, w, self.head.cout, dtype=torch.float32, device=dev)
+        ws.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws[key] = ws
+        return ws
+
+    def run(self, source_image, kp_driving, kp_source, src_n_stride=None):
+        """Launch the dense-motion kernels on the current stream; returns the reference's out_dict."""
+        m, lib = self.m, self.lib
+        B, Cc, H, W = source_image.shape
+        ws = self.workspace(B, H, W)
+        h, w = ws.h, ws.w
+        st = current_stream_ptr()
+        K, K1 = m.num_kp, m.num_kp + 1
+        dev = self.device
+        if src_n_stride is None:
+            src_n_stride = 0 if source_image.stride(0) == 0 else Cc * H * W
+        kd, keep_d = _kp_struct(kp_driving, B, K, dev)
+        ks, keep_s = _kp_struct(kp_source, B, K, dev)
+        # dense_motion.py:55 tests kp_driving only, then indexes kp_source['jacobian']
+        if kd.jacobian is None:
+            ks.jacobian = None
+        elif ks.jacobian is None:
+            raise KeyError("jacobian")
+        # a3 anti-alias downsample -> small [B,h,w,4]
+        n_small = 1 if (src_n_stride == 0 and B > 1) else B
+        small_stride = 0 if n_small == 1 and B > 1 else h * w * 4
+        if self.step != 1:
+            L.check(lib.eamm_aa_downsample(source_image.data_ptr(), src_n_stride, ws.small.data_ptr(), n_small, H, W,
+                                           self.step, self.g1.data_ptr(), st), "aa_downsample")
+        else:
+            raise RuntimeError("eamm_b200: scale_factor == 1 is not supported by the B200 path")
+        # a4-a6 keypoint stage -> hourglass input (slot e_0 of cat_0) + sparse_deformed
+        out = {}
+        sparse_deformed = torch.empty(B, K1, Cc, h, w, dtype=torch.float32, device=dev)
+        cat0 = ws.cat[0]
+        hg_in = cat0.act(c_off=cat0.s_up, c=cat0.s_sk)
+        ws.status.zero_()
+        L.check(lib.eamm_kp_stage(ws.small.data_ptr(), small_stride, C.byref(kd), C.byref(ks), K,
+                                  float(m.kp_variance), C.byref(hg_in), sparse_deformed.data_ptr(),
+                                  ws.status.data_ptr(), st), "kp_stage")
+        out["sparse_deformed"] = sparse_deformed
+        # a7 hourglass encoder: e_{i+1} = down_block_i(e_i)
+        nb = self.nb
+        for i, layer in enumerate(self.enc_layers):
+            src_buf = ws.cat[i]
+            inp = src_buf.act(c_off=src_buf.s_up, c=src_buf.s_sk)
+            if i + 1 < nb:
+                dst_buf = ws.cat[i + 1]
+                dst = dst_buf.act(c_off=dst_buf.s_up, c=layer.cout)
+            else:
+                dst = ws.bott.act(c_off=0, c=layer.cout)
+            layer.launch(lib, st, inp, out=dst)
+        # decoder: up_block_j reads e_nb (j=0) or cat_{nb-j}; writes slot 'up' of cat_{nb-1-j}
+        for j, layer in enumerate(self.dec_layers):
+            inp = ws.bott.act() if j == 0 else ws.cat[nb - j].act()
+            dst_buf = ws.cat[nb - 1 - j]
+            layer.launch(lib, st, inp, out=dst_buf.act(c_off=0, c=layer.cout))
+        # a8: mask/occlusion 7x7 conv -> logits; softmax + flow combine + sigmoid
+        self.head.launch(lib, st, ws.cat[0].act(), out_nhwc_f32=ws.logits)
+        mask = torch.empty(B, K1, h, w, dtype=torch.float32, device=dev)
+        deformation = torch.empty(B, h, w, 2, dtype=torch.float32, device=dev)
+        occ = torch.empty(B, 1, h, w, dtype=torch.float32, device=dev) if self.has_occ else None
+        L.check(lib.eamm_flow_combine(ws.logits.data_ptr(), self.head.cout, C.byref(kd), C.byref(ks), K,
+                                      1 if self.has_occ else 0, B, h, w, mask.data_ptr(), deformation.data_ptr(),
+                                      _ptr(occ), st), "flow_combine")
+        out["mask"] = mask
+        out["deformation"] = deformation
+        if occ is not None:
+            out["occlusion_map"] = occ
+        self._keep = (keep_d, keep_s)
+        self.last_status = ws.status
+        return out, ws
+
+
+def _bn_dict(bn):
+    return {"weight": bn.weight.detach().float(), "bias": bn.bias.detach().float(),
+            "running_mean": bn.running_mean.detach().float(), "running_var": bn.running_var.detach().float()}
+
+
+class GeneratorEngine:
+    """Executor for OcclusionAwareGenerator.forward (generator.py:59-97)."""
+
+    def __init__(self, module, precision):
+        self.m = module
+        self.precision = precision
+        self.lib = L.load()
+        self.impl = "simt"
+        self.mode = {"fp32_simt": "f32", "fp32": "bf16x2", "bf16": "bf16"}[precision]
+        self.calign = 4 if self.impl == "simt" else 64
+        self.nalign = 4 if self.impl == "simt" else 16
+        self.ws = {}
+        self.dm = DenseMotionEngine(module.dense_motion_network, precision) \
+            if module.dense_motion_network is not None else None
+        self._pack()
+
+    def _pack(self):
+        m, ca, na, impl = self.m, self.calign, self.nalign, self.impl
+        self.device = m.final.weight.device
+
+        def folded(blk):
+            return fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
+
+        w, b = folded(m.first)
+        self.first = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, _round_up(m.num_channels, ca), na, impl)
+        self.down = []
+        for i, blk in enumerate(m.down_blocks):
+            w, b = folded(blk)
+            self.down.append(ConvLayer("down%d" % i, L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
+                                       _round_up(blk.conv.in_channels, ca), na, impl))
+        self.res = []
+        blocks = list(m.bottleneck.children())
+        for i, blk in enumerate(blocks):
+            w1, b1 = fold_bn(blk.conv1.weight.detach().float(), blk.conv1.bias.detach().float(), _bn_dict(blk.norm2))
+            c = blk.conv1.in_channels
+            l1 = ConvLayer("res%d.conv1" % i, L.CONV_3X3, L.EPI_RELU, w1, b1, _round_up(c, ca), na, impl)
+            nxt = bn_affine(_bn_dict(blocks[i + 1].norm1)) if i + 1 < len(blocks) else (None, None)
+            l2 = ConvLayer("res%d.conv2" % i, L.CONV_3X3, 0, blk.conv2.weight.detach().float(),
+                           blk.conv2.bias.detach().float(), _round_up(c, ca), na, impl, scale2=nxt[0], shift2=nxt[1])
+            self.res.append((l1, l2))
+        self.pre = None
+        if blocks:
+            s, t = bn_affine(_bn_dict(blocks[0].norm1))
+            cpad = _round_up(s.numel(), 64)
+            self.pre = (torch.ones(cpad, device=self.device), torch.zeros(cpad, device=self.device))
+            self.pre[0][:s.numel()] = s
+            self.pre[1][:t.numel()] = t
+        self.up = []
+        for i, blk in enumerate(m.up_blocks):
+            w, b = folded(blk)
+            self.up.append(ConvLayer("up%d" % i, L.CONV_UP2_3X3, L.EPI_RELU, w, b,
+                                     _round_up(blk.conv.in_channels, ca), na, impl))
+        self.final = ConvLayer("final", L.CONV_7X7, L.EPI_SIGMOID, m.final.weight.detach().float(),
+                               m.final.bias.detach().float(), _round_up(m.final.in_channels, ca), na, impl)
+
+    def workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self.ws.get(key)
+        if ws is not None:
+            return ws
+        m, dev, ca, mode = self.m, self.device, self.calign, self.mode
+        nd = len(m.down_blocks)
+        if H % (1 << nd) or W % (1 << nd):
+            raise RuntimeError("eamm_b200: image size must be divisible by %d" % (1 << nd))
+        ws = type("WS", (), {})()
+        ws.src = ActBuf(B, H, W, self.first.cin, mode, dev)
+        ws.enc = [ActBuf(B, H, W, _round_up(m.first.conv.out_channels, ca), mode, dev)]
+        for i, blk in enumerate(m.down_blocks):
+            ws.enc.append(ActBuf(B, H >> (i + 1), W >> (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
+        fh, fw = H >> nd, W >> nd
+        cb = ws.enc[-1].c_buf
+        ws.x = [ActBuf(B, fh, fw, cb, mode, dev), ActBuf(B, fh, fw, cb, mode, dev)]
+        ws.a = ActBuf(B, fh, fw, cb, mode, dev)
+        ws.t = ActBuf(B, fh, fw, cb, mode, dev)
+        ws.dec = []
+        for i, blk in enumerate(m.up_blocks):
+            ws.dec.append(ActBuf(B, fh << (i + 1), fw << (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
+        self.ws[key] = ws
+        return ws
+
+    def run(self, source_image, kp_driving, kp_source):
+        m, lib = self.m, self.lib
+        if source_image.dim() != 4 or source_image.shape[1] != m.num_channels:
+            raise RuntimeError("eamm_b200: source_image must be [B,%d,H,W]" % m.num_channels)
+        B, Cc, H, W = source_image.shape
+        shared = source_image.stride(0) == 0 and B > 1
+        src = source_image[:1].contiguous() if shared else source_image.contiguous()
+        src_n_stride = 0 if shared else Cc * H * W
+        ws = self.workspace(B, H, W)
+        st = current_stream_ptr()
+        dev = self.device
+        nsrc = 1 if shared else B
+        # encoder (generator.py:61-63); with a shared (stride-0) source it runs once and is broadcast
+        L.check(lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(ws.src.act(n=nsrc)), st), "nchw_to_act")
+        self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
+        for i, layer in enumerate(self.down):
+            layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
+        result = {}
+        feat = ws.enc[-1]
+        blocks = self.res
+        if self.dm is not None:
+            dmo, dws = self.dm.run(src.expand(B, -1, -1, -1) if shared else src, kp_driving, kp_source,
+                                   src_n_stride=src_n_stride)
+            self.last_dm = dmo
+            result["mask"] = dmo["mask"]
+            result["sparse_deformed"] = dmo["sparse_deformed"]
+            occ = dmo.get("occlusion_map")
+            if occ is not None:
+                result["occlusion_map"] = occ
+            deformation = dmo["deformation"]
+            if deformation.shape[1] != feat.h or deformation.shape[2] != feat.w:
+                raise RuntimeError("eamm_b200: motion grid %s must match the encoder feature map %dx%d "
+                                   "(scale_factor == 2**-num_down_blocks)" % (tuple(deformation.shape[1:3]), feat.h, feat.w))
+            # a9-i feature warp x occlusion (+ fused norm1/relu of the first ResBlock)
+            fa = feat.act(n=B, broadcast=shared)
+            out2 = ws.a.act() if blocks else None
+            L.check(lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(ws.x[0].act()),
+                                          C.byref(out2) if out2 is not None else None,
+                                          _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
+                                          st), "warp_occlude")
+            # a9-ii deformed image
+            deformed = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
+            L.check(lib.eamm_warp_image(src.data_ptr(), src_n_stride, deformation.data_ptr(), deformed.data_ptr(),
+                                        B, Cc, H, W, deformation.shape[1], deformation.shape[2], st), "warp_image")
+            result["deformed"] = deformed
+            x = ws.x[0]
+        else:
+            raise RuntimeError("eamm_b200: dense_motion_params=None is not supported by the B200 path")
+        # bottleneck (generator.py:89): t = relu(bn2(conv1(a))); x' = conv2(t) + x; a' = relu(bn1'(x'))
+        cur = 0
+        for i, (l1, l2) in enumerate(blocks):
+            l1.launch(lib, st, ws.a.act(), out=ws.t.act(c=l1.cout))
+            nxt = ws.x[1 - cur]
+            last = i + 1 == len(blocks)
+            l2.launch(lib, st, ws.t.act(), out=nxt.act(c=l2.cout), residual=ws.x[cur].act(c=l2.cout),
+                      out2=None if last else ws.a.act(c=l2.cout))
+            cur = 1 - cur
+        x = ws.x[cur]
+        # decoder (generator.py:90-91)
+        for i, layer in enumerate(self.up):
+            layer.launch(lib, st, x.act(), out=ws.dec[i].act(c=layer.cout))
+            x = ws.dec[i]
+        # final conv + sigmoid (generator.py:92-93)
+        pred = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
+        self.final.launch(lib, st, x.act(), out_nchw=pred, out_nchw_c=Cc)
+        result["prediction"] = pred
+        self._keep = src
+        return result

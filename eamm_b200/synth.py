@@ -1,0 +1,114 @@
+"""Deterministic synthetic weights and inputs for the generation hot path.
+
+The reference ships no checkpoints (SURVEY.md §2 notes), so parity and benchmarks run on seeded
+random weights laid out exactly like ``OcclusionAwareGenerator.state_dict()`` of the reference
+(196 keys for the full config; key names follow /root/reference/modules/generator.py:14-48,
+dense_motion.py:12-30 and util.py:858-1052).  BatchNorm statistics and affine terms are randomised
+(default init mean 0 / var 1 would hide BN-folding bugs).
+
+Input recipe follows SURVEY.md §8(d): source ``rand(B,3,H,W)``, ``kp.value = rand*1.6-0.8``,
+``kp.jacobian = eye(2) + 0.1*randn``.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+
+def conv_layers(cfg):
+    """[(prefix, cin, cout, k, has_norm)] for every nn.Conv2d of the generator, reference key order."""
+    nc, nkp = cfg["num_channels"], cfg["num_kp"]
+    be, mf = cfg["block_expansion"], cfg["max_features"]
+    out = []
+    dm = cfg.get("dense_motion_params")
+    if dm is not None:
+        dbe, dmf, nb = dm["block_expansion"], dm["max_features"], dm["num_blocks"]
+        cin0 = (nkp + 1) * (nc + 1)
+        p = "dense_motion_network."
+        for i in range(nb):                                   # util.py:948-952
+            ci = cin0 if i == 0 else min(dmf, dbe * 2 ** i)
+            co = min(dmf, dbe * 2 ** (i + 1))
+            out.append((p + f"hourglass.encoder.down_blocks.{i}", ci, co, 3, True))
+        for j, i in enumerate(range(nb)[::-1]):               # util.py:973-977
+            ci = (1 if i == nb - 1 else 2) * min(dmf, dbe * 2 ** (i + 1))
+            co = min(dmf, dbe * 2 ** i)
+            out.append((p + f"hourglass.decoder.up_blocks.{j}", ci, co, 3, True))
+        hg_out = dbe + cin0                                    # util.py:980
+        out.append((p + "mask", hg_out, nkp + 1, 7, False))
+        if cfg.get("estimate_occlusion_map", False):
+            out.append((p + "occlusion", hg_out, 1, 7, False))
+    out.append(("first", nc, be, 7, True))
+    nd = cfg["num_down_blocks"]
+    for i in range(nd):
+        out.append((f"down_blocks.{i}", min(mf, be * 2 ** i), min(mf, be * 2 ** (i + 1)), 3, True))
+    for i in range(nd):
+        out.append((f"up_blocks.{i}", min(mf, be * 2 ** (nd - i)), min(mf, be * 2 ** (nd - i - 1)), 3, True))
+    cb = min(mf, be * 2 ** nd)
+    for i in range(cfg["num_bottleneck_blocks"]):
+        out.append((f"bottleneck.r{i}", cb, cb, 3, "res"))
+    out.append(("final", be, nc, 7, False))
+    return out
+
+
+def _bn(sd, name, c, g):
+    sd[name + ".weight"] = torch.rand(c, generator=g) + 0.5
+    sd[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+    sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+    sd[name + ".running_var"] = torch.rand(c, generator=g) + 0.5
+    sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+
+
+def _conv(sd, name, cin, cout, k, g, gain=1.0):
+    bound = gain * math.sqrt(3.0 / (cin * k * k))              # unit-gain fan-in uniform
+    sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+    sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * 0.1
+
+
+def make_state_dict(cfg, seed=0):
+    """Seeded fp32 CPU state dict with the reference's key layout."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    dm = cfg.get("dense_motion_params")
+    for prefix, cin, cout, k, kind in conv_layers(cfg):
+        if kind == "res":                                       # util.py:863-870
+            _conv(sd, prefix + ".conv1", cin, cout, k, g, gain=1.4)
+            _conv(sd, prefix + ".conv2", cin, cout, k, g, gain=0.7)
+            _bn(sd, prefix + ".norm1", cin, g)
+            _bn(sd, prefix + ".norm2", cin, g)
+        elif kind:
+            _conv(sd, prefix + ".conv", cin, cout, k, g, gain=1.4)
+            _bn(sd, prefix + ".norm", cout, g)
+        else:
+            _conv(sd, prefix, cin, cout, k, g, gain=0.5 if prefix == "final" else 2.0)
+    if dm is not None and dm.get("scale_factor", 1) != 1:       # dense_motion.py:29-30 buffer
+        sd["dense_motion_network.down.weight"] = aa_kernel(cfg["num_channels"])
+    return sd
+
+
+def aa_kernel(channels, sigma=1.5):
+    """The fixed 13x13 Gaussian buffer of AntiAliasInterpolation2d (util.py:1012-1036)."""
+    ks = 2 * round(sigma * 4) + 1
+    ax = torch.arange(ks, dtype=torch.float32)
+    mean = (ks - 1) / 2
+    g1 = torch.exp(-(ax - mean) ** 2 / (2 * sigma ** 2))
+    k2 = g1[:, None] * g1[None, :]
+    k2 = k2 / torch.sum(k2)
+    return k2.view(1, 1, ks, ks).repeat(channels, 1, 1, 1)
+
+
+def make_inputs(batch, cfg, size=256, seed=1, shared_source=False, with_jacobian=True):
+    """(source_image, kp_driving, kp_source) fp32 CPU tensors, SURVEY.md §8(d) recipe."""
+    g = torch.Generator().manual_seed(seed)
+    nkp, nc = cfg["num_kp"], cfg["num_channels"]
+    nsrc = 1 if shared_source else batch
+    src = torch.rand(nsrc, nc, size, size, generator=g)
+    kps = {"value": torch.rand(nsrc, nkp, 2, generator=g) * 1.6 - 0.8}
+    kpd = {"value": torch.rand(batch, nkp, 2, generator=g) * 1.6 - 0.8}
+    if with_jacobian:
+        eye = torch.eye(2).view(1, 1, 2, 2)
+        kps["jacobian"] = eye + 0.1 * torch.randn(nsrc, nkp, 2, 2, generator=g)
+        kpd["jacobian"] = eye + 0.1 * torch.randn(batch, nkp, 2, 2, generator=g)
+    if shared_source:
+        src = src.expand(batch, -1, -1, -1).contiguous()
+        kps = {k: v.expand(batch, *v.shape[1:]).contiguous() for k, v in kps.items()}
+    return src, kpd, kps

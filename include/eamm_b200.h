@@ -1,0 +1,148 @@
+/*
+ * eamm_b200 -- C ABI of the B200-native EAMM generation hot path.
+ *
+ * The reference (jixinya/EAMM) is pure Python/PyTorch and has no FFI: its operator API for this
+ * path is the nn.Module pair modules/generator.py:8 (OcclusionAwareGenerator) and
+ * modules/dense_motion.py:7 (DenseMotionNetwork).  The drop-in Python classes in
+ * eamm_b200/modules/ keep that API and call the entry points below through ctypes; every entry
+ * point names the reference lines it replaces.  All pointers are DEVICE pointers owned by the
+ * caller, nothing is allocated or cached inside, every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), and the return value is 0 on success, a negative
+ * EAMM_ERR_* for a rejected argument, or a positive cudaError_t from the launch.
+ *
+ * Activation layout ("eamm_act"): NHWC with the channel axis optionally holding 2 bf16 planes
+ * (hi, lo) so that value = hi + lo carries 16 mantissa bits; see DESIGN.md "Data layout in HBM".
+ */
+#ifndef EAMM_B200_H
+#define EAMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAMM_ABI_VERSION 1
+
+enum { EAMM_F32 = 0, EAMM_BF16 = 1 };
+
+enum {
+  EAMM_ERR_ARG = -1,       /* null pointer / non-positive size */
+  EAMM_ERR_SHAPE = -2,     /* shapes of the operands do not agree */
+  EAMM_ERR_DTYPE = -3,     /* dtype / plane combination not supported by this entry point */
+  EAMM_ERR_ALIGN = -4,     /* pointer or stride not aligned as the kernel requires */
+  EAMM_ERR_UNSUPPORTED = -5
+};
+
+/* NHWC activation view.  Element (n, y, x, plane p, channel ch) lives at
+ *   data[n*n_stride + (y*w + x)*planes*c_buf + p*c_buf + c_off + ch]        (in elements)
+ * A view selects channels [c_off, c_off+c) of a wider buffer, which is how the hourglass skip
+ * concatenations (util.py:982-987) are formed without a copy.  n_stride == 0 broadcasts one image
+ * over the whole batch (shared source). */
+typedef struct {
+  void* data;
+  int32_t dtype;     /* EAMM_F32 (planes must be 1) or EAMM_BF16 (planes 1 or 2) */
+  int32_t n, h, w;
+  int32_t c;
+  int32_t c_off;
+  int32_t c_buf;
+  int32_t planes;
+  int64_t n_stride;
+} eamm_act;
+
+/* Keypoints of one side (driving or source): value [n,K,2] fp32 (x,y) and optionally
+ * jacobian [n,K,2,2] fp32 (NULL when the caller's dict has no 'jacobian' key,
+ * dense_motion.py:55).  n_stride_* == 0 broadcasts one keypoint set over the batch. */
+typedef struct {
+  const float* value;
+  const float* jacobian;
+  int64_t value_stride;     /* elements between batch items, K*2 or 0 */
+  int64_t jacobian_stride;  /* K*4 or 0 */
+} eamm_kp;
+
+/* ---- conv kinds / epilogue flags for eamm_conv_* -------------------------------------------- */
+enum {
+  EAMM_CONV_3X3 = 0,       /* 3x3, padding 1 (util.py:865-866, 889-890, 909-910)            */
+  EAMM_CONV_7X7 = 1,       /* 7x7, padding 3 (generator.py:25,46; dense_motion.py:18,21)     */
+  EAMM_CONV_UP2_3X3 = 2    /* F.interpolate(x2, nearest) then 3x3 pad 1 (util.py:895-897),
+                              executed as four 2x2 convolutions on the low-res input, one per
+                              output-pixel parity class; weights are pre-combined by the host  */
+};
+enum {
+  EAMM_EPI_RELU = 1,       /* y = max(y, 0) after the folded-BN bias                          */
+  EAMM_EPI_POOL2 = 2,      /* 2x2 average pool after the activation (util.py:913,919)         */
+  EAMM_EPI_SIGMOID = 4     /* y = sigmoid(y) (generator.py:93) -- only with out_nchw          */
+};
+
+typedef struct {
+  int32_t kind;            /* EAMM_CONV_*                                                      */
+  int32_t flags;           /* EAMM_EPI_*                                                       */
+  int32_t cin, cout;
+  const eamm_act* in;      /* input view, c == cin                                             */
+  const void* weight;      /* layout depends on the implementation, see each entry point       */
+  const float* bias;       /* [cout] fp32, conv bias with eval-BN folded in                    */
+  const eamm_act* residual;/* optional: y += residual (util.py:879), same shape as out         */
+  const eamm_act* out;     /* optional NHWC output view (c == cout)                            */
+  const eamm_act* out2;    /* optional second NHWC output: relu(y*scale2 + shift2), i.e. the
+                              next ResBlock2d's norm1+relu (util.py:873-874) fused here         */
+  const float* scale2;     /* [cout] fp32                                                      */
+  const float* shift2;     /* [cout] fp32                                                      */
+  float* out_nchw;         /* optional fp32 NCHW output [n, out_nchw_c, H, W] (final prediction)*/
+  int32_t out_nchw_c;      /* channels written to out_nchw (<= cout; cout may be padded)       */
+  float* out_nhwc_f32;     /* optional fp32 NHWC raw output [n, H, W, cout] (mask/occ logits)  */
+} eamm_conv_args;
+
+/* ---- library info --------------------------------------------------------------------------- */
+int eamm_abi_version(void);
+/* 1 when the visible device is sm_100 and the kernels in this library can run on it. */
+int eamm_device_ok(int device);
+
+/* ---- a3: AntiAliasInterpolation2d (util.py:1044-1052; call site dense_motion.py:83) ---------
+ * src [n,3,H,W] fp32 NCHW -> dst [n,H/step,W/step,4] fp32 (RGB0 per pixel).  Zero pad 6, 13x13
+ * Gaussian (sigma 1.5, normalised), subsample ::step (step = int(1/scale_factor), 4 here).  g1 is the 13-tap 1-D factor (the 2-D buffer of the
+ * reference is its normalised outer product). */
+int eamm_aa_downsample(const float* src, int64_t src_n_stride, float* dst, int n, int H, int W,
+                       int step, const float* g1, void* stream);
+
+/* ---- a4+a5+a6: heatmaps, sparse motions, deformed source (dense_motion.py:32-79, util.py:815-855)
+ * small [n,h,w,4] fp32 from eamm_aa_downsample (small_n_stride 0 = shared source);
+ * writes the (K+1)*4-channel hourglass input (channel order [hm_k,R_k,G_k,B_k], dense_motion.py:93-94,
+ * remaining channels of the view zero-filled) and sparse_deformed [n,K+1,3,h,w] fp32 NCHW.
+ * status (device int32, may be NULL) gets bit 0 set when a driving Jacobian is singular
+ * (torch.inverse would raise, dense_motion.py:56). */
+int eamm_kp_stage(const float* small_img, int64_t small_n_stride, const eamm_kp* kp_driving,
+                  const eamm_kp* kp_source, int num_kp, float kp_variance, const eamm_act* hg_in,
+                  float* sparse_deformed, int32_t* status, void* stream);
+
+/* ---- a8 epilogue: softmax over K+1 mask logits, flow combine, sigmoid occlusion
+ * (dense_motion.py:98-111).  logits [n,h,w,ldl] fp32 NHWC with channels [0,K] = mask logits and
+ * channel K+1 = occlusion logit (has_occ).  Sparse motions are recomputed from the keypoints.
+ * Outputs: mask [n,K+1,h,w] fp32, deformation [n,h,w,2] fp32, occlusion [n,1,h,w] fp32. */
+int eamm_flow_combine(const float* logits, int ldl, const eamm_kp* kp_driving, const eamm_kp* kp_source,
+                      int num_kp, int has_occ, int n, int h, int w, float* mask, float* deformation,
+                      float* occlusion, void* stream);
+
+/* ---- a9-i: grid_sample(features, deformation) * occlusion (generator.py:57,79-84), fused with
+ * the first ResBlock2d's norm1+relu (out2, optional).  feat/out/out2 are NHWC views with equal
+ * h,w,c; deformation [n,h,w,2]; occlusion [n,1,h,w] or NULL. */
+int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
+                      const eamm_act* out, const eamm_act* out2, const float* scale2,
+                      const float* shift2, void* stream);
+
+/* ---- a9-ii: 'deformed' = grid_sample(source, bilinear_upsample(deformation)) (generator.py:50-57,86)
+ * src [n,C,H,W] fp32 NCHW, deformation [n,h,w,2] fp32 -> dst [n,C,H,W] fp32 NCHW. */
+int eamm_warp_image(const float* src, int64_t src_n_stride, const float* deformation, float* dst,
+                    int n, int C, int H, int W, int h, int w, void* stream);
+
+/* ---- source image NCHW fp32 -> NHWC activation view (channels beyond C zero-filled) ---------- */
+int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, const eamm_act* dst, void* stream);
+
+/* ---- convolutions (a1, a2, a7, a8-conv, a10, a11, a12) --------------------------------------
+ * eamm_conv_simt: fp32 CUDA-core implicit GEMM; weight fp32 [taps][cin][cout] (UP2: [4 classes][4 taps]).
+ *                 Accepts F32 and BF16 (1 or 2 planes) activations.  Exact-fp32 parity path. */
+int eamm_conv_simt(const eamm_conv_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAMM_B200_H */

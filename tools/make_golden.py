@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (authoring container only).
+
+Imports /root/reference (read-only), loads the seeded synthetic state dict of eamm_b200.synth into
+the real ``OcclusionAwareGenerator`` (strict=True, which also pins the 196-key layout), runs it on
+CPU fp32 and
+  1. asserts the restatement in oracle/eamm_oracle.py reproduces every output bit-for-bit,
+  2. writes the outputs as fixtures: full tensors for the tiny config, strided sub-samples plus
+     float64 checksums for the full 256x256 config (kept small on purpose).
+
+Usage:  python tools/make_golden.py            (needs /root/reference; never runs on the GPU box)
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(1, "/root/reference")
+warnings.filterwarnings("ignore")
+
+from eamm_b200.config import get_config          # noqa: E402
+from eamm_b200 import synth                      # noqa: E402
+from oracle import eamm_oracle as oracle         # noqa: E402
+
+from modules.generator import OcclusionAwareGenerator  # noqa: E402  (the reference)
+
+KEYS = ["mask", "sparse_deformed", "occlusion_map", "deformed", "prediction"]
+STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
+
+
+def run_case(name, cfg_name, batch, size, with_jacobian=True, shared_source=False, full=True):
+    cfg = get_config(cfg_name)
+    sd = synth.make_state_dict(cfg, seed=0)
+    ref = OcclusionAwareGenerator(**cfg).eval()
+    missing = ref.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=1, with_jacobian=with_jacobian,
+                                      shared_source=shared_source)
+    with torch.no_grad():
+        want = ref(src, kp_driving=kpd, kp_source=kps)
+        want_dm = ref.dense_motion_network(source_image=src, kp_driving=kpd, kp_source=kps)
+    got = oracle.generator_forward(sd, cfg, src, kpd, kps)
+    got_dm = oracle.dense_motion_forward(sd, cfg, src, kpd, kps)
+    for k in KEYS:
+        assert torch.equal(want[k], got[k]), f"{name}: oracle != reference on {k}"
+    for k in ["deformation", "mask", "occlusion_map", "sparse_deformed"]:
+        assert torch.equal(want_dm[k], got_dm[k]), f"{name}: oracle != reference on dense_motion.{k}"
+    want = dict(want)
+    want["deformation"] = want_dm["deformation"]
+    blob = {"meta": np.array([batch, size, int(with_jacobian), int(shared_source)], dtype=np.int64)}
+    blob["in_checksum"] = np.array([src.double().sum(), kpd["value"].double().sum(), kps["value"].double().sum()])
+    for k, v in want.items():
+        a = v.numpy()
+        blob["sum_" + k] = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+        if full:
+            blob[k] = a
+        else:
+            s = STRIDES[k]
+            blob[k] = a[..., ::s, ::s].copy() if k != "deformation" else a[:, ::s, ::s, :].copy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **blob)
+    stats = {k: (float(v.min()), float(v.max()), float(v.mean())) for k, v in want.items()}
+    print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB")
+    for k, s in stats.items():
+        print("   ", k, "min/max/mean = %.4f %.4f %.4f" % s)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    run_case("tiny_b2", "tiny", 2, 64)
+    run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
+    run_case("full_b2", "full", 2, 256, full=False)
+    run_case("full_b3_shared", "full", 3, 256, shared_source=True, full=False)
