@@ -54,6 +54,7 @@ _PROTOS = {
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_nchw_to_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Act), C.c_void_p]),
     "eamm_conv_simt": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "eamm_conv_tc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
 }
 
 _lib = None

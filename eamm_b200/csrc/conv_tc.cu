@@ -1,0 +1,478 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: TMA-staged NHWC tiles, UMMA (bf16 x bf16 -> fp32
+// accumulators in TMEM), warp-specialised persistent CTAs, fused epilogues.
+//
+//   GEMM view   D[128 pixels, BN couts] += A[128 pixels, 64 ch] * B[BN couts, 64 ch]^T
+//   A tile      one 4-D TMA box {64 ch, bw, bh, bn} (bw*bh*bn = 128 pixels) of the NHWC input,
+//               shifted by the filter tap (dy, dx); out-of-image pixels are zero-filled by TMA,
+//               which is exactly the conv's zero padding.  SWIZZLE_128B, K-major.
+//   B tile      2-D TMA box {64 k, BN rows} of the host-packed weight matrix [couts][K], K-major.
+//   K loop      taps x passes x (cin/64).  passes = 1 (bf16) or 3 (split-bf16 "fp32" mode:
+//               a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with activations/weights stored as hi/lo planes).
+//   roles       warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+//   pipelines   smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring so the
+//               epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
+// 2x2 convs), residual add + fused next norm1/ReLU (ResBlock2d), fp32 NHWC logits, sigmoid NCHW.
+// Reference call sites: util.py:872-880, 895-900, 915-920, 934-938; generator.py:92-93;
+// dense_motion.py:98,110.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace eamm {
+
+int conv_check_args(const eamm_conv_args* a, int cout_align);   // conv_simt.cu
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+struct ConvTcParams {
+  int N, H, W;
+  int bw, bh, bn, bw_log2, bh_log2;
+  int tiles_x, tiles_y, tiles_n, n_tiles, classes;
+  int BN, kind, flags, taps, ksize, cin_chunks, passes;
+  int a_c_off, a_c_buf;
+  int num_stages, cout;
+  int has_out, has_out2, has_res;
+  ActView out, out2, res;
+  const float* bias; const float* scale2; const float* shift2;
+  float* out_nchw; int out_nchw_c; float* out_nhwc;
+  long long total_tiles;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major SWIZZLE_128B smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 |
+// SBO(=1024B>>4)<<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int CH> struct TmemLd;
+template <> struct TmemLd<32> {
+  __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+  }
+};
+template <> struct TmemLd<16> {
+  __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+  }
+};
+
+// bf16 vector store/load of CH consecutive channels (hi plane, and lo plane when planes == 2)
+template <int CH>
+__device__ __forceinline__ void store_chunk(const ActView& v, long long off, const float* f) {
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
+#pragma unroll
+  for (int g = 0; g < CH / 8; ++g) {
+    uint2 a = float4_to_bf16x4(make_float4(f[8 * g], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3]));
+    uint2 b = float4_to_bf16x4(make_float4(f[8 * g + 4], f[8 * g + 5], f[8 * g + 6], f[8 * g + 7]));
+    *reinterpret_cast<uint4*>(p + 8 * g) = make_uint4(a.x, a.y, b.x, b.y);
+    if (v.planes == 2) {
+      float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+      uint2 la = float4_to_bf16x4(make_float4(f[8 * g] - ha.x, f[8 * g + 1] - ha.y, f[8 * g + 2] - ha.z, f[8 * g + 3] - ha.w));
+      uint2 lb = float4_to_bf16x4(make_float4(f[8 * g + 4] - hb.x, f[8 * g + 5] - hb.y, f[8 * g + 6] - hb.z, f[8 * g + 7] - hb.w));
+      *reinterpret_cast<uint4*>(p + v.c_buf + 8 * g) = make_uint4(la.x, la.y, lb.x, lb.y);
+    }
+  }
+}
+template <int CH>
+__device__ __forceinline__ void add_chunk(const ActView& v, long long off, float* f) {
+  const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(v.data) + off;
+#pragma unroll
+  for (int g = 0; g < CH / 8; ++g) {
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p + 8 * g));
+    float4 a = bf16x4_to_float4(make_uint2(r.x, r.y)), b = bf16x4_to_float4(make_uint2(r.z, r.w));
+    f[8 * g] += a.x; f[8 * g + 1] += a.y; f[8 * g + 2] += a.z; f[8 * g + 3] += a.w;
+    f[8 * g + 4] += b.x; f[8 * g + 5] += b.y; f[8 * g + 6] += b.z; f[8 * g + 7] += b.w;
+    if (v.planes == 2) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(p + v.c_buf + 8 * g));
+      float4 c = bf16x4_to_float4(make_uint2(q.x, q.y)), d = bf16x4_to_float4(make_uint2(q.z, q.w));
+      f[8 * g] += c.x; f[8 * g + 1] += c.y; f[8 * g + 2] += c.z; f[8 * g + 3] += c.w;
+      f[8 * g + 4] += d.x; f[8 * g + 5] += d.y; f[8 * g + 6] += d.z; f[8 * g + 7] += d.w;
+    }
+  }
+}
+
+struct TileCoord { int x0, y0, n0, cls, nt; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, long long tile) {
+  TileCoord t;
+  t.nt = (int)(tile % p.n_tiles); tile /= p.n_tiles;
+  t.cls = (int)(tile % p.classes); tile /= p.classes;
+  t.x0 = (int)(tile % p.tiles_x) * p.bw; tile /= p.tiles_x;
+  t.y0 = (int)(tile % p.tiles_y) * p.bh; tile /= p.tiles_y;
+  t.n0 = (int)tile * p.bn;
+  return t;
+}
+
+// Epilogue for one accumulator tile, CH columns at a time.
+template <int CH>
+__device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                              int quadrant, int lane) {
+  const int r = quadrant * 32 + lane;
+  const int xl = r & (p.bw - 1);
+  const int yl = (r >> p.bw_log2) & (p.bh - 1);
+  const int nl = r >> (p.bw_log2 + p.bh_log2);
+  const int x = tc.x0 + xl, y = tc.y0 + yl, n = tc.n0 + nl;
+  bool valid = (y < p.H) && (n < p.N);
+  const bool pool = p.flags & EAMM_EPI_POOL2;
+  int oy = y, ox = x, OH = p.H, OW = p.W;
+  if (pool) { oy = y >> 1; ox = x >> 1; OH = p.H >> 1; OW = p.W >> 1; valid = valid && !(xl & 1) && !(yl & 1); }
+  else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); OH = 2 * p.H; OW = 2 * p.W; }
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  for (int c0 = 0; c0 < p.BN; c0 += CH) {
+    uint32_t raw[CH];
+    TmemLd<CH>::ld(taddr + c0, raw);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float f[CH];
+    const int co = tc.nt * p.BN + c0;
+#pragma unroll
+    for (int g = 0; g < CH / 4; ++g) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co) + g);
+      f[4 * g] = __uint_as_float(raw[4 * g]) + b.x;
+      f[4 * g + 1] = __uint_as_float(raw[4 * g + 1]) + b.y;
+      f[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + b.z;
+      f[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + b.w;
+    }
+    if (p.flags & EAMM_EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (pool) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        float s = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
+        s += __shfl_xor_sync(0xffffffffu, s, p.bw);
+        f[j] = 0.25f * s;
+      }
+    }
+    if (valid) {
+      if (p.has_res) add_chunk<CH>(p.res, act_offset(p.res, n, oy, ox, co), f);
+      if (p.has_out) store_chunk<CH>(p.out, act_offset(p.out, n, oy, ox, co), f);
+      if (p.has_out2) {
+        float g2[CH];
+#pragma unroll
+        for (int g = 0; g < CH / 4; ++g) {
+          float4 s = __ldg(reinterpret_cast<const float4*>(p.scale2 + co) + g);
+          float4 t = __ldg(reinterpret_cast<const float4*>(p.shift2 + co) + g);
+          g2[4 * g] = fmaxf(fmaf(f[4 * g], s.x, t.x), 0.f);
+          g2[4 * g + 1] = fmaxf(fmaf(f[4 * g + 1], s.y, t.y), 0.f);
+          g2[4 * g + 2] = fmaxf(fmaf(f[4 * g + 2], s.z, t.z), 0.f);
+          g2[4 * g + 3] = fmaxf(fmaf(f[4 * g + 3], s.w, t.w), 0.f);
+        }
+        store_chunk<CH>(p.out2, act_offset(p.out2, n, oy, ox, co), g2);
+      }
+      if (p.out_nhwc != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(p.out_nhwc + (((long long)n * OH + oy) * OW + ox) * p.cout + co);
+#pragma unroll
+        for (int g = 0; g < CH / 4; ++g) dst[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+      }
+      if (p.out_nchw != nullptr) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (co + j < p.out_nchw_c) {
+            float o = f[j];
+            if (p.flags & EAMM_EPI_SIGMOID) o = 1.f / (1.f + expf(-o));
+            p.out_nchw[(((long long)n * p.out_nchw_c + co + j) * OH + oy) * OW + ox] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 16 + 4];
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dynamic smem is only guaranteed 16B-aligned by the ABI: align the ring to 1024 B by hand
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (34 + a); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int KC = p.taps * p.passes * p.cin_chunks;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int brow = tc.cls * p.cout + tc.nt * p.BN;
+        int kc = 0;
+        for (int t = 0; t < p.taps; ++t) {
+          int dy, dx;
+          if (p.kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
+          else { dy = t / p.ksize - (p.ksize >> 1); dx = t % p.ksize - (p.ksize >> 1); }
+          for (int ps = 0; ps < p.passes; ++ps) {
+            const int cbase = p.a_c_off + (ps == 2 ? p.a_c_buf : 0);
+            for (int cc = 0; cc < p.cin_chunks; ++cc, ++kc) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_4d(sa, &tmA, full_bar(stage), cbase + cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
+              tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kc * 64, brow);
+              if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps (TMEM lanes by warp%4)
+    const int quadrant = warp & 3;
+    int as = 0; uint32_t aphase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
+      if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane);
+      else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+}  // namespace eamm
+
+using namespace eamm;
+
+extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
+  int rc = conv_check_args(a, 16);
+  if (rc) return rc;
+  const eamm_act* in = a->in;
+  if (in->dtype != EAMM_BF16) return EAMM_ERR_DTYPE;
+  if (in->c_buf % 64 || in->c_off % 64 || a->cin % 64) return EAMM_ERR_ALIGN;
+  if (in->n_stride != (int64_t)in->h * in->w * in->planes * in->c_buf) return EAMM_ERR_UNSUPPORTED;
+  const eamm_act* views[3] = {a->out, a->out2, a->residual};
+  for (int i = 0; i < 3; ++i)
+    if (views[i] && (views[i]->dtype != EAMM_BF16 || views[i]->c_off % 8 || views[i]->c_buf % 8)) return EAMM_ERR_DTYPE;
+  if ((uintptr_t)in->data % 16 || (uintptr_t)a->weight % 16) return EAMM_ERR_ALIGN;
+
+  ConvTcParams p;
+  p.N = in->n; p.H = in->h; p.W = in->w;
+  // 128-pixel box: bw x bh x bn
+  int wl = ilog2_exact(in->w), hl = ilog2_exact(in->h);
+  if (wl < 1 || hl < 1) return EAMM_ERR_UNSUPPORTED;            // power-of-two maps only
+  p.bw = in->w >= 16 ? 16 : in->w;
+  p.bh = 128 / p.bw; if (p.bh > in->h) p.bh = in->h;
+  p.bn = 128 / (p.bw * p.bh);
+  p.bw_log2 = ilog2_exact(p.bw); p.bh_log2 = ilog2_exact(p.bh);
+  p.tiles_x = in->w / p.bw; p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
+  p.kind = a->kind; p.flags = a->flags; p.cout = a->cout;
+  p.ksize = a->kind == EAMM_CONV_7X7 ? 7 : 3;
+  p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : p.ksize * p.ksize;
+  p.classes = a->kind == EAMM_CONV_UP2_3X3 ? 4 : 1;
+  p.cin_chunks = a->cin / 64;
+  p.passes = in->planes == 2 ? 3 : 1;
+  p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
+  // N tile: the whole cout when it fits one UMMA (<= 256), else the largest divisor among 256/128/64
+  if (a->cout <= 256) p.BN = a->cout;
+  else if (a->cout % 256 == 0) p.BN = 256;
+  else if (a->cout % 128 == 0) p.BN = 128;
+  else if (a->cout % 64 == 0) p.BN = 64;
+  else return EAMM_ERR_UNSUPPORTED;
+  p.n_tiles = a->cout / p.BN;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return EAMM_ERR_UNSUPPORTED;
+  p.num_stages = stages;
+  p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
+  ActView dummy = make_view(in);
+  p.out = p.has_out ? make_view(a->out) : dummy;
+  p.out2 = p.has_out2 ? make_view(a->out2) : dummy;
+  p.res = p.has_res ? make_view(a->residual) : dummy;
+  p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
+  p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32;
+  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return EAMM_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmB;
+  {
+    const cuuint64_t pix = (cuuint64_t)in->planes * in->c_buf;
+    cuuint64_t dims[4] = {pix, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
+    cuuint64_t strides[3] = {pix * 2, pix * 2 * in->w, pix * 2 * in->w * in->h};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED;
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)p.taps * p.passes * a->cin;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)p.classes * a->cout};
+    cuuint64_t strides[1] = {ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    smem_set = smem;
+  }
+  long long grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}

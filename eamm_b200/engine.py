@@ -98,6 +98,36 @@ def up2_parity_weights(w):
     return torch.stack(classes, 0)
 
 
+def pack_tc_weights(full, classes, passes):
+    """[classes*taps][cout][cin] fp32 -> bf16 [classes*cout][taps*passes*cin] for eamm_conv_tc.
+
+    K order is (tap, pass, channel).  passes == 3 is the split-bf16 scheme: the weight planes
+    (hi, lo, hi) meet the activation planes (hi, hi, lo), i.e. a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.
+    """
+    ct, cout, cin = full.shape
+    taps = ct // classes
+    w = full.view(classes, taps, cout, cin).permute(0, 2, 1, 3)          # [cls][cout][taps][cin]
+    hi = w.to(torch.bfloat16)
+    if passes == 1:
+        packed = hi
+    else:
+        lo = (w - hi.float()).to(torch.bfloat16)
+        packed = torch.stack([hi, lo, hi], dim=3)                         # [cls][cout][taps][3][cin]
+    return packed.reshape(classes * cout, -1).contiguous()
+
+
+def impl_for(precision):
+    """(conv implementation, activation storage mode, channel-slot alignment, cout alignment)."""
+    import os
+    forced = os.environ.get("EAMM_B200_CONV", "")
+    if precision == "fp32_simt":
+        return "simt", "f32", 4, 4
+    mode = "bf16x2" if precision == "fp32" else "bf16"
+    if forced == "simt":
+        return "simt", mode, 4, 4
+    return ("tc3" if precision == "fp32" else "tc"), mode, 64, 16
+
+
 class ConvLayer:
     """One packed convolution: kind/flags + device tensors in the layout of the chosen kernel."""
 
@@ -121,6 +151,8 @@ class ConvLayer:
         self.bias[:cout] = b
         if impl == "simt":
             self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
+        elif impl in ("tc", "tc3"):
+            self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1)
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -150,7 +182,7 @@ class ConvLayer:
             a.out_nchw_c = out_nchw_c
         if out_nhwc_f32 is not None:
             a.out_nhwc_f32 = out_nhwc_f32.data_ptr()
-        fn = lib.eamm_conv_simt
+        fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
         L.check(fn(C.byref(a), stream), "conv %s" % self.name)
 
 
@@ -189,10 +221,7 @@ class DenseMotionEngine:
         self.m = module
         self.precision = precision
         self.lib = L.load()
-        self.impl = "simt"
-        self.mode = {"fp32_simt": "f32", "fp32": "bf16x2", "bf16": "bf16"}[precision]
-        self.calign = 4 if self.impl == "simt" else 64
-        self.nalign = 4 if self.impl == "simt" else 16
+        self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
         self.ws = {}
         self._pack()
 
@@ -362,10 +391,7 @@ class GeneratorEngine:
         self.m = module
         self.precision = precision
         self.lib = L.load()
-        self.impl = "simt"
-        self.mode = {"fp32_simt": "f32", "fp32": "bf16x2", "bf16": "bf16"}[precision]
-        self.calign = 4 if self.impl == "simt" else 64
-        self.nalign = 4 if self.impl == "simt" else 16
+        self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
         self.ws = {}
         self.dm = DenseMotionEngine(module.dense_motion_network, precision) \
             if module.dense_motion_network is not None else None

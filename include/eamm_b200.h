@@ -142,6 +142,14 @@ int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, const eamm_ac
  *                 Accepts F32 and BF16 (1 or 2 planes) activations.  Exact-fp32 parity path. */
 int eamm_conv_simt(const eamm_conv_args* args, void* stream);
 
+/* eamm_conv_tc:   tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate).  Activations must
+ *                 be EAMM_BF16 with c_buf, c_off and cin multiples of 64 and power-of-two h, w; cout a
+ *                 multiple of 16.  weight is bf16 [classes*cout][taps*passes*cin] (K contiguous),
+ *                 K ordered (tap, pass, channel); passes = 1 for single-plane inputs, 3 for hi/lo
+ *                 inputs (weight planes hi, lo, hi against activation planes hi, hi, lo).  UP2 has
+ *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout). */
+int eamm_conv_tc(const eamm_conv_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Unit check of eamm_conv_tc against eamm_conv_simt on the GPU, one subprocess per case so that a
+trap or hang in one configuration cannot take the others (or the box) down.
+
+    python tools/gpu_conv_check.py            # all cases, isolated, 90 s timeout each
+    python tools/gpu_conv_check.py --case 3   # one case in-process
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+# name, kind, flags(relu,pool), cin, cout, N, H, W, planes, residual, out2, special
+CASES = [
+    ("3x3 64->64 16x16 relu", "3x3", "r", 64, 64, 2, 16, 16, 1, 0, 0, ""),
+    ("3x3 64->64 16x16 relu x3", "3x3", "r", 64, 64, 2, 16, 16, 2, 0, 0, ""),
+    ("3x3 256->256 64x64 res+out2", "3x3", "", 256, 256, 2, 64, 64, 1, 1, 1, ""),
+    ("3x3 256->256 64x64 res+out2 x3", "3x3", "", 256, 256, 2, 64, 64, 2, 1, 1, ""),
+    ("3x3 64->128 64x64 relu pool", "3x3", "rp", 64, 128, 3, 64, 64, 1, 0, 0, ""),
+    ("3x3 64->128 64x64 relu pool x3", "3x3", "rp", 64, 128, 3, 64, 64, 2, 0, 0, ""),
+    ("up2 256->128 16x16", "up2", "r", 256, 128, 2, 16, 16, 1, 0, 0, ""),
+    ("up2 256->128 16x16 x3", "up2", "r", 256, 128, 2, 16, 16, 2, 0, 0, ""),
+    ("3x3 128->1024 4x4 N=5 pool", "3x3", "rp", 128, 1024, 5, 4, 4, 1, 0, 0, ""),
+    ("up2 1024->512 2x2 N=5", "up2", "r", 1024, 512, 5, 2, 2, 1, 0, 0, ""),
+    ("3x3 64->48 8x8 N=3", "3x3", "r", 64, 48, 3, 8, 8, 1, 0, 0, ""),
+    ("7x7 128->16 64x64 logits", "7x7", "", 128, 16, 2, 64, 64, 1, 0, 0, "nhwc"),
+    ("7x7 128->16 64x64 logits x3", "7x7", "", 128, 16, 2, 64, 64, 2, 0, 0, "nhwc"),
+    ("7x7 64->16 32x32 sigmoid nchw", "7x7", "s", 64, 16, 2, 32, 32, 1, 0, 0, "nchw"),
+]
+
+
+def run_case(idx):
+    import torch
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, ConvLayer, current_stream_ptr
+    name, kind, fl, cin, cout, N, H, W, planes, has_res, has_out2, special = CASES[idx]
+    dev = torch.device("cuda:0")
+    lib = L.load()
+    g = torch.Generator().manual_seed(100 + idx)
+    kk = {"3x3": L.CONV_3X3, "up2": L.CONV_UP2_3X3, "7x7": L.CONV_7X7}[kind]
+    ks = 7 if kind == "7x7" else 3
+    flags = (L.EPI_RELU if "r" in fl else 0) | (L.EPI_POOL2 if "p" in fl else 0) | (L.EPI_SIGMOID if "s" in fl else 0)
+    w = ((torch.rand(cout, cin, ks, ks, generator=g) * 2 - 1) * (3.0 / (cin * ks * ks)) ** 0.5).to(dev)
+    b = ((torch.rand(cout, generator=g) * 2 - 1) * 0.1).to(dev)
+    mode = "bf16x2" if planes == 2 else "bf16"
+    if planes == 1:
+        w = w.bfloat16().float()                      # same operand values for both kernels
+    x = torch.randn(N, H, W, cin, generator=g).to(dev)
+    xin = ActBuf(N, H, W, cin, mode, dev)
+    hi = x.bfloat16()
+    if planes == 2:
+        lo = (x - hi.float()).bfloat16()
+        xin.t.copy_(torch.cat([hi, lo], dim=-1))
+    else:
+        xin.t.copy_(hi)
+    s2 = (torch.rand(cout, generator=g) + 0.5).to(dev) if has_out2 else None
+    t2 = (torch.randn(cout, generator=g) * 0.1).to(dev) if has_out2 else None
+    OH, OW = H, W
+    if "p" in fl:
+        OH, OW = H // 2, W // 2
+    if kind == "up2":
+        OH, OW = 2 * H, 2 * W
+    res = None
+    if has_res:
+        res = ActBuf(N, OH, OW, cout, mode, dev)
+        r = torch.randn(N, OH, OW, cout, generator=g).to(dev)
+        rh = r.bfloat16()
+        res.t.copy_(torch.cat([rh, (r - rh.float()).bfloat16()], -1) if planes == 2 else rh)
+    st = current_stream_ptr()
+    outs = {}
+    for impl in ("simt", "tc3" if planes == 2 else "tc"):
+        layer = ConvLayer(name, kk, flags, w, b, cin, 16, impl, scale2=s2, shift2=t2)
+        o = ActBuf(N, OH, OW, cout, mode, dev) if not special else None
+        o2 = ActBuf(N, OH, OW, cout, mode, dev) if has_out2 else None
+        nhwc = torch.zeros(N, OH, OW, cout, device=dev) if special == "nhwc" else None
+        nchw = torch.zeros(N, 3, OH, OW, device=dev) if special == "nchw" else None
+        layer.launch(lib, st, xin.act(), out=o.act() if o else None, out2=o2.act() if o2 else None,
+                     residual=res.act() if res else None, out_nchw=nchw, out_nchw_c=3, out_nhwc_f32=nhwc)
+        torch.cuda.synchronize()
+        outs[impl] = [t for t in (o.to_float() if o else None, o2.to_float() if o2 else None, nhwc, nchw)
+                      if t is not None]
+    a, c = list(outs.values())
+    worst = 0.0
+    for u, v in zip(a, c):
+        d = (u - v).abs().max().item()
+        worst = max(worst, d / max(1e-6, u.abs().max().item()))
+        if not torch.isfinite(v).all():
+            worst = float("inf")
+    tol = 2e-4 if planes == 2 else 1e-2     # bf16 output rounding dominates in 1-plane mode
+    status = "OK " if worst <= tol else "BAD"
+    print("%s case %2d %-34s rel_err %.3e" % (status, idx, name, worst), flush=True)
+    return 0 if worst <= tol else 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", type=int, default=-1)
+    ap.add_argument("--timeout", type=int, default=90)
+    args = ap.parse_args()
+    if args.case >= 0:
+        return run_case(args.case)
+    bad = 0
+    for i in range(len(CASES)):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], timeout=args.timeout,
+                               capture_output=True, text=True)
+            out = (r.stdout + r.stderr).strip().splitlines()
+            keep = [l for l in out if l.startswith(("OK", "BAD"))] or out[-6:]
+            print("\n".join(keep), flush=True)
+            bad += r.returncode != 0
+        except subprocess.TimeoutExpired:
+            print("TIMEOUT case %d %s" % (i, CASES[i][0]), flush=True)
+            bad += 1
+    print("conv check: %d/%d bad" % (bad, len(CASES)))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
