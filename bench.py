@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the EAMM per-frame generation hot path on B200 (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU)
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPUs
+
+A "step" is one pass of DenseMotionNetwork + OcclusionAwareGenerator over one batch of synthetic
+256x256 frames (BASELINE.json configs[1]: batch 32, 10 keypoints; fp32-equivalent arithmetic by
+default).  One JSON line is printed by rank 0.  Work per GPU is fixed (weak scaling): with N ranks
+the job processes N*batch frames per step, frames block-partitioned, no data-path collective.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from eamm_b200 import get_config, synth, sharding           # noqa: E402
+
+ALG_GFLOP_PER_FRAME = 107.286       # 30 convs, 2*MAC, per (source, kp) frame
+METRIC = "256x256 frames/sec (DenseMotionNetwork + OcclusionAwareGenerator forward, 10 kp)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model
+
+
+def oracle_frames_per_sec(batch, repeats, warmup, threads=None):
+    """Reference algorithm (CPU oracle = the reference's own torch CPU ops) timed on the host cores."""
+    from oracle import eamm_oracle as oracle       # the one place bench.py executes oracle/ (as baseline)
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = get_config("full")
+    sd = synth.make_state_dict(cfg, seed=0)
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=256, seed=1)
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        oracle.generator_forward(sd, cfg, src, kpd, kps)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch / statistics.median(times), times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    fps, times = oracle_frames_per_sec(args.ref_batch, args.steps, args.warmup, threads)
+    total = sum(times)
+    sample = "each step = one batch of %d frames (same synthetic recipe) through the oracle's torch-CPU ops" % args.ref_batch
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: DenseMotion+Generator 256x256, 10 kp (reference arm batch %d)"
+                               % args.ref_batch, "cpu": cpu_info()},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("EAMM_B200_PRECISION", "fp32"),
+                    choices=["fp32", "bf16", "fp32_simt"])
+    ap.add_argument("--shared-source", action="store_true", help="one source image for the whole batch")
+    ap.add_argument("--ref-batch", type=int, default=16, help="frames per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch.distributed as dist
+    from eamm_b200 import engine, _lib
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = get_config("full")
+    gen = OcclusionAwareGenerator(**cfg).eval()
+    gen.load_state_dict(synth.make_state_dict(cfg, seed=0))
+    gen = gen.to(dev)
+    gen.precision = args.precision
+    gen.strict_errors = False            # singular-Jacobian flag is checked once after the timed loop
+    B = args.batch
+    total = B * world
+    start, stop = sharding.partition(total, world, rank)
+    # every rank draws the same global batch and keeps its block (identical to a scatter of the inputs)
+    src_all, kpd_all, kps_all = synth.make_inputs(total, cfg, size=256, seed=1, shared_source=args.shared_source)
+    sl = slice(start, stop)
+    h_src = src_all[sl].contiguous().pin_memory()
+    h_kpd = {k: v[sl].contiguous().pin_memory() for k, v in kpd_all.items()}
+    h_kps = {k: v[sl].contiguous().pin_memory() for k, v in kps_all.items()}
+    d_src = h_src.to(dev)
+    if args.shared_source:
+        d_src = d_src[:1].expand(B, -1, -1, -1)
+    d_kpd = {k: v.to(dev) for k, v in h_kpd.items()}
+    d_kps = {k: v.to(dev) for k, v in h_kps.items()}
+
+    def step_device():
+        return gen(d_src, kp_driving=d_kpd, kp_source=d_kps)
+
+    h_out = torch.empty(B, 3, 256, 256, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        s = h_src.to(dev, non_blocking=True)
+        if args.shared_source:
+            s = s[:1].expand(B, -1, -1, -1)
+        kd = {k: v.to(dev, non_blocking=True) for k, v in h_kpd.items()}
+        ks = {k: v.to(dev, non_blocking=True) for k, v in h_kps.items()}
+        out = gen(s, kp_driving=kd, kp_source=ks)
+        h_out.copy_(out["prediction"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the frames every step (demo.py:281)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return sharding.reduce_max(e0.elapsed_time(e1), device=dev)     # ms, max over ranks
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    ms = timed(step_device, args.steps)
+    launches = _lib.LAUNCHES - l0
+    clocks = sampler.stop() if sampler else None
+    from eamm_b200.modules.dense_motion import check_status
+    check_status(gen._eng.dm.last_status)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel roofline pass: one extra step with every launch bracketed by CUDA events
+    engine.PROFILE = []
+    step_device()
+    torch.cuda.synchronize()
+    prof, engine.PROFILE = engine.PROFILE, None
+    per = {}
+    for name, fl, nb, a, b in prof:
+        d = per.setdefault(name, [0.0, 0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b); d[1] += fl; d[2] += nb; d[3] += 1
+    peaks = load_peaks()
+    conv_ms = sum(v[0] for k, v in per.items() if k.startswith("conv:"))
+    conv_fl = sum(v[1] for k, v in per.items() if k.startswith("conv:"))
+    step_ms_prof = sum(v[0] for v in per.values())
+    # dominant kernel: the 3x3 256->256 bottleneck convolutions (12 launches, 54% of the FLOPs)
+    dom = [(k, v) for k, v in per.items() if k.startswith("conv:res")]
+    dom_ms = sum(v[0] for _, v in dom); dom_fl = sum(v[1] for _, v in dom); dom_n = sum(v[3] for _, v in dom)
+    achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (bottleneck 3x3 256->256, %d launches/step)" % dom_n,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks["source"] == "measured"
+                else "fallback (B200_PROFILING.md)",
+                "traffic": None,
+                "share_of_step": dom_ms / step_ms_prof if step_ms_prof else None,
+                "all_convs_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                "all_convs_share_of_step": conv_ms / step_ms_prof if step_ms_prof else None,
+                "note": "algorithmic FLOPs of the reference conv (2*MAC); fp32 mode executes 3 bf16 MMA passes per FLOP"}
+    wo = per.get("warp_occlude")
+    hbm = None
+    if wo:
+        gbs = wo[2] / (wo[0] * 1e-3) / 1e9
+        hbm = {"kernel": "warp_occlude_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": wo[2]}
+    kernels = {k: {"ms": round(v[0], 4), "launches": v[3]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:12]}
+
+    frames = total * args.steps
+    value = frames / (ms * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    h2d = h_src.numel() * 4 + sum(v.numel() * 4 for v in h_kpd.values()) + sum(v.numel() * 4 for v in h_kps.values())
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": {"fp32": "bf16x3 split (fp32-equivalent, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate, fp32 warp)",
+                  "fp32_simt": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: batch %d frames/GPU, 256x256, 10 kp, DenseMotion+Generator, %s"
+                               % (B, "one shared source" if args.shared_source else "distinct source per frame"),
+                   "precision": args.precision, "global_batch": total, "parallelism": "frames block-partitioned x%d" % world,
+                   "l2": "per-step working set (activations %.1f GB + weights) exceeds the 126 MB L2; no explicit flush"
+                         % (B * 0.085 if args.precision != "bf16" else B * 0.043)},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": h_out.numel() * 4 * world, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_hbm": hbm,
+        "tensor_frac_whole_step": (ALG_GFLOP_PER_FRAME * 1e9 * frames / (ms * 1e-3) / 1e12) / peak / world,
+        "kernels_ms_per_step": kernels,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, 64)
+        fps, times = oracle_frames_per_sec(args.ref_batch, 3, 1, cores)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "3 timed batches of %d frames through the oracle (reference algorithm, "
+                                          "torch CPU ops), median; cpu=%s" % (args.ref_batch, cpu_info())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

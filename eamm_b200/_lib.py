@@ -83,8 +83,13 @@ def load():
     return lib
 
 
+LAUNCHES = 0   # kernels launched through the C ABI (each entry point launches exactly one)
+
+
 def check(rc, what=""):
+    global LAUNCHES
     if rc == 0:
+        LAUNCHES += 1
         return
     if rc < 0:
         raise RuntimeError("eamm_b200: %s rejected its arguments: %s" % (what, _ERR.get(rc, rc)))

@@ -33,6 +33,22 @@ def current_stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# When set to a list, every kernel launch is bracketed by CUDA events on the launching stream and
+# (name, algorithmic_flops, algorithmic_bytes, start_event, end_event) is appended (bench.py roofline).
+PROFILE = None
+
+
+def _launch(name, fn, flops=0.0, nbytes=0.0):
+    if PROFILE is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    PROFILE.append((name, flops, nbytes, e0, e1))
+
+
 class ActBuf:
     """A zero-initialised NHWC activation buffer [n, h, w, planes*c_buf] and its eamm_act views."""
 
@@ -131,9 +147,12 @@ def impl_for(precision):
 class ConvLayer:
     """One packed convolution: kind/flags + device tensors in the layout of the chosen kernel."""
 
-    def __init__(self, name, kind, flags, w, b, cin_slot, nalign, impl, scale2=None, shift2=None):
+    def __init__(self, name, kind, flags, w, b, cin_slot, nalign, impl, scale2=None, shift2=None, cin_valid=None):
         cout, cin = w.shape[0], w.shape[1]
         self.name, self.kind, self.flags, self.impl = name, kind, flags, impl
+        # algorithmic FLOPs per input pixel of the reference conv (2*MAC; UP2 runs at 4x the pixels)
+        self.flops_per_in_pixel = 2.0 * cout * (cin_valid or cin) * w.shape[2] * w.shape[3] * \
+            (4 if kind == L.CONV_UP2_3X3 else 1)
         self.cin, self.cout_valid = cin_slot, cout
         self.cout = _round_up(cout, nalign)
         dev = w.device
@@ -183,7 +202,8 @@ class ConvLayer:
         if out_nhwc_f32 is not None:
             a.out_nhwc_f32 = out_nhwc_f32.data_ptr()
         fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
-        L.check(fn(C.byref(a), stream), "conv %s" % self.name)
+        _launch("conv:" + self.name, lambda: L.check(fn(C.byref(a), stream), "conv %s" % self.name),
+                flops=self.flops_per_in_pixel * inp.n * inp.h * inp.w)
 
 
 def _kp_struct(kp, batch, num_kp, device):
@@ -258,7 +278,7 @@ class DenseMotionEngine:
                 wp[:, :c_up] = w[:, :c_up]
                 wp[:, s_up:s_up + c_sk] = w[:, c_up:]
             self.dec_layers.append(ConvLayer("hg.dec%d" % j, L.CONV_UP2_3X3, L.EPI_RELU, wp, b, cin_slot,
-                                             self.nalign, self.impl))
+                                             self.nalign, self.impl, cin_valid=w.shape[1]))
         # mask (+ occlusion) merged into one 7x7 conv over cat(up_{nb-1} out, e_0)
         c_up, c_sk = self.dec_ch[nb - 1], cin0
         s_up, s_sk = _round_up(c_up, ca), _round_up(c_sk, ca)
@@ -270,7 +290,8 @@ class DenseMotionEngine:
         wp = torch.zeros(wm.shape[0], s_up + s_sk, 7, 7, dtype=wm.dtype, device=dev)
         wp[:, :c_up] = wm[:, :c_up]
         wp[:, s_up:s_up + c_sk] = wm[:, c_up:]
-        self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, s_up + s_sk, self.nalign, self.impl)
+        self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, s_up + s_sk, self.nalign, self.impl,
+                              cin_valid=wm.shape[1])
         # 1-D factor of the anti-alias kernel: k2 = outer(g1, g1) with sum 1 (util.py:1012-1033)
         self.step = 1
         self.g1 = None
@@ -332,8 +353,10 @@ class DenseMotionEngine:
         n_small = 1 if (src_n_stride == 0 and B > 1) else B
         small_stride = 0 if n_small == 1 and B > 1 else h * w * 4
         if self.step != 1:
-            L.check(lib.eamm_aa_downsample(source_image.data_ptr(), src_n_stride, ws.small.data_ptr(), n_small, H, W,
-                                           self.step, self.g1.data_ptr(), st), "aa_downsample")
+            _launch("aa_downsample", lambda: L.check(
+                lib.eamm_aa_downsample(source_image.data_ptr(), src_n_stride, ws.small.data_ptr(), n_small, H, W,
+                                       self.step, self.g1.data_ptr(), st), "aa_downsample"),
+                nbytes=n_small * (Cc * H * W * 4 + h * w * 16))
         else:
             raise RuntimeError("eamm_b200: scale_factor == 1 is not supported by the B200 path")
         # a4-a6 keypoint stage -> hourglass input (slot e_0 of cat_0) + sparse_deformed
@@ -342,9 +365,12 @@ class DenseMotionEngine:
         cat0 = ws.cat[0]
         hg_in = cat0.act(c_off=cat0.s_up, c=cat0.s_sk)
         ws.status.zero_()
-        L.check(lib.eamm_kp_stage(ws.small.data_ptr(), small_stride, C.byref(kd), C.byref(ks), K,
-                                  float(m.kp_variance), C.byref(hg_in), sparse_deformed.data_ptr(),
-                                  ws.status.data_ptr(), st), "kp_stage")
+        esz = 4 if self.mode != "bf16" else 2
+        _launch("kp_stage", lambda: L.check(
+            lib.eamm_kp_stage(ws.small.data_ptr(), small_stride, C.byref(kd), C.byref(ks), K,
+                              float(m.kp_variance), C.byref(hg_in), sparse_deformed.data_ptr(),
+                              ws.status.data_ptr(), st), "kp_stage"),
+            nbytes=B * h * w * (16 + K1 * 4 * esz + K1 * Cc * 4))
         out["sparse_deformed"] = sparse_deformed
         # a7 hourglass encoder: e_{i+1} = down_block_i(e_i)
         nb = self.nb
@@ -367,9 +393,11 @@ class DenseMotionEngine:
         mask = torch.empty(B, K1, h, w, dtype=torch.float32, device=dev)
         deformation = torch.empty(B, h, w, 2, dtype=torch.float32, device=dev)
         occ = torch.empty(B, 1, h, w, dtype=torch.float32, device=dev) if self.has_occ else None
-        L.check(lib.eamm_flow_combine(ws.logits.data_ptr(), self.head.cout, C.byref(kd), C.byref(ks), K,
-                                      1 if self.has_occ else 0, B, h, w, mask.data_ptr(), deformation.data_ptr(),
-                                      _ptr(occ), st), "flow_combine")
+        _launch("flow_combine", lambda: L.check(
+            lib.eamm_flow_combine(ws.logits.data_ptr(), self.head.cout, C.byref(kd), C.byref(ks), K,
+                                  1 if self.has_occ else 0, B, h, w, mask.data_ptr(), deformation.data_ptr(),
+                                  _ptr(occ), st), "flow_combine"),
+            nbytes=B * h * w * 4 * (self.head.cout + K1 + 2 + (1 if self.has_occ else 0)))
         out["mask"] = mask
         out["deformation"] = deformation
         if occ is not None:
@@ -474,7 +502,11 @@ class GeneratorEngine:
         dev = self.device
         nsrc = 1 if shared else B
         # encoder (generator.py:61-63); with a shared (stride-0) source it runs once and is broadcast
-        L.check(lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(ws.src.act(n=nsrc)), st), "nchw_to_act")
+        esz = 4 if self.mode != "bf16" else 2
+        src_act = ws.src.act(n=nsrc)
+        _launch("nchw_to_act", lambda: L.check(
+            lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(src_act), st), "nchw_to_act"),
+            nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
         self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
         for i, layer in enumerate(self.down):
             layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
@@ -497,14 +529,19 @@ class GeneratorEngine:
             # a9-i feature warp x occlusion (+ fused norm1/relu of the first ResBlock)
             fa = feat.act(n=B, broadcast=shared)
             out2 = ws.a.act() if blocks else None
-            L.check(lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(ws.x[0].act()),
-                                          C.byref(out2) if out2 is not None else None,
-                                          _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
-                                          st), "warp_occlude")
+            x0 = ws.x[0].act()
+            _launch("warp_occlude", lambda: L.check(
+                lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(x0),
+                                      C.byref(out2) if out2 is not None else None,
+                                      _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
+                                      st), "warp_occlude"),
+                nbytes=B * feat.h * feat.w * (feat.c_buf * esz * (3 if blocks else 2) + 12))
             # a9-ii deformed image
             deformed = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
-            L.check(lib.eamm_warp_image(src.data_ptr(), src_n_stride, deformation.data_ptr(), deformed.data_ptr(),
-                                        B, Cc, H, W, deformation.shape[1], deformation.shape[2], st), "warp_image")
+            _launch("warp_image", lambda: L.check(
+                lib.eamm_warp_image(src.data_ptr(), src_n_stride, deformation.data_ptr(), deformed.data_ptr(),
+                                    B, Cc, H, W, deformation.shape[1], deformation.shape[2], st), "warp_image"),
+                nbytes=B * (2 * Cc * H * W * 4 + deformation.shape[1] * deformation.shape[2] * 8))
             result["deformed"] = deformed
             x = ws.x[0]
         else:

@@ -1,0 +1,244 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the drop-in
+modules and directly through the C ABI, against the CPU oracle and the committed golden fixtures.
+
+Tolerances (max-abs):
+  fp32_simt : 2e-5 everywhere (true fp32 CUDA-core convs), warped images 2e-4
+  fp32      : prediction/mask/occlusion 3e-4, deformation 1e-4, sparse_deformed 1e-4, deformed 1e-2
+              (split-bf16 tensor cores; the tcgen05 fp32 accumulator truncates, DESIGN.md "Numerics")
+  bf16      : prediction 3e-2, mask/occlusion 3e-2 (bf16 convs; flow-sensitive outputs are not pinned)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from eamm_b200 import get_config, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {
+    "fp32_simt": {"prediction": 2e-5, "mask": 2e-5, "occlusion_map": 2e-5, "deformation": 2e-5,
+                  "sparse_deformed": 2e-5, "deformed": 2e-4},
+    "fp32": {"prediction": 3e-4, "mask": 3e-4, "occlusion_map": 3e-4, "deformation": 1e-4,
+             "sparse_deformed": 1e-4, "deformed": 1e-2},
+    "bf16": {"prediction": 3e-2, "mask": 3e-2, "occlusion_map": 3e-2, "sparse_deformed": 1e-4},
+}
+STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+_GEN = {}
+
+
+def generator(cfg_name, dev):
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    if cfg_name not in _GEN:
+        cfg = get_config(cfg_name)
+        g = OcclusionAwareGenerator(**cfg).eval()
+        g.load_state_dict(synth.make_state_dict(cfg, seed=0), strict=True)
+        _GEN[cfg_name] = (g.to(dev), cfg)
+    return _GEN[cfg_name]
+
+
+def to_dev(d, dev):
+    return {k: v.to(dev) for k, v in d.items()}
+
+
+def run_ours(cfg_name, dev, precision, src, kpd, kps, shared=False):
+    gen, cfg = generator(cfg_name, dev)
+    gen.precision = precision
+    s = src.to(dev)
+    if shared:
+        s = s[:1].expand(src.shape[0], -1, -1, -1)
+    out = gen(s, kp_driving=to_dev(kpd, dev), kp_source=to_dev(kps, dev))
+    out = dict(out)
+    out["deformation"] = gen._eng.last_dm["deformation"]
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+def test_native_library_is_the_in_tree_build_and_device_is_sm100(dev):
+    from eamm_b200 import _lib, build
+    lib = _lib.load()
+    assert os.path.dirname(build.LIBPATH).endswith(os.path.join("eamm_b200", "lib"))
+    assert lib.eamm_device_ok(0) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32", "bf16"])
+@pytest.mark.parametrize("case,cfg_name", [("tiny_b2", "tiny"), ("tiny_b3_nojac", "tiny")])
+def test_tiny_config_matches_reference_golden(dev, precision, case, cfg_name):
+    blob = np.load(os.path.join(GOLD, case + ".npz"))
+    batch, size, jac, shared = [int(v) for v in blob["meta"]]
+    cfg = get_config(cfg_name)
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=1, with_jacobian=bool(jac))
+    got = run_ours(cfg_name, dev, precision, src, kpd, kps)
+    for k, tol in TOL[precision].items():
+        err = np.abs(got[k].numpy() - blob[k]).max()
+        assert err <= tol, "%s %s %s: max-abs %.3e > %.1e" % (case, precision, k, err, tol)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["full_b2", "full_b3_shared"])
+def test_full_config_matches_reference_golden(dev, precision, case):
+    blob = np.load(os.path.join(GOLD, case + ".npz"))
+    batch, size, jac, shared = [int(v) for v in blob["meta"]]
+    cfg = get_config("full")
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=1, shared_source=bool(shared))
+    got = run_ours("full", dev, precision, src, kpd, kps, shared=bool(shared))
+    for k, tol in TOL[precision].items():
+        a = got[k].numpy()
+        s = STRIDES[k]
+        sub = a[:, ::s, ::s, :] if k == "deformation" else a[..., ::s, ::s]
+        err = np.abs(sub - blob[k]).max()
+        assert err <= tol, "%s %s %s: max-abs %.3e > %.1e" % (case, precision, k, err, tol)
+        if precision == "fp32":   # checksum of the whole tensor, not just the stored sub-sample
+            tot = a.astype(np.float64).sum()
+            assert abs(tot - blob["sum_" + k][0]) <= tol * a.size * 0.3 + 1e-3, k
+
+
+def test_full_size_batch32_properties_and_batch_invariance(dev):
+    """BASELINE configs[1] size: structural properties + frame i of the batch == the same frame run alone."""
+    cfg = get_config("full")
+    src, kpd, kps = synth.make_inputs(32, cfg, size=256, seed=7)
+    got = run_ours("full", dev, "fp32", src, kpd, kps)
+    assert all(torch.isfinite(v).all() for v in got.values())
+    assert torch.allclose(got["mask"].sum(1), torch.ones(32, 64, 64), atol=1e-5)
+    assert got["occlusion_map"].min() > 0 and got["occlusion_map"].max() < 1
+    assert got["prediction"].min() > 0 and got["prediction"].max() < 1
+    i = 17
+    one = run_ours("full", dev, "fp32", src[i:i + 1], {k: v[i:i + 1] for k, v in kpd.items()},
+                   {k: v[i:i + 1] for k, v in kps.items()})
+    for k in ("prediction", "mask", "deformed"):
+        assert torch.allclose(one[k][0], got[k][i], atol=1e-6), k
+    # the oracle on two of the 32 frames (keeps the CPU cost of this test in seconds)
+    from oracle import eamm_oracle as oracle
+    sd = synth.make_state_dict(cfg, seed=0)
+    idx = [3, 29]
+    want = oracle.generator_forward(sd, cfg, src[idx], {k: v[idx] for k, v in kpd.items()}, {k: v[idx] for k, v in kps.items()})
+    for k, tol in (("prediction", 3e-4), ("mask", 3e-4), ("occlusion_map", 3e-4), ("deformed", 1e-2)):
+        assert (got[k][idx] - want[k]).abs().max() <= tol, k
+
+
+def test_shared_source_broadcast_equals_distinct_copies(dev):
+    cfg = get_config("tiny")
+    src, kpd, kps = synth.make_inputs(4, cfg, size=64, seed=11, shared_source=True)
+    a = run_ours("tiny", dev, "fp32", src, kpd, kps, shared=True)
+    b = run_ours("tiny", dev, "fp32", src, kpd, kps, shared=False)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_identity_keypoints_give_identity_flow_and_singular_jacobian_raises(dev):
+    cfg = get_config("tiny")
+    src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=13)
+    got = run_ours("tiny", dev, "fp32_simt", src, kps, kps)          # driving == source
+    from oracle import eamm_oracle as oracle
+    ident = oracle.make_coordinate_grid(16, 16).view(1, 16, 16, 2).expand(2, -1, -1, -1)
+    assert torch.allclose(got["deformation"], ident, atol=1e-5)
+    bad = {k: v.clone() for k, v in kpd.items()}
+    bad["jacobian"][1, 2] = 0.0
+    with pytest.raises(torch.linalg.LinAlgError):
+        run_ours("tiny", dev, "fp32_simt", src, bad, kps)
+
+
+def test_dense_motion_module_alone_matches_oracle(dev):
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    from oracle import eamm_oracle as oracle
+    gen, cfg = generator("tiny", dev)
+    gen.dense_motion_network.precision = "fp32"
+    src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=17)
+    out = gen.dense_motion_network(source_image=src.to(dev), kp_driving=to_dev(kpd, dev), kp_source=to_dev(kps, dev))
+    want = oracle.dense_motion_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps)
+    assert set(out) == {"sparse_deformed", "mask", "deformation", "occlusion_map"}
+    for k in want:
+        assert (out[k].cpu() - want[k]).abs().max() <= 3e-4, k
+
+
+# ------------------------------------------------------------------ kernels through the C ABI
+def test_cabi_warp_occlude_matches_grid_sample_times_occlusion(dev):
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, current_stream_ptr
+    lib = L.load()
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c = 3, 16, 16, 64
+    feat = torch.randn(n, c, h, w, generator=g)
+    grid = torch.rand(n, h, w, 2, generator=g) * 2.4 - 1.2
+    grid[0, 0, 0] = torch.tensor([-1.0, -1.0]); grid[0, 0, 1] = torch.tensor([1.0, 1.0])   # corner unit vectors
+    occ = torch.rand(n, 1, h, w, generator=g)
+    want = F.grid_sample(feat, grid, align_corners=False) * occ
+    fin = ActBuf(n, h, w, c, "f32", dev); fin.t.copy_(feat.permute(0, 2, 3, 1))
+    fout = ActBuf(n, h, w, c, "f32", dev)
+    gd, od = grid.to(dev), occ.to(dev)
+    L.check(lib.eamm_warp_occlude(C.byref(fin.act()), gd.data_ptr(), od.data_ptr(), C.byref(fout.act()), None, None, None,
+                                  current_stream_ptr()), "warp_occlude")
+    torch.cuda.synchronize()
+    assert (fout.to_float().cpu() - want).abs().max() <= 2e-6
+    # zero padding is bit-exact: a sample fully outside the image reads exactly 0
+    grid2 = torch.full((n, h, w, 2), 3.0)
+    L.check(lib.eamm_warp_occlude(C.byref(fin.act()), grid2.to(dev).data_ptr(), None, C.byref(fout.act()), None, None, None,
+                                  current_stream_ptr()), "warp_occlude")
+    torch.cuda.synchronize()
+    assert fout.t.abs().max().item() == 0.0
+
+
+def test_cabi_aa_downsample_and_warp_image_match_oracle(dev):
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import current_stream_ptr
+    from oracle import eamm_oracle as oracle
+    lib = L.load()
+    g = torch.Generator().manual_seed(6)
+    src = torch.rand(2, 3, 64, 64, generator=g)
+    k2 = synth.aa_kernel(3)
+    want = oracle.anti_alias_down(src, k2, 0.25)
+    g1 = k2[0, 0].sum(1); g1 = (g1 / g1.sum()).to(dev)
+    out = torch.zeros(2, 16, 16, 4, device=dev)
+    sd = src.to(dev)
+    L.check(lib.eamm_aa_downsample(sd.data_ptr(), 3 * 64 * 64, out.data_ptr(), 2, 64, 64, 4, g1.data_ptr(),
+                                   current_stream_ptr()), "aa")
+    torch.cuda.synchronize()
+    assert (out[..., :3].permute(0, 3, 1, 2).cpu() - want).abs().max() <= 1e-6
+    flow = torch.rand(2, 16, 16, 2, generator=g) * 2.2 - 1.1
+    want2 = oracle.deform_input(src, flow)
+    got2 = torch.zeros(2, 3, 64, 64, device=dev)
+    L.check(lib.eamm_warp_image(sd.data_ptr(), 3 * 64 * 64, flow.to(dev).data_ptr(), got2.data_ptr(), 2, 3, 64, 64, 16, 16,
+                                current_stream_ptr()), "warp_image")
+    torch.cuda.synchronize()
+    assert (got2.cpu() - want2).abs().max() <= 1e-5
+
+
+def test_cabi_conv_tc_matches_conv_simt_on_layer_shapes(dev):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gpu_conv_check", os.path.join(os.path.dirname(GOLD), "..", "tools", "gpu_conv_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for idx in (1, 3, 5, 7, 8, 9, 10, 12, 13):
+        assert mod.run_case(idx) == 0, mod.CASES[idx][0]
+
+
+def test_cabi_rejects_bad_arguments_without_launching(dev):
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, current_stream_ptr
+    lib = L.load()
+    a = ActBuf(1, 6, 6, 64, "bf16", dev)          # 6x6 is not a power-of-two map
+    args = L.ConvArgs()
+    args.kind, args.flags, args.cin, args.cout = L.CONV_3X3, 0, 64, 16
+    act = a.act()
+    args.inp = C.pointer(act)
+    w = torch.zeros(16, 9 * 64, dtype=torch.bfloat16, device=dev)
+    b = torch.zeros(16, device=dev)
+    args.weight, args.bias = w.data_ptr(), b.data_ptr()
+    o = ActBuf(1, 6, 6, 16, "bf16", dev)
+    oa = o.act()
+    args.out = C.pointer(oa)
+    assert lib.eamm_conv_tc(C.byref(args), current_stream_ptr()) == -5      # EAMM_ERR_UNSUPPORTED
+    args.cin = 32
+    assert lib.eamm_conv_tc(C.byref(args), current_stream_ptr()) < 0

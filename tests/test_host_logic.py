@@ -1,0 +1,233 @@
+"""CPU tests: host-side packing logic, the numpy sampler pins, the drop-in module surface, the C ABI
+exports and the multi-process sharding helpers (gloo, world_size 2).  No GPU compute here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from eamm_b200 import get_config, synth, sharding
+from eamm_b200 import engine
+from oracle import eamm_oracle as oracle
+from oracle import sampler_np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ weight packing
+def test_fold_bn_matches_conv_then_bn():
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn(8, 4, 3, 3, generator=g), torch.randn(8, generator=g)
+    bn = {"weight": torch.rand(8, generator=g) + 0.5, "bias": torch.randn(8, generator=g),
+          "running_mean": torch.randn(8, generator=g), "running_var": torch.rand(8, generator=g) + 0.5}
+    x = torch.randn(2, 4, 9, 9, generator=g)
+    want = F.batch_norm(F.conv2d(x, w, b, padding=1), bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"],
+                        False, 0.1, 1e-5)
+    wf, bf = engine.fold_bn(w, b, bn)
+    assert torch.allclose(F.conv2d(x, wf, bf, padding=1), want, atol=1e-5)
+    s, t = engine.bn_affine(bn)
+    want2 = F.batch_norm(x[:, :4].repeat(1, 2, 1, 1), bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"],
+                         False, 0.1, 1e-5)
+    assert torch.allclose(x.repeat(1, 2, 1, 1) * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1), want2, atol=1e-5)
+
+
+def test_up2_parity_weights_equal_upsample_then_conv():
+    """nearest x2 + 3x3 pad 1 == four 2x2 convs on the low-res input (UpBlock2d, util.py:895-897)."""
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(5, 3, 3, 3, generator=g)
+    x = torch.randn(2, 3, 6, 4, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2), w, padding=1)
+    pw = engine.up2_parity_weights(w)                      # [4][4][cout][cin]
+    got = torch.zeros_like(want)
+    xp = F.pad(x, (1, 1, 1, 1))
+    H, W = x.shape[2:]
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = 0
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    dy, dx = a - 1 + ty, b - 1 + tx
+                    sl = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+                    acc = acc + torch.einsum("oc,nchw->nohw", pw[a * 2 + b, ty * 2 + tx], sl)
+            got[:, :, a::2, b::2] = acc
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_tc_weight_packing_order_and_split():
+    g = torch.Generator().manual_seed(2)
+    full = torch.randn(9, 16, 64, generator=g)             # [taps][cout][cin]
+    p1 = engine.pack_tc_weights(full, 1, 1)
+    assert p1.shape == (16, 9 * 64) and p1.dtype == torch.bfloat16
+    assert torch.equal(p1[3, 2 * 64:3 * 64], full[2, 3].bfloat16())
+    p3 = engine.pack_tc_weights(full, 1, 3)
+    assert p3.shape == (16, 9 * 3 * 64)
+    hi = p3[:, (2 * 3 + 0) * 64:(2 * 3 + 1) * 64].float()
+    lo = p3[:, (2 * 3 + 1) * 64:(2 * 3 + 2) * 64].float()
+    hi2 = p3[:, (2 * 3 + 2) * 64:(2 * 3 + 3) * 64].float()
+    assert torch.equal(hi, hi2)
+    assert (hi + lo - full[2]).abs().max() < 2e-5          # 16 mantissa bits survive the split
+    up = engine.pack_tc_weights(torch.randn(16, 8, 64, generator=g), 4, 1)
+    assert up.shape == (4 * 8, 4 * 64)
+
+
+# ------------------------------------------------------------------ sampler pins (index selection)
+def test_numpy_sampler_matches_torch_grid_sample_and_corner_values():
+    assert sampler_np.unnormalize(np.float32(-1.0), 64) == -0.5          # SURVEY.md §7 "hard parts"
+    assert sampler_np.unnormalize(np.float32(1.0), 64) == 63.5
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(3, 8, 8, generator=g)
+    grid = torch.rand(8, 8, 2, generator=g) * 2.6 - 1.3                     # includes out-of-range samples
+    want = F.grid_sample(img[None], grid[None], align_corners=False)[0].numpy()
+    got = sampler_np.grid_sample(img.numpy(), grid.numpy())
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    ident = oracle.make_coordinate_grid(8, 8).numpy()                       # the "identity" grid is not a copy
+    y0, x0, w, ok = sampler_np.grid_sample_taps(ident[0, 0, 0], ident[0, 0, 1], 8, 8)[0]
+    assert (y0, x0, ok) == (-1, -1, False)
+
+
+def test_bilinear_and_nearest_index_rules():
+    flow = torch.arange(16, dtype=torch.float32).view(1, 1, 4, 4)
+    up = F.interpolate(flow, size=(16, 16), mode="bilinear", align_corners=False)[0, 0]
+    for dst in (0, 1, 2, 7, 14, 15):
+        i0, i1, lam = sampler_np.bilinear_upsample_index(dst, 4, 16)
+        want = flow[0, 0, 0, i0] * (1 - lam) + flow[0, 0, 0, i1] * lam
+        assert abs(up[0, dst].item() - want.item()) < 1e-6
+    near = F.interpolate(flow, scale_factor=2)[0, 0]
+    for dst in range(8):
+        assert near[0, dst] == flow[0, 0, 0, sampler_np.nearest_up2_index(dst)]
+
+
+def test_channel_interleave_and_emotion_row_selection_are_exact():
+    """hourglass input channel order [hm_k, R_k, G_k, B_k] (dense_motion.py:93-94); demo.py:266-271 rows."""
+    cfg = get_config("tiny")
+    sd = synth.make_state_dict(cfg)
+    src, kpd, kps = synth.make_inputs(1, cfg, size=64, seed=5)
+    taps = {}
+    oracle.generator_forward(sd, cfg, src, kpd, kps, taps=taps)
+    hin, hm = taps["hourglass_in"], taps["heatmap"]
+    K1 = cfg["num_kp"] + 1
+    for k in range(K1):
+        assert torch.equal(hin[:, 4 * k], hm[:, k, 0])
+    value = torch.zeros(1, 10, 2)
+    emo = torch.arange(8, dtype=torch.float32).view(1, 4, 2) + 1
+    for dst, srcrow, scale in ((1, 0, 1.0), (4, 1, 0.2), (6, 2, 1.0)):     # demo.py:266-271
+        value[:, dst] += emo[:, srcrow] * scale
+    assert value[0, 1].tolist() == [1.0, 2.0] and value[0, 6].tolist() == [5.0, 6.0]
+    assert torch.allclose(value[0, 4], torch.tensor([0.6, 0.8]))
+
+
+# ------------------------------------------------------------------ drop-in module surface
+def test_dropin_modules_keep_reference_state_dict_layout_and_refuse_cpu():
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    from eamm_b200.modules.dense_motion import DenseMotionNetwork
+    cfg = get_config("full")
+    gen = OcclusionAwareGenerator(**cfg).eval()
+    sd = synth.make_state_dict(cfg)
+    assert len(sd) == 196
+    res = gen.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert list(gen.state_dict().keys())[:2] == ["dense_motion_network.hourglass.encoder.down_blocks.0.conv.weight",
+                                                 "dense_motion_network.hourglass.encoder.down_blocks.0.conv.bias"]
+    assert gen.num_channels == 3 and isinstance(gen.dense_motion_network, DenseMotionNetwork)
+    assert "OcclusionAwareGenerator" in repr(gen)
+    src, kpd, kps = synth.make_inputs(1, cfg, size=256)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gen(src, kp_driving=kpd, kp_source=kps)
+    gen.train()
+    with pytest.raises(RuntimeError, match="inference path only"):
+        gen(src, kp_driving=kpd, kp_source=kps)
+    with pytest.raises(ValueError):
+        gen.precision = "fp64"
+
+
+def test_conv_layer_table_matches_reference_flop_count():
+    cfg = get_config("full")
+    flops = 0.0
+    res = {"dense": 64, "first": 256, "final": 256}
+    for prefix, cin, cout, k, kind in synth.conv_layers(cfg):
+        if "hourglass.encoder" in prefix:
+            hw = 64 >> int(prefix[-1])
+        elif "hourglass.decoder" in prefix:
+            hw = 4 << int(prefix[-1])
+        elif prefix.startswith("dense_motion"):
+            hw = 64
+        elif prefix.startswith("down_blocks"):
+            hw = 256 >> int(prefix[-1])
+        elif prefix.startswith("up_blocks"):
+            hw = 128 << int(prefix[-1])
+        elif prefix.startswith("bottleneck"):
+            hw = 64
+        else:
+            hw = 256
+        n = 2 if kind == "res" else 1
+        flops += n * 2.0 * cin * cout * k * k * hw * hw
+    assert abs(flops / 1e9 - 107.286) < 0.01
+
+
+# ------------------------------------------------------------------ C ABI
+def test_shared_library_exports_every_declared_symbol():
+    from eamm_b200 import build, _lib
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "eamm_b200.h")).read()
+    declared = set(re.findall(r"\bint\s+(eamm_\w+)\s*\(", header))
+    assert declared == set(_lib.exported_symbols())
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.eamm_abi_version.restype = ctypes.c_int
+    assert lib.eamm_abi_version() == 1
+    null = ctypes.c_void_p(0)
+    lib.eamm_warp_image.restype = ctypes.c_int
+    assert lib.eamm_warp_image(null, 0, null, null, 1, 3, 8, 8, 2, 2, null) == -1      # EAMM_ERR_ARG, no launch
+
+
+# ------------------------------------------------------------------ sharding (gloo, world_size 2)
+def test_partition_covers_every_frame_once():
+    for total in (0, 1, 7, 32, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.partition(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from eamm_b200 import sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+total = 7
+a, b = sharding.partition(total, 2, rank)
+frames = torch.arange(a, b, dtype=torch.float32).view(-1, 1) * 10.0       # "generated frames" of this rank
+allf = sharding.gather_frames(frames, total, dst=0)
+mx = sharding.reduce_max(1.0 + rank)
+sm = sharding.reduce_sum(float(b - a))
+if rank == 0:
+    assert allf.view(-1).tolist() == [10.0 * i for i in range(total)], allf
+    print("OK", mx, sm)
+assert mx == 2.0 and sm == total
+dist.destroy_process_group()
+"""
+
+
+def test_gloo_two_rank_gather_and_max_reduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK 2.0 7.0" in outs[0]

@@ -1,0 +1,69 @@
+"""The CPU oracle against the golden fixtures generated from the real reference (tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eamm_b200 import get_config, synth
+from oracle import eamm_oracle as oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
+CASES = [("tiny_b2", "tiny", True), ("tiny_b3_nojac", "tiny", True), ("full_b2", "full", False),
+         ("full_b3_shared", "full", False)]
+
+
+def load_case(name, cfg_name):
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, size, jac, shared = [int(v) for v in blob["meta"]]
+    cfg = get_config(cfg_name)
+    sd = synth.make_state_dict(cfg, seed=0)
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=1, with_jacobian=bool(jac), shared_source=bool(shared))
+    return blob, cfg, sd, src, kpd, kps
+
+
+def subsample(k, a, full):
+    if full:
+        return a
+    s = STRIDES[k]
+    return a[:, ::s, ::s, :] if k == "deformation" else a[..., ::s, ::s]
+
+
+@pytest.mark.parametrize("name,cfg_name,full", CASES)
+def test_oracle_reproduces_reference_golden(name, cfg_name, full):
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    blob, cfg, sd, src, kpd, kps = load_case(name, cfg_name)
+    chk = np.array([src.double().sum(), kpd["value"].double().sum(), kps["value"].double().sum()])
+    np.testing.assert_allclose(chk, blob["in_checksum"], rtol=0, atol=0)      # seeded inputs are reproducible
+    got = oracle.generator_forward(sd, cfg, src, kpd, kps)
+    got["deformation"] = oracle.dense_motion_forward(sd, cfg, src, kpd, kps)["deformation"]
+    for k, v in got.items():
+        a = v.numpy()
+        # same torch build on both boxes -> bit-exact; the tolerance only absorbs a different BLAS thread split
+        np.testing.assert_allclose(subsample(k, a, full), blob[k], rtol=0, atol=2e-6, err_msg=k)
+        s = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+        np.testing.assert_allclose(s, blob["sum_" + k], rtol=1e-6, err_msg="checksum " + k)
+
+
+def test_structural_known_answers():
+    """mask sums to 1, occlusion/prediction in (0,1), identity keypoints give identity flows."""
+    cfg = get_config("tiny")
+    sd = synth.make_state_dict(cfg, seed=0)
+    src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=3)
+    out = oracle.generator_forward(sd, cfg, src, kpd, kps)
+    assert torch.allclose(out["mask"].sum(1), torch.ones(2, 16, 16), atol=1e-6)
+    assert out["occlusion_map"].min() > 0 and out["occlusion_map"].max() < 1
+    assert out["prediction"].min() > 0 and out["prediction"].max() < 1
+    same = {"value": kpd["value"], "jacobian": torch.eye(2).expand(2, cfg["num_kp"], 2, 2).contiguous()}
+    sm = oracle.sparse_motions(same, same, 16, 16)
+    ident = oracle.make_coordinate_grid(16, 16).view(1, 1, 16, 16, 2).expand_as(sm)
+    assert torch.allclose(sm, ident, atol=1e-6)
+
+
+def test_singular_jacobian_raises_like_reference():
+    cfg = get_config("tiny")
+    src, kpd, kps = synth.make_inputs(1, cfg, size=64, seed=3)
+    kpd["jacobian"][0, 0] = 0.0
+    with pytest.raises(Exception):
+        oracle.sparse_motions(kpd, kps, 16, 16)
