@@ -9,7 +9,7 @@ import os
 from . import build as _build
 
 EAMM_F32, EAMM_BF16 = 0, 1
-CONV_3X3, CONV_7X7, CONV_UP2_3X3 = 0, 1, 2
+CONV_3X3, CONV_7X7, CONV_UP2_3X3, CONV_ROW7_PACKED = 0, 1, 2, 3
 EPI_RELU, EPI_POOL2, EPI_SIGMOID = 1, 2, 4
 
 _ERR = {-1: "EAMM_ERR_ARG", -2: "EAMM_ERR_SHAPE", -3: "EAMM_ERR_DTYPE", -4: "EAMM_ERR_ALIGN",
@@ -35,7 +35,7 @@ class ConvArgs(C.Structure):
                 ("inp", C.POINTER(Act)), ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("residual", C.POINTER(Act)), ("out", C.POINTER(Act)), ("out2", C.POINTER(Act)),
                 ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("out_nchw", C.c_void_p),
-                ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p)]
+                ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/eamm_b200.h
@@ -55,6 +55,8 @@ _PROTOS = {
     "eamm_nchw_to_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Act), C.c_void_p]),
     "eamm_conv_simt": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "eamm_conv_tc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "eamm_conv_tc_uses_halo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "eamm_pack_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -157,7 +157,7 @@ conv_simt_kernel(ConvSimtParams p) {
 int conv_check_args(const eamm_conv_args* a, int cout_align) {
   if (!a || !a->in || !a->weight || !a->bias) return EAMM_ERR_ARG;
   int rc = check_view(a->in); if (rc) return rc;
-  if (a->kind < EAMM_CONV_3X3 || a->kind > EAMM_CONV_UP2_3X3) return EAMM_ERR_UNSUPPORTED;
+  if (a->kind < EAMM_CONV_3X3 || a->kind > EAMM_CONV_ROW7_PACKED) return EAMM_ERR_UNSUPPORTED;
   if (a->cin != a->in->c || a->cout <= 0 || a->cout % cout_align) return EAMM_ERR_SHAPE;
   if ((a->in->h & 1) || (a->in->w & 1)) return EAMM_ERR_SHAPE;
   const bool pool = a->flags & EAMM_EPI_POOL2;
@@ -186,6 +186,7 @@ using namespace eamm;
 extern "C" int eamm_conv_simt(const eamm_conv_args* a, void* stream) {
   int rc = conv_check_args(a, 4);
   if (rc) return rc;
+  if (a->kind == EAMM_CONV_ROW7_PACKED) return EAMM_ERR_UNSUPPORTED;
   ConvSimtParams p;
   p.in = make_view(a->in);
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;

@@ -16,6 +16,7 @@
 // Reference call sites: util.py:872-880, 895-900, 915-920, 934-938; generator.py:92-93;
 // dense_motion.py:98,110.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace eamm {
@@ -32,6 +33,8 @@ struct ConvTcParams {
   int tiles_x, tiles_y, tiles_n, n_tiles, classes;
   int BN, kind, flags, taps, ksize, cin_chunks, passes;
   int a_c_off, a_c_buf;
+  int halo;            // 7x7 with a 134-pixel halo row per ky: the 7 kx taps are shifted smem views
+  int a_slot_bytes;    // bytes reserved for the A operand in a stage
   int num_stages, cout;
   int has_out, has_out2, has_res;
   ActView out, out2, res;
@@ -256,7 +259,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem is only guaranteed 16B-aligned by the ABI: align the ring to 1024 B by hand
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
+  const uint32_t stage_bytes = (uint32_t)p.a_slot_bytes + b_bytes;
+  const uint32_t tx_bytes = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
@@ -279,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int KC = p.taps * p.passes * p.cin_chunks;
+  const int KC = (p.halo ? 7 : p.taps) * p.passes * p.cin_chunks;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -289,18 +294,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord tc = decode_tile(p, tile);
         const int brow = tc.cls * p.cout + tc.nt * p.BN;
         int kc = 0;
-        for (int t = 0; t < p.taps; ++t) {
+        const int ntap = p.halo ? 7 : p.taps;
+        for (int t = 0; t < ntap; ++t) {
           int dy, dx;
-          if (p.kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
+          if (p.halo) { dy = t - 3; dx = -3; }
+          else if (p.kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; }
+          else if (p.kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
           else { dy = t / p.ksize - (p.ksize >> 1); dx = t % p.ksize - (p.ksize >> 1); }
           for (int ps = 0; ps < p.passes; ++ps) {
-            const int cbase = p.a_c_off + (ps == 2 ? p.a_c_buf : 0);
+            int cbase = p.a_c_off + (ps == 2 ? p.a_c_buf : 0);
+            if (p.kind == EAMM_CONV_ROW7_PACKED) cbase = 0;      // both planes live inside the 64-wide K window
             for (int cc = 0; cc < p.cin_chunks; ++cc, ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t sa = smem_base + stage * stage_bytes;
-              mbar_expect_tx(full_bar(stage), stage_bytes);
+              mbar_expect_tx(full_bar(stage), tx_bytes);
               tma_load_4d(sa, &tmA, full_bar(stage), cbase + cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-              tma_load_2d(sa + TC_A_BYTES, &tmB, full_bar(stage), kc * 64, brow);
+              tma_load_2d(sa + p.a_slot_bytes, &tmB, full_bar(stage), kc * 64, brow);
               if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
             }
           }
@@ -321,10 +330,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + TC_A_BYTES);
+          const uint32_t sb = sa + (uint32_t)p.a_slot_bytes;
+          if (p.halo) {
+            // one halo row of 134 pixels serves the 7 kx taps: tap kx reads rows [kx, kx+128)
+#pragma unroll 1
+            for (int kx = 0; kx < 7; ++kx) {
+              // (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
+              //  row-shifted start address needs no base_offset in the descriptor)
+              const uint64_t da = make_sw128_desc(sa + (uint32_t)kx * 128u);
+              const uint64_t db = make_sw128_desc(sb + (uint32_t)(kx * p.BN) * 128u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | kx | k) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          }
           tc_commit(empty_bar(stage));
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -388,9 +412,14 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   int rc = conv_check_args(a, 16);
   if (rc) return rc;
   const eamm_act* in = a->in;
+  const bool row7 = a->kind == EAMM_CONV_ROW7_PACKED;
   if (in->dtype != EAMM_BF16) return EAMM_ERR_DTYPE;
-  if (in->c_buf % 64 || in->c_off % 64 || a->cin % 64) return EAMM_ERR_ALIGN;
-  if (in->n_stride != (int64_t)in->h * in->w * in->planes * in->c_buf) return EAMM_ERR_UNSUPPORTED;
+  if (row7) {
+    if (in->c != 8 || in->c_buf != 8 || in->c_off != 0 || in->planes != 1 || a->cin != 8) return EAMM_ERR_SHAPE;
+    if (a->pack_passes != 1 && a->pack_passes != 2) return EAMM_ERR_ARG;
+  } else if (in->c_buf % 64 || in->c_off % 64 || a->cin % 64) {
+    return EAMM_ERR_ALIGN;
+  }
   const eamm_act* views[3] = {a->out, a->out2, a->residual};
   for (int i = 0; i < 3; ++i)
     if (views[i] && (views[i]->dtype != EAMM_BF16 || views[i]->c_off % 8 || views[i]->c_buf % 8)) return EAMM_ERR_DTYPE;
@@ -398,20 +427,14 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
 
   ConvTcParams p;
   p.N = in->n; p.H = in->h; p.W = in->w;
-  // 128-pixel box: bw x bh x bn
   int wl = ilog2_exact(in->w), hl = ilog2_exact(in->h);
   if (wl < 1 || hl < 1) return EAMM_ERR_UNSUPPORTED;            // power-of-two maps only
-  p.bw = in->w >= 16 ? 16 : in->w;
-  p.bh = 128 / p.bw; if (p.bh > in->h) p.bh = in->h;
-  p.bn = 128 / (p.bw * p.bh);
-  p.bw_log2 = ilog2_exact(p.bw); p.bh_log2 = ilog2_exact(p.bh);
-  p.tiles_x = in->w / p.bw; p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
   p.kind = a->kind; p.flags = a->flags; p.cout = a->cout;
   p.ksize = a->kind == EAMM_CONV_7X7 ? 7 : 3;
-  p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : p.ksize * p.ksize;
+  p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : (row7 ? 7 : p.ksize * p.ksize);
   p.classes = a->kind == EAMM_CONV_UP2_3X3 ? 4 : 1;
-  p.cin_chunks = a->cin / 64;
-  p.passes = in->planes == 2 ? 3 : 1;
+  p.cin_chunks = row7 ? 1 : a->cin / 64;
+  p.passes = row7 ? a->pack_passes : (in->planes == 2 ? 3 : 1);
   p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
   // N tile: the whole cout when it fits one UMMA (<= 256), else the largest divisor among 256/128/64
   if (a->cout <= 256) p.BN = a->cout;
@@ -420,7 +443,21 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   else if (a->cout % 64 == 0) p.BN = 64;
   else return EAMM_ERR_UNSUPPORTED;
   p.n_tiles = a->cout / p.BN;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)p.BN * 128u;
+  // 7x7 with few couts on wide maps: one 134-pixel halo row per ky, kx taps are shifted smem views
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("EAMM_TC_HALO"); halo_env = e ? atoi(e) : 1; }
+  p.halo = (a->kind == EAMM_CONV_7X7 && halo_env > 0 && in->w % 128 == 0 && a->cout <= 32) ? 1 : 0;
+  // 128-pixel box: bw x bh x bn
+  if (p.halo) { p.bw = 128; p.bh = 1; p.bn = 1; }
+  else {
+    p.bw = in->w >= 16 ? 16 : in->w;
+    p.bh = 128 / p.bw; if (p.bh > in->h) p.bh = in->h;
+    p.bn = 128 / (p.bw * p.bh);
+  }
+  p.bw_log2 = ilog2_exact(p.bw); p.bh_log2 = ilog2_exact(p.bh);
+  p.tiles_x = in->w / p.bw; p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
+  p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
+  const uint32_t stage_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
   int stages = (int)((200u * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
@@ -438,26 +475,40 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   if (!encode) return EAMM_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmB;
   {
-    const cuuint64_t pix = (cuuint64_t)in->planes * in->c_buf;
-    cuuint64_t dims[4] = {pix, (cuuint64_t)in->w, (cuuint64_t)in->h, (cuuint64_t)in->n};
-    cuuint64_t strides[3] = {pix * 2, pix * 2 * in->w, pix * 2 * in->w * in->h};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.halo ? 134 : p.bw), (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+    if (row7) {
+      // Overlapping windows: the buffer is the source image packed as [n][H+6][W+8][8 ch] bf16 with a
+      // zero border (3 rows top/bottom, 3 columns left, 5 right).  Row x of the map is the 64-element
+      // window of 8 consecutive pixels starting at padded column x, i.e. dimension 1 has a 16-byte
+      // stride although dimension 0 spans 128 bytes.
+      const cuuint64_t wp = (cuuint64_t)in->w + 8, hp = (cuuint64_t)in->h + 6;
+      dims[0] = 64; dims[1] = (cuuint64_t)in->w; dims[2] = hp; dims[3] = (cuuint64_t)in->n;
+      strides[0] = 16; strides[1] = wp * 16; strides[2] = wp * hp * 16;
+    } else {
+      const cuuint64_t pix = (cuuint64_t)in->planes * in->c_buf;
+      if (in->n_stride != (int64_t)in->h * in->w * (int64_t)pix) return EAMM_ERR_UNSUPPORTED;
+      dims[0] = pix; dims[1] = (cuuint64_t)in->w; dims[2] = (cuuint64_t)in->h; dims[3] = (cuuint64_t)in->n;
+      strides[0] = pix * 2; strides[1] = pix * 2 * in->w; strides[2] = pix * 2 * in->w * in->h;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED;
+    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 100 - (int)r;      // distinguishable in bring-up logs
   }
   {
-    const cuuint64_t ktot = (cuuint64_t)p.taps * p.passes * a->cin;
-    cuuint64_t dims[2] = {ktot, (cuuint64_t)p.classes * a->cout};
+    // halo mode: rows = (kx, cout), K = (ky, pass, channel); otherwise rows = (class, cout), K = (tap, pass, channel)
+    const cuuint64_t ktot = (cuuint64_t)(p.halo ? 7 : p.taps) * p.passes * (row7 ? 64 : a->cin);
+    const cuuint64_t rows = (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout;
+    cuuint64_t dims[2] = {ktot, rows};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : p.BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED;
+    if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
   static int num_sms = 0;
   if (!num_sms) {
@@ -475,4 +526,11 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   EAMM_LAUNCH_CHECK();
   return 0;
+}
+
+/* Whether eamm_conv_tc uses the halo-row scheme for this 7x7 layer (decides the weight packing). */
+extern "C" int eamm_conv_tc_uses_halo(int kind, int w, int cout) {
+  const char* e = getenv("EAMM_TC_HALO");
+  int halo_env = e ? atoi(e) : 1;
+  return (kind == EAMM_CONV_7X7 && halo_env > 0 && w % 128 == 0 && cout <= 32) ? 1 : 0;
 }

@@ -319,6 +319,30 @@ nchw_to_act_kernel(const float* __restrict__ src, int C, ActView dst, long long 
   }
 }
 
+// =============================================================================================
+// source image NCHW fp32 -> zero-bordered [n][H+6][W+8][8] bf16 (hi0,hi1,hi2,0,lo0,lo1,lo2,0):
+// the operand of the packed 7x7 `first` convolution (one 16-byte pixel, 8 pixels = one K window).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+pack_image_kernel(const float* __restrict__ src, int C, int H, int W, int split, uint4* __restrict__ dst,
+                  long long total) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(idx % W);
+    int y = (int)((idx / W) % H);
+    int n = (int)(idx / ((long long)W * H));
+    float v[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) v[c] = __ldg(src + (((long long)n * C + c) * H + y) * W + x);
+    uint2 hi = float4_to_bf16x4(make_float4(v[0], v[1], v[2], 0.f));
+    uint2 lo = make_uint2(0u, 0u);
+    if (split) {
+      float4 h = bf16x4_to_float4(hi);
+      lo = float4_to_bf16x4(make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, 0.f));
+    }
+    dst[((long long)n * (H + 6) + (y + 3)) * (W + 8) + (x + 3)] = make_uint4(hi.x, hi.y, lo.x, lo.y);
+  }
+}
+
 static inline KpDev to_dev(const eamm_kp* k) {
   KpDev d; d.value = k->value; d.jac = k->jacobian; d.vs = k->value_stride; d.js = k->jacobian_stride;
   return d;
@@ -429,6 +453,17 @@ extern "C" int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, co
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   nchw_to_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, d, total);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_pack_image(const float* src, int n, int C, int H, int W, int split, void* dst, void* stream) {
+  if (!src || !dst || n <= 0 || C <= 0 || C > 3 || H <= 0 || W <= 0) return EAMM_ERR_ARG;
+  if ((uintptr_t)dst % 16) return EAMM_ERR_ALIGN;
+  long long total = (long long)n * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, H, W, split, (uint4*)dst, total);
   EAMM_LAUNCH_CHECK();
   return 0;
 }

@@ -132,6 +132,37 @@ def pack_tc_weights(full, classes, passes):
     return packed.reshape(classes * cout, -1).contiguous()
 
 
+def pack_tc_weights_halo(full, passes):
+    """7x7 halo-row scheme of eamm_conv_tc: [49 taps][cout][cin] -> bf16 [7 kx * cout][7 ky * passes * cin]."""
+    _, cout, cin = full.shape
+    w = full.view(7, 7, cout, cin).permute(1, 2, 0, 3)                   # [kx][cout][ky][cin]
+    hi = w.to(torch.bfloat16)
+    if passes == 1:
+        packed = hi
+    else:
+        lo = (w - hi.float()).to(torch.bfloat16)
+        packed = torch.stack([hi, lo, hi], dim=3)                         # [kx][cout][ky][3][cin]
+    return packed.reshape(7 * cout, -1).contiguous()
+
+
+def pack_tc_weights_row7(w, cout_pad, passes):
+    """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
+
+    K window of one ky = 8 pixels x 8 channels (hi0..2, 0, lo0..2, 0); k = kx*8 + channel, kx = 7 is
+    padding.  Pass 0 holds w_hi against both the hi and the lo activation channels, pass 1 (split
+    mode) holds w_lo against the hi channels: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo.
+    """
+    cout, C = w.shape[0], w.shape[1]
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    out = torch.zeros(cout_pad, 7, passes, 8, 8, dtype=torch.bfloat16, device=w.device)   # [co][ky][pass][kx][ch]
+    out[:cout, :, 0, :7, :C] = hi.permute(0, 2, 3, 1)
+    if passes == 2:
+        out[:cout, :, 0, :7, 4:4 + C] = hi.permute(0, 2, 3, 1)
+        out[:cout, :, 1, :7, :C] = lo.permute(0, 2, 3, 1)
+    return out.reshape(cout_pad, -1).contiguous()
+
+
 def impl_for(precision):
     """(conv implementation, activation storage mode, channel-slot alignment, cout alignment)."""
     import os
@@ -172,6 +203,7 @@ class ConvLayer:
             self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
         elif impl in ("tc", "tc3"):
             self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1)
+            self.weight_halo = None          # packed on first use when eamm_conv_tc picks the halo-row scheme
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -187,6 +219,10 @@ class ConvLayer:
         a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
         a.inp = C.pointer(inp)
         a.weight = self.weight.data_ptr()
+        if self.impl != "simt" and self.kind == L.CONV_7X7 and lib.eamm_conv_tc_uses_halo(self.kind, inp.w, self.cout):
+            if self.weight_halo is None:
+                self.weight_halo = pack_tc_weights_halo(self.w_ref, 3 if self.impl == "tc3" else 1)
+            a.weight = self.weight_halo.data_ptr()
         a.bias = self.bias.data_ptr()
         if residual is not None:
             a.residual = C.pointer(residual)
@@ -204,6 +240,50 @@ class ConvLayer:
         fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
         _launch("conv:" + self.name, lambda: L.check(fn(C.byref(a), stream), "conv %s" % self.name),
                 flops=self.flops_per_in_pixel * inp.n * inp.h * inp.w)
+
+
+class FirstConvTC:
+    """`first` (generator.py:25,61: 7x7, <=3 -> block_expansion channels, BN, ReLU) on tensor cores.
+
+    The source image is packed once per call by eamm_pack_image into a zero-bordered
+    [n][H+6][W+8][8] bf16 buffer; eamm_conv_tc (kind ROW7_PACKED) reads 8-pixel windows of it with an
+    overlapping-stride TMA map, so the whole 7x7x3 filter is 7 K-chunks instead of 49.
+    """
+
+    def __init__(self, w, b, nalign, split):
+        cout, cin = w.shape[0], w.shape[1]
+        if cin > 3:
+            raise RuntimeError("eamm_b200: the packed first conv supports at most 3 input channels")
+        self.name = "first"
+        self.split = split
+        self.passes = 2 if split else 1
+        self.cout_valid, self.cout = cout, _round_up(cout, nalign)
+        self.weight = pack_tc_weights_row7(w, self.cout, self.passes)
+        self.bias = torch.zeros(self.cout, dtype=torch.float32, device=w.device)
+        self.bias[:cout] = b
+        self.flops_per_in_pixel = 2.0 * cout * cin * 49
+        self.cin = 8
+
+    def buffer(self, n, H, W, device):
+        return torch.zeros(n, H + 6, W + 8, 8, dtype=torch.bfloat16, device=device)
+
+    def launch(self, lib, stream, src, nsrc, C_, H, W, packed, out):
+        _launch("pack_image", lambda: L.check(
+            lib.eamm_pack_image(src.data_ptr(), nsrc, C_, H, W, 1 if self.split else 0, packed.data_ptr(), stream),
+            "pack_image"), nbytes=nsrc * H * W * (C_ * 4 + 16))
+        inp = L.Act()
+        inp.data = packed.data_ptr()
+        inp.dtype, inp.n, inp.h, inp.w = L.EAMM_BF16, nsrc, H, W
+        inp.c, inp.c_off, inp.c_buf, inp.planes = 8, 0, 8, 1
+        inp.n_stride = (H + 6) * (W + 8) * 8
+        a = L.ConvArgs()
+        a.kind, a.flags, a.cin, a.cout = L.CONV_ROW7_PACKED, L.EPI_RELU, 8, self.cout
+        a.inp = C.pointer(inp)
+        a.weight, a.bias = self.weight.data_ptr(), self.bias.data_ptr()
+        a.out = C.pointer(out)
+        a.pack_passes = self.passes
+        _launch("conv:first", lambda: L.check(lib.eamm_conv_tc(C.byref(a), stream), "conv first (packed)"),
+                flops=self.flops_per_in_pixel * nsrc * H * W)
 
 
 def _kp_struct(kp, batch, num_kp, device):
@@ -433,7 +513,12 @@ class GeneratorEngine:
             return fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
 
         w, b = folded(m.first)
-        self.first = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, _round_up(m.num_channels, ca), na, impl)
+        import os
+        self.first_packed = impl != "simt" and m.num_channels <= 3 and os.environ.get("EAMM_TC_ROW7", "1") != "0"
+        if self.first_packed:
+            self.first = FirstConvTC(w, b, na, split=(impl == "tc3"))
+        else:
+            self.first = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, _round_up(m.num_channels, ca), na, impl)
         self.down = []
         for i, blk in enumerate(m.down_blocks):
             w, b = folded(blk)
@@ -474,7 +559,10 @@ class GeneratorEngine:
         if H % (1 << nd) or W % (1 << nd):
             raise RuntimeError("eamm_b200: image size must be divisible by %d" % (1 << nd))
         ws = type("WS", (), {})()
-        ws.src = ActBuf(B, H, W, self.first.cin, mode, dev)
+        if self.first_packed:
+            ws.src_packed = self.first.buffer(B, H, W, dev)
+        else:
+            ws.src = ActBuf(B, H, W, self.first.cin, mode, dev)
         ws.enc = [ActBuf(B, H, W, _round_up(m.first.conv.out_channels, ca), mode, dev)]
         for i, blk in enumerate(m.down_blocks):
             ws.enc.append(ActBuf(B, H >> (i + 1), W >> (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
@@ -503,11 +591,14 @@ class GeneratorEngine:
         nsrc = 1 if shared else B
         # encoder (generator.py:61-63); with a shared (stride-0) source it runs once and is broadcast
         esz = 4 if self.mode != "bf16" else 2
-        src_act = ws.src.act(n=nsrc)
-        _launch("nchw_to_act", lambda: L.check(
-            lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(src_act), st), "nchw_to_act"),
-            nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
-        self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
+        if self.first_packed:
+            self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed, ws.enc[0].act(c=self.first.cout, n=nsrc))
+        else:
+            src_act = ws.src.act(n=nsrc)
+            _launch("nchw_to_act", lambda: L.check(
+                lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(src_act), st), "nchw_to_act"),
+                nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
+            self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
         for i, layer in enumerate(self.down):
             layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
         result = {}

@@ -64,9 +64,13 @@ typedef struct {
 enum {
   EAMM_CONV_3X3 = 0,       /* 3x3, padding 1 (util.py:865-866, 889-890, 909-910)            */
   EAMM_CONV_7X7 = 1,       /* 7x7, padding 3 (generator.py:25,46; dense_motion.py:18,21)     */
-  EAMM_CONV_UP2_3X3 = 2    /* F.interpolate(x2, nearest) then 3x3 pad 1 (util.py:895-897),
+  EAMM_CONV_UP2_3X3 = 2,   /* F.interpolate(x2, nearest) then 3x3 pad 1 (util.py:895-897),
                               executed as four 2x2 convolutions on the low-res input, one per
                               output-pixel parity class; weights are pre-combined by the host  */
+  EAMM_CONV_ROW7_PACKED = 3 /* 7x7 pad 3 over a <=3-channel image packed by eamm_pack_image
+                              (generator.py:25 `first`): K = (ky) x [8 pixels x 8 channels], the
+                              kx taps and both bf16 planes live inside one 64-wide K window;
+                              eamm_conv_tc only                                                 */
 };
 enum {
   EAMM_EPI_RELU = 1,       /* y = max(y, 0) after the folded-BN bias                          */
@@ -90,6 +94,7 @@ typedef struct {
   float* out_nchw;         /* optional fp32 NCHW output [n, out_nchw_c, H, W] (final prediction)*/
   int32_t out_nchw_c;      /* channels written to out_nchw (<= cout; cout may be padded)       */
   float* out_nhwc_f32;     /* optional fp32 NHWC raw output [n, H, W, cout] (mask/occ logits)  */
+  int32_t pack_passes;     /* EAMM_CONV_ROW7_PACKED only: 1 (bf16) or 2 (hi/lo split) weight passes */
 } eamm_conv_args;
 
 /* ---- library info --------------------------------------------------------------------------- */
@@ -149,6 +154,16 @@ int eamm_conv_simt(const eamm_conv_args* args, void* stream);
  *                 inputs (weight planes hi, lo, hi against activation planes hi, hi, lo).  UP2 has
  *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout). */
 int eamm_conv_tc(const eamm_conv_args* args, void* stream);
+
+/* 1 when eamm_conv_tc runs this 7x7 layer with the halo-row scheme, whose weight matrix is
+ * bf16 [7 kx * cout][7 ky * passes * cin] instead of [cout][49 taps * passes * cin]. */
+int eamm_conv_tc_uses_halo(int kind, int w, int cout);
+
+/* ---- source image for EAMM_CONV_ROW7_PACKED: src [n,C<=3,H,W] fp32 NCHW -> dst bf16
+ * [n][H+6][W+8][8] with channels [hi0,hi1,hi2,0,lo0,lo1,lo2,0] (lo = bf16(v-hi); zero when
+ * split == 0).  The zero border (3 rows top/bottom, 3 columns left, 5 right) must already be
+ * zero in dst (allocate it zeroed once); only the interior is written. */
+int eamm_pack_image(const float* src, int n, int C, int H, int W, int split, void* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,12 @@ CASES = [
     ("7x7 128->16 64x64 logits", "7x7", "", 128, 16, 2, 64, 64, 1, 0, 0, "nhwc"),
     ("7x7 128->16 64x64 logits x3", "7x7", "", 128, 16, 2, 64, 64, 2, 0, 0, "nhwc"),
     ("7x7 64->16 32x32 sigmoid nchw", "7x7", "s", 64, 16, 2, 32, 32, 1, 0, 0, "nchw"),
+    ("7x7 halo 64->16 128x128 sigmoid", "7x7", "s", 64, 16, 2, 128, 128, 1, 0, 0, "nchw"),
+    ("7x7 halo 64->16 256x256 sig x3", "7x7", "s", 64, 16, 2, 256, 256, 2, 0, 0, "nchw"),
+    ("7x7 halo 128->16 128x128 logits", "7x7", "", 128, 16, 1, 128, 128, 1, 0, 0, "nhwc"),
+    ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
+    ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
+    ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
 ]
 
 
@@ -40,6 +46,8 @@ def run_case(idx):
     dev = torch.device("cuda:0")
     lib = L.load()
     g = torch.Generator().manual_seed(100 + idx)
+    if kind == "first":
+        return run_first(idx)
     kk = {"3x3": L.CONV_3X3, "up2": L.CONV_UP2_3X3, "7x7": L.CONV_7X7}[kind]
     ks = 7 if kind == "7x7" else 3
     flags = (L.EPI_RELU if "r" in fl else 0) | (L.EPI_POOL2 if "p" in fl else 0) | (L.EPI_SIGMOID if "s" in fl else 0)
@@ -95,15 +103,55 @@ def run_case(idx):
     return 0 if worst <= tol else 1
 
 
+def run_first(idx):
+    """Packed 7x7 first conv (ROW7) against the SIMT 7x7 conv on the same image."""
+    import ctypes as C
+    import torch
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, ConvLayer, FirstConvTC, current_stream_ptr
+    name, kind, fl, cin, cout, N, H, W, planes, _, _, _ = CASES[idx]
+    dev = torch.device("cuda:0")
+    lib = L.load()
+    g = torch.Generator().manual_seed(100 + idx)
+    w = ((torch.rand(cout, cin, 7, 7, generator=g) * 2 - 1) * (3.0 / (cin * 49)) ** 0.5).to(dev)
+    b = ((torch.rand(cout, generator=g) * 2 - 1) * 0.1).to(dev)
+    if planes == 1:
+        w = w.bfloat16().float()
+    img = torch.rand(N, cin, H, W, generator=g).to(dev)
+    mode = "bf16x2" if planes == 2 else "bf16"
+    st = current_stream_ptr()
+    # reference: NHWC activation (4-channel slot) + SIMT 7x7
+    xin = ActBuf(N, H, W, 4, mode, dev)
+    L.check(lib.eamm_nchw_to_act(img.data_ptr(), N, cin, H, W, C.byref(xin.act()), st), "nchw_to_act")
+    ref_layer = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, 4, 16, "simt")
+    o_ref = ActBuf(N, H, W, ref_layer.cout, mode, dev)
+    ref_layer.launch(lib, st, xin.act(), out=o_ref.act())
+    tc = FirstConvTC(w, b, 16, split=(planes == 2))
+    packed = tc.buffer(N, H, W, dev)
+    o_tc = ActBuf(N, H, W, tc.cout, mode, dev)
+    tc.launch(lib, st, img, N, cin, H, W, packed, o_tc.act())
+    torch.cuda.synchronize()
+    u, v = o_ref.to_float(), o_tc.to_float()
+    worst = (u - v).abs().max().item() / max(1e-6, u.abs().max().item())
+    if not torch.isfinite(v).all():
+        worst = float("inf")
+    tol = 2e-4 if planes == 2 else 1e-2
+    print("%s case %2d %-34s rel_err %.3e" % ("OK " if worst <= tol else "BAD", idx, name, worst), flush=True)
+    return 0 if worst <= tol else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", type=int, default=-1)
     ap.add_argument("--timeout", type=int, default=90)
+    ap.add_argument("--only", default="", help="substring filter on case names")
     args = ap.parse_args()
     if args.case >= 0:
         return run_case(args.case)
     bad = 0
     for i in range(len(CASES)):
+        if args.only and args.only not in CASES[i][0]:
+            continue
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], timeout=args.timeout,
                                capture_output=True, text=True)
