@@ -55,7 +55,7 @@ _PROTOS = {
     "eamm_nchw_to_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Act), C.c_void_p]),
     "eamm_conv_simt": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "eamm_conv_tc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
-    "eamm_conv_tc_uses_halo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "eamm_conv_tc_uses_halo": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "eamm_pack_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

@@ -34,6 +34,9 @@ struct ConvTcParams {
   int BN, kind, flags, taps, ksize, cin_chunks, passes;
   int a_c_off, a_c_buf;
   int halo;            // 7x7 with a 134-pixel halo row per ky: the 7 kx taps are shifted smem views
+  int kxn;             // 7x7 -> <=4 NCHW channels: the 7 kx taps live in the N dimension (N = 7*4 -> 32),
+                       // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns
+  int x_stride;        // pixels between consecutive x tiles (122 in kxn mode, else bw)
   int a_slot_bytes;    // bytes reserved for the A operand in a stage
   int num_stages, cout;
   int has_out, has_out2, has_res;
@@ -168,7 +171,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, long lon
   TileCoord t;
   t.nt = (int)(tile % p.n_tiles); tile /= p.n_tiles;
   t.cls = (int)(tile % p.classes); tile /= p.classes;
-  t.x0 = (int)(tile % p.tiles_x) * p.bw; tile /= p.tiles_x;
+  t.x0 = (int)(tile % p.tiles_x) * p.x_stride; tile /= p.tiles_x;
   t.y0 = (int)(tile % p.tiles_y) * p.bh; tile /= p.tiles_y;
   t.n0 = (int)tile * p.bn;
   return t;
@@ -250,6 +253,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   }
 }
 
+// kx-in-N epilogue (7x7 -> <=4 channels, sigmoid, NCHW fp32): accumulator row p holds, for the input
+// column x0-3+p, the partial sums D[p][kx*4+co] over (ky, channels).  out[x0+j][co] = bias +
+// sum_kx D[j+kx][kx*4+co]; the shifted rows are exchanged through shared memory (S, stride 29).
+__device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                             int quadrant, int lane, float* S) {
+  const int r = quadrant * 32 + lane;
+  uint32_t raw[32];
+  TmemLd<32>::ld(tmem_acc + ((uint32_t)(quadrant * 32) << 16), raw);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int c = 0; c < 28; ++c) S[r * 29 + c] = __uint_as_float(raw[c]);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int x = tc.x0 + r;
+  if (r < 122 && x < p.W && tc.y0 < p.H && tc.n0 < p.N) {
+    for (int co = 0; co < p.out_nchw_c; ++co) {
+      float acc = __ldg(p.bias + co);
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) acc += S[(r + kx) * 29 + kx * 4 + co];
+      if (p.flags & EAMM_EPI_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+      p.out_nchw[(((long long)tc.n0 * p.out_nchw_c + co) * p.H + tc.y0) * p.W + x] = acc;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
@@ -284,7 +311,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int KC = (p.halo ? 7 : p.taps) * p.passes * p.cin_chunks;
+  const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -294,10 +321,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord tc = decode_tile(p, tile);
         const int brow = tc.cls * p.cout + tc.nt * p.BN;
         int kc = 0;
-        const int ntap = p.halo ? 7 : p.taps;
+        const int ntap = (p.halo || p.kxn) ? 7 : p.taps;
         for (int t = 0; t < ntap; ++t) {
           int dy, dx;
-          if (p.halo) { dy = t - 3; dx = -3; }
+          if (p.halo || p.kxn) { dy = t - 3; dx = -3; }
           else if (p.kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; }
           else if (p.kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
           else { dy = t / p.ksize - (p.ksize >> 1); dx = t % p.ksize - (p.ksize >> 1); }
@@ -365,7 +392,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
-      if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane);
+      if (p.kxn) epilogue_kxn(p, tc, tmem_acc, quadrant, lane,
+                              reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
+                                                       (size_t)p.num_stages * stage_bytes) + as * (128 * 29));
+      else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane);
       tc_fence_before();
       __syncwarp();
@@ -408,6 +438,16 @@ static int ilog2_exact(int v) {
 
 using namespace eamm;
 
+/* Which 7x7 scheme eamm_conv_tc uses (decides the weight packing): 0 = one TMA tile per tap,
+ * 1 = halo row with kx-shifted smem views, 2 = kx taps in the N dimension (<= 4 NCHW channels). */
+extern "C" int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c) {
+  const char* e = getenv("EAMM_TC_HALO");
+  const int halo_env = e ? atoi(e) : 1;
+  if (kind != EAMM_CONV_7X7 || halo_env <= 0 || w % 128 != 0) return 0;
+  if (out_nchw_c >= 1 && out_nchw_c <= 4 && halo_env != 3) return 2;
+  return cout <= 32 ? 1 : 0;
+}
+
 extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   int rc = conv_check_args(a, 16);
   if (rc) return rc;
@@ -436,29 +476,48 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   p.cin_chunks = row7 ? 1 : a->cin / 64;
   p.passes = row7 ? a->pack_passes : (in->planes == 2 ? 3 : 1);
   p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
-  // N tile: the whole cout when it fits one UMMA (<= 256), else the largest divisor among 256/128/64
-  if (a->cout <= 256) p.BN = a->cout;
-  else if (a->cout % 256 == 0) p.BN = 256;
-  else if (a->cout % 128 == 0) p.BN = 128;
-  else if (a->cout % 64 == 0) p.BN = 64;
-  else return EAMM_ERR_UNSUPPORTED;
-  p.n_tiles = a->cout / p.BN;
-  // 7x7 with few couts on wide maps: one 134-pixel halo row per ky, kx taps are shifted smem views
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("EAMM_TC_HALO"); halo_env = e ? atoi(e) : 1; }
-  p.halo = (a->kind == EAMM_CONV_7X7 && halo_env > 0 && in->w % 128 == 0 && a->cout <= 32) ? 1 : 0;
+  const int mode7 = halo_env > 0 ? eamm_conv_tc_uses_halo(a->kind, in->w, a->cout,
+                                                          (a->out || a->out2 || a->out_nhwc_f32) ? 0 : a->out_nchw_c) : 0;
+  p.kxn = mode7 == 2; p.halo = mode7 == 1;
   // 128-pixel box: bw x bh x bn
-  if (p.halo) { p.bw = 128; p.bh = 1; p.bn = 1; }
+  if (p.halo || p.kxn) { p.bw = 128; p.bh = 1; p.bn = 1; }
   else {
     p.bw = in->w >= 16 ? 16 : in->w;
     p.bh = 128 / p.bw; if (p.bh > in->h) p.bh = in->h;
     p.bn = 128 / (p.bw * p.bh);
   }
   p.bw_log2 = ilog2_exact(p.bw); p.bh_log2 = ilog2_exact(p.bh);
-  p.tiles_x = in->w / p.bw; p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
+  p.x_stride = p.kxn ? 122 : p.bw;
+  p.tiles_x = (in->w + p.x_stride - 1) / p.x_stride;
+  p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // N tile: the widest UMMA N (<= 256) dividing cout that still yields at least one tile per SM;
+  // small maps (hourglass 8x8 ... 2x2) prefer narrow N tiles so that more SMs stream the weights.
+  if (p.kxn) p.BN = 32;
+  else {
+    const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes;
+    p.BN = 0;
+    const int cand[5] = {256, 128, 64, 32, 16};
+    if (a->cout <= 256 && m_tiles >= num_sms) p.BN = a->cout;
+    for (int i = 0; i < 5 && !p.BN; ++i)
+      if (cand[i] <= a->cout && a->cout % cand[i] == 0 && m_tiles * (a->cout / cand[i]) >= num_sms) p.BN = cand[i];
+    if (!p.BN) {                       // cannot fill the chip: narrowest tile of at least 64 columns
+      if (a->cout % 64 == 0) p.BN = 64;
+      else if (a->cout <= 256) p.BN = a->cout;
+      else return EAMM_ERR_UNSUPPORTED;
+    }
+  }
+  p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
   const uint32_t stage_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
-  int stages = (int)((200u * 1024u) / stage_bytes);
+  const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
+  int stages = (int)((200u * 1024u - extra_smem) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
   p.num_stages = stages;
@@ -499,8 +558,9 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   }
   {
     // halo mode: rows = (kx, cout), K = (ky, pass, channel); otherwise rows = (class, cout), K = (tap, pass, channel)
-    const cuuint64_t ktot = (cuuint64_t)(p.halo ? 7 : p.taps) * p.passes * (row7 ? 64 : a->cin);
-    const cuuint64_t rows = (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout;
+    // kxn mode : rows = 32 (kx*4 + cout), K = (ky, pass, channel)
+    const cuuint64_t ktot = (cuuint64_t)((p.halo || p.kxn) ? 7 : p.taps) * p.passes * (row7 ? 64 : a->cin);
+    const cuuint64_t rows = p.kxn ? 32 : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout;
     cuuint64_t dims[2] = {ktot, rows};
     cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : p.BN)};
@@ -510,12 +570,7 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -528,9 +583,3 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   return 0;
 }
 
-/* Whether eamm_conv_tc uses the halo-row scheme for this 7x7 layer (decides the weight packing). */
-extern "C" int eamm_conv_tc_uses_halo(int kind, int w, int cout) {
-  const char* e = getenv("EAMM_TC_HALO");
-  int halo_env = e ? atoi(e) : 1;
-  return (kind == EAMM_CONV_7X7 && halo_env > 0 && w % 128 == 0 && cout <= 32) ? 1 : 0;
-}

@@ -145,6 +145,21 @@ def pack_tc_weights_halo(full, passes):
     return packed.reshape(7 * cout, -1).contiguous()
 
 
+def pack_tc_weights_kxn(full, nchw_c, passes):
+    """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][7 ky * passes * cin]."""
+    _, cout, cin = full.shape
+    w = full.view(7, 7, cout, cin)[:, :, :nchw_c]                         # [ky][kx][co][cin]
+    rows = torch.zeros(8, 4, 7, cin, dtype=torch.float32, device=full.device)   # [kx(8)][co(4)][ky][cin]
+    rows[:7, :nchw_c] = w.permute(1, 2, 0, 3)
+    hi = rows.to(torch.bfloat16)
+    if passes == 1:
+        packed = hi
+    else:
+        lo = (rows - hi.float()).to(torch.bfloat16)
+        packed = torch.stack([hi, lo, hi], dim=3)                         # [kx][co][ky][3][cin]
+    return packed.reshape(32, -1).contiguous()
+
+
 def pack_tc_weights_row7(w, cout_pad, passes):
     """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
 
@@ -203,7 +218,7 @@ class ConvLayer:
             self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
         elif impl in ("tc", "tc3"):
             self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1)
-            self.weight_halo = None          # packed on first use when eamm_conv_tc picks the halo-row scheme
+            self.weight_alt = {}             # 7x7 schemes 1/2 of eamm_conv_tc, packed on first use
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -219,10 +234,16 @@ class ConvLayer:
         a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
         a.inp = C.pointer(inp)
         a.weight = self.weight.data_ptr()
-        if self.impl != "simt" and self.kind == L.CONV_7X7 and lib.eamm_conv_tc_uses_halo(self.kind, inp.w, self.cout):
-            if self.weight_halo is None:
-                self.weight_halo = pack_tc_weights_halo(self.w_ref, 3 if self.impl == "tc3" else 1)
-            a.weight = self.weight_halo.data_ptr()
+        if self.impl != "simt" and self.kind == L.CONV_7X7:
+            nchw_only = out_nchw is not None and out is None and out2 is None and out_nhwc_f32 is None
+            scheme = lib.eamm_conv_tc_uses_halo(self.kind, inp.w, self.cout, out_nchw_c if nchw_only else 0)
+            if scheme:
+                key = (scheme, out_nchw_c if scheme == 2 else 0)
+                if key not in self.weight_alt:
+                    passes = 3 if self.impl == "tc3" else 1
+                    self.weight_alt[key] = (pack_tc_weights_halo(self.w_ref, passes) if scheme == 1
+                                            else pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes))
+                a.weight = self.weight_alt[key].data_ptr()
         a.bias = self.bias.data_ptr()
         if residual is not None:
             a.residual = C.pointer(residual)

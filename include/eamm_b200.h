@@ -155,9 +155,12 @@ int eamm_conv_simt(const eamm_conv_args* args, void* stream);
  *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout). */
 int eamm_conv_tc(const eamm_conv_args* args, void* stream);
 
-/* 1 when eamm_conv_tc runs this 7x7 layer with the halo-row scheme, whose weight matrix is
- * bf16 [7 kx * cout][7 ky * passes * cin] instead of [cout][49 taps * passes * cin]. */
-int eamm_conv_tc_uses_halo(int kind, int w, int cout);
+/* Which scheme eamm_conv_tc uses for a 7x7 layer, i.e. which weight matrix it expects:
+ *   0  one TMA tile per tap           bf16 [cout][49 taps * passes * cin]
+ *   1  halo row, kx-shifted views     bf16 [7 kx * cout][7 ky * passes * cin]      (w % 128 == 0, cout <= 32)
+ *   2  kx taps in the GEMM N axis     bf16 [32 = kx*4 + co][7 ky * passes * cin]   (w % 128 == 0, only
+ *      out_nchw with <= 4 channels; out_nchw_c = 0 when the call has any NHWC output) */
+int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c);
 
 /* ---- source image for EAMM_CONV_ROW7_PACKED: src [n,C<=3,H,W] fp32 NCHW -> dst bf16
  * [n][H+6][W+8][8] with channels [hi0,hi1,hi2,0,lo0,lo1,lo2,0] (lo = bf16(v-hi); zero when
