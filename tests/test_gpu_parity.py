@@ -242,3 +242,21 @@ def test_cabi_rejects_bad_arguments_without_launching(dev):
     assert lib.eamm_conv_tc(C.byref(args), current_stream_ptr()) == -5      # EAMM_ERR_UNSUPPORTED
     args.cin = 32
     assert lib.eamm_conv_tc(C.byref(args), current_stream_ptr()) < 0
+
+
+def test_frame_pipeline_equals_direct_forward(dev):
+    """Host-in / host-out pipelining (three streams) returns exactly what direct calls return."""
+    from eamm_b200.pipeline import FramePipeline
+    gen, cfg = generator("tiny", dev)
+    gen.precision = "fp32"
+    batches = [synth.make_inputs(3, cfg, size=64, seed=40 + i) for i in range(5)]
+    want = [run_ours("tiny", dev, "fp32", *b)["prediction"] for b in batches]
+    pipe = FramePipeline(gen, depth=2)
+    outs = [torch.empty(3, 3, 64, 64).pin_memory() for _ in batches]
+    pinned = [(s.pin_memory(), {k: v.pin_memory() for k, v in kd.items()}, {k: v.pin_memory() for k, v in ks.items()})
+              for s, kd, ks in batches]
+    for (s, kd, ks), o in zip(pinned, outs):
+        pipe.submit(s, kd, ks, o)
+    pipe.close()
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
