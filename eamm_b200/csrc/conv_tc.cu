@@ -6,8 +6,9 @@
 //               shifted by the filter tap (dy, dx); out-of-image pixels are zero-filled by TMA,
 //               which is exactly the conv's zero padding.  SWIZZLE_128B, K-major.
 //   B tile      2-D TMA box {64 k, BN rows} of the host-packed weight matrix [couts][K], K-major.
-//   K loop      taps x passes x (cin/64).  passes = 1 (bf16) or 3 (split-bf16 "fp32" mode:
-//               a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with activations/weights stored as hi/lo planes).
+//   K loop      passes x taps x (cin/64).  passes = 1 (bf16) or 3 (split-bf16 "fp32" mode:
+//               a_hi*b_lo + a_lo*b_hi + a_hi*b_hi with activations/weights stored as hi/lo planes;
+//               small terms first, see the producer).
 //   roles       warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
 //   pipelines   smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring so the
 //               epilogue of tile i overlaps the main loop of tile i+1.
@@ -17,6 +18,7 @@
 // dense_motion.py:98,110.
 #include <cuda.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include "common.cuh"
 
 namespace eamm {
@@ -37,6 +39,8 @@ struct ConvTcParams {
   int kxn;             // 7x7 -> <=4 NCHW channels: the 7 kx taps live in the N dimension (N = 7*4 -> 32),
                        // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns
   int x_stride;        // pixels between consecutive x tiles (122 in kxn mode, else bw)
+  int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
+  unsigned long long* prof;  // EAMM_TC_PROF: per-CTA cycle counters [grid][8] (bring-up instrumentation)
   int a_slot_bytes;    // bytes reserved for the A operand in a stage
   int num_stages, cout;
   int has_out, has_out2, has_res;
@@ -81,6 +85,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -167,12 +176,12 @@ __device__ __forceinline__ void add_chunk(const ActView& v, long long off, float
 
 struct TileCoord { int x0, y0, n0, cls, nt; };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, long long tile) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t tile) {
   TileCoord t;
-  t.nt = (int)(tile % p.n_tiles); tile /= p.n_tiles;
-  t.cls = (int)(tile % p.classes); tile /= p.classes;
-  t.x0 = (int)(tile % p.tiles_x) * p.x_stride; tile /= p.tiles_x;
-  t.y0 = (int)(tile % p.tiles_y) * p.bh; tile /= p.tiles_y;
+  uint32_t q = tile / (uint32_t)p.n_tiles; t.nt = (int)(tile - q * p.n_tiles); tile = q;
+  q = tile / (uint32_t)p.classes; t.cls = (int)(tile - q * p.classes); tile = q;
+  q = tile / (uint32_t)p.tiles_x; t.x0 = (int)(tile - q * p.tiles_x) * p.x_stride; tile = q;
+  q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.bh; tile = q;
   t.n0 = (int)tile * p.bn;
   return t;
 }
@@ -313,83 +322,131 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_smem;
   const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
 
+  // Both single-issuer roles run as warp-uniform loops (all 32 lanes wait, one elected lane issues):
+  // ptxas then keeps descriptors/coordinates in uniform registers instead of emitting a divergent
+  // "waterfall" around every UTMALDG/UTCHMMA, which is what bounds short-K layers otherwise.
+  const uint32_t total_tiles = (uint32_t)p.total_tiles;
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int brow = tc.cls * p.cout + tc.nt * p.BN;
-        int kc = 0;
-        const int ntap = (p.halo || p.kxn) ? 7 : p.taps;
+    const int ntap = (p.halo || p.kxn) ? 7 : p.taps;
+    const int passes = p.passes, chunks = p.cin_chunks, kind = p.kind, ksize = p.ksize, khalf = p.ksize >> 1;
+    const int nstages = p.num_stages, a_slot = p.a_slot_bytes, dbg = p.debug;
+    const bool haloish = p.halo || p.kxn;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
+    long long prof_acc[2] = {0, 0};
+    const long long prof_start = p.prof ? clock64() : 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int brow = tc.cls * p.cout + tc.nt * p.BN;
+      int kcol = 0;
+      // K order = (pass, tap, chunk).  In split mode the two cross terms (a_hi*b_lo, a_lo*b_hi) are
+      // accumulated first, while the TMEM accumulator is still small, and the dominant a_hi*b_hi
+      // term last: the tensor core truncates on every accumulate, so the bias it leaves scales with
+      // |accumulator| x (number of steps taken at that magnitude).
+      for (int ps = 0; ps < passes; ++ps) {
+        int cbase = p.a_c_off + ((passes == 3 && ps == 1) ? p.a_c_buf : 0);
+        if (kind == EAMM_CONV_ROW7_PACKED) cbase = 0;            // both planes live inside the 64-wide K window
         for (int t = 0; t < ntap; ++t) {
           int dy, dx;
-          if (p.halo || p.kxn) { dy = t - 3; dx = -3; }
-          else if (p.kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; }
-          else if (p.kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
-          else { dy = t / p.ksize - (p.ksize >> 1); dx = t % p.ksize - (p.ksize >> 1); }
-          for (int ps = 0; ps < p.passes; ++ps) {
-            int cbase = p.a_c_off + (ps == 2 ? p.a_c_buf : 0);
-            if (p.kind == EAMM_CONV_ROW7_PACKED) cbase = 0;      // both planes live inside the 64-wide K window
-            for (int cc = 0; cc < p.cin_chunks; ++cc, ++kc) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = smem_base + stage * stage_bytes;
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              tma_load_4d(sa, &tmA, full_bar(stage), cbase + cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-              tma_load_2d(sa + p.a_slot_bytes, &tmB, full_bar(stage), kc * 64, brow);
-              if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          if (haloish) { dy = t - 3; dx = -3; }
+          else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; }
+          else if (kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
+          else { dy = t / ksize - khalf; dx = t - (t / ksize) * ksize - khalf; }
+          const int ax = tc.x0 + dx, ay = tc.y0 + dy;
+          for (int cc = 0; cc < chunks; ++cc, kcol += 64) {
+            long long t0 = 0;
+            if (p.prof) t0 = clock64();
+            mbar_wait(eb, phase ^ 1u);
+            if (p.prof) { long long t1 = clock64(); prof_acc[0] += t1 - t0; }
+            if (elect_one()) {
+              if (dbg == 1) { mbar_arrive(fb); }
+              else {
+                mbar_expect_tx(fb, tx_bytes);
+                tma_load_4d(sa, &tmA, fb, cbase + cc * 64, ax, ay, tc.n0);
+                tma_load_2d(sa + a_slot, &tmB, fb, kcol, brow);
+              }
             }
+            ++stage; sa += stage_bytes; fb += 8; eb += 8;
+            if (stage == nstages) { stage = 0; phase ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
           }
         }
       }
     }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = prof_acc[0];                    // producer: cycles waiting for a free slot
+      p.prof[blockIdx.x * 8 + 1] = clock64() - prof_start;         // producer: total
+    }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+    // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const int nstages = p.num_stages, halo = p.halo, dbg = p.debug, BN = p.BN;
+    const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
+    int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
+    uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
+    long long pm[3] = {0, 0, 0};
+    const long long pm_start = p.prof ? clock64() : 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      long long t0 = 0;
+      if (p.prof) t0 = clock64();
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      if (p.prof) pm[0] += clock64() - t0;
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * 256u;
+      for (int kc = 0; kc < KC; ++kc) {
+        if (p.prof) t0 = clock64();
+        mbar_wait(fb, phase);
+        if (p.prof) pm[1] += clock64() - t0;
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
-        for (int kc = 0; kc < KC; ++kc) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + (uint32_t)p.a_slot_bytes;
-          if (p.halo) {
+        if (elect_one()) {
+          const uint32_t sb = sa + a_slot;
+          if (dbg == 2) {
+          } else if (halo) {
             // one halo row of 134 pixels serves the 7 kx taps: tap kx reads rows [kx, kx+128)
+            // (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
+            //  row-shifted start address needs no base_offset in the descriptor)
 #pragma unroll 1
             for (int kx = 0; kx < 7; ++kx) {
-              // (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
-              //  row-shifted start address needs no base_offset in the descriptor)
               const uint64_t da = make_sw128_desc(sa + (uint32_t)kx * 128u);
-              const uint64_t db = make_sw128_desc(sb + (uint32_t)(kx * p.BN) * 128u);
+              const uint64_t db = make_sw128_desc(sb + (uint32_t)(kx * BN) * 128u);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | kx | k) ? 1u : 0u);
             }
           } else {
             const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sb);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+            tc_mma_bf16(tmem_acc, da, db, idesc, kc ? 1u : 0u);
+            tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+            tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
+            tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
           }
-          tc_commit(empty_bar(stage));
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          tc_commit(eb);
+          if (kc == KC - 1) tc_commit(tfull_bar(as));
         }
-        tc_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        ++stage; sa += stage_bytes; fb += 8; eb += 8;
+        if (stage == nstages) { stage = 0; phase ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
       }
+      as ^= 1u; if (as == 0) aphase ^= 1u;
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 2] = pm[0];                          // MMA: waiting for a free accumulator
+      p.prof[blockIdx.x * 8 + 3] = pm[1];                          // MMA: waiting for operands
+      p.prof[blockIdx.x * 8 + 4] = clock64() - pm_start;           // MMA: total
     }
   } else {
     // ================================================================ epilogue warps (TMEM lanes by warp%4)
     const int quadrant = warp & 3;
     int as = 0; uint32_t aphase = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    long long pe = 0;
+    const long long pe_start = p.prof ? clock64() : 0;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
+      long long t0 = 0;
+      if (p.prof) t0 = clock64();
       mbar_wait(tfull_bar(as), aphase);
+      if (p.prof) pe += clock64() - t0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
       if (p.kxn) epilogue_kxn(p, tc, tmem_acc, quadrant, lane,
@@ -401,6 +458,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (p.prof && warp == 2 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 5] = pe;                             // epilogue warp 0: waiting for an accumulator
+      p.prof[blockIdx.x * 8 + 6] = clock64() - pe_start;           // epilogue: total
     }
   }
   tc_fence_before();
@@ -481,6 +542,9 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   const int mode7 = halo_env > 0 ? eamm_conv_tc_uses_halo(a->kind, in->w, a->cout,
                                                           (a->out || a->out2 || a->out_nhwc_f32) ? 0 : a->out_nchw_c) : 0;
   p.kxn = mode7 == 2; p.halo = mode7 == 1;
+  static int debug_env = -1;
+  if (debug_env < 0) { const char* e = getenv("EAMM_TC_DEBUG"); debug_env = e ? atoi(e) : 0; }
+  p.debug = debug_env;
   // 128-pixel box: bw x bh x bn
   if (p.halo || p.kxn) { p.bw = 128; p.bh = 1; p.bn = 1; }
   else {
@@ -529,6 +593,7 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
+  if (p.total_tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
 
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return EAMM_ERR_UNSUPPORTED;
@@ -578,8 +643,32 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
     smem_set = smem;
   }
   long long grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  static int prof_env = -1;
+  static unsigned long long* prof_buf = nullptr;
+  if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
+  p.prof = nullptr;
+  if (prof_env) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 1024 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(prof_buf, 0, 1024 * 8 * sizeof(unsigned long long), (cudaStream_t)stream);
+    p.prof = prof_buf;
+  }
   conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   EAMM_LAUNCH_CHECK();
+  if (prof_env) {        // bring-up instrumentation only: synchronous read-back and print
+    static unsigned long long host[1024 * 8];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(host, prof_buf, grid * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long b = 0; b < grid; ++b) for (int j = 0; j < 8; ++j) acc[j] += (double)host[b * 8 + j];
+    const double tiles_per_cta = (double)p.total_tiles / (double)grid;
+    const int KCh = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
+    fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%d KC=%d tiles/cta=%.1f | per tile (cycles): "
+            "total=%.0f prod_wait_empty=%.0f mma_wait_acc=%.0f mma_wait_full=%.0f epi_wait_full=%.0f epi_busy=%.0f | per stage=%.0f\n",
+            p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, KCh, tiles_per_cta,
+            acc[4] / grid / tiles_per_cta, acc[0] / grid / tiles_per_cta, acc[2] / grid / tiles_per_cta,
+            acc[3] / grid / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
+            acc[4] / grid / tiles_per_cta / KCh);
+  }
   return 0;
 }
 

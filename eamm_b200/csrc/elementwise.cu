@@ -249,6 +249,75 @@ warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float
   }
 }
 
+// bf16 fast path of a9-i: 8 channels (one 16-byte vector per plane) per thread, so the per-pixel
+// sampling setup is amortised over twice the data and every access is a 128-bit transaction.
+__device__ __forceinline__ void bf16x8_fma(uint4 r, float q, float* acc) {
+  float4 a = bf16x4_to_float4(make_uint2(r.x, r.y)), b = bf16x4_to_float4(make_uint2(r.z, r.w));
+  acc[0] = fmaf(a.x, q, acc[0]); acc[1] = fmaf(a.y, q, acc[1]); acc[2] = fmaf(a.z, q, acc[2]); acc[3] = fmaf(a.w, q, acc[3]);
+  acc[4] = fmaf(b.x, q, acc[4]); acc[5] = fmaf(b.y, q, acc[5]); acc[6] = fmaf(b.z, q, acc[6]); acc[7] = fmaf(b.w, q, acc[7]);
+}
+template <int PLANES>
+__device__ __forceinline__ void bf16x8_tap(const __nv_bfloat16* base, long long off, int c_buf, float q, float* acc) {
+  bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off)), q, acc);
+  if (PLANES == 2) bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off + c_buf)), q, acc);
+}
+template <int PLANES>
+__device__ __forceinline__ void bf16x8_store(const ActView& v, long long off, const float* f) {
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
+  uint2 a = float4_to_bf16x4(make_float4(f[0], f[1], f[2], f[3]));
+  uint2 b = float4_to_bf16x4(make_float4(f[4], f[5], f[6], f[7]));
+  *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b.x, b.y);
+  if (PLANES == 2) {
+    float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+    uint2 la = float4_to_bf16x4(make_float4(f[0] - ha.x, f[1] - ha.y, f[2] - ha.z, f[3] - ha.w));
+    uint2 lb = float4_to_bf16x4(make_float4(f[4] - hb.x, f[5] - hb.y, f[6] - hb.z, f[7] - hb.w));
+    *reinterpret_cast<uint4*>(p + v.c_buf) = make_uint4(la.x, la.y, lb.x, lb.y);
+  }
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(256)
+warp_occlude_bf16_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
+                         ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
+                         const float* __restrict__ shift2, long long total) {
+  const int c8 = feat.c >> 3;
+  const __nv_bfloat16* fbase = static_cast<const __nv_bfloat16*>(feat.data);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % c8);
+    const long long pix = idx / c8;
+    const int x = (int)(pix % feat.w);
+    const int y = (int)((pix / feat.w) % feat.h);
+    const int n = (int)(pix / ((long long)feat.w * feat.h));
+    const float2 d = __ldg(deform + pix);
+    const Bilinear b = bilinear_setup(d.x, d.y, feat.w, feat.h);
+    const float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
+    const bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
+    const bool yin0 = b.y0 >= 0 && b.y0 < feat.h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < feat.h;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (yin0 && xin0) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0, b.x0, 8 * cg), feat.c_buf, wy0 * wx0, acc);
+    if (yin0 && xin1) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0, b.x0 + 1, 8 * cg), feat.c_buf, wy0 * b.wx1, acc);
+    if (yin1 && xin0) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0 + 1, b.x0, 8 * cg), feat.c_buf, b.wy1 * wx0, acc);
+    if (yin1 && xin1) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 8 * cg), feat.c_buf, b.wy1 * b.wx1, acc);
+    if (occ != nullptr) {
+      const float o = __ldg(occ + pix);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= o;
+    }
+    bf16x8_store<PLANES>(out, act_offset(out, n, y, x, 8 * cg), acc);
+    if (has_out2) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale2) + 2 * cg), s1 = __ldg(reinterpret_cast<const float4*>(scale2) + 2 * cg + 1);
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift2) + 2 * cg), t1 = __ldg(reinterpret_cast<const float4*>(shift2) + 2 * cg + 1);
+      float r[8];
+      r[0] = fmaxf(fmaf(acc[0], s0.x, t0.x), 0.f); r[1] = fmaxf(fmaf(acc[1], s0.y, t0.y), 0.f);
+      r[2] = fmaxf(fmaf(acc[2], s0.z, t0.z), 0.f); r[3] = fmaxf(fmaf(acc[3], s0.w, t0.w), 0.f);
+      r[4] = fmaxf(fmaf(acc[4], s1.x, t1.x), 0.f); r[5] = fmaxf(fmaf(acc[5], s1.y, t1.y), 0.f);
+      r[6] = fmaxf(fmaf(acc[6], s1.z, t1.z), 0.f); r[7] = fmaxf(fmaf(acc[7], s1.w, t1.w), 0.f);
+      bf16x8_store<PLANES>(out2, act_offset(out2, n, y, x, 8 * cg), r);
+    }
+  }
+}
+
 // =============================================================================================
 // a9-ii  deformed = grid_sample(source, interpolate(deformation, (H,W), bilinear))  (generator.py:50-57,86)
 // The flow upsample (align_corners=False: src = (dst+0.5)*h/H - 0.5, clamped at 0, upper tap
@@ -425,6 +494,23 @@ extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation,
     if (!scale2 || !shift2) return EAMM_ERR_ARG;
     if (out2->n != feat->n || out2->h != feat->h || out2->w != feat->w || out2->c != feat->c) return EAMM_ERR_SHAPE;
     o2 = make_view(out2); has2 = 1;
+  }
+  auto vec_ok = [](const ActView& v, int planes) {
+    return v.dtype == EAMM_BF16 && v.planes == planes && v.c % 8 == 0 && v.c_off % 8 == 0 && v.c_buf % 8 == 0 &&
+           ((uintptr_t)v.data % 16) == 0 && v.n_stride % 8 == 0;
+  };
+  if (f.dtype == EAMM_BF16 && vec_ok(f, f.planes) && vec_ok(o, f.planes) && (!has2 || vec_ok(o2, f.planes))) {
+    long long total = (long long)f.n * f.h * f.w * (f.c / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (f.planes == 2)
+      warp_occlude_bf16_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
+                                                                           has2, scale2, shift2, total);
+    else
+      warp_occlude_bf16_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
+                                                                           has2, scale2, shift2, total);
+    EAMM_LAUNCH_CHECK();
+    return 0;
   }
   long long total = (long long)f.n * f.h * f.w * (f.c / 4);
   int blocks = (int)((total + 255) / 256);

@@ -117,8 +117,9 @@ def up2_parity_weights(w):
 def pack_tc_weights(full, classes, passes):
     """[classes*taps][cout][cin] fp32 -> bf16 [classes*cout][taps*passes*cin] for eamm_conv_tc.
 
-    K order is (tap, pass, channel).  passes == 3 is the split-bf16 scheme: the weight planes
-    (hi, lo, hi) meet the activation planes (hi, hi, lo), i.e. a_hi*b_hi + a_hi*b_lo + a_lo*b_hi.
+    K order is (pass, tap, channel).  passes == 3 is the split-bf16 scheme: the weight planes
+    (lo, hi, hi) meet the activation planes (hi, lo, hi), i.e. a_hi*b_lo + a_lo*b_hi + a_hi*b_hi
+    (cross terms first: the tensor-core accumulator truncates, see conv_tc.cu).
     """
     ct, cout, cin = full.shape
     taps = ct // classes
@@ -128,12 +129,12 @@ def pack_tc_weights(full, classes, passes):
         packed = hi
     else:
         lo = (w - hi.float()).to(torch.bfloat16)
-        packed = torch.stack([hi, lo, hi], dim=3)                         # [cls][cout][taps][3][cin]
+        packed = torch.stack([lo, hi, hi], dim=2)                         # [cls][cout][3][taps][cin]
     return packed.reshape(classes * cout, -1).contiguous()
 
 
 def pack_tc_weights_halo(full, passes):
-    """7x7 halo-row scheme of eamm_conv_tc: [49 taps][cout][cin] -> bf16 [7 kx * cout][7 ky * passes * cin]."""
+    """7x7 halo-row scheme of eamm_conv_tc: [49 taps][cout][cin] -> bf16 [7 kx * cout][passes * 7 ky * cin]."""
     _, cout, cin = full.shape
     w = full.view(7, 7, cout, cin).permute(1, 2, 0, 3)                   # [kx][cout][ky][cin]
     hi = w.to(torch.bfloat16)
@@ -141,12 +142,12 @@ def pack_tc_weights_halo(full, passes):
         packed = hi
     else:
         lo = (w - hi.float()).to(torch.bfloat16)
-        packed = torch.stack([hi, lo, hi], dim=3)                         # [kx][cout][ky][3][cin]
+        packed = torch.stack([lo, hi, hi], dim=2)                         # [kx][cout][3][ky][cin]
     return packed.reshape(7 * cout, -1).contiguous()
 
 
 def pack_tc_weights_kxn(full, nchw_c, passes):
-    """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][7 ky * passes * cin]."""
+    """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][passes * 7 ky * cin]."""
     _, cout, cin = full.shape
     w = full.view(7, 7, cout, cin)[:, :, :nchw_c]                         # [ky][kx][co][cin]
     rows = torch.zeros(8, 4, 7, cin, dtype=torch.float32, device=full.device)   # [kx(8)][co(4)][ky][cin]
@@ -156,7 +157,7 @@ def pack_tc_weights_kxn(full, nchw_c, passes):
         packed = hi
     else:
         lo = (rows - hi.float()).to(torch.bfloat16)
-        packed = torch.stack([hi, lo, hi], dim=3)                         # [kx][co][ky][3][cin]
+        packed = torch.stack([lo, hi, hi], dim=2)                         # [kx][co][3][ky][cin]
     return packed.reshape(32, -1).contiguous()
 
 
@@ -164,17 +165,18 @@ def pack_tc_weights_row7(w, cout_pad, passes):
     """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
 
     K window of one ky = 8 pixels x 8 channels (hi0..2, 0, lo0..2, 0); k = kx*8 + channel, kx = 7 is
-    padding.  Pass 0 holds w_hi against both the hi and the lo activation channels, pass 1 (split
-    mode) holds w_lo against the hi channels: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo.
+    padding.  K order (pass, ky, k).  In split mode pass 0 holds w_lo against the hi channels and the
+    last pass holds w_hi against both the hi and the lo channels: a_hi*b_lo, then a_hi*b_hi + a_lo*b_hi.
     """
     cout, C = w.shape[0], w.shape[1]
     hi = w.to(torch.bfloat16)
     lo = (w - hi.float()).to(torch.bfloat16)
-    out = torch.zeros(cout_pad, 7, passes, 8, 8, dtype=torch.bfloat16, device=w.device)   # [co][ky][pass][kx][ch]
-    out[:cout, :, 0, :7, :C] = hi.permute(0, 2, 3, 1)
+    out = torch.zeros(cout_pad, passes, 7, 8, 8, dtype=torch.bfloat16, device=w.device)   # [co][pass][ky][kx][ch]
+    main = passes - 1                                    # the pass holding w_hi runs last
+    out[:cout, main, :, :7, :C] = hi.permute(0, 2, 3, 1)
     if passes == 2:
-        out[:cout, :, 0, :7, 4:4 + C] = hi.permute(0, 2, 3, 1)
-        out[:cout, :, 1, :7, :C] = lo.permute(0, 2, 3, 1)
+        out[:cout, main, :, :7, 4:4 + C] = hi.permute(0, 2, 3, 1)
+        out[:cout, 0, :, :7, :C] = lo.permute(0, 2, 3, 1)
     return out.reshape(cout_pad, -1).contiguous()
 
 

@@ -149,16 +149,17 @@ int eamm_conv_simt(const eamm_conv_args* args, void* stream);
 
 /* eamm_conv_tc:   tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate).  Activations must
  *                 be EAMM_BF16 with c_buf, c_off and cin multiples of 64 and power-of-two h, w; cout a
- *                 multiple of 16.  weight is bf16 [classes*cout][taps*passes*cin] (K contiguous),
- *                 K ordered (tap, pass, channel); passes = 1 for single-plane inputs, 3 for hi/lo
- *                 inputs (weight planes hi, lo, hi against activation planes hi, hi, lo).  UP2 has
+ *                 multiple of 16.  weight is bf16 [classes*cout][passes*taps*cin] (K contiguous),
+ *                 K ordered (pass, tap, channel); passes = 1 for single-plane inputs, 3 for hi/lo
+ *                 inputs (weight planes lo, hi, hi against activation planes hi, lo, hi: the two
+ *                 cross terms first, the dominant hi*hi term last).  UP2 has
  *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout). */
 int eamm_conv_tc(const eamm_conv_args* args, void* stream);
 
 /* Which scheme eamm_conv_tc uses for a 7x7 layer, i.e. which weight matrix it expects:
- *   0  one TMA tile per tap           bf16 [cout][49 taps * passes * cin]
- *   1  halo row, kx-shifted views     bf16 [7 kx * cout][7 ky * passes * cin]      (w % 128 == 0, cout <= 32)
- *   2  kx taps in the GEMM N axis     bf16 [32 = kx*4 + co][7 ky * passes * cin]   (w % 128 == 0, only
+ *   0  one TMA tile per tap           bf16 [cout][passes * 49 taps * cin]
+ *   1  halo row, kx-shifted views     bf16 [7 kx * cout][passes * 7 ky * cin]      (w % 128 == 0, cout <= 32)
+ *   2  kx taps in the GEMM N axis     bf16 [32 = kx*4 + co][passes * 7 ky * cin]   (w % 128 == 0, only
  *      out_nchw with <= 4 channels; out_nchw_c = 0 when the call has any NHWC output) */
 int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c);
 

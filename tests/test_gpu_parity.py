@@ -3,8 +3,8 @@ modules and directly through the C ABI, against the CPU oracle and the committed
 
 Tolerances (max-abs):
   fp32_simt : 2e-5 everywhere (true fp32 CUDA-core convs), warped images 2e-4
-  fp32      : prediction/mask/occlusion 3e-4, deformation 1e-4, sparse_deformed 1e-4, deformed 1e-2
-              (split-bf16 tensor cores; the tcgen05 fp32 accumulator truncates, DESIGN.md "Numerics")
+  fp32      : prediction/mask/occlusion/deformation 1e-4, sparse_deformed 1e-4, deformed 3e-3
+              (split-bf16 tensor cores; `deformed` samples a white-noise image, DESIGN.md "Numerics")
   bf16      : prediction 3e-2, mask/occlusion 3e-2 (bf16 convs; flow-sensitive outputs are not pinned)
 """
 import ctypes as C
@@ -22,8 +22,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {
     "fp32_simt": {"prediction": 2e-5, "mask": 2e-5, "occlusion_map": 2e-5, "deformation": 2e-5,
                   "sparse_deformed": 2e-5, "deformed": 2e-4},
-    "fp32": {"prediction": 3e-4, "mask": 3e-4, "occlusion_map": 3e-4, "deformation": 1e-4,
-             "sparse_deformed": 1e-4, "deformed": 1e-2},
+    "fp32": {"prediction": 1e-4, "mask": 1e-4, "occlusion_map": 1e-4, "deformation": 1e-4,
+             "sparse_deformed": 1e-4, "deformed": 3e-3},
     "bf16": {"prediction": 3e-2, "mask": 3e-2, "occlusion_map": 3e-2, "sparse_deformed": 1e-4},
 }
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
@@ -123,7 +123,7 @@ def test_full_size_batch32_properties_and_batch_invariance(dev):
     sd = synth.make_state_dict(cfg, seed=0)
     idx = [3, 29]
     want = oracle.generator_forward(sd, cfg, src[idx], {k: v[idx] for k, v in kpd.items()}, {k: v[idx] for k, v in kps.items()})
-    for k, tol in (("prediction", 3e-4), ("mask", 3e-4), ("occlusion_map", 3e-4), ("deformed", 1e-2)):
+    for k, tol in (("prediction", 1e-4), ("mask", 1e-4), ("occlusion_map", 1e-4), ("deformed", 3e-3)):
         assert (got[k][idx] - want[k]).abs().max() <= tol, k
 
 
@@ -159,7 +159,7 @@ def test_dense_motion_module_alone_matches_oracle(dev):
     want = oracle.dense_motion_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps)
     assert set(out) == {"sparse_deformed", "mask", "deformation", "occlusion_map"}
     for k in want:
-        assert (out[k].cpu() - want[k]).abs().max() <= 3e-4, k
+        assert (out[k].cpu() - want[k]).abs().max() <= 1e-4, k
 
 
 # ------------------------------------------------------------------ kernels through the C ABI

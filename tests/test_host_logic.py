@@ -65,10 +65,9 @@ def test_tc_weight_packing_order_and_split():
     assert p1.shape == (16, 9 * 64) and p1.dtype == torch.bfloat16
     assert torch.equal(p1[3, 2 * 64:3 * 64], full[2, 3].bfloat16())
     p3 = engine.pack_tc_weights(full, 1, 3)
-    assert p3.shape == (16, 9 * 3 * 64)
-    hi = p3[:, (2 * 3 + 0) * 64:(2 * 3 + 1) * 64].float()
-    lo = p3[:, (2 * 3 + 1) * 64:(2 * 3 + 2) * 64].float()
-    hi2 = p3[:, (2 * 3 + 2) * 64:(2 * 3 + 3) * 64].float()
+    assert p3.shape == (16, 3 * 9 * 64)
+    blk = lambda ps, t: p3[:, (ps * 9 + t) * 64:(ps * 9 + t + 1) * 64].float()      # K order (pass, tap, channel)
+    lo, hi, hi2 = blk(0, 2), blk(1, 2), blk(2, 2)
     assert torch.equal(hi, hi2)
     assert (hi + lo - full[2]).abs().max() < 2e-5          # 16 mantissa bits survive the split
     up = engine.pack_tc_weights(torch.randn(16, 8, 64, generator=g), 4, 1)

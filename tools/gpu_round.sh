@@ -12,7 +12,7 @@ echo "== bench fp32 B=32"; timeout 600 python bench.py --steps 5 --warmup 3 2>&1
 echo "== bench bf16 B=32"; timeout 600 python bench.py --steps 5 --warmup 3 --precision bf16 --no-cpu-baseline 2>&1 | grep -v -i warn | tee $OUT/bench_bf16_$TAG.json
 if [ -n "$QUICK" ]; then exit 0; fi
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 3 2>&1 | grep -v -i warn | tee $OUT/bench_ref_$TAG.json
-KREGEX='regex:conv_tc_kernel|conv_simt_kernel|aa_downsample_kernel|kp_stage_kernel|flow_combine_kernel|warp_occlude_kernel|warp_image_kernel|nchw_to_act_kernel|pack_image_kernel'
+KREGEX='regex:conv_tc_kernel|conv_simt_kernel|aa_downsample_kernel|kp_stage_kernel|flow_combine_kernel|warp_occlude|warp_image_kernel|nchw_to_act_kernel|pack_image_kernel'
 echo "== ncu launch list (our kernels, 2 steps after 3 warm-up steps)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 108 -c 72 --csv --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1; tail -2 $OUT/ncu_bench_$TAG.log | cut -c1-200
 echo "== ncu --set full: one bottleneck conv + warp_occlude"
