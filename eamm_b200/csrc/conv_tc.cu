@@ -9,7 +9,8 @@
 //   K loop      passes x taps x (cin/64).  passes = 1 (bf16) or 3 (split-bf16 "fp32" mode:
 //               a_hi*b_lo + a_lo*b_hi + a_hi*b_hi with activations/weights stored as hi/lo planes;
 //               small terms first, see the producer).
-//   roles       warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+//   roles       warps 0-3 = epilogue (TMEM lane quadrant = warp id), warps 4-6 = TMA producers
+//               (round-robin over the ring stages), warp 7 = MMA issuer (+TMEM alloc).
 //   pipelines   smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring so the
 //               epilogue of tile i overlaps the main loop of tile i+1.
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -25,7 +26,9 @@ namespace eamm {
 
 int conv_check_args(const eamm_conv_args* a, int cout_align);   // conv_simt.cu
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_PRODUCERS = 3;                 // TMA producer warps (warps 4 .. 4+TC_PRODUCERS-1)
+constexpr int TC_MMA_WARP = 4 + TC_PRODUCERS;   // single MMA-issuing warp, highest warp id
+constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
 constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
 constexpr uint32_t TC_TMEM_COLS = 512;
 
@@ -39,6 +42,8 @@ struct ConvTcParams {
   int kxn;             // 7x7 -> <=4 NCHW channels: the 7 kx taps live in the N dimension (N = 7*4 -> 32),
                        // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns
   int x_stride;        // pixels between consecutive x tiles (122 in kxn mode, else bw)
+  int ksub;            // 64-channel K chunks per pipeline stage (1..4)
+  int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
   unsigned long long* prof;  // EAMM_TC_PROF: per-CTA cycle counters [grid][8] (bring-up instrumentation)
   int a_slot_bytes;    // bytes reserved for the A operand in a stage
@@ -62,18 +67,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 28); ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
-  }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+// Slow path, out of line so that the hot loops stay a few hundred bytes of code.  Bounded: a
+// protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 28); ++it)
+    if (mbar_try_wait(bar, parity)) return;
   __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
@@ -286,6 +298,9 @@ __device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCo
   }
 }
 
+// INSTR = true compiles the bring-up instrumentation (EAMM_TC_PROF cycle counters, EAMM_TC_DEBUG
+// role isolation); the production instantiation carries none of it.
+template <bool INSTR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
@@ -294,11 +309,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem is only guaranteed 16B-aligned by the ABI: align the ring to 1024 B by hand
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t bar0 = smem_u32(bars);
+  // opaque copies: keep ptxas from re-deriving the shared-window base (S2R) inside the hot loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(smem_base));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bar0));
+  const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
-  const uint32_t stage_bytes = (uint32_t)p.a_slot_bytes + b_bytes;
-  const uint32_t tx_bytes = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;
-  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t KS = (uint32_t)p.ksub;                         // 64-channel sub-chunks per pipeline stage
+  const uint32_t stage_bytes = KS * (a_slot + b_bytes);
+  const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
@@ -311,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -321,108 +341,125 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
-
-  // Both single-issuer roles run as warp-uniform loops (all 32 lanes wait, one elected lane issues):
-  // ptxas then keeps descriptors/coordinates in uniform registers instead of emitting a divergent
-  // "waterfall" around every UTMALDG/UTCHMMA, which is what bounds short-K layers otherwise.
   const uint32_t total_tiles = (uint32_t)p.total_tiles;
-  if (warp == 0) {
-    // ================================================================ TMA producer
-    const int ntap = (p.halo || p.kxn) ? 7 : p.taps;
-    const int passes = p.passes, chunks = p.cin_chunks, kind = p.kind, ksize = p.ksize, khalf = p.ksize >> 1;
-    const int nstages = p.num_stages, a_slot = p.a_slot_bytes, dbg = p.debug;
+  const int dbg = INSTR ? p.debug : 0;
+
+  // Both single-issuer roles run as warp-uniform loops (all 32 lanes wait, one elected lane issues) so
+  // ptxas keeps descriptors/coordinates in uniform registers.  One pipeline stage carries KS
+  // consecutive 64-channel K chunks: the barrier round trip and loop bookkeeping of these
+  // latency-bound single-warp loops are paid once per stage, not once per chunk.
+  if (warp >= 4 && warp < 4 + TC_PRODUCERS) {
+    // ================================================================ TMA producers
+    // TC_PRODUCERS warps share the ring round-robin: producer w fills the stages whose running index
+    // is congruent to w.  A lone warp retires a dependent scalar instruction every ~8-10 cycles, so
+    // one producer could not feed short-K layers (measured 600-800 cycles per 64-channel chunk).
+    const uint32_t w = (uint32_t)(warp - 4);
+    const uint32_t ntap = (p.halo || p.kxn) ? 7u : (uint32_t)p.taps;
+    const uint32_t chunk_shift = (uint32_t)p.chunk_shift, chunk_mask = (1u << chunk_shift) - 1u;
+    const int passes = p.passes, kind = p.kind;
+    const uint32_t nstages = (uint32_t)p.num_stages;
+    const uint32_t SPT = ((uint32_t)KC + KS - 1u) / KS;          // stages per tile
     const bool haloish = p.halo || p.kxn;
-    int stage = 0; uint32_t phase = 0;
-    uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
-    long long prof_acc[2] = {0, 0};
-    const long long prof_start = p.prof ? clock64() : 0;
+    uint32_t slot = 0, phase = 0, si = w;
+    for (uint32_t i = 0; i < w; ++i) { if (++slot == nstages) { slot = 0; phase ^= 1u; } }
+    long long pw = 0, pstart = 0;
+    if (INSTR) pstart = clock64();
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const int brow = tc.cls * p.cout + tc.nt * p.BN;
-      int kcol = 0;
-      // K order = (pass, tap, chunk).  In split mode the two cross terms (a_hi*b_lo, a_lo*b_hi) are
-      // accumulated first, while the TMEM accumulator is still small, and the dominant a_hi*b_hi
-      // term last: the tensor core truncates on every accumulate, so the bias it leaves scales with
-      // |accumulator| x (number of steps taken at that magnitude).
-      for (int ps = 0; ps < passes; ++ps) {
-        int cbase = p.a_c_off + ((passes == 3 && ps == 1) ? p.a_c_buf : 0);
-        if (kind == EAMM_CONV_ROW7_PACKED) cbase = 0;            // both planes live inside the 64-wide K window
-        for (int t = 0; t < ntap; ++t) {
-          int dy, dx;
-          if (haloish) { dy = t - 3; dx = -3; }
-          else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; }
-          else if (kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
-          else { dy = t / ksize - khalf; dx = t - (t / ksize) * ksize - khalf; }
-          const int ax = tc.x0 + dx, ay = tc.y0 + dy;
-          for (int cc = 0; cc < chunks; ++cc, kcol += 64) {
-            long long t0 = 0;
-            if (p.prof) t0 = clock64();
-            mbar_wait(eb, phase ^ 1u);
-            if (p.prof) { long long t1 = clock64(); prof_acc[0] += t1 - t0; }
-            if (elect_one()) {
-              if (dbg == 1) { mbar_arrive(fb); }
-              else {
-                mbar_expect_tx(fb, tx_bytes);
-                tma_load_4d(sa, &tmA, fb, cbase + cc * 64, ax, ay, tc.n0);
-                tma_load_2d(sa + a_slot, &tmB, fb, kcol, brow);
-              }
+      for (; si < SPT; si += TC_PRODUCERS) {
+        const uint32_t kc0 = si * KS;
+        const uint32_t nsub = (uint32_t)KC - kc0 < KS ? (uint32_t)KC - kc0 : KS;
+        const uint32_t sa = smem_base + slot * stage_bytes, fb = full_bar((int)slot);
+        long long t0 = 0;
+        if (INSTR) t0 = clock64();
+        mbar_wait(empty_bar((int)slot), phase ^ 1u);
+        if (INSTR) pw += clock64() - t0;
+        if (elect_one()) {
+          if (INSTR && (dbg == 1 || dbg == 4 || dbg == 5)) mbar_arrive(fb);
+          else {
+            mbar_expect_tx(fb, nsub * sub_tx);
+            for (uint32_t sub = 0; sub < nsub; ++sub) {
+              // K order = (pass, tap, chunk).  In split mode the two cross terms (a_hi*b_lo, a_lo*b_hi)
+              // are accumulated first, while the TMEM accumulator is still small, and the dominant
+              // a_hi*b_hi term last: the tensor core truncates on every accumulate, so the bias it
+              // leaves scales with |accumulator| x (number of steps taken at that magnitude).
+              const uint32_t kc = kc0 + sub;
+              const uint32_t cc = kc & chunk_mask, q = kc >> chunk_shift;          // q = pass * ntap + tap
+              const uint32_t ps = q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u);
+              const int t = (int)(q - ps * ntap);
+              int cbase = p.a_c_off + ((passes == 3 && ps == 1u) ? p.a_c_buf : 0);
+              int dy, dx;
+              if (haloish) { dy = t - 3; dx = -3; }
+              else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; cbase = 0; }   // both planes inside the K window
+              else if (kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
+              else if (kind == EAMM_CONV_3X3) { const int ty = (t * 11) >> 5; dy = ty - 1; dx = t - 3 * ty - 1; }
+              else { const int ty = (t * 37) >> 8; dy = ty - 3; dx = t - 7 * ty - 3; }   // 7x7 per-tap
+              tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
+              tma_load_2d(sa + KS * a_slot + sub * b_bytes, &tmB, fb, (int)kc * 64, brow);
             }
-            ++stage; sa += stage_bytes; fb += 8; eb += 8;
-            if (stage == nstages) { stage = 0; phase ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
           }
         }
+        slot += TC_PRODUCERS;
+        while (slot >= nstages) { slot -= nstages; phase ^= 1u; }
       }
+      si -= SPT;
     }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 8 + 0] = prof_acc[0];                    // producer: cycles waiting for a free slot
-      p.prof[blockIdx.x * 8 + 1] = clock64() - prof_start;         // producer: total
+    if (INSTR && p.prof && w == 0 && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = pw;                             // producer 0: cycles waiting for a free slot
+      p.prof[blockIdx.x * 8 + 1] = clock64() - pstart;             // producer 0: total
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_MMA_WARP) {
     // ================================================================ MMA issuer
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
-    const int nstages = p.num_stages, halo = p.halo, dbg = p.debug, BN = p.BN;
-    const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
+    const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
-    long long pm[3] = {0, 0, 0};
-    const long long pm_start = p.prof ? clock64() : 0;
+    long long pm0 = 0, pm1 = 0, pstart = 0;
+    if (INSTR) pstart = clock64();
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       long long t0 = 0;
-      if (p.prof) t0 = clock64();
+      if (INSTR) t0 = clock64();
       mbar_wait(tempty_bar(as), aphase ^ 1u);
-      if (p.prof) pm[0] += clock64() - t0;
+      if (INSTR) pm0 += clock64() - t0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * 256u;
-      for (int kc = 0; kc < KC; ++kc) {
-        if (p.prof) t0 = clock64();
+      for (int kc = 0; kc < KC; kc += (int)KS) {
+        const uint32_t nsub = (uint32_t)(KC - kc) < KS ? (uint32_t)(KC - kc) : KS;
+        if (INSTR) t0 = clock64();
         mbar_wait(fb, phase);
-        if (p.prof) pm[1] += clock64() - t0;
+        if (INSTR) pm1 += clock64() - t0;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sb = sa + a_slot;
-          if (dbg == 2) {
-          } else if (halo) {
-            // one halo row of 134 pixels serves the 7 kx taps: tap kx reads rows [kx, kx+128)
-            // (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
-            //  row-shifted start address needs no base_offset in the descriptor)
+          for (uint32_t sub = 0; sub < nsub; ++sub) {
+            const uint32_t sA = sa + sub * a_slot, sB = sa + KS * a_slot + sub * b_bytes;
+            const uint32_t first = (kc | (int)sub) ? 1u : 0u;
+            if (INSTR && (dbg == 2 || dbg == 4 || dbg == 5)) {
+            } else if (INSTR && dbg == 3) {
+              tc_mma_bf16(tmem_acc, make_sw128_desc(sA), make_sw128_desc(sB), idesc, first);
+            } else if (halo) {
+              // one halo row of 134 pixels serves the 7 kx taps: tap kx reads rows [kx, kx+128)
+              // (measured on B200: the 128B swizzle is a function of the absolute smem address, so a
+              //  row-shifted start address needs no base_offset in the descriptor)
 #pragma unroll 1
-            for (int kx = 0; kx < 7; ++kx) {
-              const uint64_t da = make_sw128_desc(sa + (uint32_t)kx * 128u);
-              const uint64_t db = make_sw128_desc(sb + (uint32_t)(kx * BN) * 128u);
+              for (int kx = 0; kx < 7; ++kx) {
+                const uint64_t da = make_sw128_desc(sA + (uint32_t)kx * 128u);
+                const uint64_t db = make_sw128_desc(sB + (uint32_t)(kx * BN) * 128u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | kx | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first | (uint32_t)kx | (uint32_t)k) ? 1u : 0u);
+              }
+            } else {
+              const uint64_t da = make_sw128_desc(sA), db = make_sw128_desc(sB);
+              tc_mma_bf16(tmem_acc, da, db, idesc, first);
+              tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+              tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
+              tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
             }
-          } else {
-            const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sb);
-            tc_mma_bf16(tmem_acc, da, db, idesc, kc ? 1u : 0u);
-            tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
-            tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
-            tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
           }
           tc_commit(eb);
-          if (kc == KC - 1) tc_commit(tfull_bar(as));
+          if (kc + (int)KS >= KC) tc_commit(tfull_bar(as));
         }
         __syncwarp();
         ++stage; sa += stage_bytes; fb += 8; eb += 8;
@@ -430,28 +467,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       as ^= 1u; if (as == 0) aphase ^= 1u;
     }
-    if (p.prof && lane == 0) {
-      p.prof[blockIdx.x * 8 + 2] = pm[0];                          // MMA: waiting for a free accumulator
-      p.prof[blockIdx.x * 8 + 3] = pm[1];                          // MMA: waiting for operands
-      p.prof[blockIdx.x * 8 + 4] = clock64() - pm_start;           // MMA: total
+    if (INSTR && p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 2] = pm0;                            // MMA: waiting for a free accumulator
+      p.prof[blockIdx.x * 8 + 3] = pm1;                            // MMA: waiting for operands
+      p.prof[blockIdx.x * 8 + 4] = clock64() - pstart;             // MMA: total
     }
   } else {
     // ================================================================ epilogue warps (TMEM lanes by warp%4)
     const int quadrant = warp & 3;
     int as = 0; uint32_t aphase = 0;
-    long long pe = 0;
-    const long long pe_start = p.prof ? clock64() : 0;
+    long long pe = 0, pstart = 0;
+    if (INSTR) pstart = clock64();
+    float* kxn_smem = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
+                                               (size_t)p.num_stages * stage_bytes);
     for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       long long t0 = 0;
-      if (p.prof) t0 = clock64();
+      if (INSTR) t0 = clock64();
       mbar_wait(tfull_bar(as), aphase);
-      if (p.prof) pe += clock64() - t0;
+      if (INSTR) pe += clock64() - t0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
-      if (p.kxn) epilogue_kxn(p, tc, tmem_acc, quadrant, lane,
-                              reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
-                                                       (size_t)p.num_stages * stage_bytes) + as * (128 * 29));
+      if (INSTR && dbg >= 5) {                     // 5: protocol only, 6: real main loop, no epilogue work
+      } else if (p.kxn) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29));
       else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane);
       tc_fence_before();
@@ -459,14 +497,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
-    if (p.prof && warp == 2 && lane == 0) {
+    if (INSTR && p.prof && warp == 0 && lane == 0) {
       p.prof[blockIdx.x * 8 + 5] = pe;                             // epilogue warp 0: waiting for an accumulator
-      p.prof[blockIdx.x * 8 + 6] = clock64() - pe_start;           // epilogue: total
+      p.prof[blockIdx.x * 8 + 6] = clock64() - pstart;             // epilogue: total
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
@@ -535,6 +573,8 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : (row7 ? 7 : p.ksize * p.ksize);
   p.classes = a->kind == EAMM_CONV_UP2_3X3 ? 4 : 1;
   p.cin_chunks = row7 ? 1 : a->cin / 64;
+  p.chunk_shift = ilog2_exact(p.cin_chunks);
+  if (p.chunk_shift < 0) return EAMM_ERR_UNSUPPORTED;          // cin/64 must be a power of two
   p.passes = row7 ? a->pack_passes : (in->planes == 2 ? 3 : 1);
   p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
   static int halo_env = -1;
@@ -579,9 +619,22 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
-  const uint32_t stage_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
+  const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
   const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
-  int stages = (int)((200u * 1024u - extra_smem) / stage_bytes);
+  const uint32_t ring_bytes = 200u * 1024u - extra_smem;
+  // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
+  // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
+  static int ksub_env = -1;
+  if (ksub_env < 0) { const char* e = getenv("EAMM_TC_KSUB"); ksub_env = e ? atoi(e) : 0; }
+  const int kc_total = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
+  int ksub = 1;
+  for (int k = 4; k >= 2; --k)
+    if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
+  if (ksub == 1 && 2u * chunk_bytes * 3u <= ring_bytes && kc_total >= 2 && p.BN < 256) ksub = 2;
+  if (ksub_env > 0) ksub = ksub_env;
+  p.ksub = ksub;
+  const uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
+  int stages = (int)(ring_bytes / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
   p.num_stages = stages;
@@ -638,7 +691,8 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }
@@ -652,7 +706,8 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
     cudaMemsetAsync(prof_buf, 0, 1024 * 8 * sizeof(unsigned long long), (cudaStream_t)stream);
     p.prof = prof_buf;
   }
-  conv_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  if (prof_env || p.debug) conv_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  else conv_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   EAMM_LAUNCH_CHECK();
   if (prof_env) {        // bring-up instrumentation only: synchronous read-back and print
     static unsigned long long host[1024 * 8];
@@ -662,9 +717,9 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
     for (long long b = 0; b < grid; ++b) for (int j = 0; j < 8; ++j) acc[j] += (double)host[b * 8 + j];
     const double tiles_per_cta = (double)p.total_tiles / (double)grid;
     const int KCh = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
-    fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%d KC=%d tiles/cta=%.1f | per tile (cycles): "
+    fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%dx%d KC=%d tiles/cta=%.1f | per tile (cycles): "
             "total=%.0f prod_wait_empty=%.0f mma_wait_acc=%.0f mma_wait_full=%.0f epi_wait_full=%.0f epi_busy=%.0f | per stage=%.0f\n",
-            p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, KCh, tiles_per_cta,
+            p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, p.ksub, KCh, tiles_per_cta,
             acc[4] / grid / tiles_per_cta, acc[0] / grid / tiles_per_cta, acc[2] / grid / tiles_per_cta,
             acc[3] / grid / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
             acc[4] / grid / tiles_per_cta / KCh);
