@@ -9,8 +9,9 @@
 //   K loop      passes x taps x (cin/64).  passes = 1 (bf16) or 3 (split-bf16 "fp32" mode:
 //               a_hi*b_lo + a_lo*b_hi + a_hi*b_hi with activations/weights stored as hi/lo planes;
 //               small terms first, see the producer).
-//   roles       warps 0-3 = epilogue (TMEM lane quadrant = warp id), warps 4-6 = TMA producers
-//               (round-robin over the ring stages), warp 7 = MMA issuer (+TMEM alloc).
+//   roles       warps 0-7 = epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant splitting
+//               the accumulator columns), warps 8-10 = TMA producers (round-robin over the ring
+//               stages), warp 11 = MMA issuer (+TMEM alloc).
 //   pipelines   smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring so the
 //               epilogue of tile i overlaps the main loop of tile i+1.
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -26,8 +27,9 @@ namespace eamm {
 
 int conv_check_args(const eamm_conv_args* a, int cout_align);   // conv_simt.cu
 
-constexpr int TC_PRODUCERS = 3;                 // TMA producer warps (warps 4 .. 4+TC_PRODUCERS-1)
-constexpr int TC_MMA_WARP = 4 + TC_PRODUCERS;   // single MMA-issuing warp, highest warp id
+constexpr int TC_EPI_WARPS = 8;                 // epilogue warps: TMEM lane quadrant = warp % 4, column half = warp / 4
+constexpr int TC_PRODUCERS = 3;                 // TMA producer warps (warps TC_EPI_WARPS .. +TC_PRODUCERS-1)
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PRODUCERS;   // single MMA-issuing warp, highest warp id
 constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
 constexpr int TC_A_BYTES = 128 * 128;          // 128 pixels x 64 bf16
 constexpr uint32_t TC_TMEM_COLS = 512;
@@ -201,7 +203,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
 // Epilogue for one accumulator tile, CH columns at a time.
 template <int CH>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
-                                              int quadrant, int lane) {
+                                              int quadrant, int lane, int half) {
   const int r = quadrant * 32 + lane;
   const int xl = r & (p.bw - 1);
   const int yl = (r >> p.bw_log2) & (p.bh - 1);
@@ -213,7 +215,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   if (pool) { oy = y >> 1; ox = x >> 1; OH = p.H >> 1; OW = p.W >> 1; valid = valid && !(xl & 1) && !(yl & 1); }
   else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); OH = 2 * p.H; OW = 2 * p.W; }
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
-  for (int c0 = 0; c0 < p.BN; c0 += CH) {
+  for (int c0 = half * CH; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * CH) {
     uint32_t raw[CH];
     TmemLd<CH>::ld(taddr + c0, raw);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -326,7 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -348,12 +350,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ptxas keeps descriptors/coordinates in uniform registers.  One pipeline stage carries KS
   // consecutive 64-channel K chunks: the barrier round trip and loop bookkeeping of these
   // latency-bound single-warp loops are paid once per stage, not once per chunk.
-  if (warp >= 4 && warp < 4 + TC_PRODUCERS) {
+  if (warp >= TC_EPI_WARPS && warp < TC_EPI_WARPS + TC_PRODUCERS) {
     // ================================================================ TMA producers
     // TC_PRODUCERS warps share the ring round-robin: producer w fills the stages whose running index
     // is congruent to w.  A lone warp retires a dependent scalar instruction every ~8-10 cycles, so
     // one producer could not feed short-K layers (measured 600-800 cycles per 64-channel chunk).
-    const uint32_t w = (uint32_t)(warp - 4);
+    const uint32_t w = (uint32_t)(warp - TC_EPI_WARPS);
     const uint32_t ntap = (p.halo || p.kxn) ? 7u : (uint32_t)p.taps;
     const uint32_t chunk_shift = (uint32_t)p.chunk_shift, chunk_mask = (1u << chunk_shift) - 1u;
     const int passes = p.passes, kind = p.kind;
@@ -474,7 +476,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================================================================ epilogue warps (TMEM lanes by warp%4)
-    const int quadrant = warp & 3;
+    const int quadrant = warp & 3, half = warp >> 2;
     int as = 0; uint32_t aphase = 0;
     long long pe = 0, pstart = 0;
     if (INSTR) pstart = clock64();
@@ -489,9 +491,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
       if (INSTR && dbg >= 5) {                     // 5: protocol only, 6: real main loop, no epilogue work
-      } else if (p.kxn) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29));
-      else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane);
-      else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane);
+      } else if (p.kxn) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
+      else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+      else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
