@@ -88,6 +88,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU set local to GPU `index` (NVML affinity) before any pinned host
+    buffer is allocated: first-touch then places the staging buffers on the GPU's NUMA node, which
+    keeps the H2D/D2H copies of the e2e path at PCIe speed instead of crossing the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def cpu_info():
     model = "unknown"
     try:
@@ -169,6 +186,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -266,7 +284,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks["source"] == "measured"
                 else "fallback (B200_PROFILING.md)",
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the ncu --set full capture
+                # summarised in profiles/ (138.5 MB + 83.6 MB at B=32, fp32 mode); scales with the batch
+                "traffic": (138.53e6 + 83.61e6) * B / 32.0 if args.precision == "fp32" else None,
                 "share_of_step": dom_ms / step_ms_prof if step_ms_prof else None,
                 "all_convs_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                 "all_convs_share_of_step": conv_ms / step_ms_prof if step_ms_prof else None,
