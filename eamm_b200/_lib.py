@@ -35,7 +35,8 @@ class ConvArgs(C.Structure):
                 ("inp", C.POINTER(Act)), ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("residual", C.POINTER(Act)), ("out", C.POINTER(Act)), ("out2", C.POINTER(Act)),
                 ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("out_nchw", C.c_void_p),
-                ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32)]
+                ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32),
+                ("weight_fold", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/eamm_b200.h
@@ -56,6 +57,8 @@ _PROTOS = {
     "eamm_conv_simt": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "eamm_conv_tc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "eamm_conv_tc_uses_halo": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "eamm_conv_tc_fold": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "eamm_conv_tc_query": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_int)]),
     "eamm_pack_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

@@ -159,8 +159,9 @@ int conv_check_args(const eamm_conv_args* a, int cout_align) {
   int rc = check_view(a->in); if (rc) return rc;
   if (a->kind < EAMM_CONV_3X3 || a->kind > EAMM_CONV_ROW7_PACKED) return EAMM_ERR_UNSUPPORTED;
   if (a->cin != a->in->c || a->cout <= 0 || a->cout % cout_align) return EAMM_ERR_SHAPE;
-  if ((a->in->h & 1) || (a->in->w & 1)) return EAMM_ERR_SHAPE;
   const bool pool = a->flags & EAMM_EPI_POOL2;
+  // the SIMT kernel walks 2x2 quads (cout_align == 4); the tensor-core kernel only needs even maps to pool
+  if (((a->in->h & 1) || (a->in->w & 1)) && (pool || cout_align == 4)) return EAMM_ERR_SHAPE;
   if (pool && a->kind == EAMM_CONV_UP2_3X3) return EAMM_ERR_UNSUPPORTED;
   int OH = a->in->h, OW = a->in->w;
   if (pool) { OH >>= 1; OW >>= 1; }

@@ -44,6 +44,12 @@ struct ConvTcParams {
   int kxn;             // 7x7 -> <=4 NCHW channels: the 7 kx taps live in the N dimension (N = 7*4 -> 32),
                        // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns
   int x_stride;        // pixels between consecutive x tiles (122 in kxn mode, else bw)
+  int fold;            // split mode with 2*BN <= 256: the weight planes are stacked along N.  Chunk type 0 =
+                       // a_hi x [b_hi; b_lo] (N = 2*BN), type 1 = a_lo x b_hi (N = BN); the epilogue adds
+                       // accumulator columns [BN, 2BN) (the a_hi*b_lo cross term) to [0, BN).  2 A loads and
+                       // 8 MMAs per (tap, 64 channels) instead of 3 and 12.  fold == 2: every chunk is type 0
+                       // (packed `first` conv: both activation planes already sit in one K window).
+  int b_rows_total;    // rows of one weight plane block (classes * cout): the lo block starts there
   int ksub;            // 64-channel K chunks per pipeline stage (1..4)
   int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
@@ -218,6 +224,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   for (int c0 = half * CH; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * CH) {
     uint32_t raw[CH];
     TmemLd<CH>::ld(taddr + c0, raw);
+    if (p.fold) {                                   // add the a_hi*b_lo columns kept at [BN, 2BN)
+      uint32_t raw2[CH];
+      TmemLd<CH>::ld(taddr + p.BN + c0, raw2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     float f[CH];
     const int co = tc.nt * p.BN + c0;
@@ -284,6 +297,13 @@ __device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCo
   const int r = quadrant * 32 + lane;
   uint32_t raw[32];
   TmemLd<32>::ld(tmem_acc + ((uint32_t)(quadrant * 32) << 16), raw);
+  if (p.fold) {
+    uint32_t raw2[32];
+    TmemLd<32>::ld(tmem_acc + ((uint32_t)(quadrant * 32) << 16) + 32u, raw2);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < 28; ++c) raw[c] = __float_as_uint(__uint_as_float(raw[c]) + __uint_as_float(raw2[c]));
+  }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int c = 0; c < 28; ++c) S[r * 29 + c] = __uint_as_float(raw[c]);
@@ -317,10 +337,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("mov.u32 %0, %0;" : "+r"(smem_base));
   asm volatile("mov.u32 %0, %0;" : "+r"(bar0));
   const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
+  const uint32_t fold = (uint32_t)p.fold;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));   // B sub-slot size
   const uint32_t KS = (uint32_t)p.ksub;                         // 64-channel sub-chunks per pipeline stage
   const uint32_t stage_bytes = KS * (a_slot + b_bytes);
-  const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;
+  const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;   // bytes of a type-0 chunk
+  const uint32_t b_half = (uint32_t)p.BN * 128u;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
@@ -342,7 +364,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
+  const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
   const uint32_t total_tiles = (uint32_t)p.total_tiles;
   const int dbg = INSTR ? p.debug : 0;
 
@@ -361,6 +383,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int passes = p.passes, kind = p.kind;
     const uint32_t nstages = (uint32_t)p.num_stages;
     const uint32_t SPT = ((uint32_t)KC + KS - 1u) / KS;          // stages per tile
+    const uint32_t foldT = (uint32_t)KC >> 1;                    // fold == 1: (tap, chunk) pairs per tile
     const bool haloish = p.halo || p.kxn;
     uint32_t slot = 0, phase = 0, si = w;
     for (uint32_t i = 0; i < w; ++i) { if (++slot == nstages) { slot = 0; phase ^= 1u; } }
@@ -380,25 +403,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
           if (INSTR && (dbg == 1 || dbg == 4 || dbg == 5)) mbar_arrive(fb);
           else {
-            mbar_expect_tx(fb, nsub * sub_tx);
+            // fold == 1 chunk order: kc 0 = type 0 (zero-initialises both accumulator halves), kc 1..T =
+            // type 1 (a_lo x b_hi, small terms first), kc T+1..2T-1 = type 0; type 1 carries half the B bytes
+            uint32_t tx = nsub * sub_tx;
+            if (fold == 1) {
+              const uint32_t lo1 = kc0 > 1u ? kc0 : 1u, hi1 = kc0 + nsub < foldT + 1u ? kc0 + nsub : foldT + 1u;
+              if (hi1 > lo1) tx -= (hi1 - lo1) * b_half;
+            }
+            mbar_expect_tx(fb, tx);
             for (uint32_t sub = 0; sub < nsub; ++sub) {
               // K order = (pass, tap, chunk).  In split mode the two cross terms (a_hi*b_lo, a_lo*b_hi)
               // are accumulated first, while the TMEM accumulator is still small, and the dominant
               // a_hi*b_hi term last: the tensor core truncates on every accumulate, so the bias it
               // leaves scales with |accumulator| x (number of steps taken at that magnitude).
+              // (fold mode keeps a_hi*b_lo in its own accumulator columns instead.)
               const uint32_t kc = kc0 + sub;
-              const uint32_t cc = kc & chunk_mask, q = kc >> chunk_shift;          // q = pass * ntap + tap
+              const uint32_t type1 = (fold == 1 && kc >= 1u && kc <= foldT) ? 1u : 0u;
+              const uint32_t kq = fold == 1 ? (kc == 0u ? 0u : (type1 ? kc - 1u : kc - foldT)) : kc;
+              const uint32_t cc = kq & chunk_mask, q = kq >> chunk_shift;          // q = pass * ntap + tap
               const uint32_t ps = q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u);
               const int t = (int)(q - ps * ntap);
-              int cbase = p.a_c_off + ((passes == 3 && ps == 1u) ? p.a_c_buf : 0);
+              int cbase = p.a_c_off + (((passes == 3 && ps == 1u) || type1) ? p.a_c_buf : 0);
               int dy, dx;
               if (haloish) { dy = t - 3; dx = -3; }
               else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; cbase = 0; }   // both planes inside the K window
               else if (kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
               else if (kind == EAMM_CONV_3X3) { const int ty = (t * 11) >> 5; dy = ty - 1; dx = t - 3 * ty - 1; }
               else { const int ty = (t * 37) >> 8; dy = ty - 3; dx = t - 7 * ty - 3; }   // 7x7 per-tap
+              const uint32_t sB = sa + KS * a_slot + sub * b_bytes;
               tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-              tma_load_2d(sa + KS * a_slot + sub * b_bytes, &tmB, fb, (int)kc * 64, brow);
+              tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
+              if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
             }
           }
         }
@@ -414,7 +449,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == TC_MMA_WARP) {
     // ================================================================ MMA issuer
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*BN
     const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
@@ -437,6 +473,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (uint32_t sub = 0; sub < nsub; ++sub) {
             const uint32_t sA = sa + sub * a_slot, sB = sa + KS * a_slot + sub * b_bytes;
             const uint32_t first = (kc | (int)sub) ? 1u : 0u;
+            const uint32_t kcs = (uint32_t)kc + sub;
+            const uint32_t idesc = (fold == 2 || (fold == 1 && (kcs == 0u || kcs > ((uint32_t)KC >> 1)))) ? idesc2 : idesc1;
             if (INSTR && (dbg == 2 || dbg == 4 || dbg == 5)) {
             } else if (INSTR && dbg == 3) {
               tc_mma_bf16(tmem_acc, make_sw128_desc(sA), make_sw128_desc(sB), idesc, first);
@@ -549,7 +587,28 @@ extern "C" int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c)
   return cout <= 32 ? 1 : 0;
 }
 
-extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
+/* Whether eamm_conv_tc folds the weight planes into the N axis for this layer (decides the packing):
+ * 0 = K holds (pass, tap, channel); 1 = rows [hi block | lo block], K = (tap, channel), type-0/1 chunks;
+ * 2 = packed first conv with both row blocks used by every chunk. */
+extern "C" int eamm_conv_tc_fold(int kind, int split, int cout, int halo_scheme) {
+  const char* e = getenv("EAMM_TC_FOLD");
+  const int fold_env = e ? atoi(e) : 1;
+  if (!fold_env || !split || halo_scheme == 1 || (halo_scheme != 2 && cout > 128)) return 0;
+  return kind == EAMM_CONV_ROW7_PACKED ? 2 : 1;
+}
+
+static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query);
+
+extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) { return conv_tc_run(a, stream, nullptr); }
+
+/* Dry run of eamm_conv_tc's planning: fills out[0..3] = {N tile, 7x7 scheme, fold, K chunks per stage}
+ * for these arguments (a->weight_fold is ignored) without launching anything. */
+extern "C" int eamm_conv_tc_query(const eamm_conv_args* a, int* out) {
+  if (!out) return EAMM_ERR_ARG;
+  return conv_tc_run(a, nullptr, out);
+}
+
+static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   int rc = conv_check_args(a, 16);
   if (rc) return rc;
   const eamm_act* in = a->in;
@@ -569,7 +628,7 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   ConvTcParams p;
   p.N = in->n; p.H = in->h; p.W = in->w;
   int wl = ilog2_exact(in->w), hl = ilog2_exact(in->h);
-  if (wl < 1 || hl < 1) return EAMM_ERR_UNSUPPORTED;            // power-of-two maps only
+  if (wl < 0 || hl < 0) return EAMM_ERR_UNSUPPORTED;            // power-of-two maps only (1x1 included)
   p.kind = a->kind; p.flags = a->flags; p.cout = a->cout;
   p.ksize = a->kind == EAMM_CONV_7X7 ? 7 : 3;
   p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : (row7 ? 7 : p.ksize * p.ksize);
@@ -620,15 +679,26 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
     }
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
+  static int fold_env = -1;
+  if (fold_env < 0) { const char* e = getenv("EAMM_TC_FOLD"); fold_env = e ? atoi(e) : 1; }
+  p.fold = 0;
+  // decided from the layer's cout, not from the batch-dependent N tile, so that a frame's result does
+  // not depend on how many other frames share the launch
+  if (fold_env && !p.halo && (p.kxn || a->cout <= 128)) {
+    if (row7 && a->pack_passes == 2) p.fold = 2;
+    else if (!row7 && p.passes == 3) p.fold = 1;
+  }
+  if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
+  p.b_rows_total = p.kxn ? 32 : p.classes * a->cout;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
-  const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : 1u);
+  const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u));
   const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
   const uint32_t ring_bytes = 200u * 1024u - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
   // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
   static int ksub_env = -1;
   if (ksub_env < 0) { const char* e = getenv("EAMM_TC_KSUB"); ksub_env = e ? atoi(e) : 0; }
-  const int kc_total = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
+  const int kc_total = ((p.halo || p.kxn) ? 7 : p.taps) * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
   int ksub = 1;
   for (int k = 4; k >= 2; --k)
     if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
@@ -640,6 +710,7 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
   p.num_stages = stages;
+  if (query) { query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub; return 0; }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
   ActView dummy = make_view(in);
   p.out = p.has_out ? make_view(a->out) : dummy;
@@ -679,8 +750,9 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
   {
     // halo mode: rows = (kx, cout), K = (ky, pass, channel); otherwise rows = (class, cout), K = (tap, pass, channel)
     // kxn mode : rows = 32 (kx*4 + cout), K = (ky, pass, channel)
-    const cuuint64_t ktot = (cuuint64_t)((p.halo || p.kxn) ? 7 : p.taps) * p.passes * (row7 ? 64 : a->cin);
-    const cuuint64_t rows = p.kxn ? 32 : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout;
+    // fold mode: K = (tap, channel) only, rows = [hi block | lo block]
+    const cuuint64_t ktot = (cuuint64_t)((p.halo || p.kxn) ? 7 : p.taps) * (p.fold ? 1 : p.passes) * (row7 ? 64 : a->cin);
+    const cuuint64_t rows = (p.kxn ? 32 : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout) * (p.fold ? 2 : 1);
     cuuint64_t dims[2] = {ktot, rows};
     cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : p.BN)};
@@ -718,7 +790,7 @@ extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (long long b = 0; b < grid; ++b) for (int j = 0; j < 8; ++j) acc[j] += (double)host[b * 8 + j];
     const double tiles_per_cta = (double)p.total_tiles / (double)grid;
-    const int KCh = ((p.halo || p.kxn) ? 7 : p.taps) * p.passes * p.cin_chunks;
+    const int KCh = kc_total;
     fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%dx%d KC=%d tiles/cta=%.1f | per tile (cycles): "
             "total=%.0f prod_wait_empty=%.0f mma_wait_acc=%.0f mma_wait_full=%.0f epi_wait_full=%.0f epi_busy=%.0f | per stage=%.0f\n",
             p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, p.ksub, KCh, tiles_per_cta,

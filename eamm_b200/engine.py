@@ -133,6 +133,16 @@ def pack_tc_weights(full, classes, passes):
     return packed.reshape(classes * cout, -1).contiguous()
 
 
+def pack_tc_weights_fold(full, classes):
+    """Fold scheme 1 of eamm_conv_tc: bf16 rows [hi block (classes*cout) | lo block], K = (tap, channel)."""
+    ct, cout, cin = full.shape
+    taps = ct // classes
+    w = full.view(classes, taps, cout, cin).permute(0, 2, 1, 3).reshape(classes * cout, taps * cin)
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=0).contiguous()
+
+
 def pack_tc_weights_halo(full, passes):
     """7x7 halo-row scheme of eamm_conv_tc: [49 taps][cout][cin] -> bf16 [7 kx * cout][passes * 7 ky * cin]."""
     _, cout, cin = full.shape
@@ -146,13 +156,17 @@ def pack_tc_weights_halo(full, passes):
     return packed.reshape(7 * cout, -1).contiguous()
 
 
-def pack_tc_weights_kxn(full, nchw_c, passes):
-    """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][passes * 7 ky * cin]."""
+def pack_tc_weights_kxn(full, nchw_c, passes, fold=0):
+    """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][passes * 7 ky * cin]
+    (fold: rows [32 hi | 32 lo], K = (ky, channel))."""
     _, cout, cin = full.shape
     w = full.view(7, 7, cout, cin)[:, :, :nchw_c]                         # [ky][kx][co][cin]
     rows = torch.zeros(8, 4, 7, cin, dtype=torch.float32, device=full.device)   # [kx(8)][co(4)][ky][cin]
     rows[:7, :nchw_c] = w.permute(1, 2, 0, 3)
     hi = rows.to(torch.bfloat16)
+    if fold:
+        lo = (rows - hi.float()).to(torch.bfloat16)
+        return torch.cat([hi.reshape(32, -1), lo.reshape(32, -1)], dim=0).contiguous()
     if passes == 1:
         packed = hi
     else:
@@ -161,7 +175,7 @@ def pack_tc_weights_kxn(full, nchw_c, passes):
     return packed.reshape(32, -1).contiguous()
 
 
-def pack_tc_weights_row7(w, cout_pad, passes):
+def pack_tc_weights_row7(w, cout_pad, passes, fold=0):
     """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
 
     K window of one ky = 8 pixels x 8 channels (hi0..2, 0, lo0..2, 0); k = kx*8 + channel, kx = 7 is
@@ -171,6 +185,12 @@ def pack_tc_weights_row7(w, cout_pad, passes):
     cout, C = w.shape[0], w.shape[1]
     hi = w.to(torch.bfloat16)
     lo = (w - hi.float()).to(torch.bfloat16)
+    if fold:     # rows [w_hi vs (a_hi, a_lo) | w_lo vs a_hi], K = (ky, kx, channel)
+        out = torch.zeros(2, cout_pad, 7, 8, 8, dtype=torch.bfloat16, device=w.device)
+        out[0, :cout, :, :7, :C] = hi.permute(0, 2, 3, 1)
+        out[0, :cout, :, :7, 4:4 + C] = hi.permute(0, 2, 3, 1)
+        out[1, :cout, :, :7, :C] = lo.permute(0, 2, 3, 1)
+        return out.reshape(2 * cout_pad, -1).contiguous()
     out = torch.zeros(cout_pad, passes, 7, 8, 8, dtype=torch.bfloat16, device=w.device)   # [co][pass][ky][kx][ch]
     main = passes - 1                                    # the pass holding w_hi runs last
     out[:cout, main, :, :7, :C] = hi.permute(0, 2, 3, 1)
@@ -220,7 +240,8 @@ class ConvLayer:
             self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
         elif impl in ("tc", "tc3"):
             self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1)
-            self.weight_alt = {}             # 7x7 schemes 1/2 of eamm_conv_tc, packed on first use
+            self.weight_alt = {}             # other packings eamm_conv_tc may ask for (7x7 schemes, fold)
+            self.plan_cache = {}             # (input shape, outputs) -> (weight tensor, fold)
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -236,16 +257,39 @@ class ConvLayer:
         a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
         a.inp = C.pointer(inp)
         a.weight = self.weight.data_ptr()
-        if self.impl != "simt" and self.kind == L.CONV_7X7:
-            nchw_only = out_nchw is not None and out is None and out2 is None and out_nhwc_f32 is None
-            scheme = lib.eamm_conv_tc_uses_halo(self.kind, inp.w, self.cout, out_nchw_c if nchw_only else 0)
-            if scheme:
-                key = (scheme, out_nchw_c if scheme == 2 else 0)
-                if key not in self.weight_alt:
+        a.bias = self.bias.data_ptr()
+        self._fill_outputs(a, out, out2, residual, out_nchw, out_nchw_c, out_nhwc_f32)
+        if self.impl != "simt":
+            key = (inp.n, inp.h, inp.w, out_nchw_c if out_nchw is not None else -1, out is not None,
+                   out_nhwc_f32 is not None)
+            sel = self.plan_cache.get(key)
+            if sel is None:
+                q = (C.c_int * 4)()
+                L.check(lib.eamm_conv_tc_query(C.byref(a), q), "conv %s (plan)" % self.name)
+                L.LAUNCHES -= 1                      # a query launches nothing
+                scheme, fold = q[1], q[2]
+                wkey = (scheme, fold, out_nchw_c if scheme == 2 else 0)
+                if wkey not in self.weight_alt:
                     passes = 3 if self.impl == "tc3" else 1
-                    self.weight_alt[key] = (pack_tc_weights_halo(self.w_ref, passes) if scheme == 1
-                                            else pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes))
-                a.weight = self.weight_alt[key].data_ptr()
+                    classes = 4 if self.kind == L.CONV_UP2_3X3 else 1
+                    if scheme == 2:
+                        wt = pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes, fold)
+                    elif scheme == 1:
+                        wt = pack_tc_weights_halo(self.w_ref, passes)
+                    elif fold:
+                        wt = pack_tc_weights_fold(self.w_ref, classes)
+                    else:
+                        wt = self.weight
+                    self.weight_alt[wkey] = wt
+                sel = (self.weight_alt[wkey], fold)
+                self.plan_cache[key] = sel
+            a.weight = sel[0].data_ptr()
+            a.weight_fold = sel[1]
+        fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
+        _launch("conv:" + self.name, lambda: L.check(fn(C.byref(a), stream), "conv %s" % self.name),
+                flops=self.flops_per_in_pixel * inp.n * inp.h * inp.w)
+
+    def _fill_outputs(self, a, out, out2, residual, out_nchw, out_nchw_c, out_nhwc_f32):
         a.bias = self.bias.data_ptr()
         if residual is not None:
             a.residual = C.pointer(residual)
@@ -260,9 +304,6 @@ class ConvLayer:
             a.out_nchw_c = out_nchw_c
         if out_nhwc_f32 is not None:
             a.out_nhwc_f32 = out_nhwc_f32.data_ptr()
-        fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
-        _launch("conv:" + self.name, lambda: L.check(fn(C.byref(a), stream), "conv %s" % self.name),
-                flops=self.flops_per_in_pixel * inp.n * inp.h * inp.w)
 
 
 class FirstConvTC:
@@ -281,7 +322,9 @@ class FirstConvTC:
         self.split = split
         self.passes = 2 if split else 1
         self.cout_valid, self.cout = cout, _round_up(cout, nalign)
-        self.weight = pack_tc_weights_row7(w, self.cout, self.passes)
+        self.w_src = w
+        self.weights = {}                    # fold flag -> packed weights
+        self.plan_cache = {}
         self.bias = torch.zeros(self.cout, dtype=torch.float32, device=w.device)
         self.bias[:cout] = b
         self.flops_per_in_pixel = 2.0 * cout * cin * 49
@@ -302,9 +345,20 @@ class FirstConvTC:
         a = L.ConvArgs()
         a.kind, a.flags, a.cin, a.cout = L.CONV_ROW7_PACKED, L.EPI_RELU, 8, self.cout
         a.inp = C.pointer(inp)
-        a.weight, a.bias = self.weight.data_ptr(), self.bias.data_ptr()
+        a.bias = self.bias.data_ptr()
         a.out = C.pointer(out)
         a.pack_passes = self.passes
+        fold = self.plan_cache.get((nsrc, H, W))
+        if fold is None:
+            q = (C.c_int * 4)()
+            a.weight = self.bias.data_ptr()          # any valid pointer: the query does not read it
+            L.check(lib.eamm_conv_tc_query(C.byref(a), q), "conv first (plan)")
+            L.LAUNCHES -= 1
+            fold = self.plan_cache[(nsrc, H, W)] = q[2]
+        if fold not in self.weights:
+            self.weights[fold] = pack_tc_weights_row7(self.w_src, self.cout, self.passes, fold)
+        a.weight = self.weights[fold].data_ptr()
+        a.weight_fold = fold
         _launch("conv:first", lambda: L.check(lib.eamm_conv_tc(C.byref(a), stream), "conv first (packed)"),
                 flops=self.flops_per_in_pixel * nsrc * H * W)
 
@@ -600,11 +654,27 @@ class GeneratorEngine:
         self.ws[key] = ws
         return ws
 
+    def _empty_result(self, source_image, kp_driving):
+        m = self.m
+        _, Cc, H, W = source_image.shape
+        dev, K1 = source_image.device, m.dense_motion_network.num_kp + 1
+        h, w = H // self.dm.step, W // self.dm.step
+        z = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        out = {"mask": z(0, K1, h, w), "sparse_deformed": z(0, K1, Cc, h, w)}
+        if self.dm.has_occ:
+            out["occlusion_map"] = z(0, 1, h, w)
+        out["deformed"] = z(0, Cc, H, W)
+        out["prediction"] = z(0, Cc, H, W)
+        self.dm.last_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        return out
+
     def run(self, source_image, kp_driving, kp_source):
         m, lib = self.m, self.lib
         if source_image.dim() != 4 or source_image.shape[1] != m.num_channels:
             raise RuntimeError("eamm_b200: source_image must be [B,%d,H,W]" % m.num_channels)
         B, Cc, H, W = source_image.shape
+        if B == 0:                                   # empty batch: the reference returns empty tensors
+            return self._empty_result(source_image, kp_driving)
         shared = source_image.stride(0) == 0 and B > 1
         src = source_image[:1].contiguous() if shared else source_image.contiguous()
         src_n_stride = 0 if shared else Cc * H * W

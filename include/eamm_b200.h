@@ -95,6 +95,8 @@ typedef struct {
   int32_t out_nchw_c;      /* channels written to out_nchw (<= cout; cout may be padded)       */
   float* out_nhwc_f32;     /* optional fp32 NHWC raw output [n, H, W, cout] (mask/occ logits)  */
   int32_t pack_passes;     /* EAMM_CONV_ROW7_PACKED only: 1 (bf16) or 2 (hi/lo split) weight passes */
+  int32_t weight_fold;     /* eamm_conv_tc: the scheme `weight` was packed for, must equal
+                              eamm_conv_tc_fold(...) for this layer (0 when not folded)         */
 } eamm_conv_args;
 
 /* ---- library info --------------------------------------------------------------------------- */
@@ -162,6 +164,19 @@ int eamm_conv_tc(const eamm_conv_args* args, void* stream);
  *   2  kx taps in the GEMM N axis     bf16 [32 = kx*4 + co][passes * 7 ky * cin]   (w % 128 == 0, only
  *      out_nchw with <= 4 channels; out_nchw_c = 0 when the call has any NHWC output) */
 int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c);
+
+/* Split (hi/lo) layers with cout <= 128 (and the kx-in-N 7x7 scheme) stack the two weight planes along N:
+ *   0  not folded: K = (pass, tap, channel) as described at eamm_conv_tc
+ *   1  rows [hi block (classes*cout) | lo block], K = (tap, channel); per (tap, 64 channels) the kernel runs
+ *      a_lo x b_hi (N = bn; all of them first) and a_hi x [b_hi; b_lo] (N = 2*bn); the epilogue adds the halves
+ *   2  EAMM_CONV_ROW7_PACKED with pack_passes == 2: rows [w_hi vs (a_hi, a_lo) | w_lo vs a_hi], K = (ky, 64)
+ * `split` = input has hi/lo planes (or pack_passes == 2); `halo_scheme` = eamm_conv_tc_uses_halo(...). */
+int eamm_conv_tc_fold(int kind, int split, int cout, int halo_scheme);
+
+/* Planning dry run of eamm_conv_tc for `args` (weight_fold ignored, nothing launched):
+ * out[0] = N tile, out[1] = 7x7 scheme (eamm_conv_tc_uses_halo), out[2] = fold (eamm_conv_tc_fold),
+ * out[3] = K chunks per pipeline stage.  The host packs the weights for out[1]/out[2]. */
+int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
 
 /* ---- source image for EAMM_CONV_ROW7_PACKED: src [n,C<=3,H,W] fp32 NCHW -> dst bf16
  * [n][H+6][W+8][8] with channels [hi0,hi1,hi2,0,lo0,lo1,lo2,0] (lo = bf16(v-hi); zero when

@@ -260,3 +260,27 @@ def test_frame_pipeline_equals_direct_forward(dev):
     pipe.close()
     for o, w in zip(outs, want):
         assert torch.equal(o, w)
+
+
+@pytest.mark.parametrize("size,batch", [(128, 3), (512, 1), (256, 5)])
+def test_other_image_sizes_and_ragged_batches_match_oracle(dev, size, batch):
+    """Full config at 128/512 px and a batch that does not fill the 128-pixel tiles of the small maps."""
+    from oracle import eamm_oracle as oracle
+    cfg = get_config("full")
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=50 + size)
+    got = run_ours("full", dev, "fp32", src, kpd, kps)
+    want = oracle.generator_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps)
+    for k, tol in (("prediction", 1e-4), ("mask", 1e-4), ("occlusion_map", 1e-4), ("sparse_deformed", 1e-4), ("deformed", 5e-3)):
+        assert got[k].shape == want[k].shape, k
+        err = (got[k] - want[k]).abs().max().item()
+        assert err <= tol, "%dpx B=%d %s: %.3e" % (size, batch, k, err)
+
+
+def test_empty_batch_returns_empty_tensors(dev):
+    gen, cfg = generator("tiny", dev)
+    gen.precision = "fp32"
+    src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=3)
+    out = gen(src[:0].to(dev), kp_driving={k: v[:0].to(dev) for k, v in kpd.items()},
+              kp_source={k: v[:0].to(dev) for k, v in kps.items()})
+    assert out["prediction"].shape == (0, 3, 64, 64) and out["mask"].shape == (0, 4, 16, 16)
+    assert out["sparse_deformed"].shape == (0, 4, 3, 16, 16) and out["deformed"].shape == (0, 3, 64, 64)
