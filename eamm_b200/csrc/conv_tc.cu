@@ -50,6 +50,7 @@ struct ConvTcParams {
                        // 8 MMAs per (tap, 64 channels) instead of 3 and 12.  fold == 2: every chunk is type 0
                        // (packed `first` conv: both activation planes already sit in one K window).
   int b_rows_total;    // rows of one weight plane block (classes * cout): the lo block starts there
+  int cta2;            // CTA pairs with cta_group::2 MMAs (cout == 256 3x3 layers with an even number of M tiles)
   int ksub;            // 64-channel K chunks per pipeline stage (1..4)
   int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
@@ -106,6 +107,41 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants -------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {     // own smem address -> peer CTA's
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster,
+                                             int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint32_t bar) {       // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -322,7 +358,12 @@ __device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCo
 
 // INSTR = true compiles the bring-up instrumentation (EAMM_TC_PROF cycle counters, EAMM_TC_DEBUG
 // role isolation); the production instantiation carries none of it.
-template <bool INSTR>
+// CTA2 = true: CTA pairs (cluster of 2) run `tcgen05.mma.cta_group::2`, M = 256 pixels x N = 256
+// couts per instruction.  Each CTA stages its own 128-pixel A tile and HALF of the weight tile, so
+// the shared-memory operand fetch per SM and the weight traffic per SM halve (the N=256 layers are
+// bound by that fetch: ~190 cycles per K=16 step with cta_group::1 vs 128 of math).  The leader CTA
+// (rank 0) owns the "full" barriers and issues every MMA; both CTAs run producers and epilogues.
+template <bool INSTR, bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
@@ -338,7 +379,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("mov.u32 %0, %0;" : "+r"(bar0));
   const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
   const uint32_t fold = (uint32_t)p.fold;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));   // B sub-slot size
+  // B sub-slot size (a CTA of a pair stages only its half of the N tile)
+  const uint32_t b_bytes = CTA2 ? (uint32_t)p.BN * 64u : (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));
   const uint32_t KS = (uint32_t)p.ksub;                         // 64-channel sub-chunks per pipeline stage
   const uint32_t stage_bytes = KS * (a_slot + b_bytes);
   const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;   // bytes of a type-0 chunk
@@ -347,26 +389,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (34 + a); };
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == TC_MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
   const uint32_t total_tiles = (uint32_t)p.total_tiles;
   const int dbg = INSTR ? p.debug : 0;
+  // tile walk: CTA i takes tiles i, i+grid, ...; a CTA pair takes adjacent M tiles (2c + rank), (2c + rank) + grid, ...
+  const uint32_t tile0 = blockIdx.x, tile_step = gridDim.x;
 
   // Both single-issuer roles run as warp-uniform loops (all 32 lanes wait, one elected lane issues) so
   // ptxas keeps descriptors/coordinates in uniform registers.  One pipeline stage carries KS
@@ -389,13 +441,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (uint32_t i = 0; i < w; ++i) { if (++slot == nstages) { slot = 0; phase ^= 1u; } }
     long long pw = 0, pstart = 0;
     if (INSTR) pstart = clock64();
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(p, tile);
-      const int brow = tc.cls * p.cout + tc.nt * p.BN;
+      // CTA pair: this CTA stages rows [rank*BN/2, +BN/2) of the N tile; "full" lives in the leader CTA
+      const int brow = tc.cls * p.cout + tc.nt * p.BN + (CTA2 ? (int)cta_rank * (p.BN >> 1) : 0);
       for (; si < SPT; si += TC_PRODUCERS) {
         const uint32_t kc0 = si * KS;
         const uint32_t nsub = (uint32_t)KC - kc0 < KS ? (uint32_t)KC - kc0 : KS;
-        const uint32_t sa = smem_base + slot * stage_bytes, fb = full_bar((int)slot);
+        const uint32_t sa = smem_base + slot * stage_bytes;
+        const uint32_t fb = CTA2 ? mapa_shared(full_bar((int)slot), 0u) : full_bar((int)slot);
         long long t0 = 0;
         if (INSTR) t0 = clock64();
         mbar_wait(empty_bar((int)slot), phase ^ 1u);
@@ -410,7 +464,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t lo1 = kc0 > 1u ? kc0 : 1u, hi1 = kc0 + nsub < foldT + 1u ? kc0 + nsub : foldT + 1u;
               if (hi1 > lo1) tx -= (hi1 - lo1) * b_half;
             }
-            mbar_expect_tx(fb, tx);
+            if (CTA2) { if (cta_rank == 0u) mbar_expect_tx(full_bar((int)slot), 2u * tx); }   // both CTAs' bytes
+            else mbar_expect_tx(fb, tx);
             for (uint32_t sub = 0; sub < nsub; ++sub) {
               // K order = (pass, tap, chunk).  In split mode the two cross terms (a_hi*b_lo, a_lo*b_hi)
               // are accumulated first, while the TMEM accumulator is still small, and the dominant
@@ -431,9 +486,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else if (kind == EAMM_CONV_3X3) { const int ty = (t * 11) >> 5; dy = ty - 1; dx = t - 3 * ty - 1; }
               else { const int ty = (t * 37) >> 8; dy = ty - 3; dx = t - 7 * ty - 3; }   // 7x7 per-tap
               const uint32_t sB = sa + KS * a_slot + sub * b_bytes;
-              tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-              tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
-              if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+              if (CTA2) {
+                tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
+                tma2_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
+              } else {
+                tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
+                tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
+                if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+              }
             }
           }
         }
@@ -446,17 +506,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.prof[blockIdx.x * 8 + 0] = pw;                             // producer 0: cycles waiting for a free slot
       p.prof[blockIdx.x * 8 + 1] = clock64() - pstart;             // producer 0: total
     }
-  } else if (warp == TC_MMA_WARP) {
-    // ================================================================ MMA issuer
+  } else if (warp == TC_MMA_WARP && (!CTA2 || cta_rank == 0u)) {
+    // ================================================================ MMA issuer (leader CTA of a pair)
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
-    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*BN
     const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
     long long pm0 = 0, pm1 = 0, pstart = 0;
     if (INSTR) pstart = clock64();
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
       long long t0 = 0;
       if (INSTR) t0 = clock64();
       mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -492,14 +552,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             } else {
               const uint64_t da = make_sw128_desc(sA), db = make_sw128_desc(sB);
-              tc_mma_bf16(tmem_acc, da, db, idesc, first);
-              tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
-              tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
-              tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+              if (CTA2) {
+                tc2_mma_bf16(tmem_acc, da, db, idesc, first);
+                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
+                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+              } else {
+                tc_mma_bf16(tmem_acc, da, db, idesc, first);
+                tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+                tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
+                tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+              }
             }
           }
-          tc_commit(eb);
-          if (kc + (int)KS >= KC) tc_commit(tfull_bar(as));
+          if (CTA2) { tc2_commit_mc(eb); if (kc + (int)KS >= KC) tc2_commit_mc(tfull_bar(as)); }
+          else { tc_commit(eb); if (kc + (int)KS >= KC) tc_commit(tfull_bar(as)); }
         }
         __syncwarp();
         ++stage; sa += stage_bytes; fb += 8; eb += 8;
@@ -512,7 +579,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.prof[blockIdx.x * 8 + 3] = pm1;                            // MMA: waiting for operands
       p.prof[blockIdx.x * 8 + 4] = clock64() - pstart;             // MMA: total
     }
-  } else {
+  } else if (warp < TC_EPI_WARPS) {
     // ================================================================ epilogue warps (TMEM lanes by warp%4)
     const int quadrant = warp & 3, half = warp >> 2;
     int as = 0; uint32_t aphase = 0;
@@ -520,7 +587,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (INSTR) pstart = clock64();
     float* kxn_smem = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
                                                (size_t)p.num_stages * stage_bytes);
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(p, tile);
       long long t0 = 0;
       if (INSTR) t0 = clock64();
@@ -534,7 +601,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0u));     // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (INSTR && p.prof && warp == 0 && lane == 0) {
@@ -544,9 +614,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // no CTA of the pair may exit while the other can still signal it
   if (warp == TC_MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -689,9 +761,19 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     else if (!row7 && p.passes == 3) p.fold = 1;
   }
   if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
+  static int cta2_env = -1, prof_env = -1;
+  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 1; }
+  if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
+  const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
+  {
+    const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
+    p.cta2 = (cta2_env && !instr && !p.halo && !p.kxn && !row7 && !p.fold && a->cout == 256 && p.BN == 256 &&
+              tiles_all % 2 == 0 && tiles_all >= num_sms && (num_sms % 2) == 0) ? 1 : 0;
+  }
   p.b_rows_total = p.kxn ? 32 : p.classes * a->cout;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
-  const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes + (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u));
+  const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes +
+      (p.cta2 ? (uint32_t)p.BN * 64u : (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u)));
   const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
   const uint32_t ring_bytes = 200u * 1024u - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
@@ -703,6 +785,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   for (int k = 4; k >= 2; --k)
     if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
   if (ksub == 1 && 2u * chunk_bytes * 3u <= ring_bytes && kc_total >= 2 && p.BN < 256) ksub = 2;
+  if (p.cta2) ksub = 1;
   if (ksub_env > 0) ksub = ksub_env;
   p.ksub = ksub;
   const uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
@@ -755,7 +838,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     const cuuint64_t rows = (p.kxn ? 32 : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout) * (p.fold ? 2 : 1);
     cuuint64_t dims[2] = {ktot, rows};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : p.BN)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : (p.cta2 ? p.BN / 2 : p.BN))};
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -765,23 +848,32 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem;
   static size_t smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }
   long long grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  static int prof_env = -1;
   static unsigned long long* prof_buf = nullptr;
-  if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
   p.prof = nullptr;
   if (prof_env) {
     if (!prof_buf) cudaMalloc(&prof_buf, 1024 * 8 * sizeof(unsigned long long));
     cudaMemsetAsync(prof_buf, 0, 1024 * 8 * sizeof(unsigned long long), (cudaStream_t)stream);
     p.prof = prof_buf;
   }
-  if (prof_env || p.debug) conv_tc_kernel<true><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
-  else conv_tc_kernel<false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  if (p.cta2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, p);
+    if (e != cudaSuccess) return (int)e;
+  } else if (instr) conv_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  else conv_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   EAMM_LAUNCH_CHECK();
   if (prof_env) {        // bring-up instrumentation only: synchronous read-back and print
     static unsigned long long host[1024 * 8];

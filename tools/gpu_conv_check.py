@@ -32,6 +32,9 @@ CASES = [
     ("7x7 halo 64->16 128x128 sigmoid", "7x7", "s", 64, 16, 2, 128, 128, 1, 0, 0, "nchw"),
     ("7x7 halo 64->16 256x256 sig x3", "7x7", "s", 64, 16, 2, 256, 256, 2, 0, 0, "nchw"),
     ("7x7 halo 128->16 128x128 logits", "7x7", "", 128, 16, 1, 128, 128, 1, 0, 0, "nhwc"),
+    ("cta2 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 1, 1, 1, ""),
+    ("cta2 3x3 256->256 64x64 N=8 r+o2 x3", "3x3", "", 256, 256, 8, 64, 64, 2, 1, 1, ""),
+    ("cta2 3x3 128->256 128x128 N=2 pool x3", "3x3", "rp", 128, 256, 2, 128, 128, 2, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
