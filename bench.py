@@ -280,13 +280,13 @@ def main():
     dom_ms = sum(v[0] for _, v in dom); dom_fl = sum(v[1] for _, v in dom); dom_n = sum(v[3] for _, v in dom)
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (bottleneck 3x3 256->256, %d launches/step)" % dom_n,
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<cta_group::2> (bottleneck 3x3 256->256, %d launches/step)" % dom_n,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks["source"] == "measured"
                 else "fallback (B200_PROFILING.md)",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the ncu --set full capture
-                # summarised in profiles/ (138.5 MB + 83.6 MB at B=32, fp32 mode); scales with the batch
-                "traffic": (138.53e6 + 83.61e6) * B / 32.0 if args.precision == "fp32" else None,
+                # summarised in profiles/ (138.9 MB + 86.0 MB at B=32, fp32 mode); scales with the batch
+                "traffic": (138.91e6 + 85.99e6) * B / 32.0 if args.precision == "fp32" else None,
                 "share_of_step": dom_ms / step_ms_prof if step_ms_prof else None,
                 "all_convs_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                 "all_convs_share_of_step": conv_ms / step_ms_prof if step_ms_prof else None,
