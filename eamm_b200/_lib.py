@@ -45,6 +45,10 @@ _PROTOS = {
     "eamm_device_ok": (C.c_int, [C.c_int]),
     "eamm_aa_downsample": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p]),
+    "eamm_aa_downsample_act": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.POINTER(Act), C.c_void_p]),
+    "eamm_kp_head": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_kp_stage": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_float,
                                 C.POINTER(Act), C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_flow_combine": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_int, C.c_int,

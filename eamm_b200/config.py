@@ -43,5 +43,25 @@ TINY_CONFIG = {
 }
 
 
+# KPDetector / KPDetector_a constructor kwargs: kp_detector_params + common_params / audio_params of
+# /root/reference/config/MEAD_emo_video_aug_delta_4_crop_random_crop.yaml:27-41 (demo.py:59-66).
+FULL_KP_CONFIG = {
+    "temperature": 0.1, "block_expansion": 32, "max_features": 1024, "scale_factor": 0.25, "num_blocks": 5,
+    "num_kp": 10, "num_channels": 3, "estimate_jacobian": True,
+}
+TINY_KP_CONFIG = {
+    "temperature": 0.1, "block_expansion": 8, "max_features": 32, "scale_factor": 0.25, "num_blocks": 2,
+    "num_kp": 3, "num_channels": 3, "estimate_jacobian": True,
+}
+
+
+def get_kp_config(name="full", audio=False):
+    """kwargs of KPDetector (audio=False) or KPDetector_a (audio=True: adds num_channels_a, yaml:31-35)."""
+    cfg = copy.deepcopy({"full": FULL_KP_CONFIG, "tiny": TINY_KP_CONFIG}[name])
+    if audio:
+        cfg["num_channels_a"] = 3
+    return cfg
+
+
 def get_config(name="full"):
     return copy.deepcopy({"full": FULL_CONFIG, "tiny": TINY_CONFIG}[name])

@@ -18,7 +18,7 @@ constexpr int AA_TR = 4;  // output rows per block
 
 __global__ void __launch_bounds__(256)
 aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, float4* __restrict__ dst,
-                     int H, int W, int Ho, int Wo, int step, const float* __restrict__ g1) {
+                     int H, int W, int Ho, int Wo, int step, const float* __restrict__ g1, ActView act, int to_act) {
   extern __shared__ float tmp[];  // [3][rows][Wo]
   __shared__ float g[AA_TAPS];
   const int n = blockIdx.y;
@@ -59,7 +59,8 @@ aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, floa
       for (int u = 0; u < AA_TAPS; ++u) acc = fmaf(g[u], tmp[(c * rows + i * step + u) * Wo + j], acc);
       o[c] = acc;
     }
-    dst[((long long)n * Ho + (r0 + i)) * Wo + j] = make_float4(o[0], o[1], o[2], 0.f);
+    if (to_act) act_store4(act, act_offset(act, n, r0 + i, j, 0), make_float4(o[0], o[1], o[2], 0.f));
+    else dst[((long long)n * Ho + (r0 + i)) * Wo + j] = make_float4(o[0], o[1], o[2], 0.f);
   }
 }
 
@@ -412,6 +413,101 @@ pack_image_kernel(const float* __restrict__ src, int C, int H, int W, int split,
   }
 }
 
+// =============================================================================================
+// keypoint heads  (keypoint_detector.py:40-50 gaussian2kp, :88-103 / :187-203)
+//   heatmap_k = softmax(logit_k / T) over the (h-6+2pad) x (w-6+2pad) window of the same-padded 7x7 map,
+//   value_k = sum heatmap_k * grid,  jacobian_k = sum heatmap_k * jacobian_map_k   (4 maps per keypoint)
+// One block per image: each thread walks pixels of the window and keeps per-keypoint partial
+// max / sums in registers; block reductions use warp shuffles + one shared-memory hop.
+// =============================================================================================
+constexpr int KH_MAX = 16;       // keypoints per image handled by the register arrays
+constexpr int KH_THREADS = 256;
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < KH_THREADS / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(KH_THREADS)
+kp_head_kernel(const float* __restrict__ logits, int ldl, int h, int w, int K, int J, int off, int hh, int ww,
+               float inv_t, float* __restrict__ heatmap, float* __restrict__ value, float* __restrict__ jac) {
+  __shared__ float red[KH_THREADS / 32];
+  __shared__ float s_max[KH_MAX], s_sum[KH_MAX];
+  const int n = blockIdx.x;
+  const float* img = logits + (long long)n * h * w * ldl;
+  const int npix = hh * ww;
+  // pass 1: per-keypoint maximum of logit / T
+  float m[KH_MAX];
+#pragma unroll
+  for (int k = 0; k < KH_MAX; ++k) m[k] = -INFINITY;
+  for (int p = threadIdx.x; p < npix; p += KH_THREADS) {
+    const float* px = img + ((long long)(p / ww + off) * w + (p % ww + off)) * ldl;
+#pragma unroll
+    for (int k = 0; k < KH_MAX; ++k) if (k < K) m[k] = fmaxf(m[k], __ldg(px + k) * inv_t);
+  }
+#pragma unroll
+  for (int k = 0; k < KH_MAX; ++k)
+    if (k < K) { float r = block_reduce(m[k], red, true); if (threadIdx.x == 0) s_max[k] = r; }
+  __syncthreads();
+  // pass 2: sums of e, e*x, e*y and e*jacobian maps
+  float se[KH_MAX], sx[KH_MAX], sy[KH_MAX], sj[KH_MAX][4];
+#pragma unroll
+  for (int k = 0; k < KH_MAX; ++k) { se[k] = sx[k] = sy[k] = 0.f; sj[k][0] = sj[k][1] = sj[k][2] = sj[k][3] = 0.f; }
+  for (int p = threadIdx.x; p < npix; p += KH_THREADS) {
+    const int y = p / ww, x = p % ww;
+    const float* px = img + ((long long)(y + off) * w + (x + off)) * ldl;
+    const float gx = grid_coord(x, ww), gy = grid_coord(y, hh);
+#pragma unroll
+    for (int k = 0; k < KH_MAX; ++k) {
+      if (k < K) {
+        const float e = expf(__ldg(px + k) * inv_t - s_max[k]);
+        se[k] += e; sx[k] += e * gx; sy[k] += e * gy;
+        if (J > 0) {
+          const float* jm = px + K + 4 * (J == 1 ? 0 : k);
+          sj[k][0] += e * __ldg(jm); sj[k][1] += e * __ldg(jm + 1); sj[k][2] += e * __ldg(jm + 2); sj[k][3] += e * __ldg(jm + 3);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KH_MAX; ++k) {
+    if (k >= K) break;
+    const float tot = block_reduce(se[k], red, false);
+    const float vx = block_reduce(sx[k], red, false), vy = block_reduce(sy[k], red, false);
+    if (threadIdx.x == 0) {
+      s_sum[k] = tot;
+      value[((long long)n * K + k) * 2] = vx / tot;
+      value[((long long)n * K + k) * 2 + 1] = vy / tot;
+    }
+    if (J > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float r = block_reduce(sj[k][c], red, false);
+        if (threadIdx.x == 0) jac[((long long)n * K + k) * 4 + c] = r / tot;
+      }
+    }
+  }
+  __syncthreads();
+  // pass 3: the normalised heatmap itself (an output of the module, keypoint_detector.py:90 / :189)
+  if (heatmap != nullptr) {
+    for (int idx = threadIdx.x; idx < K * npix; idx += KH_THREADS) {
+      const int k = idx / npix, p = idx - k * npix;
+      const float* px = img + ((long long)(p / ww + off) * w + (p % ww + off)) * ldl;
+      heatmap[((long long)n * K + k) * npix + p] = expf(__ldg(px + k) * inv_t - s_max[k]) / s_sum[k];
+    }
+  }
+}
+
 static inline KpDev to_dev(const eamm_kp* k) {
   KpDev d; d.value = k->value; d.jac = k->jacobian; d.vs = k->value_stride; d.js = k->jacobian_stride;
   return d;
@@ -441,7 +537,27 @@ extern "C" int eamm_aa_downsample(const float* src, int64_t src_n_stride, float*
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(aa_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((Ho + AA_TR - 1) / AA_TR, n);
-  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, (float4*)dst, H, W, Ho, Wo, step, g1);
+  ActView none = {};
+  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, (float4*)dst, H, W, Ho, Wo, step, g1, none, 0);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, int n, int H, int W, int step,
+                                      const float* g1, const eamm_act* dst, void* stream) {
+  if (!src || !g1 || n <= 0 || H <= 0 || W <= 0 || step <= 0) return EAMM_ERR_ARG;
+  if (H % step || W % step) return EAMM_ERR_SHAPE;
+  int rc = check_view(dst); if (rc) return rc;
+  int Ho = H / step, Wo = W / step;
+  if (dst->n != n || dst->h != Ho || dst->w != Wo || dst->c < 4) return EAMM_ERR_SHAPE;
+  int rows = (AA_TR - 1) * step + AA_TAPS;
+  size_t smem = (size_t)3 * rows * Wo * sizeof(float);
+  if (smem > 200 * 1024) return EAMM_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(aa_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((Ho + AA_TR - 1) / AA_TR, n);
+  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, nullptr, H, W, Ho, Wo, step, g1,
+                                                                 make_view(dst), 1);
   EAMM_LAUNCH_CHECK();
   return 0;
 }
@@ -550,6 +666,22 @@ extern "C" int eamm_pack_image(const float* src, int n, int C, int H, int W, int
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, C, H, W, split, (uint4*)dst, total);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_kp_head(const float* logits, int ldl, int n, int h, int w, int num_kp, int num_jac_maps, int pad,
+                            float temperature, float* heatmap, float* value, float* jacobian, void* stream) {
+  if (!logits || !value || n <= 0 || h <= 0 || w <= 0 || !(temperature > 0.f)) return EAMM_ERR_ARG;
+  if (num_kp <= 0 || num_kp > KH_MAX) return EAMM_ERR_UNSUPPORTED;
+  if (num_jac_maps != 0 && num_jac_maps != 1 && num_jac_maps != num_kp) return EAMM_ERR_ARG;
+  if (num_jac_maps && !jacobian) return EAMM_ERR_ARG;
+  if (pad < 0 || pad > 3) return EAMM_ERR_UNSUPPORTED;
+  if (ldl < num_kp + 4 * num_jac_maps) return EAMM_ERR_SHAPE;
+  const int off = 3 - pad, hh = h - 2 * off, ww = w - 2 * off;
+  if (hh < 2 || ww < 2) return EAMM_ERR_SHAPE;
+  kp_head_kernel<<<n, KH_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, h, w, num_kp, num_jac_maps, off, hh, ww,
+                                                              1.f / temperature, heatmap, value, jacobian);
   EAMM_LAUNCH_CHECK();
   return 0;
 }

@@ -391,6 +391,74 @@ def _kp_struct(kp, batch, num_kp, device):
     return s, keep
 
 
+class HourglassPlan:
+    """Packed Hourglass = Encoder + Decoder (util.py:941-1002), shared by the dense-motion network and
+    the keypoint detector.  Level L owns one buffer [up-block output | encoder map e_L]; the skip
+    `torch.cat`s of util.py:982-987 are channel-slot views of those buffers."""
+
+    def __init__(self, hourglass, cin0, calign, nalign, impl, prefix="hg"):
+        enc, dec = hourglass.encoder.down_blocks, hourglass.decoder.up_blocks
+        dev = enc[0].conv.weight.device
+        nb = len(enc)
+        self.nb, self.calign = nb, calign
+        self.enc_ch = [cin0] + [blk.conv.out_channels for blk in enc]       # e_0 .. e_nb
+        self.dec_ch = [blk.conv.out_channels for blk in dec]                # up_j output channels
+        self.enc_layers, self.dec_layers = [], []
+        for i, blk in enumerate(enc):
+            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
+            self.enc_layers.append(ConvLayer("%s.enc%d" % (prefix, i), L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
+                                             _round_up(self.enc_ch[i], calign), nalign, impl))
+        for j, blk in enumerate(dec):
+            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
+            # input of up_block j: e_nb for j == 0, else cat(up_{j-1} out, e_{nb-j}) with padded slots
+            if j == 0:
+                cin_slot = _round_up(self.enc_ch[nb], calign)
+                wp = w
+            else:
+                wp, cin_slot = self.split_cat_weights(w, self.dec_ch[j - 1], self.enc_ch[nb - j])
+            self.dec_layers.append(ConvLayer("%s.dec%d" % (prefix, j), L.CONV_UP2_3X3, L.EPI_RELU, wp, b, cin_slot,
+                                             nalign, impl, cin_valid=w.shape[1]))
+
+    def split_cat_weights(self, w, c_up, c_sk):
+        """Re-index a conv over cat(up, skip) channels to the padded two-slot buffer layout."""
+        s_up, s_sk = _round_up(c_up, self.calign), _round_up(c_sk, self.calign)
+        wp = torch.zeros(w.shape[0], s_up + s_sk, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+        wp[:, :c_up] = w[:, :c_up]
+        wp[:, s_up:s_up + c_sk] = w[:, c_up:]
+        return wp, s_up + s_sk
+
+    def buffers(self, B, h, w, mode, dev):
+        nb, ca = self.nb, self.calign
+        if h >> nb < 1 or w >> nb < 1 or (h % (1 << nb)) or (w % (1 << nb)):
+            raise RuntimeError("eamm_b200: %dx%d map cannot be halved %d times" % (h, w, nb))
+        cat = []
+        for lvl in range(nb):
+            s_up = _round_up(self.dec_ch[nb - 1 - lvl], ca)
+            s_sk = _round_up(self.enc_ch[lvl], ca)
+            buf = ActBuf(B, h >> lvl, w >> lvl, s_up + s_sk, mode, dev)
+            buf.s_up, buf.s_sk = s_up, s_sk
+            cat.append(buf)
+        bott = ActBuf(B, h >> nb, w >> nb, _round_up(self.enc_ch[nb], ca), mode, dev)
+        return cat, bott
+
+    def run(self, lib, st, cat, bott):
+        """cat[0]'s skip slot holds the input; afterwards cat[0] holds [decoder output | input]."""
+        nb = self.nb
+        for i, layer in enumerate(self.enc_layers):          # e_{i+1} = down_block_i(e_i)
+            src_buf = cat[i]
+            inp = src_buf.act(c_off=src_buf.s_up, c=src_buf.s_sk)
+            if i + 1 < nb:
+                dst_buf = cat[i + 1]
+                dst = dst_buf.act(c_off=dst_buf.s_up, c=layer.cout)
+            else:
+                dst = bott.act(c_off=0, c=layer.cout)
+            layer.launch(lib, st, inp, out=dst)
+        for j, layer in enumerate(self.dec_layers):          # up_block_j reads e_nb / cat_{nb-j}, fills cat_{nb-1-j}
+            inp = bott.act() if j == 0 else cat[nb - j].act()
+            dst_buf = cat[nb - 1 - j]
+            layer.launch(lib, st, inp, out=dst_buf.act(c_off=0, c=layer.cout))
+
+
 class DenseMotionEngine:
     """Executor for DenseMotionNetwork.forward (dense_motion.py:81-113)."""
 
@@ -407,35 +475,12 @@ class DenseMotionEngine:
         m = self.m
         dev = m.mask.weight.device
         self.device = dev
-        nb = len(m.hourglass.encoder.down_blocks)
-        self.nb = nb
         K1 = m.num_kp + 1
         cin0 = K1 * (m.num_channels + 1)
-        enc = m.hourglass.encoder.down_blocks
-        dec = m.hourglass.decoder.up_blocks
         ca = self.calign
-        self.enc_ch = [cin0] + [blk.conv.out_channels for blk in enc]       # e_0 .. e_nb
-        self.dec_ch = [blk.conv.out_channels for blk in dec]                # up_j output channels
-        self.enc_layers, self.dec_layers = [], []
-        for i, blk in enumerate(enc):
-            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
-            self.enc_layers.append(ConvLayer("hg.enc%d" % i, L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
-                                             _round_up(self.enc_ch[i], ca), self.nalign, self.impl))
-        for j, blk in enumerate(dec):
-            w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
-            # input of up_block j: e_nb for j == 0, else cat(up_{j-1} out, e_{nb-j}) with padded slots
-            if j == 0:
-                cin_slot = _round_up(self.enc_ch[nb], ca)
-                wp = w
-            else:
-                c_up, c_sk = self.dec_ch[j - 1], self.enc_ch[nb - j]
-                s_up, s_sk = _round_up(c_up, ca), _round_up(c_sk, ca)
-                cin_slot = s_up + s_sk
-                wp = torch.zeros(w.shape[0], cin_slot, 3, 3, dtype=w.dtype, device=dev)
-                wp[:, :c_up] = w[:, :c_up]
-                wp[:, s_up:s_up + c_sk] = w[:, c_up:]
-            self.dec_layers.append(ConvLayer("hg.dec%d" % j, L.CONV_UP2_3X3, L.EPI_RELU, wp, b, cin_slot,
-                                             self.nalign, self.impl, cin_valid=w.shape[1]))
+        self.hg = HourglassPlan(m.hourglass, cin0, ca, self.nalign, self.impl)
+        nb = self.nb = self.hg.nb
+        self.enc_ch, self.dec_ch = self.hg.enc_ch, self.hg.dec_ch
         # mask (+ occlusion) merged into one 7x7 conv over cat(up_{nb-1} out, e_0)
         c_up, c_sk = self.dec_ch[nb - 1], cin0
         s_up, s_sk = _round_up(c_up, ca), _round_up(c_sk, ca)
@@ -444,10 +489,8 @@ class DenseMotionEngine:
         if self.has_occ:
             wm = torch.cat([wm, m.occlusion.weight.detach().float()], 0)
             bm = torch.cat([bm, m.occlusion.bias.detach().float()], 0)
-        wp = torch.zeros(wm.shape[0], s_up + s_sk, 7, 7, dtype=wm.dtype, device=dev)
-        wp[:, :c_up] = wm[:, :c_up]
-        wp[:, s_up:s_up + c_sk] = wm[:, c_up:]
-        self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, s_up + s_sk, self.nalign, self.impl,
+        wp, cin_slot = self.hg.split_cat_weights(wm, c_up, c_sk)
+        self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, cin_slot, self.nalign, self.impl,
                               cin_valid=wm.shape[1])
         # 1-D factor of the anti-alias kernel: k2 = outer(g1, g1) with sum 1 (util.py:1012-1033)
         self.step = 1
@@ -466,22 +509,12 @@ class DenseMotionEngine:
         ws = self.ws.get(key)
         if ws is not None:
             return ws
-        dev, ca, nb = self.device, self.calign, self.nb
+        dev = self.device
         h, w = H // self.step, W // self.step
-        if h >> nb < 1 or w >> nb < 1 or (h % (1 << nb)) or (w % (1 << nb)):
-            raise RuntimeError("eamm_b200: %dx%d motion grid cannot be halved %d times" % (h, w, nb))
         ws = type("WS", (), {})()
         ws.h, ws.w = h, w
         ws.small = torch.zeros(B, h, w, 4, dtype=torch.float32, device=dev)
-        # cat_L = [up_{nb-1-L} out | e_L] at spatial (h>>L, w>>L), L = 0..nb-1; e_nb standalone
-        ws.cat = []
-        for lvl in range(nb):
-            s_up = _round_up(self.dec_ch[nb - 1 - lvl], ca)
-            s_sk = _round_up(self.enc_ch[lvl], ca)
-            buf = ActBuf(B, h >> lvl, w >> lvl, s_up + s_sk, self.mode, dev)
-            buf.s_up, buf.s_sk = s_up, s_sk
-            ws.cat.append(buf)
-        ws.bott = ActBuf(B, h >> nb, w >> nb, _round_up(self.enc_ch[nb], ca), self.mode, dev)
+        ws.cat, ws.bott = self.hg.buffers(B, h, w, self.mode, dev)
         K1 = self.m.num_kp + 1
         ws.logits = torch.empty(B, h, w, self.head.cout, dtype=torch.float32, device=dev)
         ws.status = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -529,22 +562,8 @@ class DenseMotionEngine:
                               ws.status.data_ptr(), st), "kp_stage"),
             nbytes=B * h * w * (16 + K1 * 4 * esz + K1 * Cc * 4))
         out["sparse_deformed"] = sparse_deformed
-        # a7 hourglass encoder: e_{i+1} = down_block_i(e_i)
-        nb = self.nb
-        for i, layer in enumerate(self.enc_layers):
-            src_buf = ws.cat[i]
-            inp = src_buf.act(c_off=src_buf.s_up, c=src_buf.s_sk)
-            if i + 1 < nb:
-                dst_buf = ws.cat[i + 1]
-                dst = dst_buf.act(c_off=dst_buf.s_up, c=layer.cout)
-            else:
-                dst = ws.bott.act(c_off=0, c=layer.cout)
-            layer.launch(lib, st, inp, out=dst)
-        # decoder: up_block_j reads e_nb (j=0) or cat_{nb-j}; writes slot 'up' of cat_{nb-1-j}
-        for j, layer in enumerate(self.dec_layers):
-            inp = ws.bott.act() if j == 0 else ws.cat[nb - j].act()
-            dst_buf = ws.cat[nb - 1 - j]
-            layer.launch(lib, st, inp, out=dst_buf.act(c_off=0, c=layer.cout))
+        # a7 hourglass
+        self.hg.run(lib, st, ws.cat, ws.bott)
         # a8: mask/occlusion 7x7 conv -> logits; softmax + flow combine + sigmoid
         self.head.launch(lib, st, ws.cat[0].act(), out_nhwc_f32=ws.logits)
         mask = torch.empty(B, K1, h, w, dtype=torch.float32, device=dev)

@@ -85,6 +85,43 @@ def make_state_dict(cfg, seed=0):
     return sd
 
 
+def make_kp_state_dict(cfg, seed=2):
+    """Seeded state dict laid out like KPDetector / KPDetector_a (keypoint_detector.py:14-37, 117-140):
+    `predictor` Hourglass, `kp` and `jacobian` 7x7 convs, `down.weight` buffer."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    be, mf, nb = cfg["block_expansion"], cfg["max_features"], cfg["num_blocks"]
+    cin0 = cfg.get("num_channels_a", cfg["num_channels"])
+    for i in range(nb):
+        ci = cin0 if i == 0 else min(mf, be * 2 ** i)
+        co = min(mf, be * 2 ** (i + 1))
+        _conv(sd, f"predictor.encoder.down_blocks.{i}.conv", ci, co, 3, g, gain=1.4)
+        _bn(sd, f"predictor.encoder.down_blocks.{i}.norm", co, g)
+    for j, i in enumerate(range(nb)[::-1]):
+        ci = (1 if i == nb - 1 else 2) * min(mf, be * 2 ** (i + 1))
+        co = min(mf, be * 2 ** i)
+        _conv(sd, f"predictor.decoder.up_blocks.{j}.conv", ci, co, 3, g, gain=1.4)
+        _bn(sd, f"predictor.decoder.up_blocks.{j}.norm", co, g)
+    feat = be + cin0
+    _conv(sd, "kp", feat, cfg["num_kp"], 7, g, gain=1.0)
+    if cfg.get("estimate_jacobian", False):
+        maps = 1 if cfg.get("single_jacobian_map", False) else cfg["num_kp"]
+        _conv(sd, "jacobian", feat, 4 * maps, 7, g, gain=0.5)
+        sd["jacobian.bias"] = sd["jacobian.bias"] + torch.tensor([1.0, 0.0, 0.0, 1.0] * maps)
+    if cfg.get("scale_factor", 1) != 1:
+        sd["down.weight"] = aa_kernel(cfg["num_channels"])
+    return sd
+
+
+def make_kp_inputs(cfg, batch, size, audio, seed=5):
+    """Seeded input of the keypoint detectors: an image for KPDetector, a feature map for KPDetector_a."""
+    g = torch.Generator().manual_seed(seed)
+    if audio:
+        step = int(1 / cfg["scale_factor"])
+        return torch.randn(batch, cfg["block_expansion"] + cfg["num_channels_a"], size // step, size // step, generator=g)
+    return torch.rand(batch, cfg["num_channels"], size, size, generator=g)
+
+
 def aa_kernel(channels, sigma=1.5):
     """The fixed 13x13 Gaussian buffer of AntiAliasInterpolation2d (util.py:1012-1036)."""
     ks = 2 * round(sigma * 4) + 1

@@ -111,6 +111,21 @@ int eamm_device_ok(int device);
 int eamm_aa_downsample(const float* src, int64_t src_n_stride, float* dst, int n, int H, int W,
                        int step, const float* g1, void* stream);
 
+/* Same filter, written as channels [0,4) = (R,G,B,0) of an NHWC activation view (the keypoint detector's
+ * hourglass input, keypoint_detector.py:78-79); remaining channels of the view are left untouched. */
+int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, int n, int H, int W, int step,
+                           const float* g1, const eamm_act* dst, void* stream);
+
+/* ---- keypoint heads (keypoint_detector.py:40-50, 82-103, 183-203) --------
+ * logits [n,h,w,ldl] fp32 NHWC of a SAME-padded 7x7 conv over the detector's feature map: channels [0,K) =
+ * `kp` logits, [K, K+4J) = `jacobian` maps (J = K, 1 for single_jacobian_map, 0 without).  The reference
+ * convolves with padding `pad` (0 in every config); its (h-6+2pad) x (w-6+2pad) output is the window of the
+ * same-padded map at offset 3-pad.  Per (image, keypoint): heatmap = softmax(logit / temperature) over the
+ * window; value = sum heatmap * make_coordinate_grid(window); jacobian = sum heatmap * map.
+ * Outputs: heatmap [n,K,hh,ww] (may be NULL), value [n,K,2], jacobian [n,K,2,2] (NULL when J == 0). */
+int eamm_kp_head(const float* logits, int ldl, int n, int h, int w, int num_kp, int num_jac_maps, int pad,
+                 float temperature, float* heatmap, float* value, float* jacobian, void* stream);
+
 /* ---- a4+a5+a6: heatmaps, sparse motions, deformed source (dense_motion.py:32-79, util.py:815-855)
  * small [n,h,w,4] fp32 from eamm_aa_downsample (small_n_stride 0 = shared source);
  * writes the (K+1)*4-channel hourglass input (channel order [hm_k,R_k,G_k,B_k], dense_motion.py:93-94,

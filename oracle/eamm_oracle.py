@@ -218,3 +218,45 @@ def generator_forward(sd, cfg, source_image, kp_driving, kp_source, taps=None):
         out = F.conv2d(out, sd["final.weight"], sd["final.bias"], padding=3)
         result["prediction"] = torch.sigmoid(out)
     return result
+
+
+# ----------------------------------------------------------------------------- keypoint detector heads
+# the step immediately before the generation path (demo.py:206-219).
+def gaussian2kp(heatmap):
+    """KPDetector.gaussian2kp, keypoint_detector.py:40-50: value = sum(heatmap * grid) over (h, w)."""
+    h, w = heatmap.shape[2:]
+    grid = make_coordinate_grid(h, w).unsqueeze(0).unsqueeze(0)
+    return (heatmap.unsqueeze(-1) * grid).sum(dim=(2, 3))
+
+
+def kp_heads(feature_map, sd, cfg):
+    """The tail shared by KPDetector.forward (keypoint_detector.py:82-103) and KPDetector_a.forward (:183-203)."""
+    pad = cfg.get("pad", 0)
+    prediction = F.conv2d(feature_map, sd["kp.weight"], sd["kp.bias"], padding=pad)
+    shape = prediction.shape
+    heatmap = F.softmax(prediction.view(shape[0], shape[1], -1) / cfg["temperature"], dim=2).view(*shape)
+    out = {"value": gaussian2kp(heatmap), "heatmap": heatmap}
+    if cfg.get("estimate_jacobian", False):
+        maps = 1 if cfg.get("single_jacobian_map", False) else cfg["num_kp"]
+        jm = F.conv2d(feature_map, sd["jacobian.weight"], sd["jacobian.bias"], padding=pad)
+        jm = jm.reshape(shape[0], maps, 4, shape[2], shape[3])
+        jac = (heatmap.unsqueeze(2) * jm).view(shape[0], shape[1], 4, -1).sum(dim=-1)
+        out["jacobian"] = jac.view(shape[0], shape[1], 2, 2)
+    return out
+
+
+def kp_detector_forward(sd, cfg, x, taps=None):
+    """KPDetector.forward, keypoint_detector.py:77-105: anti-alias down, Hourglass predictor, heads."""
+    with torch.no_grad():
+        if cfg.get("scale_factor", 1) != 1:
+            x = anti_alias_down(x, sd["down.weight"], cfg["scale_factor"])
+        feature_map = hourglass(x, sd, "predictor", cfg["num_blocks"])
+        if taps is not None:
+            taps["feature_map"] = feature_map
+        return kp_heads(feature_map, sd, cfg)
+
+
+def kp_detector_a_forward(sd, cfg, feature_map):
+    """KPDetector_a.forward, keypoint_detector.py:180-205: heads only (its predictor is never called)."""
+    with torch.no_grad():
+        return kp_heads(feature_map, sd, cfg)

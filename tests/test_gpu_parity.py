@@ -284,3 +284,28 @@ def test_empty_batch_returns_empty_tensors(dev):
               kp_source={k: v[:0].to(dev) for k, v in kps.items()})
     assert out["prediction"].shape == (0, 3, 64, 64) and out["mask"].shape == (0, 4, 16, 16)
     assert out["sparse_deformed"].shape == (0, 4, 3, 16, 16) and out["deformed"].shape == (0, 3, 64, 64)
+
+
+# ------------------------------------------------------------------ keypoint heads
+@pytest.mark.parametrize("precision,tol_v,tol_h", [("fp32_simt", 2e-5, 2e-6), ("fp32", 2e-4, 2e-5)])
+@pytest.mark.parametrize("name,cfg_name,audio", [("kp_tiny_b2", "tiny", False), ("kp_a_tiny_b3", "tiny", True),
+                                                 ("kp_full_b2", "full", False), ("kp_a_full_b2", "full", True)])
+def test_kp_detector_heads_match_reference_golden(dev, precision, tol_v, tol_h, name, cfg_name, audio):
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, size, _ = [int(v) for v in blob["meta"]]
+    cfg = get_kp_config(cfg_name, audio=audio)
+    det = (KPDetector_a if audio else KPDetector)(**cfg).eval()
+    det.load_state_dict(synth.make_kp_state_dict(cfg, seed=3 if audio else 2), strict=True)
+    det = det.to(dev)
+    det.precision = precision
+    out = det(synth.make_kp_inputs(cfg, batch, size, audio).to(dev))
+    torch.cuda.synchronize()
+    assert set(out) == {"value", "heatmap", "jacobian"}
+    hm = out["heatmap"].cpu().numpy()
+    sub = hm[..., ::2, ::2] if cfg_name == "full" else hm
+    assert np.abs(sub - blob["heatmap"]).max() <= tol_h
+    assert np.abs(out["value"].cpu().numpy() - blob["value"]).max() <= tol_v
+    assert np.abs(out["jacobian"].cpu().numpy() - blob["jacobian"]).max() <= tol_v * 5
+    assert np.allclose(hm.sum((2, 3)), 1.0, atol=1e-4)

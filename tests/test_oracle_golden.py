@@ -67,3 +67,23 @@ def test_singular_jacobian_raises_like_reference():
     kpd["jacobian"][0, 0] = 0.0
     with pytest.raises(Exception):
         oracle.sparse_motions(kpd, kps, 16, 16)
+
+
+@pytest.mark.parametrize("name,cfg_name,audio", [("kp_tiny_b2", "tiny", False), ("kp_a_tiny_b3", "tiny", True),
+                                                 ("kp_full_b2", "full", False), ("kp_a_full_b2", "full", True)])
+def test_kp_detector_oracle_reproduces_reference_golden(name, cfg_name, audio):
+    """KPDetector / KPDetector_a heads, pinned to the real reference by tools/make_golden.py."""
+    from eamm_b200.config import get_kp_config
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, size, _ = [int(v) for v in blob["meta"]]
+    cfg = get_kp_config(cfg_name, audio=audio)
+    sd = synth.make_kp_state_dict(cfg, seed=3 if audio else 2)
+    x = synth.make_kp_inputs(cfg, batch, size, audio)
+    np.testing.assert_allclose(np.array([x.double().sum()]), blob["in_checksum"], rtol=0, atol=0)
+    got = (oracle.kp_detector_a_forward if audio else oracle.kp_detector_forward)(sd, cfg, x)
+    for k in ("value", "heatmap", "jacobian"):
+        a = got[k].numpy()
+        sub = a[..., ::2, ::2] if (k == "heatmap" and cfg_name == "full") else a
+        np.testing.assert_allclose(sub, blob[k], rtol=0, atol=2e-6, err_msg=k)
+    assert np.allclose(got["heatmap"].sum((2, 3)).numpy(), 1.0, atol=1e-5)       # each heatmap is a distribution

@@ -26,7 +26,9 @@ from eamm_b200.config import get_config          # noqa: E402
 from eamm_b200 import synth                      # noqa: E402
 from oracle import eamm_oracle as oracle         # noqa: E402
 
+from eamm_b200.config import get_kp_config     # noqa: E402
 from modules.generator import OcclusionAwareGenerator  # noqa: E402  (the reference)
+from modules.keypoint_detector import KPDetector, KPDetector_a  # noqa: E402  (the reference)
 
 KEYS = ["mask", "sparse_deformed", "occlusion_map", "deformed", "prediction"]
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
@@ -69,9 +71,34 @@ def run_case(name, cfg_name, batch, size, with_jacobian=True, shared_source=Fals
         print("   ", k, "min/max/mean = %.4f %.4f %.4f" % s)
 
 
+def run_kp_case(name, cfg_name, batch, size, audio):
+    cfg = get_kp_config(cfg_name, audio=audio)
+    sd = synth.make_kp_state_dict(cfg, seed=3 if audio else 2)
+    ref = (KPDetector_a if audio else KPDetector)(**cfg).eval()
+    res = ref.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    x = synth.make_kp_inputs(cfg, batch, size, audio)
+    with torch.no_grad():
+        want = ref(x)
+    got = (oracle.kp_detector_a_forward if audio else oracle.kp_detector_forward)(sd, cfg, x)
+    blob = {"meta": np.array([batch, size, int(audio)], dtype=np.int64), "in_checksum": np.array([x.double().sum()])}
+    for k in ("value", "heatmap", "jacobian"):
+        assert torch.equal(want[k], got[k]), f"{name}: oracle != reference on {k}"
+        a = want[k].numpy()
+        blob["sum_" + k] = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+        blob[k] = a[..., ::2, ::2].copy() if (k == "heatmap" and cfg_name == "full") else a
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **blob)
+    print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB", "value absmax %.3f" % want["value"].abs().max())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run_case("tiny_b2", "tiny", 2, 64)
     run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
     run_case("full_b2", "full", 2, 256, full=False)
     run_case("full_b3_shared", "full", 3, 256, shared_source=True, full=False)
+    run_kp_case("kp_tiny_b2", "tiny", 2, 64, audio=False)
+    run_kp_case("kp_a_tiny_b3", "tiny", 3, 64, audio=True)
+    run_kp_case("kp_full_b2", "full", 2, 256, audio=False)
+    run_kp_case("kp_a_full_b2", "full", 2, 256, audio=True)
