@@ -287,7 +287,7 @@ def test_empty_batch_returns_empty_tensors(dev):
 
 
 # ------------------------------------------------------------------ keypoint heads
-@pytest.mark.parametrize("precision,tol_v,tol_h", [("fp32_simt", 2e-5, 2e-6), ("fp32", 2e-4, 2e-5)])
+@pytest.mark.parametrize("precision,tol_v,tol_h", [("fp32_simt", 2e-5, 2e-5), ("fp32", 2e-4, 1e-4)])
 @pytest.mark.parametrize("name,cfg_name,audio", [("kp_tiny_b2", "tiny", False), ("kp_a_tiny_b3", "tiny", True),
                                                  ("kp_full_b2", "full", False), ("kp_a_full_b2", "full", True)])
 def test_kp_detector_heads_match_reference_golden(dev, precision, tol_v, tol_h, name, cfg_name, audio):
