@@ -785,8 +785,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   for (int k = 4; k >= 2; --k)
     if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
   if (ksub == 1 && 2u * chunk_bytes * 3u <= ring_bytes && kc_total >= 2 && p.BN < 256) ksub = 2;
-  if (p.cta2) ksub = 1;
+  static int cta2_ksub_env = -1;
+  if (cta2_ksub_env < 0) { const char* e = getenv("EAMM_TC_CTA2_KSUB"); cta2_ksub_env = e ? atoi(e) : 1; }
+  if (p.cta2) ksub = cta2_ksub_env > 0 ? cta2_ksub_env : 1;
   if (ksub_env > 0) ksub = ksub_env;
+  while (ksub > 1 && (uint32_t)ksub * chunk_bytes * 2u > ring_bytes) --ksub;      // keep at least two stages
   p.ksub = ksub;
   const uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
   int stages = (int)(ring_bytes / stage_bytes);

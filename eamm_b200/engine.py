@@ -521,8 +521,9 @@ class DenseMotionEngine:
         self.ws[key] = ws
         return ws
 
-    def run(self, source_image, kp_driving, kp_source, src_n_stride=None):
-        """Launch the dense-motion kernels on the current stream; returns the reference's out_dict."""
+    def run(self, source_image, kp_driving, kp_source, src_n_stride=None, reuse_small=False):
+        """Launch the dense-motion kernels on the current stream; returns the reference's out_dict.
+        reuse_small: the anti-aliased source of the previous call is still valid (generator source cache)."""
         m, lib = self.m, self.lib
         B, Cc, H, W = source_image.shape
         ws = self.workspace(B, H, W)
@@ -542,7 +543,9 @@ class DenseMotionEngine:
         # a3 anti-alias downsample -> small [B,h,w,4]
         n_small = 1 if (src_n_stride == 0 and B > 1) else B
         small_stride = 0 if n_small == 1 and B > 1 else h * w * 4
-        if self.step != 1:
+        if self.step != 1 and reuse_small:
+            pass
+        elif self.step != 1:
             _launch("aa_downsample", lambda: L.check(
                 lib.eamm_aa_downsample(source_image.data_ptr(), src_n_stride, ws.small.data_ptr(), n_small, H, W,
                                        self.step, self.g1.data_ptr(), st), "aa_downsample"),
@@ -701,24 +704,34 @@ class GeneratorEngine:
         st = current_stream_ptr()
         dev = self.device
         nsrc = 1 if shared else B
-        # encoder (generator.py:61-63); with a shared (stride-0) source it runs once and is broadcast
+        # encoder (generator.py:61-63); with a shared (stride-0) source it runs once and is broadcast.
+        # Opt-in (`generator.cache_source = True`): when the very same source tensor (storage, version
+        # counter, shape) comes back -- demo.py:279 passes one `source` for every frame of a clip -- the
+        # kp-independent encoder maps and the anti-aliased copy are reused instead of recomputed.
+        src_key = None
+        if getattr(m, "cache_source", False):
+            src_key = (source_image.data_ptr(), source_image._version, tuple(source_image.shape),
+                       tuple(source_image.stride()), B, H, W)
+        reuse = src_key is not None and getattr(ws, "src_key", None) == src_key
         esz = 4 if self.mode != "bf16" else 2
-        if self.first_packed:
-            self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed, ws.enc[0].act(c=self.first.cout, n=nsrc))
-        else:
-            src_act = ws.src.act(n=nsrc)
-            _launch("nchw_to_act", lambda: L.check(
-                lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(src_act), st), "nchw_to_act"),
-                nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
-            self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
-        for i, layer in enumerate(self.down):
-            layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
+        if not reuse:
+            if self.first_packed:
+                self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed, ws.enc[0].act(c=self.first.cout, n=nsrc))
+            else:
+                src_act = ws.src.act(n=nsrc)
+                _launch("nchw_to_act", lambda: L.check(
+                    lib.eamm_nchw_to_act(src.data_ptr(), nsrc, Cc, H, W, C.byref(src_act), st), "nchw_to_act"),
+                    nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
+                self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
+            for i, layer in enumerate(self.down):
+                layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
+        ws.src_key = src_key
         result = {}
         feat = ws.enc[-1]
         blocks = self.res
         if self.dm is not None:
             dmo, dws = self.dm.run(src.expand(B, -1, -1, -1) if shared else src, kp_driving, kp_source,
-                                   src_n_stride=src_n_stride)
+                                   src_n_stride=src_n_stride, reuse_small=reuse)
             self.last_dm = dmo
             result["mask"] = dmo["mask"]
             result["sparse_deformed"] = dmo["sparse_deformed"]

@@ -43,6 +43,9 @@ class OcclusionAwareGenerator(_EngineMixin, nn.Module):
         self.final = nn.Conv2d(block_expansion, num_channels, kernel_size=(7, 7), padding=(3, 3))
         self.estimate_occlusion_map = estimate_occlusion_map
         self.num_channels = num_channels
+        # opt-in: reuse the encoder feature maps while the caller keeps passing the same source tensor
+        # (same storage, same version counter) -- what demo.py:279 does for a whole clip
+        self.cache_source = False
         self._init_engine_state()
 
     def forward(self, source_image, kp_driving, kp_source):
