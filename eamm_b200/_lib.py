@@ -29,6 +29,12 @@ class Kp(C.Structure):
                 ("jacobian_stride", C.c_int64)]
 
 
+class OneEuro(C.Structure):
+    """eamm_one_euro."""
+    _fields_ = [("mincutoff", C.c_float), ("beta", C.c_float), ("dcutoff", C.c_float), ("freq", C.c_float),
+                ("scale", C.c_float)]
+
+
 class ConvArgs(C.Structure):
     """eamm_conv_args."""
     _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
@@ -49,6 +55,10 @@ _PROTOS = {
                                          C.POINTER(Act), C.c_void_p]),
     "eamm_kp_head": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eamm_kp_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.POINTER(OneEuro), C.POINTER(OneEuro), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
     "eamm_kp_stage": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_float,
                                 C.POINTER(Act), C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_flow_combine": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_int, C.c_int,

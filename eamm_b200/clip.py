@@ -1,0 +1,56 @@
+"""Per-clip keypoint glue on the device.
+
+`smooth_and_normalize` is the batched equivalent of demo.py:228-278: One-Euro smoothing of the per-frame
+detector outputs, the emotion-row accumulation and `normalize_kp`, for all T frames in one kernel.  Its
+result feeds `OcclusionAwareGenerator.forward` as a batch of T driving keypoints.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import current_stream_ptr
+
+EMO_ROWS = ((1, 0, 0.2), (4, 1, 1.0), (6, 2, 1.0))       # demo.py:266-271 ('linear_3')
+KP_FILTER = (0.05, 8.0, 1.0, 100.0, 10.0)                 # mincutoff, beta, dcutoff, freq, scale (demo.py:241-245)
+EMO_FILTER = (1.0, 0.2, 1.0, 100.0, 100.0)                # demo.py:231-236
+
+
+def movement_scale(kp_source, kp_driving_initial):
+    """sqrt(area(source hull)) / sqrt(area(initial driving hull)), demo.py:114-117 (host side, once per clip)."""
+    from scipy.spatial import ConvexHull
+    sa = ConvexHull(kp_source["value"][0].detach().cpu().numpy()).volume
+    da = ConvexHull(kp_driving_initial["value"][0].detach().cpu().numpy()).volume
+    return float(np.sqrt(sa) / np.sqrt(da))
+
+
+def smooth_and_normalize(kp_driving_all, kp_source, kp_driving_initial, emo_driving_all=None, relative=True,
+                         scale=1.0, emo_rows=EMO_ROWS):
+    """kp_driving_all / emo_driving_all: {'value': [T,K,2], 'jacobian': [T,K,2,2]} CUDA fp32 (the stacked
+    per-frame detector outputs); kp_source / kp_driving_initial: batch-1 dicts.  Returns the batch of T
+    normalised driving keypoints."""
+    dv, dj = kp_driving_all["value"].contiguous(), kp_driving_all["jacobian"].contiguous()
+    if dv.device.type != "cuda" or dv.dtype != torch.float32:
+        raise RuntimeError("eamm_b200: keypoints must be fp32 CUDA tensors")
+    T, K = dv.shape[:2]
+    lib = L.load()
+    dev = dv.device
+    out_v, out_j = torch.empty_like(dv), torch.empty_like(dj)
+    ev = ej = scratch = rows = gains = None
+    Ke = 0
+    if emo_driving_all is not None:
+        ev, ej = emo_driving_all["value"].contiguous(), emo_driving_all["jacobian"].contiguous()
+        Ke = ev.shape[1]
+        scratch = torch.empty(T * Ke * 6, dtype=torch.float32, device=dev)
+        rows = torch.tensor([[d, s] for d, s, _ in emo_rows], dtype=torch.int32, device=dev)
+        gains = torch.tensor([g for _, _, g in emo_rows], dtype=torch.float32, device=dev)
+    fk, fe = L.OneEuro(*KP_FILTER), L.OneEuro(*EMO_FILTER)
+    sv, sj = kp_source["value"][:1].contiguous(), kp_source["jacobian"][:1].contiguous()
+    iv, ij = kp_driving_initial["value"][:1].contiguous(), kp_driving_initial["jacobian"][:1].contiguous()
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        L.check(lib.eamm_kp_clip(p(dv), p(dj), p(ev), p(ej), T, K, Ke, C.byref(fk), C.byref(fe), p(rows), p(gains),
+                                 len(emo_rows) if ev is not None else 0, p(sv), p(sj), p(iv), p(ij), float(scale),
+                                 1 if relative else 0, p(out_v), p(out_j), p(scratch), current_stream_ptr()), "kp_clip")
+    return {"value": out_v, "jacobian": out_j}

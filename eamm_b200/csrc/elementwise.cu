@@ -508,6 +508,92 @@ kp_head_kernel(const float* __restrict__ logits, int ldl, int h, int w, int K, i
   }
 }
 
+// =============================================================================================
+// per-clip keypoint glue  (filter1.py:14-47, demo.py:231-248, :263-271, :112-132)
+// One block.  Phase A: one thread per scalar series (K*2 values + K*4 jacobian entries, same for the
+// emotion keypoints) runs the One-Euro filter over the T frames -- the only sequential dependency of the
+// clip.  Phase B: one thread per (frame, keypoint) adds the emotion rows and applies normalize_kp.
+// Arithmetic mirrors the reference's float32 steps (separate multiplies/adds, IEEE division).
+// =============================================================================================
+struct OneEuroDev { float mincutoff, beta, alpha_d, one_minus_alpha_d, freq, scale, two_pi, te; };
+
+__device__ __forceinline__ void one_euro_series(const float* __restrict__ in, float* __restrict__ out, int T, int stride,
+                                                const OneEuroDev f) {
+  float prev_x = 0.f, prev_dx = 0.f, prev_xf = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float x = __fmul_rn(in[(long long)t * stride], f.scale);
+    float xf;
+    if (t == 0) { xf = x; prev_dx = 0.f; }
+    else {
+      const float dx = __fmul_rn(__fsub_rn(x, prev_x), f.freq);
+      const float edx = __fadd_rn(__fmul_rn(f.alpha_d, dx), __fmul_rn(f.one_minus_alpha_d, prev_dx));
+      prev_dx = edx;
+      const float cutoff = __fadd_rn(f.mincutoff, __fmul_rn(f.beta, fabsf(edx)));
+      const float tau = __fdiv_rn(1.0f, __fmul_rn(f.two_pi, cutoff));
+      const float a = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fdiv_rn(tau, f.te)));
+      xf = __fadd_rn(__fmul_rn(a, x), __fmul_rn(__fsub_rn(1.0f, a), prev_xf));
+    }
+    prev_x = x; prev_xf = xf;
+    out[(long long)t * stride] = __fdiv_rn(xf, f.scale);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kp_clip_kernel(const float* __restrict__ drv_value, const float* __restrict__ drv_jac,
+               const float* __restrict__ emo_value, const float* __restrict__ emo_jac, int T, int K, int Ke,
+               OneEuroDev f_kp, OneEuroDev f_emo, const int* __restrict__ emo_rows, const float* __restrict__ emo_gain,
+               int n_rows, const float* __restrict__ src_value, const float* __restrict__ src_jac,
+               const float* __restrict__ init_value, const float* __restrict__ init_jac, float movement_scale,
+               int relative, float* __restrict__ out_value, float* __restrict__ out_jac, float* __restrict__ emo_scratch) {
+  // ---- phase A: filters (note filter1.py: the very first frame passes through, dx of frame 0 is 0 and is
+  // fed to the dx low-pass as its initial state)
+  const int nkp = K * 6, nemo = (emo_value != nullptr) ? Ke * 6 : 0;
+  for (int e = threadIdx.x; e < nkp + nemo; e += blockDim.x) {
+    if (e < nkp) {
+      if (e < K * 2) one_euro_series(drv_value + e, out_value + e, T, K * 2, f_kp);
+      else one_euro_series(drv_jac + (e - K * 2), out_jac + (e - K * 2), T, K * 4, f_kp);
+    } else {
+      const int q = e - nkp;
+      if (q < Ke * 2) one_euro_series(emo_value + q, emo_scratch + q, T, Ke * 2, f_emo);
+      else one_euro_series(emo_jac + (q - Ke * 2), emo_scratch + (long long)T * Ke * 2 + (q - Ke * 2), T, Ke * 4, f_emo);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: emotion rows + normalize_kp
+  for (int idx = threadIdx.x; idx < T * K; idx += blockDim.x) {
+    const int t = idx / K, k = idx % K;
+    float v[2] = {out_value[(long long)idx * 2], out_value[(long long)idx * 2 + 1]};
+    float j[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) j[c] = out_jac[(long long)idx * 4 + c];
+    if (nemo) {
+      for (int r = 0; r < n_rows; ++r) {
+        if (emo_rows[2 * r] == k) {
+          const int s = emo_rows[2 * r + 1];
+          const float g = emo_gain[r];
+          const float* ev = emo_scratch + ((long long)t * Ke + s) * 2;
+          const float* ej = emo_scratch + (long long)T * Ke * 2 + ((long long)t * Ke + s) * 4;
+          v[0] = __fadd_rn(v[0], __fmul_rn(ev[0], g)); v[1] = __fadd_rn(v[1], __fmul_rn(ev[1], g));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) j[c] = __fadd_rn(j[c], __fmul_rn(ej[c], g));
+        }
+      }
+    }
+    if (relative) {
+      v[0] = __fadd_rn(__fmul_rn(__fsub_rn(v[0], init_value[k * 2]), movement_scale), src_value[k * 2]);
+      v[1] = __fadd_rn(__fmul_rn(__fsub_rn(v[1], init_value[k * 2 + 1]), movement_scale), src_value[k * 2 + 1]);
+      float M[4];
+      kp_affine(init_jac + k * 4, j, M);                  // M = j * inv(init)
+      const float* sj = src_jac + k * 4;
+      j[0] = M[0] * sj[0] + M[1] * sj[2]; j[1] = M[0] * sj[1] + M[1] * sj[3];
+      j[2] = M[2] * sj[0] + M[3] * sj[2]; j[3] = M[2] * sj[1] + M[3] * sj[3];
+    }
+    out_value[(long long)idx * 2] = v[0]; out_value[(long long)idx * 2 + 1] = v[1];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out_jac[(long long)idx * 4 + c] = j[c];
+  }
+}
+
 static inline KpDev to_dev(const eamm_kp* k) {
   KpDev d; d.value = k->value; d.jac = k->jacobian; d.vs = k->value_stride; d.js = k->jacobian_stride;
   return d;
@@ -682,6 +768,35 @@ extern "C" int eamm_kp_head(const float* logits, int ldl, int n, int h, int w, i
   if (hh < 2 || ww < 2) return EAMM_ERR_SHAPE;
   kp_head_kernel<<<n, KH_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, h, w, num_kp, num_jac_maps, off, hh, ww,
                                                               1.f / temperature, heatmap, value, jacobian);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+static OneEuroDev one_euro_dev(const eamm_one_euro* f) {
+  // compute_alpha(dcutoff) is evaluated in double by the reference (python floats) and then multiplies fp32 tensors
+  const double te = 1.0 / (double)f->freq;
+  const double tau = 1.0 / (2.0 * 3.141592653589793 * (double)f->dcutoff);
+  const double a_d = 1.0 / (1.0 + tau / te);
+  OneEuroDev d;
+  d.mincutoff = f->mincutoff; d.beta = f->beta; d.alpha_d = (float)a_d; d.one_minus_alpha_d = (float)(1.0 - a_d);
+  d.freq = f->freq; d.scale = f->scale; d.two_pi = (float)(2.0 * 3.141592653589793); d.te = (float)te;
+  return d;
+}
+
+extern "C" int eamm_kp_clip(const float* drv_value, const float* drv_jac, const float* emo_value, const float* emo_jac,
+                            int T, int K, int Ke, const eamm_one_euro* f_kp, const eamm_one_euro* f_emo,
+                            const int32_t* emo_rows, const float* emo_gain, int n_emo_rows, const float* src_value,
+                            const float* src_jac, const float* init_value, const float* init_jac, float movement_scale,
+                            int relative, float* out_value, float* out_jac, float* emo_scratch, void* stream) {
+  if (!drv_value || !drv_jac || !f_kp || !out_value || !out_jac || T <= 0 || K <= 0) return EAMM_ERR_ARG;
+  if (relative && (!src_value || !src_jac || !init_value || !init_jac)) return EAMM_ERR_ARG;
+  if ((emo_value == nullptr) != (emo_jac == nullptr)) return EAMM_ERR_ARG;
+  if (emo_value && (!f_emo || !emo_scratch || Ke <= 0 || n_emo_rows < 0 || (n_emo_rows && (!emo_rows || !emo_gain)))) return EAMM_ERR_ARG;
+  OneEuroDev fe = emo_value ? one_euro_dev(f_emo) : one_euro_dev(f_kp);
+  kp_clip_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(drv_value, drv_jac, emo_value, emo_jac, T, K, Ke, one_euro_dev(f_kp), fe,
+                                                      emo_rows, emo_gain, emo_value ? n_emo_rows : 0, src_value, src_jac,
+                                                      init_value, init_jac, movement_scale, relative, out_value, out_jac,
+                                                      emo_scratch);
   EAMM_LAUNCH_CHECK();
   return 0;
 }

@@ -122,6 +122,18 @@ def make_kp_inputs(cfg, batch, size, audio, seed=5):
     return torch.rand(batch, cfg["num_channels"], size, size, generator=g)
 
 
+def make_clip_inputs(T=12, K=10, Ke=4, seed=7):
+    """Seeded per-frame detector outputs of a clip: driving kp [T,K,...], emotion kp [T,Ke,...], source and
+    initial-driving keypoints (batch 1).  Shapes follow demo.py:206-228."""
+    g = torch.Generator().manual_seed(seed)
+    eye = torch.eye(2).view(1, 1, 2, 2)
+    drv = {"value": torch.rand(T, K, 2, generator=g) * 1.2 - 0.6, "jacobian": eye + 0.1 * torch.randn(T, K, 2, 2, generator=g)}
+    emo = {"value": torch.randn(T, Ke, 2, generator=g) * 0.05, "jacobian": 0.05 * torch.randn(T, Ke, 2, 2, generator=g)}
+    src = {"value": torch.rand(1, K, 2, generator=g) * 1.2 - 0.6, "jacobian": eye + 0.1 * torch.randn(1, K, 2, 2, generator=g)}
+    init = {"value": drv["value"][:1].clone(), "jacobian": drv["jacobian"][:1].clone()}
+    return drv, emo, src, init
+
+
 def aa_kernel(channels, sigma=1.5):
     """The fixed 13x13 Gaussian buffer of AntiAliasInterpolation2d (util.py:1012-1036)."""
     ks = 2 * round(sigma * 4) + 1

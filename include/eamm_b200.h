@@ -126,6 +126,21 @@ int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, int n, int H,
 int eamm_kp_head(const float* logits, int ldl, int n, int h, int w, int num_kp, int num_jac_maps, int pad,
                  float temperature, float* heatmap, float* value, float* jacobian, void* stream);
 
+/* ---- per-clip keypoint glue between the detector and the generator ------
+ * One-Euro smoothing of the detector outputs over the T frames of a clip (filter1.py:14-47 as driven by
+ * demo.py:231-248), emotion-row accumulation (demo.py:263-271: kp row emo_rows[2r] += gain[r] * emotion row
+ * emo_rows[2r+1]) and normalize_kp with relative movement/jacobian (demo.py:112-132; `movement_scale` is the
+ * ConvexHull ratio of :114-117, computed on the host once per clip).  All arrays fp32 on the device:
+ * drv_value [T,K,2], drv_jac [T,K,2,2], emo_* [T,Ke,...] or NULL, src_/init_ [K,...]; outputs [T,K,2], [T,K,2,2];
+ * emo_scratch [T*Ke*6].  Removes the per-frame device<->host round trips of demo.py:235-248 and lets the
+ * generator run batched over T. */
+typedef struct { float mincutoff, beta, dcutoff, freq, scale; } eamm_one_euro;
+int eamm_kp_clip(const float* drv_value, const float* drv_jac, const float* emo_value, const float* emo_jac,
+                 int T, int K, int Ke, const eamm_one_euro* f_kp, const eamm_one_euro* f_emo,
+                 const int32_t* emo_rows, const float* emo_gain, int n_emo_rows, const float* src_value,
+                 const float* src_jac, const float* init_value, const float* init_jac, float movement_scale,
+                 int relative, float* out_value, float* out_jac, float* emo_scratch, void* stream);
+
 /* ---- a4+a5+a6: heatmaps, sparse motions, deformed source (dense_motion.py:32-79, util.py:815-855)
  * small [n,h,w,4] fp32 from eamm_aa_downsample (small_n_stride 0 = shared source);
  * writes the (K+1)*4-channel hourglass input (channel order [hm_k,R_k,G_k,B_k], dense_motion.py:93-94,

@@ -336,3 +336,25 @@ def test_source_cache_and_cuda_graph_replay_equal_eager(dev):
         got = graphed(s, to_dev(kd, dev), ks)["prediction"]
         torch.cuda.synchronize()
         assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------ per-clip keypoint glue
+@pytest.mark.parametrize("name", ["kp_glue_emo_t12", "kp_glue_plain_t40"])
+def test_kp_clip_glue_matches_reference_golden(dev, name):
+    from eamm_b200 import clip
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    T, with_emo = [int(v) for v in blob["meta"]]
+    drv, emo, src, init = synth.make_clip_inputs(T=T)
+    out = clip.smooth_and_normalize(to_dev(drv, dev), to_dev(src, dev), to_dev(init, dev),
+                                    emo_driving_all=to_dev(emo, dev) if with_emo else None,
+                                    relative=True, scale=float(blob["scale"][0]))
+    torch.cuda.synchronize()
+    assert np.abs(out["value"].cpu().numpy() - blob["value"]).max() <= 2e-6
+    assert np.abs(out["jacobian"].cpu().numpy() - blob["jacobian"]).max() <= 5e-6
+    assert abs(clip.movement_scale(src, init) - float(blob["scale"][0])) < 1e-6
+    # the result is a valid batched kp_driving for the generator
+    gen, cfg = generator("full", dev)
+    gen.precision = "fp32"
+    img = synth.make_inputs(1, cfg, size=256, seed=1)[0].to(dev)
+    res = gen(img.expand(T, -1, -1, -1), kp_driving=out, kp_source={k: v.expand(T, *v.shape[1:]) for k, v in to_dev(src, dev).items()})
+    assert res["prediction"].shape == (T, 3, 256, 256) and torch.isfinite(res["prediction"]).all()

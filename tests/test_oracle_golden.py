@@ -87,3 +87,18 @@ def test_kp_detector_oracle_reproduces_reference_golden(name, cfg_name, audio):
         sub = a[..., ::2, ::2] if (k == "heatmap" and cfg_name == "full") else a
         np.testing.assert_allclose(sub, blob[k], rtol=0, atol=2e-6, err_msg=k)
     assert np.allclose(got["heatmap"].sum((2, 3)).numpy(), 1.0, atol=1e-5)       # each heatmap is a distribution
+
+
+@pytest.mark.parametrize("name", ["kp_glue_emo_t12", "kp_glue_plain_t40"])
+def test_kp_glue_oracle_reproduces_reference_golden(name):
+    """One-Euro smoothing + emotion rows + normalize_kp over a clip (demo.py:228-278)."""
+    from oracle import kp_glue
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    T, with_emo = [int(v) for v in blob["meta"]]
+    drv, emo, src, init = synth.make_clip_inputs(T=T)
+    v, j = kp_glue.clip_glue(drv["value"], drv["jacobian"], emo["value"] if with_emo else None,
+                             emo["jacobian"] if with_emo else None, src, init, movement_scale=float(blob["scale"][0]))
+    np.testing.assert_array_equal(v.numpy(), blob["value"])
+    np.testing.assert_array_equal(j.numpy(), blob["jacobian"])
+    # the filter starts from the first frame and the smoothed track stays within the raw track's range
+    assert v.shape == (T, 10, 2) and j.shape == (T, 10, 2, 2)

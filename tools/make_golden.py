@@ -92,6 +92,54 @@ def run_kp_case(name, cfg_name, batch, size, audio):
     print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB", "value absmax %.3f" % want["value"].abs().max())
 
 
+def run_glue_case(name, T, with_emo):
+    """execute the reference's own OneEuroFilter (filter1.py) and normalize_kp (demo.py)
+    source text on a seeded clip, following demo.py:228-278, and pin oracle/kp_glue.py to it bit-for-bit."""
+    from scipy.spatial import ConvexHull
+    from oracle import kp_glue
+    txt = open("/root/reference/filter1.py").read()
+    ns = {"np": np}
+    exec(txt[txt.index("class LowPassFilter"):], ns)
+    one_euro = ns["OneEuroFilter"]
+    demo = open("/root/reference/demo.py").read()
+    a = demo.index("def normalize_kp(")
+    ns2 = {"np": np, "torch": torch, "ConvexHull": ConvexHull}
+    exec(demo[a:demo.index("\ndef ", a + 10)], ns2)
+    drv, emo, src, init = synth.make_clip_inputs(T=T)
+    kp_all = [{k: v[t:t + 1].clone() for k, v in drv.items()} for t in range(T)]
+    emo_all = [{k: v[t:t + 1].clone() for k, v in emo.items()} for t in range(T)]
+    if with_emo:                                                     # demo.py:231-238
+        fv, fj = one_euro(mincutoff=1, beta=0.2, dcutoff=1.0, freq=100), one_euro(mincutoff=1, beta=0.2, dcutoff=1.0, freq=100)
+        for j in range(T):
+            emo_all[j]["value"] = fv.process(emo_all[j]["value"] * 100) / 100
+            emo_all[j]["jacobian"] = fj.process(emo_all[j]["jacobian"] * 100) / 100
+    fv, fj = one_euro(mincutoff=0.05, beta=8, dcutoff=1.0, freq=100), one_euro(mincutoff=0.05, beta=8, dcutoff=1.0, freq=100)
+    for j in range(T):                                               # demo.py:241-248
+        kp_all[j]["value"] = fv.process(kp_all[j]["value"] * 10) / 10
+        kp_all[j]["jacobian"] = fj.process(kp_all[j]["jacobian"] * 10) / 10
+    rv, rj = [], []
+    for t in range(T):                                               # demo.py:251-278
+        kd, em = kp_all[t], emo_all[t]
+        if with_emo:
+            kd["value"][:, 1] = kd["value"][:, 1] + em["value"][:, 0] * 0.2
+            kd["jacobian"][:, 1] = kd["jacobian"][:, 1] + em["jacobian"][:, 0] * 0.2
+            kd["value"][:, 4] = kd["value"][:, 4] + em["value"][:, 1]
+            kd["jacobian"][:, 4] = kd["jacobian"][:, 4] + em["jacobian"][:, 1]
+            kd["value"][:, 6] = kd["value"][:, 6] + em["value"][:, 2]
+            kd["jacobian"][:, 6] = kd["jacobian"][:, 6] + em["jacobian"][:, 2]
+        n = ns2["normalize_kp"](kp_source=src, kp_driving=kd, kp_driving_initial=init, use_relative_movement=True,
+                                use_relative_jacobian=True, adapt_movement_scale=True)
+        rv.append(n["value"]); rj.append(n["jacobian"])
+    rv, rj = torch.cat(rv), torch.cat(rj)
+    scale = float(np.sqrt(ConvexHull(src["value"][0].numpy()).volume) / np.sqrt(ConvexHull(init["value"][0].numpy()).volume))
+    ov, oj = kp_glue.clip_glue(drv["value"], drv["jacobian"], emo["value"] if with_emo else None,
+                               emo["jacobian"] if with_emo else None, src, init, movement_scale=scale, relative=True)
+    assert torch.equal(ov, rv) and torch.equal(oj, rj), name + ": oracle != reference"
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, meta=np.array([T, int(with_emo)]), scale=np.array([scale]), value=rv.numpy(), jacobian=rj.numpy())
+    print(name, "ok ->", path, "scale %.6f" % scale)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run_case("tiny_b2", "tiny", 2, 64)
@@ -102,3 +150,5 @@ if __name__ == "__main__":
     run_kp_case("kp_a_tiny_b3", "tiny", 3, 64, audio=True)
     run_kp_case("kp_full_b2", "full", 2, 256, audio=False)
     run_kp_case("kp_a_full_b2", "full", 2, 256, audio=True)
+    run_glue_case("kp_glue_emo_t12", 12, True)
+    run_glue_case("kp_glue_plain_t40", 40, False)
