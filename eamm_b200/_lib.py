@@ -42,7 +42,7 @@ class ConvArgs(C.Structure):
                 ("residual", C.POINTER(Act)), ("out", C.POINTER(Act)), ("out2", C.POINTER(Act)),
                 ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("out_nchw", C.c_void_p),
                 ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32),
-                ("weight_fold", C.c_int32)]
+                ("weight_fold", C.c_int32), ("out_u8_nhwc", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/eamm_b200.h

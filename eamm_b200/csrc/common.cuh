@@ -118,6 +118,11 @@ __device__ __forceinline__ Bilinear bilinear_setup(float gx, float gy, int W, in
   return b;
 }
 
+// skimage.img_as_ubyte of a float32 image value in [0,1]: rint(v * 255) (round half to even), clipped to [0,255]
+__device__ __forceinline__ unsigned char to_ubyte(float v) {
+  return (unsigned char)fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f);
+}
+
 // J = J_s * inv(J_d) for one keypoint (dense_motion.py:56); closed-form 2x2 inverse.
 // Returns false when J_d is singular (torch.inverse raises there).
 __device__ __forceinline__ bool kp_affine(const float* jd, const float* js, float* J) {

@@ -22,6 +22,7 @@ struct ConvSimtParams {
   const float* shift2;
   float* out_nchw;
   float* out_nhwc;
+  unsigned char* out_u8;
   int kind, flags, cin, cout, taps, ksize, out_nchw_c;
   int has_out, has_out2, has_res;
   long long quads;     // n * (h/2) * (w/2)
@@ -147,6 +148,7 @@ conv_simt_kernel(ConvSimtParams p) {
           float o = vv[j];
           if (p.flags & EAMM_EPI_SIGMOID) o = 1.f / (1.f + expf(-o));
           p.out_nchw[(((long long)n * p.out_nchw_c + co + j) * OH + oy) * OW + ox] = o;
+          if (p.out_u8 != nullptr) p.out_u8[(((long long)n * OH + oy) * OW + ox) * p.out_nchw_c + co + j] = to_ubyte(o);
         }
       }
     }
@@ -176,6 +178,7 @@ int conv_check_args(const eamm_conv_args* a, int cout_align) {
   if (a->out2 && (!a->scale2 || !a->shift2)) return EAMM_ERR_ARG;
   if (a->out_nchw && (a->out_nchw_c <= 0 || a->out_nchw_c > a->cout)) return EAMM_ERR_SHAPE;
   if ((a->flags & EAMM_EPI_SIGMOID) && !a->out_nchw) return EAMM_ERR_UNSUPPORTED;
+  if (a->out_u8_nhwc && !a->out_nchw) return EAMM_ERR_ARG;
   if (!a->out && !a->out2 && !a->out_nchw && !a->out_nhwc_f32) return EAMM_ERR_ARG;
   return 0;
 }
@@ -197,6 +200,7 @@ extern "C" int eamm_conv_simt(const eamm_conv_args* a, void* stream) {
   p.w = static_cast<const float*>(a->weight);
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nhwc = a->out_nhwc_f32; p.out_nchw_c = a->out_nchw_c;
+  p.out_u8 = a->out_u8_nhwc;
   p.kind = a->kind; p.flags = a->flags; p.cin = a->cin; p.cout = a->cout;
   p.ksize = a->kind == EAMM_CONV_7X7 ? 7 : 3;
   p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : p.ksize * p.ksize;

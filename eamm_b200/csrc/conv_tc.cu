@@ -60,7 +60,7 @@ struct ConvTcParams {
   int has_out, has_out2, has_res;
   ActView out, out2, res;
   const float* bias; const float* scale2; const float* shift2;
-  float* out_nchw; int out_nchw_c; float* out_nhwc;
+  float* out_nchw; int out_nchw_c; float* out_nhwc; unsigned char* out_u8;
   long long total_tiles;
 };
 
@@ -318,6 +318,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
             float o = f[j];
             if (p.flags & EAMM_EPI_SIGMOID) o = 1.f / (1.f + expf(-o));
             p.out_nchw[(((long long)n * p.out_nchw_c + co + j) * OH + oy) * OW + ox] = o;
+            if (p.out_u8 != nullptr) p.out_u8[(((long long)n * OH + oy) * OW + ox) * p.out_nchw_c + co + j] = to_ubyte(o);
           }
         }
       }
@@ -352,6 +353,7 @@ __device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCo
       for (int kx = 0; kx < 7; ++kx) acc += S[(r + kx) * 29 + kx * 4 + co];
       if (p.flags & EAMM_EPI_SIGMOID) acc = 1.f / (1.f + expf(-acc));
       p.out_nchw[(((long long)tc.n0 * p.out_nchw_c + co) * p.H + tc.y0) * p.W + x] = acc;
+      if (p.out_u8 != nullptr) p.out_u8[(((long long)tc.n0 * p.H + tc.y0) * p.W + x) * p.out_nchw_c + co] = to_ubyte(acc);
     }
   }
 }
@@ -803,7 +805,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.out2 = p.has_out2 ? make_view(a->out2) : dummy;
   p.res = p.has_res ? make_view(a->residual) : dummy;
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
-  p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32;
+  p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
   if (p.total_tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
 

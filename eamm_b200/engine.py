@@ -252,13 +252,15 @@ class ConvLayer:
             self.shift2[:cout] = shift2
 
     def launch(self, lib, stream, inp, out=None, out2=None, residual=None, out_nchw=None, out_nchw_c=0,
-               out_nhwc_f32=None):
+               out_nhwc_f32=None, out_u8=None):
         a = L.ConvArgs()
         a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
         a.inp = C.pointer(inp)
         a.weight = self.weight.data_ptr()
         a.bias = self.bias.data_ptr()
         self._fill_outputs(a, out, out2, residual, out_nchw, out_nchw_c, out_nhwc_f32)
+        if out_u8 is not None:
+            a.out_u8_nhwc = out_u8.data_ptr()
         if self.impl != "simt":
             key = (inp.n, inp.h, inp.w, out_nchw_c if out_nchw is not None else -1, out is not None,
                    out_nhwc_f32 is not None)
@@ -778,7 +780,10 @@ class GeneratorEngine:
             x = ws.dec[i]
         # final conv + sigmoid (generator.py:92-93)
         pred = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
-        self.final.launch(lib, st, x.act(), out_nchw=pred, out_nchw_c=Cc)
+        pred_u8 = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=dev) if getattr(m, "emit_u8", False) else None
+        self.final.launch(lib, st, x.act(), out_nchw=pred, out_nchw_c=Cc, out_u8=pred_u8)
         result["prediction"] = pred
+        if pred_u8 is not None:
+            result["prediction_u8"] = pred_u8      # [B,H,W,C] frames as demo.py:281,507 builds them on the host
         self._keep = src
         return result

@@ -46,6 +46,9 @@ class OcclusionAwareGenerator(_EngineMixin, nn.Module):
         # opt-in: reuse the encoder feature maps while the caller keeps passing the same source tensor
         # (same storage, same version counter) -- what demo.py:279 does for a whole clip
         self.cache_source = False
+        # opt-in: also return 'prediction_u8' [B,H,W,C] uint8 = img_as_ubyte(prediction), the
+        # frames demo.py:281,507 assembles on the host; written by the final conv's epilogue
+        self.emit_u8 = False
         self._init_engine_state()
 
     def forward(self, source_image, kp_driving, kp_source):

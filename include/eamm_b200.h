@@ -97,6 +97,9 @@ typedef struct {
   int32_t pack_passes;     /* EAMM_CONV_ROW7_PACKED only: 1 (bf16) or 2 (hi/lo split) weight passes */
   int32_t weight_fold;     /* eamm_conv_tc: the scheme `weight` was packed for, must equal
                               eamm_conv_tc_fold(...) for this layer (0 when not folded)         */
+  uint8_t* out_u8_nhwc;    /* optional, only together with out_nchw: [n, H, W, out_nchw_c] uint8 frames,
+                              clip(rint(y * 255), 0, 255) of the value written to out_nchw -- skimage
+                              img_as_ubyte of a float image in [0,1] (demo.py:281,507) */
 } eamm_conv_args;
 
 /* ---- library info --------------------------------------------------------------------------- */

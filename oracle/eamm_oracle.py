@@ -260,3 +260,13 @@ def kp_detector_a_forward(sd, cfg, feature_map):
     """KPDetector_a.forward, keypoint_detector.py:180-205: heads only (its predictor is never called)."""
     with torch.no_grad():
         return kp_heads(feature_map, sd, cfg)
+
+
+def frames_u8(prediction):
+    """What demo.py does with `out['prediction']` before writing the video: :281 NCHW -> NHWC, :507
+    `skimage.img_as_ubyte` (scikit-image is an unpinned, un-vendored dependency, requirements.txt:9; absent
+    here).  Published semantics of skimage.util.dtype._convert for a float32 image in [-1, 1] -> uint8:
+    multiply by 255 in float32, np.rint (round half to even), clip to [0, 255], cast."""
+    import numpy as np
+    a = prediction.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)
+    return torch.from_numpy(np.clip(np.rint(a * np.float32(255.0)), 0, 255).astype(np.uint8))

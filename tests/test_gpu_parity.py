@@ -358,3 +358,22 @@ def test_kp_clip_glue_matches_reference_golden(dev, name):
     img = synth.make_inputs(1, cfg, size=256, seed=1)[0].to(dev)
     res = gen(img.expand(T, -1, -1, -1), kp_driving=out, kp_source={k: v.expand(T, *v.shape[1:]) for k, v in to_dev(src, dev).items()})
     assert res["prediction"].shape == (T, 3, 256, 256) and torch.isfinite(res["prediction"]).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_u8_frame_output_matches_img_as_ubyte(dev, precision):
+    """optional uint8 NHWC frames from the final conv's epilogue."""
+    from oracle import eamm_oracle as oracle
+    gen, cfg = generator("full", dev)
+    gen.precision = precision
+    src, kpd, kps = synth.make_inputs(2, cfg, size=256, seed=70)
+    gen.emit_u8 = True
+    try:
+        out = gen(src.to(dev), kp_driving=to_dev(kpd, dev), kp_source=to_dev(kps, dev))
+    finally:
+        gen.emit_u8 = False
+    u8 = out["prediction_u8"].cpu()
+    assert u8.dtype == torch.uint8 and u8.shape == (2, 256, 256, 3)
+    assert torch.equal(u8, oracle.frames_u8(out["prediction"].cpu()))          # exact w.r.t. our own fp32 prediction
+    want = oracle.frames_u8(oracle.generator_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps)["prediction"])
+    assert (u8.int() - want.int()).abs().max() <= 1                            # at most one grey level vs the reference
