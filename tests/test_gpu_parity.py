@@ -377,3 +377,46 @@ def test_u8_frame_output_matches_img_as_ubyte(dev, precision):
     assert torch.equal(u8, oracle.frames_u8(out["prediction"].cpu()))          # exact w.r.t. our own fp32 prediction
     want = oracle.frames_u8(oracle.generator_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps)["prediction"])
     assert (u8.int() - want.int()).abs().max() <= 1                            # at most one grey level vs the reference
+
+
+def test_whole_clip_chain_matches_oracle_chain(dev):
+    """Detector heads -> clip glue -> generator (shared source, batched over T) -> uint8 frames, i.e. the widened
+    path of demo.py:206-281 for one clip, against the same chain evaluated with the CPU oracles."""
+    from eamm_b200 import clip
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    from oracle import eamm_oracle as oracle, kp_glue
+    T = 6
+    cfg = get_config("full")
+    kcfg, acfg = get_kp_config("full"), get_kp_config("full", audio=True)
+    sd, ksd, asd = synth.make_state_dict(cfg, seed=0), synth.make_kp_state_dict(kcfg, seed=2), synth.make_kp_state_dict(acfg, seed=3)
+    src = synth.make_inputs(1, cfg, size=256, seed=80)[0]
+    fmap = synth.make_kp_inputs(acfg, T, 256, True, seed=81) * 0.3           # stand-in for AT_net2's deco_out[:, t]
+    # ---- oracle chain (CPU)
+    o_src = oracle.kp_detector_forward(ksd, kcfg, src)
+    o_drv = oracle.kp_detector_a_forward(asd, acfg, fmap)
+    o_init = {k: o_drv[k][:1] for k in ("value", "jacobian")}
+    scale = clip.movement_scale(o_src, o_init)
+    nv, nj = kp_glue.clip_glue(o_drv["value"], o_drv["jacobian"], None, None, o_src, o_init, movement_scale=scale)
+    o_out = oracle.generator_forward(sd, cfg, src.expand(T, -1, -1, -1).contiguous(), {"value": nv, "jacobian": nj},
+                                     {k: o_src[k].expand(T, *o_src[k].shape[1:]).contiguous() for k in ("value", "jacobian")})
+    # ---- CUDA chain
+    gen, _ = generator("full", dev)
+    gen.precision = "fp32"
+    det = KPDetector(**kcfg).eval(); det.load_state_dict(ksd); det = det.to(dev); det.precision = "fp32"
+    det_a = KPDetector_a(**acfg).eval(); det_a.load_state_dict(asd); det_a = det_a.to(dev); det_a.precision = "fp32"
+    s = src.to(dev)
+    k_src = det(s)
+    k_drv = det_a(fmap.to(dev))
+    k_init = {k: k_drv[k][:1] for k in ("value", "jacobian")}
+    k_norm = clip.smooth_and_normalize(k_drv, k_src, k_init, relative=True, scale=clip.movement_scale(k_src, k_init))
+    gen.emit_u8 = True
+    try:
+        out = gen(s.expand(T, -1, -1, -1), kp_driving=k_norm,
+                  kp_source={k: k_src[k].expand(T, *k_src[k].shape[1:]) for k in ("value", "jacobian")})
+    finally:
+        gen.emit_u8 = False
+    torch.cuda.synchronize()
+    assert (k_norm["value"].cpu() - nv).abs().max() <= 5e-4
+    assert (out["prediction"].cpu() - o_out["prediction"]).abs().max() <= 2e-3     # detector error enters through the flow
+    assert (out["prediction_u8"].cpu().int() - oracle.frames_u8(o_out["prediction"]).int()).abs().max() <= 2
