@@ -12,8 +12,17 @@
 //   roles       warps 0-7 = epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant splitting
 //               the accumulator columns), warps 8-10 = TMA producers (round-robin over the ring
 //               stages), warp 11 = MMA issuer (+TMEM alloc).
-//   pipelines   smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring so the
-//               epilogue of tile i overlaps the main loop of tile i+1.
+//   pipelines   smem ring (full/empty mbarriers, 1-2 K chunks per stage) and a 2-deep TMEM accumulator
+//               ring so the epilogue of tile i overlaps the main loop of tile i+1.
+//   variants    UP2        nearest-x2 + 3x3 as four parity classes of 2x2 taps, scattered by the epilogue
+//               halo row   7x7: one 134-pixel row per ky, the 7 kx taps are row-shifted smem views
+//               kx-in-N    7x7 -> <=4 NCHW channels: the 7 kx taps are GEMM columns, epilogue sums shifts
+//               row7       7x7 over a packed <=3-channel image: K window = 8 pixels x (hi,lo) channels
+//               fold       split mode, cout <= 128: weight planes stacked along N (2 A loads, not 3)
+//               CTA pair   cout == 256: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
+//   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant, EAMM_TC_KSUB / _CTA2_KSUB force the
+//               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
+//               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
 // 2x2 convs), residual add + fused next norm1/ReLU (ResBlock2d), fp32 NHWC logits, sigmoid NCHW.
 // Reference call sites: util.py:872-880, 895-900, 915-920, 934-938; generator.py:92-93;
