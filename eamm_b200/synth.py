@@ -134,6 +134,50 @@ def make_clip_inputs(T=12, K=10, Ke=4, seed=7):
     return drv, emo, src, init
 
 
+def _linear(sd, name, cin, cout, g, gain=1.4):
+    sd[name + ".weight"] = (torch.rand(cout, cin, generator=g) * 2 - 1) * (gain * math.sqrt(3.0 / cin))
+    sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * 0.1
+
+
+def make_at_state_dict(seed=4):
+    """Seeded state dict laid out like AT_net2 (util.py:514-577) minus its unused StyleGAN2 `generator.*` branch
+    (only reached with jaco_net == 'gan'; every shipped config uses 'cnn').  35.3 M parameters."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for i in range(8):                                          # util.py:518-522
+        ci, co = (3 if i == 0 else 2 * 2 ** i), 2 * 2 ** (i + 1)
+        _conv(sd, f"down_blocks.{i}.conv", ci, co, 3, g, gain=1.6)
+        _bn(sd, f"down_blocks.{i}.norm", co, g)
+    _linear(sd, "pose_encoder.0", 6, 128, g)
+    _linear(sd, "pose_encoder.2", 128, 256, g)
+    for i, (ci, co) in zip((0, 1, 3, 4, 5), ((1, 64), (64, 128), (128, 256), (256, 256), (256, 512))):
+        _conv(sd, f"audio_eocder.{i}.0", ci, co, 3, g, gain=1.6)
+        del sd[f"audio_eocder.{i}.0.bias"]                      # util.py:1745: no bias under a normaliser
+        _bn(sd, f"audio_eocder.{i}.1", co, g)
+    _linear(sd, "audio_eocder_fc.0", 1024 * 12, 2048, g)
+    _linear(sd, "audio_eocder_fc.2", 2048, 256, g)
+    for l in range(3):                                          # nn.LSTM(1024, 256, 3); wider than the default U(-1/16, 1/16) so h is not tiny
+        for nm, shape in (("weight_ih", (1024, 1024 if l == 0 else 256)), ("weight_hh", (1024, 256)),
+                          ("bias_ih", (1024,)), ("bias_hh", (1024,))):
+            sd[f"lstm.{nm}_l{l}"] = (torch.rand(*shape, generator=g) * 2 - 1) / (16.0 if shape[-1] == 1024 else 5.0)
+    for i, (ci, co, k) in zip((0, 3, 6, 9, 12), ((256, 256, 6), (256, 128, 4), (128, 128, 4), (128, 128, 4), (128, 35, 4))):
+        taps = 1 if k == 6 else 4                              # input taps that reach one output pixel
+        sd[f"decon.{i}.weight"] = (torch.rand(ci, co, k, k, generator=g) * 2 - 1) * (1.6 * math.sqrt(3.0 / (ci * taps)))
+        sd[f"decon.{i}.bias"] = (torch.rand(co, generator=g) * 2 - 1) * 0.1
+        if i != 12:
+            _bn(sd, f"decon.{i + 1}", co, g)
+    return sd
+
+
+def make_at_inputs(B, T, seed=6):
+    """(example_image [B,3,256,256], mfcc windows [B,T,28,12], pose [B,T,6]); value ranges of demo.py:316-343."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, 3, 256, 256, generator=g)
+    mfcc = torch.randn(B, T, 28, 12, generator=g) * 0.5
+    pose = torch.randn(B, T, 6, generator=g) * 0.3
+    return img, mfcc, pose
+
+
 def aa_kernel(channels, sigma=1.5):
     """The fixed 13x13 Gaussian buffer of AntiAliasInterpolation2d (util.py:1012-1036)."""
     ks = 2 * round(sigma * 4) + 1

@@ -270,3 +270,83 @@ def frames_u8(prediction):
     import numpy as np
     a = prediction.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)
     return torch.from_numpy(np.clip(np.rint(a * np.float32(255.0)), 0, 255).astype(np.uint8))
+
+
+# ----------------------------------------------------------------------------- AT_net2
+def _bn2d(x, sd, p):
+    """nn.BatchNorm2d in eval mode (eps 1e-5), used by util.py:1757 (`conv2d` helper) and the `decon` stack."""
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.1, 1e-5)
+
+
+def at_audio_encoder(x, sd):
+    """AT_net2.audio_eocder, util.py:540-548: five conv3x3(no bias)+BN+ReLU (util.py:1740-1753) and two
+    MaxPool2d(3) with strides (1,2) and (2,2).  x [B,1,28,12] -> [B,512,12,2]."""
+    def cbr(x, i):
+        p = "audio_eocder.%d" % i
+        return F.relu(_bn2d(F.conv2d(x, sd[p + ".0.weight"], None, padding=1), sd, p + ".1"))
+    x = cbr(cbr(x, 0), 1)
+    x = F.max_pool2d(x, 3, stride=(1, 2))
+    x = cbr(cbr(cbr(x, 3), 4), 5)
+    return F.max_pool2d(x, 3, stride=(2, 2))
+
+
+def at_decon(z, sd):
+    """AT_net2.decon, util.py:559-575: ConvTranspose2d(256,256,6,2,1) and four ConvTranspose2d(.,.,4,2,1), BN+ReLU
+    between them.  z [B,256,1,1] -> [B,35,64,64]."""
+    for i in (0, 3, 6, 9):
+        z = F.conv_transpose2d(z, sd["decon.%d.weight" % i], sd["decon.%d.bias" % i], stride=2, padding=1)
+        z = F.relu(_bn2d(z, sd, "decon.%d" % (i + 1)))
+    return F.conv_transpose2d(z, sd["decon.12.weight"], sd["decon.12.bias"], stride=2, padding=1)
+
+
+def lstm_explicit(x, sd, layers=3):
+    """The recurrence nn.LSTM documents (gate order i, f, g, o; c' = f*c + i*g; h' = o*tanh(c')), zero initial
+    state, batch_first.  Restated step by step; `at_net2_forward` itself calls torch's fused op, and the tests
+    hold the two within float rounding of each other."""
+    B, T, _ = x.shape
+    for l in range(layers):
+        wi, wh = sd["lstm.weight_ih_l%d" % l], sd["lstm.weight_hh_l%d" % l]
+        b = sd["lstm.bias_ih_l%d" % l] + sd["lstm.bias_hh_l%d" % l]
+        H = wh.shape[1]
+        h, c = torch.zeros(B, H), torch.zeros(B, H)
+        outs = []
+        for t in range(T):
+            g = x[:, t] @ wi.t() + h @ wh.t() + b
+            i_, f_, g_, o_ = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+            c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+            h = torch.sigmoid(o_) * torch.tanh(c)
+            outs.append(h)
+        x = torch.stack(outs, 1)
+    return x
+
+
+def at_net2_forward(sd, example_image, audio, pose, weight, taps=None):
+    """AT_net2.forward with jaco_net == 'cnn', util.py:580-613.
+    example_image [B,3,256,256], audio [B,T,28,12] (MFCC windows), pose [B,T,6] -> [B,T,35,64,64]."""
+    with torch.no_grad():
+        B, T = audio.shape[:2]
+        outs = example_image
+        for i in range(8):                                              # util.py:583-586
+            outs = down_block(outs, sd, "down_blocks.%d" % i)
+        image_feature = outs.view(B, -1)
+        lstm_input = []
+        for t in range(T):                                              # util.py:588-595
+            cur = at_audio_encoder(audio[:, t].unsqueeze(1), sd)
+            cur = cur.view(B, -1)
+            cur = F.relu(F.linear(cur, sd["audio_eocder_fc.0.weight"], sd["audio_eocder_fc.0.bias"]))
+            cur = F.relu(F.linear(cur, sd["audio_eocder_fc.2.weight"], sd["audio_eocder_fc.2.bias"])) * weight
+            p = F.relu(F.linear(pose[:, t], sd["pose_encoder.0.weight"], sd["pose_encoder.0.bias"]))
+            p = F.relu(F.linear(p, sd["pose_encoder.2.weight"], sd["pose_encoder.2.bias"]))
+            lstm_input.append(torch.cat([image_feature, cur, p], 1))
+        lstm_input = torch.stack(lstm_input, dim=1)
+        flat = []
+        for l in range(3):
+            flat += [sd["lstm.weight_ih_l%d" % l], sd["lstm.weight_hh_l%d" % l],
+                     sd["lstm.bias_ih_l%d" % l], sd["lstm.bias_hh_l%d" % l]]
+        hx = (torch.zeros(3, B, 256), torch.zeros(3, B, 256))           # util.py:581-582
+        lstm_out = torch._VF.lstm(lstm_input, hx, flat, True, 3, 0.0, False, False, True)[0]   # nn.LSTM.forward
+        if taps is not None:
+            taps["lstm_input"], taps["lstm_out"] = lstm_input, lstm_out
+        deco = [at_decon(lstm_out[:, t, :].unsqueeze(2).unsqueeze(3), sd) for t in range(T)]   # util.py:600-606
+        return torch.stack(deco, dim=1)

@@ -102,3 +102,27 @@ def test_kp_glue_oracle_reproduces_reference_golden(name):
     np.testing.assert_array_equal(j.numpy(), blob["jacobian"])
     # the filter starts from the first frame and the smoothed track stays within the raw track's range
     assert v.shape == (T, 10, 2) and j.shape == (T, 10, 2, 2)
+
+
+@pytest.mark.parametrize("name", ["at_b2_t3", "at_b1_t6"])
+def test_at_net2_oracle_reproduces_reference_golden(name):
+    """AT_net2 (MFCC conv encoder + pose MLP + image DownBlocks -> 3-layer LSTM -> ConvTranspose
+    stack), pinned to the real reference by tools/make_golden.py."""
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    B, T = [int(v) for v in blob["meta"]]
+    sd = synth.make_at_state_dict()
+    img, mfcc, pose = synth.make_at_inputs(B, T)
+    chk = np.array([img.double().sum(), mfcc.double().sum(), pose.double().sum()])
+    np.testing.assert_allclose(chk, blob["in_checksum"], rtol=0, atol=0)
+    taps = {}
+    got = oracle.at_net2_forward(sd, img, mfcc, pose, 1.6, taps)
+    assert got.shape == (B, T, 35, 64, 64)
+    np.testing.assert_allclose(got.numpy()[..., ::4, ::4], blob["out"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(taps["lstm_out"].numpy(), blob["lstm_out"], rtol=0, atol=1e-6)
+    # the step-by-step restatement of the LSTM recurrence agrees with torch's fused op
+    np.testing.assert_allclose(oracle.lstm_explicit(taps["lstm_input"], sd).numpy(), blob["lstm_out"], rtol=0, atol=1e-6)
+    # frames of one clip differ (the audio drives them) and the first frame depends on nothing later
+    assert float((got[:, 0] - got[:, 1]).abs().mean()) > 1e-2
+    head = oracle.at_net2_forward(sd, img, mfcc[:, :1], pose[:, :1], 1.6)
+    np.testing.assert_allclose(head[:, 0].numpy(), got[:, 0].numpy(), rtol=0, atol=5e-6)

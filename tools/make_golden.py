@@ -140,6 +140,29 @@ def run_glue_case(name, T, with_emo):
     print(name, "ok ->", path, "scale %.6f" % scale)
 
 
+def run_at_case(name, B, T):
+    """the real AT_net2 (util.py:514-613) on CPU.  Its forward hard-codes `.cuda()` for the
+    initial LSTM state (util.py:581-582); this script (not the reference) makes that call an identity."""
+    from modules.util import AT_net2
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    sd = synth.make_at_state_dict()
+    ref = AT_net2().eval()
+    res = ref.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("generator.") for k in res.missing_keys)
+    img, mfcc, pose = synth.make_at_inputs(B, T)
+    with torch.no_grad():
+        want = ref(img, mfcc, pose, "cnn", 1.6)
+    taps = {}
+    got = oracle.at_net2_forward(sd, img, mfcc, pose, 1.6, taps)
+    assert torch.equal(want, got), name + ": oracle != reference"
+    a = want.numpy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, meta=np.array([B, T]), out=a[..., ::4, ::4].copy(), lstm_out=taps["lstm_out"].numpy(),
+                        in_checksum=np.array([img.double().sum(), mfcc.double().sum(), pose.double().sum()]),
+                        sum_out=np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()]))
+    print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB", "abs mean %.4f" % np.abs(a).mean())
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     run_case("tiny_b2", "tiny", 2, 64)
@@ -152,3 +175,5 @@ if __name__ == "__main__":
     run_kp_case("kp_a_full_b2", "full", 2, 256, audio=True)
     run_glue_case("kp_glue_emo_t12", 12, True)
     run_glue_case("kp_glue_plain_t40", 40, False)
+    run_at_case("at_b2_t3", 2, 3)
+    run_at_case("at_b1_t6", 1, 6)
