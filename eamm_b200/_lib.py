@@ -73,6 +73,10 @@ _PROTOS = {
     "eamm_conv_tc_uses_halo": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "eamm_conv_tc_fold": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "eamm_conv_tc_query": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_int)]),
+    "eamm_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "eamm_maxpool": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "eamm_lstm_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_pack_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

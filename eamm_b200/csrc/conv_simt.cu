@@ -25,7 +25,7 @@ struct ConvSimtParams {
   unsigned char* out_u8;
   int kind, flags, cin, cout, taps, ksize, out_nchw_c;
   int has_out, has_out2, has_res;
-  long long quads;     // n * (h/2) * (w/2)
+  long long quads;     // n * ceil(h/2) * ceil(w/2)
 };
 
 __global__ void __launch_bounds__(256)
@@ -34,7 +34,7 @@ conv_simt_kernel(ConvSimtParams p) {
   __shared__ __align__(16) float Bs[SM_BK][SM_BN];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int H = p.in.h, W = p.in.w, hq = H >> 1, wq = W >> 1;
+  const int H = p.in.h, W = p.in.w, hq = (H + 1) >> 1, wq = (W + 1) >> 1;   // odd maps: the last quads hang over the edge
   const int cls = blockIdx.z;                    // parity class for UP2 (a = cls>>1, b = cls&1)
   const int pa = cls >> 1, pb = cls & 1;
   const int n0 = blockIdx.y * SM_BN;
@@ -121,6 +121,7 @@ conv_simt_kernel(ConvSimtParams p) {
     if (p.flags & EAMM_EPI_POOL2) { oy = qy; ox = qx; OH = hq; OW = wq; }
     else {
       int y = qy * 2 + (i >> 1), x = qx * 2 + (i & 1);
+      if (y >= H || x >= W) continue;
       if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + pa; ox = 2 * x + pb; OH = 2 * H; OW = 2 * W; }
       else { oy = y; ox = x; OH = H; OW = W; }
     }
@@ -162,8 +163,7 @@ int conv_check_args(const eamm_conv_args* a, int cout_align) {
   if (a->kind < EAMM_CONV_3X3 || a->kind > EAMM_CONV_ROW7_PACKED) return EAMM_ERR_UNSUPPORTED;
   if (a->cin != a->in->c || a->cout <= 0 || a->cout % cout_align) return EAMM_ERR_SHAPE;
   const bool pool = a->flags & EAMM_EPI_POOL2;
-  // the SIMT kernel walks 2x2 quads (cout_align == 4); the tensor-core kernel only needs even maps to pool
-  if (((a->in->h & 1) || (a->in->w & 1)) && (pool || cout_align == 4)) return EAMM_ERR_SHAPE;
+  if (((a->in->h & 1) || (a->in->w & 1)) && pool) return EAMM_ERR_SHAPE;     // only pooling needs even maps
   if (pool && a->kind == EAMM_CONV_UP2_3X3) return EAMM_ERR_UNSUPPORTED;
   int OH = a->in->h, OW = a->in->w;
   if (pool) { OH >>= 1; OW >>= 1; }
@@ -204,7 +204,7 @@ extern "C" int eamm_conv_simt(const eamm_conv_args* a, void* stream) {
   p.kind = a->kind; p.flags = a->flags; p.cin = a->cin; p.cout = a->cout;
   p.ksize = a->kind == EAMM_CONV_7X7 ? 7 : 3;
   p.taps = a->kind == EAMM_CONV_UP2_3X3 ? 4 : p.ksize * p.ksize;
-  p.quads = (long long)p.in.n * (p.in.h >> 1) * (p.in.w >> 1);
+  p.quads = (long long)p.in.n * ((p.in.h + 1) >> 1) * ((p.in.w + 1) >> 1);
   long long tiles = (p.quads + 15) / 16;
   if (tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
   dim3 grid((unsigned)tiles, (p.cout + SM_BN - 1) / SM_BN, a->kind == EAMM_CONV_UP2_3X3 ? 4 : 1);

@@ -215,7 +215,10 @@ def impl_for(precision):
 class ConvLayer:
     """One packed convolution: kind/flags + device tensors in the layout of the chosen kernel."""
 
-    def __init__(self, name, kind, flags, w, b, cin_slot, nalign, impl, scale2=None, shift2=None, cin_valid=None):
+    def __init__(self, name, kind, flags, w, b, cin_slot, nalign, impl, scale2=None, shift2=None, cin_valid=None,
+                 parity=None):
+        """`parity` [4][4][cout][cin] replaces the nearest-x2 parity weights of an UP2 layer (at_engine.py uses the
+        UP2 kernels for ConvTranspose2d)."""
         cout, cin = w.shape[0], w.shape[1]
         self.name, self.kind, self.flags, self.impl = name, kind, flags, impl
         # algorithmic FLOPs per input pixel of the reference conv (2*MAC; UP2 runs at 4x the pixels)
@@ -225,7 +228,7 @@ class ConvLayer:
         self.cout = _round_up(cout, nalign)
         dev = w.device
         if kind == L.CONV_UP2_3X3:
-            wt = up2_parity_weights(w)                                  # [4][4][cout][cin]
+            wt = up2_parity_weights(w) if parity is None else parity    # [4][4][cout][cin]
             wt = wt.reshape(16, cout, cin)
         else:
             k = w.shape[2]

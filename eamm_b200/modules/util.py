@@ -107,3 +107,11 @@ class AntiAliasInterpolation2d(_Fused):
         self.groups = channels
         self.scale = scale
         self.int_inv_scale = int(1 / scale)
+
+
+def __getattr__(name):
+    """`modules.util.AT_net2` (util.py:514) lives in audio_net.py; resolved lazily to keep the import graph acyclic."""
+    if name == "AT_net2":
+        from .audio_net import AT_net2
+        return AT_net2
+    raise AttributeError(name)

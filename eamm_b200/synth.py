@@ -162,7 +162,7 @@ def make_at_state_dict(seed=4):
             sd[f"lstm.{nm}_l{l}"] = (torch.rand(*shape, generator=g) * 2 - 1) / (16.0 if shape[-1] == 1024 else 5.0)
     for i, (ci, co, k) in zip((0, 3, 6, 9, 12), ((256, 256, 6), (256, 128, 4), (128, 128, 4), (128, 128, 4), (128, 35, 4))):
         taps = 1 if k == 6 else 4                              # input taps that reach one output pixel
-        sd[f"decon.{i}.weight"] = (torch.rand(ci, co, k, k, generator=g) * 2 - 1) * (1.6 * math.sqrt(3.0 / (ci * taps)))
+        sd[f"decon.{i}.weight"] = (torch.rand(ci, co, k, k, generator=g) * 2 - 1) * ((0.8 if i == 12 else 1.6) * math.sqrt(3.0 / (ci * taps)))
         sd[f"decon.{i}.bias"] = (torch.rand(co, generator=g) * 2 - 1) * 0.1
         if i != 12:
             _bn(sd, f"decon.{i + 1}", co, g)

@@ -217,6 +217,25 @@ int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
  * zero in dst (allocate it zeroed once); only the interior is written. */
 int eamm_pack_image(const float* src, int n, int C, int H, int W, int split, void* dst, void* stream);
 
+/* ---- AT_net2, the per-clip audio -> motion-feature network (replaces the ATen ops behind
+ * /root/reference/modules/util.py:580-613; its convolutions run through eamm_conv_simt: DownBlock2d as 3x3+POOL2,
+ * ConvTranspose2d(k=4, s=2, p=1) as EAMM_CONV_UP2_3X3 with parity-class weights W[cin][cout][3-a-2ty][3-b-2tx]).
+ *
+ * eamm_linear: y[m][n] = scale * act(sum_k x[m][k] w[k][n] + bias[n] + add_rows[m / add_period][n])
+ *   nn.Linear (util.py:532-556), the LSTM input projections (util.py:557) and the 1x1 -> 4x4 ConvTranspose2d
+ *   (util.py:560).  x [M][ldx] fp32, w [K][N] fp32 (the transpose of nn.Linear.weight), bias [N] or NULL,
+ *   add_rows [ceil(M/add_period)][N] or NULL, y [M][ldy]; N and ldy multiples of 4; relu != 0 applies ReLU. */
+int eamm_linear(const float* x, int ldx, const float* w, const float* bias, const float* add_rows, int add_period,
+                float* y, int ldy, int M, int K, int N, int relu, float scale, void* stream);
+
+/* eamm_maxpool: nn.MaxPool2d(k, stride=(stride_y, stride_x)), no padding, floor mode (util.py:543,547). */
+int eamm_maxpool(const eamm_act* in, const eamm_act* out, int k, int stride_y, int stride_x, void* stream);
+
+/* eamm_lstm_layer: the recurrence of one nn.LSTM layer (util.py:557,597; gate order i,f,g,o; zero initial state)
+ * over whole sequences.  gates_x [B][T][4*hidden] = W_ih x_t + b_ih + b_hh (eamm_linear), w_hh [4*hidden][hidden]
+ * (nn.LSTM.weight_hh_l*, as stored), h_out [B][T][hidden].  hidden must be 256.  One 8-CTA cluster per sequence. */
+int eamm_lstm_layer(const float* gates_x, const float* w_hh, float* h_out, int B, int T, int hidden, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -420,3 +420,99 @@ def test_whole_clip_chain_matches_oracle_chain(dev):
     assert (k_norm["value"].cpu() - nv).abs().max() <= 5e-4
     assert (out["prediction"].cpu() - o_out["prediction"]).abs().max() <= 2e-3     # detector error enters through the flow
     assert (out["prediction_u8"].cpu().int() - oracle.frames_u8(o_out["prediction"]).int()).abs().max() <= 2
+
+
+# ------------------------------------------------------------------ AT_net2 (BASELINE config 5)
+_AT = {}
+
+
+def at_net(dev):
+    from eamm_b200.modules.util import AT_net2
+    if "m" not in _AT:
+        m = AT_net2().eval()
+        m.load_state_dict(synth.make_at_state_dict(), strict=True)
+        _AT["m"] = m.to(dev)
+    return _AT["m"]
+
+
+@pytest.mark.parametrize("name", ["at_b2_t3", "at_b1_t6"])
+def test_at_net2_matches_reference_golden(dev, name):
+    """MFCC conv encoder + pose MLP + image DownBlocks -> LSTM (cluster kernel) -> ConvTranspose stack, fp32.
+    Tolerance 1e-4 max-abs on outputs of magnitude ~1 (fp32 sums in a different order than ATen's)."""
+    blob = np.load(os.path.join(GOLD, name + ".npz"))
+    B, T = [int(v) for v in blob["meta"]]
+    img, mfcc, pose = synth.make_at_inputs(B, T)
+    m = at_net(dev)
+    out = m(img.to(dev), mfcc.to(dev), pose.to(dev), "cnn", 1.6)
+    torch.cuda.synchronize()
+    assert out.shape == (B, T, 35, 64, 64)
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got[..., ::4, ::4] - blob["out"]).max() <= 1e-4
+    s = np.array([got.astype(np.float64).sum(), np.abs(got.astype(np.float64)).sum()])
+    assert abs(s[1] - blob["sum_out"][1]) <= 2e-6 * blob["sum_out"][1]
+    lstm = m._eng.ws[(B, T, 256, 256)].h[2].view(B, T, 256).cpu().numpy()
+    assert np.abs(lstm - blob["lstm_out"]).max() <= 2e-5
+
+
+def test_at_net2_long_clip_is_causal_and_batch_consistent(dev):
+    """Size-independent properties at a clip length the oracle would take minutes for: frame t depends only on windows
+    <= t (LSTM causality), and sequences of a batch do not interact."""
+    T = 96
+    img, mfcc, pose = synth.make_at_inputs(2, T, seed=9)
+    m = at_net(dev)
+    full = m(img.to(dev), mfcc.to(dev), pose.to(dev), "cnn", 1.6)
+    head = m(img.to(dev), mfcc[:, :40].to(dev), pose[:, :40].to(dev), "cnn", 1.6)
+    one = m(img[1:].to(dev), mfcc[1:].to(dev), pose[1:].to(dev), "cnn", 1.6)
+    torch.cuda.synchronize()
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[:, :40], head)
+    assert torch.equal(full[1:], one)
+    assert float((full[:, -1] - full[:, -2]).abs().mean()) > 1e-3
+
+
+def test_audio_to_frames_chain_psnr(dev):
+    """BASELINE.json config 5 in miniature: MFCC windows -> AT_net2 -> KPDetector_a per frame -> clip glue -> generator
+    (demo.py:345, :206-281) against the same chain run with the CPU oracles.  Stated tolerance: PSNR >= 60 dB on
+    [0,1] frames and max-abs 2e-3 (keypoint softmax at temperature 0.1 amplifies the fp32 rounding of the stages before)."""
+    from eamm_b200 import clip
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    from oracle import eamm_oracle as oracle, kp_glue
+    T = 6
+    cfg = get_config("full")
+    kcfg, acfg = get_kp_config("full"), get_kp_config("full", audio=True)
+    sd, ksd, asd = synth.make_state_dict(cfg, seed=0), synth.make_kp_state_dict(kcfg, seed=2), synth.make_kp_state_dict(acfg, seed=3)
+    atsd = synth.make_at_state_dict()
+    img, mfcc, pose = synth.make_at_inputs(1, T, seed=21)
+    # ---- oracle chain (CPU)
+    o_deco = oracle.at_net2_forward(atsd, img, mfcc, pose, 1.6)
+    o_src = oracle.kp_detector_forward(ksd, kcfg, img)
+    o_drv = oracle.kp_detector_a_forward(asd, acfg, o_deco[0])
+    o_init = {k: o_drv[k][:1] for k in ("value", "jacobian")}
+    scale = clip.movement_scale(o_src, o_init)
+    nv, nj = kp_glue.clip_glue(o_drv["value"], o_drv["jacobian"], None, None, o_src, o_init, movement_scale=scale)
+    o_out = oracle.generator_forward(sd, cfg, img.expand(T, -1, -1, -1).contiguous(), {"value": nv, "jacobian": nj},
+                                     {k: o_src[k].expand(T, *o_src[k].shape[1:]).contiguous() for k in ("value", "jacobian")})
+    # ---- CUDA chain
+    gen, _ = generator("full", dev)
+    gen.precision = "fp32"
+    det = KPDetector(**kcfg).eval(); det.load_state_dict(ksd); det = det.to(dev); det.precision = "fp32_simt"
+    det_a = KPDetector_a(**acfg).eval(); det_a.load_state_dict(asd); det_a = det_a.to(dev); det_a.precision = "fp32_simt"
+    s = img.to(dev)
+    deco = at_net(dev)(s, mfcc.to(dev), pose.to(dev), "cnn", 1.6)
+    k_src = det(s)
+    k_drv = det_a(deco[0])
+    k_init = {k: k_drv[k][:1] for k in ("value", "jacobian")}
+    k_norm = clip.smooth_and_normalize(k_drv, k_src, k_init, relative=True, scale=clip.movement_scale(k_src, k_init))
+    out = gen(s.expand(T, -1, -1, -1), kp_driving=k_norm,
+              kp_source={k: k_src[k].expand(T, *k_src[k].shape[1:]) for k in ("value", "jacobian")})
+    torch.cuda.synchronize()
+    assert (deco.cpu() - o_deco).abs().max() <= 1e-4
+    assert (k_norm["value"].cpu() - nv).abs().max() <= 5e-4
+    err = out["prediction"].cpu() - o_out["prediction"]
+    psnr = -10.0 * torch.log10((err ** 2).mean())
+    assert float(psnr) >= 60.0, float(psnr)
+    assert err.abs().max() <= 2e-3
+    # the clip actually moves: driven frames differ from each other
+    assert float((o_out["prediction"][0] - o_out["prediction"][-1]).abs().mean()) > 1e-4

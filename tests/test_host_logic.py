@@ -230,3 +230,80 @@ def test_gloo_two_rank_gather_and_max_reduce(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK 2.0 7.0" in outs[0]
+
+
+# ------------------------------------------------------------------ AT_net2 packing
+def _emulate_up2(layer, x):
+    """What the UP2 kernels compute from ConvLayer.w_ref ([16][cout][cin]): out(2y+a, 2x+b) = sum over taps."""
+    cout = layer.cout
+    pw = layer.w_ref.view(4, 4, cout, -1)
+    N, _, H, W = x.shape
+    out = torch.zeros(N, cout, 2 * H, 2 * W)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = layer.bias.view(1, -1, 1, 1)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    dy, dx = a - 1 + ty, b - 1 + tx
+                    acc = acc + torch.einsum("oc,nchw->nohw", pw[a * 2 + b, ty * 2 + tx], xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W])
+            out[:, :, a::2, b::2] = acc
+    return F.relu(out) if layer.flags & 1 else out
+
+
+def _emulate_conv3(layer, x):
+    w = layer.w_ref.view(3, 3, layer.cout, -1).permute(2, 3, 0, 1)
+    y = F.conv2d(F.pad(x, (0, 0, 0, 0, 0, w.shape[1] - x.shape[1])), w, layer.bias, padding=1)
+    y = F.relu(y) if layer.flags & 1 else y
+    return F.avg_pool2d(y, 2) if layer.flags & 2 else y
+
+
+def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
+    """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
+    the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
+    a GEMM and ConvTranspose(k4,s2,p1) as UP2 parity classes."""
+    from eamm_b200.modules.util import AT_net2
+    from eamm_b200.at_engine import ATNet2Engine
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    sd = synth.make_at_state_dict()
+    m = AT_net2().eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        eng = ATNet2Engine(m)
+    B, T = 1, 2
+    img, mfcc, pose = synth.make_at_inputs(B, T)
+    taps = {}
+    want = oracle.at_net2_forward(sd, img, mfcc, pose, 1.6, taps)
+    lin = lambda l, x, scale=1.0, add=0: (F.relu(x @ l.w + (l.b if l.b is not None else 0) + add) if l.relu
+                                         else x @ l.w + (l.b if l.b is not None else 0) + add) * scale
+    x = img
+    for lay in eng.img:
+        x = _emulate_conv3(lay, x)
+    img_feat = x.view(B, 512)
+    a = mfcc.view(B * T, 1, 28, 12)
+    a = _emulate_conv3(eng.aud[1], _emulate_conv3(eng.aud[0], a))
+    a = F.max_pool2d(a, 3, stride=(1, 2))
+    a = _emulate_conv3(eng.aud[5], _emulate_conv3(eng.aud[4], _emulate_conv3(eng.aud[3], a)))
+    a = F.max_pool2d(a, 3, stride=(2, 2))
+    flat = a.permute(0, 2, 3, 1).reshape(B * T, -1)                        # NHWC flatten, as the engine's buffer
+    x2 = torch.cat([lin(eng.fc2, lin(eng.fc1, flat), 1.6), lin(eng.pose2, lin(eng.pose1, pose.view(B * T, 6)))], 1)
+    want_in = taps["lstm_input"].view(B * T, -1)
+    assert torch.allclose(x2, want_in[:, 512:], atol=2e-4)
+    assert torch.allclose(img_feat, want_in[:1, :512], atol=1e-5)
+    h = x2
+    for l, ((p_img, p_x), whh) in enumerate(eng.lstm):
+        add = lin(p_img, img_feat).repeat_interleave(T, 0) if p_img is not None else 0
+        gates = lin(p_x, h, add=add).view(B, T, 1024)
+        hs, hh, cc = [], torch.zeros(B, 256), torch.zeros(B, 256)
+        for t in range(T):
+            g = gates[:, t] + hh @ whh.t()
+            cc = torch.sigmoid(g[:, 256:512]) * cc + torch.sigmoid(g[:, :256]) * torch.tanh(g[:, 512:768])
+            hh = torch.sigmoid(g[:, 768:]) * torch.tanh(cc)
+            hs.append(hh)
+        h = torch.stack(hs, 1).view(B * T, 256)
+    assert torch.allclose(h, taps["lstm_out"].view(B * T, 256), atol=1e-5)
+    d = lin(eng.dec0, h).view(B * T, 4, 4, 256).permute(0, 3, 1, 2)
+    for lay in eng.dec:
+        d = _emulate_up2(lay, d)
+    got = d[:, :35].view(B, T, 35, 64, 64)
+    assert torch.allclose(got, want, atol=2e-4), float((got - want).abs().max())
