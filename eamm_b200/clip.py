@@ -54,3 +54,34 @@ def smooth_and_normalize(kp_driving_all, kp_source, kp_driving_initial, emo_driv
                                  len(emo_rows) if ev is not None else 0, p(sv), p(sj), p(iv), p(ij), float(scale),
                                  1 if relative else 0, p(out_v), p(out_j), p(scratch), current_stream_ptr()), "kp_clip")
     return {"value": out_v, "jacobian": out_j}
+
+
+def animate_audio_clip(at_net, kp_detector, kp_detector_a, generator, example_image, mfcc, pose, weight=1.6,
+                       relative=True, adapt_movement_scale=True, emo_driving_all=None, chunk=64, emit_u8=True):
+    """One audio-driven clip, batched over its T frames: `test_auido` + `make_animation_smooth` of the reference
+    (demo.py:345 and :206-281) without the per-frame host round trips.
+
+    example_image [1,3,256,256] fp32 CUDA in [0,1]; mfcc [1,T,28,12] (the windows of demo.py:323-328); pose [1,T,6].
+    emo_driving_all: optional stacked outputs of the (out-of-scope) emotion detector, as `smooth_and_normalize` takes.
+    Returns the frames as uint8 [T,256,256,3] (emit_u8; what demo.py:507 writes) or fp32 [T,3,256,256].
+    """
+    T = mfcc.shape[1]
+    deco = at_net(example_image, mfcc, pose, "cnn", weight)                      # demo.py:345
+    kp_source = kp_detector(example_image)                                       # demo.py:206
+    kp_all = kp_detector_a(deco[0])                                              # demo.py:207,219 for every frame at once
+    kp_init = {k: kp_all[k][:1] for k in ("value", "jacobian")}
+    scale = movement_scale(kp_source, kp_init) if adapt_movement_scale else 1.0  # demo.py:114-119
+    kp_norm = smooth_and_normalize(kp_all, kp_source, kp_init, emo_driving_all, relative=relative, scale=scale)
+    frames = []
+    prev = generator.emit_u8
+    generator.emit_u8 = bool(emit_u8)
+    try:
+        for t0 in range(0, T, chunk):
+            n = min(chunk, T - t0)
+            out = generator(example_image[:1].expand(n, -1, -1, -1),
+                            kp_driving={k: v[t0:t0 + n] for k, v in kp_norm.items()},
+                            kp_source={k: kp_source[k][:1].expand(n, *kp_source[k].shape[1:]) for k in ("value", "jacobian")})
+            frames.append(out["prediction_u8"] if emit_u8 else out["prediction"])
+    finally:
+        generator.emit_u8 = prev
+    return torch.cat(frames, 0)

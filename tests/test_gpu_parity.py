@@ -516,3 +516,8 @@ def test_audio_to_frames_chain_psnr(dev):
     assert err.abs().max() <= 2e-3
     # the clip actually moves: driven frames differ from each other
     assert float((o_out["prediction"][0] - o_out["prediction"][-1]).abs().mean()) > 1e-4
+    # the one-call clip API (chunked over T, uint8 frames) gives the same frames
+    det.precision = det_a.precision = "fp32_simt"
+    frames = clip.animate_audio_clip(at_net(dev), det, det_a, gen, s, mfcc.to(dev), pose.to(dev), 1.6, chunk=4)
+    assert frames.shape == (T, 256, 256, 3) and frames.dtype == torch.uint8
+    assert (frames.cpu().int() - oracle.frames_u8(o_out["prediction"]).int()).abs().max() <= 2
