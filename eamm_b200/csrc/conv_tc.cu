@@ -243,8 +243,12 @@ struct TileCoord { int x0, y0, n0, cls, nt; };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t tile) {
   TileCoord t;
+  // CTA pairs: tiles 2i and 2i+1 are adjacent M tiles of the same (class, N tile) -- they share the weights
+  const uint32_t rank = p.cta2 ? (tile & 1u) : 0u;
+  if (p.cta2) tile >>= 1;
   uint32_t q = tile / (uint32_t)p.n_tiles; t.nt = (int)(tile - q * p.n_tiles); tile = q;
   q = tile / (uint32_t)p.classes; t.cls = (int)(tile - q * p.classes); tile = q;
+  if (p.cta2) tile = 2u * tile + rank;
   q = tile / (uint32_t)p.tiles_x; t.x0 = (int)(tile - q * p.tiles_x) * p.x_stride; tile = q;
   q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.bh; tile = q;
   t.n0 = (int)tile * p.bn;
@@ -391,11 +395,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_slot = (uint32_t)p.a_slot_bytes;
   const uint32_t fold = (uint32_t)p.fold;
   // B sub-slot size (a CTA of a pair stages only its half of the N tile)
-  const uint32_t b_bytes = CTA2 ? (uint32_t)p.BN * 64u : (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));
+  const uint32_t b_bytes = CTA2 ? (uint32_t)p.BN * (fold ? 128u : 64u)
+                                : (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));
   const uint32_t KS = (uint32_t)p.ksub;                         // 64-channel sub-chunks per pipeline stage
   const uint32_t stage_bytes = KS * (a_slot + b_bytes);
   const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;   // bytes of a type-0 chunk
-  const uint32_t b_half = (uint32_t)p.BN * 128u;
+  const uint32_t b_half = (uint32_t)p.BN * (CTA2 ? 64u : 128u);        // fold: offset of the b_lo rows inside a B slot
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (32 + a); };
@@ -500,6 +505,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (CTA2) {
                 tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
                 tma2_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
+                if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
               } else {
                 tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
                 tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
@@ -521,7 +527,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================================ MMA issuer (leader CTA of a pair)
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*BN
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 2) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);   // N = 2*BN
     const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
@@ -564,10 +570,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               const uint64_t da = make_sw128_desc(sA), db = make_sw128_desc(sB);
               if (CTA2) {
-                tc2_mma_bf16(tmem_acc, da, db, idesc, first);
-                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
-                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u);
-                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+                // pair + fold: a CTA's B slot is [its half of b_hi | its half of b_lo]; an N = 2*BN step would
+                // interleave the columns as [hi|lo|hi|lo], so the type-0 chunk runs as two N = BN steps instead
+                // (b_hi halves -> columns [0,BN), b_lo halves -> [BN,2BN)): same column layout and the same
+                // per-column accumulation order as the single-CTA kernel, i.e. bit-identical results
+                tc2_mma_bf16(tmem_acc, da, db, idesc1, first);
+                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc1, 1u);
+                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc1, 1u);
+                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc1, 1u);
+                if (fold == 1 && idesc == idesc2) {
+                  const uint64_t dl = db + (uint64_t)(b_half >> 4);
+                  const uint32_t acc2 = tmem_acc + (uint32_t)BN;
+                  tc2_mma_bf16(acc2, da, dl, idesc1, first);
+                  tc2_mma_bf16(acc2, da + 2, dl + 2, idesc1, 1u);
+                  tc2_mma_bf16(acc2, da + 4, dl + 4, idesc1, 1u);
+                  tc2_mma_bf16(acc2, da + 6, dl + 6, idesc1, 1u);
+                }
               } else {
                 tc_mma_bf16(tmem_acc, da, db, idesc, first);
                 tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
@@ -747,6 +765,16 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   // N tile: the widest UMMA N (<= 256) dividing cout that still yields at least one tile per SM;
   // small maps (hourglass 8x8 ... 2x2) prefer narrow N tiles so that more SMs stream the weights.
+  static int fold_env = -1;
+  if (fold_env < 0) { const char* e = getenv("EAMM_TC_FOLD"); fold_env = e ? atoi(e) : 1; }
+  p.fold = 0;
+  // decided from the layer's cout, not from the batch-dependent N tile, so that a frame's result does
+  // not depend on how many other frames share the launch
+  if (fold_env && !p.halo && (p.kxn || a->cout <= 128)) {
+    if (row7 && a->pack_passes == 2) p.fold = 2;
+    else if (!row7 && p.passes == 3) p.fold = 1;
+  }
+  if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
   if (p.kxn) p.BN = 32;
   else {
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes;
@@ -762,29 +790,26 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     }
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
-  static int fold_env = -1;
-  if (fold_env < 0) { const char* e = getenv("EAMM_TC_FOLD"); fold_env = e ? atoi(e) : 1; }
-  p.fold = 0;
-  // decided from the layer's cout, not from the batch-dependent N tile, so that a frame's result does
-  // not depend on how many other frames share the launch
-  if (fold_env && !p.halo && (p.kxn || a->cout <= 128)) {
-    if (row7 && a->pack_passes == 2) p.fold = 2;
-    else if (!row7 && p.passes == 3) p.fold = 1;
-  }
-  if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
   static int cta2_env = -1, prof_env = -1;
-  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 1; }
+  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 3; }   // bit 0: pairs, bit 1: folded pairs
   if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
   const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
   {
     const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
-    p.cta2 = (cta2_env && !instr && !p.halo && !p.kxn && !row7 && !p.fold && a->cout == 256 && p.BN == 256 &&
-              tiles_all % 2 == 0 && tiles_all >= num_sms && (num_sms % 2) == 0) ? 1 : 0;
+    const bool common = cta2_env && !instr && !p.halo && !p.kxn && !row7 && (num_sms % 2) == 0;
+    // (a) unfolded cout == 256 layers, (b) folded layers (split mode, cout <= 128) with at least 32 columns; both
+    // once they fill the chip and when a pair's two M tiles exist (even count).  The arithmetic (per-column
+    // accumulation order) is the same as the single-CTA kernel's, so the choice may depend on the batch.
+    const long long m_tiles_pc = (long long)p.tiles_x * p.tiles_y * p.tiles_n;     // M tiles per (class, N tile)
+    const bool pair_a = !p.fold && a->cout == 256 && p.BN == 256;
+    const bool pair_b = (cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0;
+    const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
+    p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
   }
   p.b_rows_total = p.kxn ? 32 : p.classes * a->cout;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
   const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes +
-      (p.cta2 ? (uint32_t)p.BN * 64u : (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u)));
+      (p.cta2 ? (uint32_t)p.BN * (p.fold ? 128u : 64u) : (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u)));
   const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
   const uint32_t ring_bytes = 200u * 1024u - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
@@ -798,7 +823,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (ksub == 1 && 2u * chunk_bytes * 3u <= ring_bytes && kc_total >= 2 && p.BN < 256) ksub = 2;
   static int cta2_ksub_env = -1;
   if (cta2_ksub_env < 0) { const char* e = getenv("EAMM_TC_CTA2_KSUB"); cta2_ksub_env = e ? atoi(e) : 1; }
-  if (p.cta2) ksub = cta2_ksub_env > 0 ? cta2_ksub_env : 1;
+  if (p.cta2) ksub = p.fold ? 2 : (cta2_ksub_env > 0 ? cta2_ksub_env : 1);   // folded pairs: an N = BN step alone is shorter than the stage overhead
   if (ksub_env > 0) ksub = ksub_env;
   while (ksub > 1 && (uint32_t)ksub * chunk_bytes * 2u > ring_bytes) --ksub;      // keep at least two stages
   p.ksub = ksub;

@@ -35,6 +35,10 @@ CASES = [
     ("cta2 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 1, 1, 1, ""),
     ("cta2 3x3 256->256 64x64 N=8 r+o2 x3", "3x3", "", 256, 256, 8, 64, 64, 2, 1, 1, ""),
     ("cta2 3x3 128->256 128x128 N=2 pool x3", "3x3", "rp", 128, 256, 2, 128, 128, 2, 0, 0, ""),
+    ("pairfold 3x3 64->128 256x256 N=2 pool x3", "3x3", "rp", 64, 128, 2, 256, 256, 2, 0, 0, ""),
+    ("pairfold up2 128->64 128x128 N=2 x3", "up2", "r", 128, 64, 2, 128, 128, 2, 0, 0, ""),
+    ("pairfold 3x3 128->128 32x32 N=3 r+o2 x3", "3x3", "", 128, 128, 3, 32, 32, 2, 1, 1, ""),
+    ("pairfold up2 256->128 64x64 N=5 x3", "up2", "r", 256, 128, 5, 64, 64, 2, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
