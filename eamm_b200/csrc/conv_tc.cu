@@ -791,17 +791,17 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   static int cta2_env = -1, prof_env = -1;
-  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 3; }   // bit 0: pairs, bit 1: folded pairs
+  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 7; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256
   if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
   const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
   {
     const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
     const bool common = cta2_env && !instr && !p.halo && !p.kxn && !row7 && (num_sms % 2) == 0;
-    // (a) unfolded cout == 256 layers, (b) folded layers (split mode, cout <= 128) with at least 32 columns; both
+    // (a) unfolded layers (3-pass cout > 128, every single-plane layer), (b) folded layers (split mode, cout <= 128); both
     // once they fill the chip and when a pair's two M tiles exist (even count).  The arithmetic (per-column
     // accumulation order) is the same as the single-CTA kernel's, so the choice may depend on the batch.
     const long long m_tiles_pc = (long long)p.tiles_x * p.tiles_y * p.tiles_n;     // M tiles per (class, N tile)
-    const bool pair_a = !p.fold && a->cout == 256 && p.BN == 256;
+    const bool pair_a = !p.fold && (p.BN == 256 || ((cta2_env & 4) && p.BN % 32 == 0));
     const bool pair_b = (cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0;
     const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
     p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
@@ -823,7 +823,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (ksub == 1 && 2u * chunk_bytes * 3u <= ring_bytes && kc_total >= 2 && p.BN < 256) ksub = 2;
   static int cta2_ksub_env = -1;
   if (cta2_ksub_env < 0) { const char* e = getenv("EAMM_TC_CTA2_KSUB"); cta2_ksub_env = e ? atoi(e) : 1; }
-  if (p.cta2) ksub = p.fold ? 2 : (cta2_ksub_env > 0 ? cta2_ksub_env : 1);   // folded pairs: an N = BN step alone is shorter than the stage overhead
+  // pairs: N = 256 stages are long enough with one chunk; narrower ones (and folded pairs, whose N = BN step
+  // alone is shorter than the per-stage overhead) take two
+  if (p.cta2) ksub = p.BN == 256 && !p.fold ? (cta2_ksub_env > 0 ? cta2_ksub_env : 1) : (kc_total >= 2 ? 2 : 1);
   if (ksub_env > 0) ksub = ksub_env;
   while (ksub > 1 && (uint32_t)ksub * chunk_bytes * 2u > ring_bytes) --ksub;      // keep at least two stages
   p.ksub = ksub;

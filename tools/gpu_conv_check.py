@@ -39,6 +39,11 @@ CASES = [
     ("pairfold up2 128->64 128x128 N=2 x3", "up2", "r", 128, 64, 2, 128, 128, 2, 0, 0, ""),
     ("pairfold 3x3 128->128 32x32 N=3 r+o2 x3", "3x3", "", 128, 128, 3, 32, 32, 2, 1, 1, ""),
     ("pairfold up2 256->128 64x64 N=5 x3", "up2", "r", 256, 128, 5, 64, 64, 2, 0, 0, ""),
+    ("pair 3x3 64->128 256x256 N=2 pool", "3x3", "rp", 64, 128, 2, 256, 256, 1, 0, 0, ""),
+    ("pair up2 128->64 128x128 N=2", "up2", "r", 128, 64, 2, 128, 128, 1, 0, 0, ""),
+    ("pair 3x3 64->64 64x64 N=8 pool", "3x3", "rp", 64, 64, 8, 64, 64, 1, 0, 0, ""),
+    ("pair 3x3 256->512 8x8 N=32 pool x3", "3x3", "rp", 256, 512, 32, 8, 8, 2, 0, 0, ""),
+    ("pair up2 512->256 4x4 N=32", "up2", "r", 512, 256, 32, 4, 4, 1, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
