@@ -791,7 +791,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   static int cta2_env = -1, prof_env = -1;
-  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 7; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256
+  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 3; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256 (measured slower in
+                                                                                             // single-plane mode: the leader's one MMA warp issues for both CTAs; off by default)
   if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
   const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
   {
