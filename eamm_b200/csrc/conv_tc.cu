@@ -19,8 +19,9 @@
 //               kx-in-N    7x7 -> <=4 NCHW channels: the 7 kx taps are GEMM columns, epilogue sums shifts
 //               row7       7x7 over a packed <=3-channel image: K window = 8 pixels x (hi,lo) channels
 //               fold       split mode, cout <= 128: weight planes stacked along N (2 A loads, not 3)
-//               CTA pair   cout == 256: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
-//   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant, EAMM_TC_KSUB / _CTA2_KSUB force the
+//               CTA pair   N tile 256 and folded layers: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
+//   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
+//               pairs, 4 narrow unfolded pairs -- default 3), EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -59,7 +60,7 @@ struct ConvTcParams {
                        // 8 MMAs per (tap, 64 channels) instead of 3 and 12.  fold == 2: every chunk is type 0
                        // (packed `first` conv: both activation planes already sit in one K window).
   int b_rows_total;    // rows of one weight plane block (classes * cout): the lo block starts there
-  int cta2;            // CTA pairs with cta_group::2 MMAs (cout == 256 3x3 layers with an even number of M tiles)
+  int cta2;            // CTA pairs with cta_group::2 MMAs (tiles 2i, 2i+1 = adjacent M tiles of one class / N tile)
   int ksub;            // 64-channel K chunks per pipeline stage (1..4)
   int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
