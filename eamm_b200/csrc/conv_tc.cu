@@ -21,7 +21,7 @@
 //               fold       split mode, cout <= 128: weight planes stacked along N (2 A loads, not 3)
 //               CTA pair   N tile 256 and folded layers: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
-//               pairs, 4 narrow unfolded pairs -- default 3), EAMM_TC_KSUB / _CTA2_KSUB force the
+//               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step -- default 3), EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -52,8 +52,16 @@ struct ConvTcParams {
   int a_c_off, a_c_buf;
   int halo;            // 7x7 with a 134-pixel halo row per ky: the 7 kx taps are shifted smem views
   int kxn;             // 7x7 -> <=4 NCHW channels: the 7 kx taps live in the N dimension (N = 7*4 -> 32),
-                       // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns
-  int x_stride;        // pixels between consecutive x tiles (122 in kxn mode, else bw)
+                       // one MMA group per (ky, pass, chunk); the epilogue sums the kx-shifted columns.
+                       // kxn == 2: four output rows per tile as well -- N = (dr, kx, co) = 4*7*4 = 112, the K loop walks
+                       // the 10 input rows y0-3 .. y0+6 (B row block j holds w[ky = j - dr], zero outside the filter):
+                       // 80 wide MMAs per 4 rows instead of 224 narrow ones (these layers are bound by the
+                       // per-instruction cost of fetching the 128-pixel A slab, not by the math).
+                       // kxn == 3: full-width tiles of a <=128-wide map with <=16 fp32 NHWC couts (mask+occlusion):
+                       // N = (kx, co) = 7*16 = 112, tile = (128/W) whole rows, no x halo (it is the zero padding)
+  int x_stride;        // pixels between consecutive x tiles (122 in kxn mode 1/2, else bw)
+  int y_stride;        // rows between consecutive y tiles (4 for kxn == 2, else bh)
+  int ntap;            // K-loop taps: 7 (halo, kxn 1/3), 10 (kxn 2), else taps
   int fold;            // split mode with 2*BN <= 256: the weight planes are stacked along N.  Chunk type 0 =
                        // a_hi x [b_hi; b_lo] (N = 2*BN), type 1 = a_lo x b_hi (N = BN); the epilogue adds
                        // accumulator columns [BN, 2BN) (the a_hi*b_lo cross term) to [0, BN).  2 A loads and
@@ -61,6 +69,9 @@ struct ConvTcParams {
                        // (packed `first` conv: both activation planes already sit in one K window).
   int b_rows_total;    // rows of one weight plane block (classes * cout): the lo block starts there
   int cta2;            // CTA pairs with cta_group::2 MMAs (tiles 2i, 2i+1 = adjacent M tiles of one class / N tile)
+  int pf_wide;         // folded pairs: a type-0 chunk is ONE N = 2*BN step.  CTA 0 stages all BN rows of b_hi, CTA 1 all
+                       // BN rows of b_lo (a pair MMA takes B rows [0, N/2) from CTA 0 and [N/2, N) from CTA 1), so the
+                       // accumulator columns are [hi | lo] as in the single-CTA kernel and A is fetched once, not twice
   int ksub;            // 64-channel K chunks per pipeline stage (1..4)
   int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
@@ -251,7 +262,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
   q = tile / (uint32_t)p.classes; t.cls = (int)(tile - q * p.classes); tile = q;
   if (p.cta2) tile = 2u * tile + rank;
   q = tile / (uint32_t)p.tiles_x; t.x0 = (int)(tile - q * p.tiles_x) * p.x_stride; tile = q;
-  q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.bh; tile = q;
+  q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.y_stride; tile = q;
   t.n0 = (int)tile * p.bn;
   return t;
 }
@@ -372,6 +383,65 @@ __device__ __forceinline__ void epilogue_kxn(const ConvTcParams& p, const TileCo
   }
 }
 
+// kx-in-N epilogue for the 112-column variants (kxn == 2: (dr, kx, co) = 4*7*4, NCHW + sigmoid; kxn == 3:
+// (kx, co) = 7*16, fp32 NHWC logits).  All eight epilogue warps move the accumulator to shared memory (row
+// stride 113 floats: conflict-free for lanes = rows; single buffer, the TMEM ring still decouples the MMA warp),
+// then each thread sums the kx-shifted entries of a few outputs, in the same order as the 32-column variant.
+constexpr int KXW_COLS = 112, KXW_LD = 113;
+__device__ __forceinline__ void epilogue_kxn_wide(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                                  int quadrant, int lane, int half, float* S) {
+  const int r = quadrant * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  for (int c0 = half * 16; c0 < KXW_COLS; c0 += 32) {
+    uint32_t raw[16];
+    TmemLd<16>::ld(taddr + (uint32_t)c0, raw);
+    if (p.fold) {
+      uint32_t raw2[16];
+      TmemLd<16>::ld(taddr + (uint32_t)(KXW_COLS + c0), raw2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) S[r * KXW_LD + c0 + j] = __uint_as_float(raw[j]);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const int tid = (half * 4 + quadrant) * 32 + lane;
+  if (p.kxn == 2) {
+    const int nc = p.out_nchw_c;
+    for (int i = tid; i < 4 * nc * 128; i += 256) {
+      const int rr = i & 127, q = i >> 7;
+      const int dr = q / nc, co = q - dr * nc;
+      const int x = tc.x0 + rr, y = tc.y0 + dr;
+      if (rr < 122 && x < p.W && y < p.H && tc.n0 < p.N) {
+        float acc = __ldg(p.bias + co);
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) acc += S[(rr + kx) * KXW_LD + dr * 28 + kx * 4 + co];
+        if (p.flags & EAMM_EPI_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+        p.out_nchw[(((long long)tc.n0 * nc + co) * p.H + y) * p.W + x] = acc;
+        if (p.out_u8 != nullptr) p.out_u8[(((long long)tc.n0 * p.H + y) * p.W + x) * nc + co] = to_ubyte(acc);
+      }
+    }
+  } else {
+    for (int i = tid; i < 128 * 16; i += 256) {
+      const int co = i & 15, px = i >> 4;
+      const int xl = px & (p.bw - 1), yl = px >> p.bw_log2;
+      const int y = tc.y0 + yl;
+      if (y < p.H && tc.n0 < p.N) {
+        float acc = __ldg(p.bias + co);
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int xs = xl + kx - 3;
+          if (xs >= 0 && xs < p.W) acc += S[(px + kx - 3) * KXW_LD + kx * 16 + co];
+        }
+        p.out_nhwc[(((long long)tc.n0 * p.H + y) * p.W + xl) * p.cout + co] = acc;
+      }
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");      // S is reused by the next tile
+}
+
 // INSTR = true compiles the bring-up instrumentation (EAMM_TC_PROF cycle counters, EAMM_TC_DEBUG
 // role isolation); the production instantiation carries none of it.
 // CTA2 = true: CTA pairs (cluster of 2) run `tcgen05.mma.cta_group::2`, M = 256 pixels x N = 256
@@ -431,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CTA2) cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int KC = ((p.halo || p.kxn) ? 7 : p.taps) * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
+  const int KC = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
   const uint32_t total_tiles = (uint32_t)p.total_tiles;
   const int dbg = INSTR ? p.debug : 0;
   // tile walk: CTA i takes tiles i, i+grid, ...; a CTA pair takes adjacent M tiles (2c + rank), (2c + rank) + grid, ...
@@ -447,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // is congruent to w.  A lone warp retires a dependent scalar instruction every ~8-10 cycles, so
     // one producer could not feed short-K layers (measured 600-800 cycles per 64-channel chunk).
     const uint32_t w = (uint32_t)(warp - TC_EPI_WARPS);
-    const uint32_t ntap = (p.halo || p.kxn) ? 7u : (uint32_t)p.taps;
+    const uint32_t ntap = (uint32_t)p.ntap;
     const uint32_t chunk_shift = (uint32_t)p.chunk_shift, chunk_mask = (1u << chunk_shift) - 1u;
     const int passes = p.passes, kind = p.kind;
     const uint32_t nstages = (uint32_t)p.num_stages;
@@ -497,7 +567,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int t = (int)(q - ps * ntap);
               int cbase = p.a_c_off + (((passes == 3 && ps == 1u) || type1) ? p.a_c_buf : 0);
               int dy, dx;
-              if (haloish) { dy = t - 3; dx = -3; }
+              if (haloish) { dy = t - 3; dx = p.kxn == 3 ? 0 : -3; }
               else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; cbase = 0; }   // both planes inside the K window
               else if (kind == EAMM_CONV_UP2_3X3) { dy = (tc.cls >> 1) - 1 + (t >> 1); dx = (tc.cls & 1) - 1 + (t & 1); }
               else if (kind == EAMM_CONV_3X3) { const int ty = (t * 11) >> 5; dy = ty - 1; dx = t - 3 * ty - 1; }
@@ -505,8 +575,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t sB = sa + KS * a_slot + sub * b_bytes;
               if (CTA2) {
                 tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-                tma2_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
-                if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+                if (fold && !type1 && p.pf_wide) {
+                  // wide step: this CTA stages every row of ONE weight plane of the N tile (rank 0: hi, rank 1: lo)
+                  const int prow = tc.cls * p.cout + tc.nt * p.BN + (int)cta_rank * p.b_rows_total;
+                  tma2_load_2d(sB, &tmB, fb, (int)kq * 64, prow);
+                  tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, prow + (p.BN >> 1));
+                } else {
+                  tma2_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
+                  if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+                }
               } else {
                 tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
                 tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
@@ -575,11 +652,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // interleave the columns as [hi|lo|hi|lo], so the type-0 chunk runs as two N = BN steps instead
                 // (b_hi halves -> columns [0,BN), b_lo halves -> [BN,2BN)): same column layout and the same
                 // per-column accumulation order as the single-CTA kernel, i.e. bit-identical results
-                tc2_mma_bf16(tmem_acc, da, db, idesc1, first);
-                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc1, 1u);
-                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc1, 1u);
-                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc1, 1u);
-                if (fold == 1 && idesc == idesc2) {
+                // (pf_wide: the producers staged plane-per-CTA instead, and the type-0 chunk is one N = 2*BN step)
+                const uint32_t idw = (fold == 1 && p.pf_wide) ? idesc : idesc1;
+                tc2_mma_bf16(tmem_acc, da, db, idw, first);
+                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idw, 1u);
+                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idw, 1u);
+                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idw, 1u);
+                if (fold == 1 && idesc == idesc2 && !p.pf_wide) {
                   const uint64_t dl = db + (uint64_t)(b_half >> 4);
                   const uint32_t acc2 = tmem_acc + (uint32_t)BN;
                   tc2_mma_bf16(acc2, da, dl, idesc1, first);
@@ -626,7 +705,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
       if (INSTR && dbg >= 5) {                     // 5: protocol only, 6: real main loop, no epilogue work
-      } else if (p.kxn) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
+      } else if (p.kxn == 1) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
+      else if (p.kxn) epilogue_kxn_wide(p, tc, tmem_acc, quadrant, lane, half, kxn_smem);
       else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
       tc_fence_before();
@@ -703,8 +783,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query);
 
 extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) { return conv_tc_run(a, stream, nullptr); }
 
-/* Dry run of eamm_conv_tc's planning: fills out[0..3] = {N tile, 7x7 scheme, fold, K chunks per stage}
- * for these arguments (a->weight_fold is ignored) without launching anything. */
+/* Dry run of eamm_conv_tc's planning: fills out[0..5] = {N tile, 7x7 scheme, fold, K chunks per stage,
+ * CTA pairs (bit 0) / wide folded step (bit 1), pipeline stages} for these arguments (a->weight_fold is ignored) without launching anything. */
 extern "C" int eamm_conv_tc_query(const eamm_conv_args* a, int* out) {
   if (!out) return EAMM_ERR_ARG;
   return conv_tc_run(a, nullptr, out);
@@ -742,23 +822,34 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("EAMM_TC_HALO"); halo_env = e ? atoi(e) : 1; }
-  const int mode7 = halo_env > 0 ? eamm_conv_tc_uses_halo(a->kind, in->w, a->cout,
-                                                          (a->out || a->out2 || a->out_nhwc_f32) ? 0 : a->out_nchw_c) : 0;
-  p.kxn = mode7 == 2; p.halo = mode7 == 1;
+  int mode7 = halo_env > 0 ? eamm_conv_tc_uses_halo(a->kind, in->w, a->cout,
+                                                    (a->out || a->out2 || a->out_nhwc_f32) ? 0 : a->out_nchw_c) : 0;
+  // 112-column kx-in-N variants (EAMM_TC_KXW bit 0: scheme 3 = four output rows per tile for the <=4-channel
+  // NCHW layer; bit 1: scheme 4 = full-width tiles for a <=128-wide map with 16 fp32 NHWC couts)
+  static int kxw_env = -1;
+  if (kxw_env < 0) { const char* e = getenv("EAMM_TC_KXW"); kxw_env = e ? atoi(e) : 0; }
+  if (mode7 == 2 && (kxw_env & 1) && in->h % 4 == 0) mode7 = 3;
+  if (halo_env > 0 && (kxw_env & 2) && a->kind == EAMM_CONV_7X7 && a->cout == 16 && a->flags == 0 && a->out_nhwc_f32 &&
+      !(a->out || a->out2 || a->out_nchw || a->residual) && in->w <= 128 && in->w * in->h >= 128)
+    mode7 = 4;
+  p.kxn = mode7 >= 2 ? mode7 - 1 : 0; p.halo = mode7 == 1;
   static int debug_env = -1;
   if (debug_env < 0) { const char* e = getenv("EAMM_TC_DEBUG"); debug_env = e ? atoi(e) : 0; }
   p.debug = debug_env;
   // 128-pixel box: bw x bh x bn
-  if (p.halo || p.kxn) { p.bw = 128; p.bh = 1; p.bn = 1; }
+  if (p.kxn == 3) { p.bw = in->w; p.bh = 128 / in->w; p.bn = 1; }
+  else if (p.halo || p.kxn) { p.bw = 128; p.bh = 1; p.bn = 1; }
   else {
     p.bw = in->w >= 16 ? 16 : in->w;
     p.bh = 128 / p.bw; if (p.bh > in->h) p.bh = in->h;
     p.bn = 128 / (p.bw * p.bh);
   }
   p.bw_log2 = ilog2_exact(p.bw); p.bh_log2 = ilog2_exact(p.bh);
-  p.x_stride = p.kxn ? 122 : p.bw;
+  p.x_stride = (p.kxn == 1 || p.kxn == 2) ? 122 : p.bw;
+  p.y_stride = p.kxn == 2 ? 4 : p.bh;
+  p.ntap = p.kxn == 2 ? 10 : ((p.halo || p.kxn) ? 7 : p.taps);
   p.tiles_x = (in->w + p.x_stride - 1) / p.x_stride;
-  p.tiles_y = (in->h + p.bh - 1) / p.bh; p.tiles_n = (in->n + p.bn - 1) / p.bn;
+  p.tiles_y = (in->h + p.y_stride - 1) / p.y_stride; p.tiles_n = (in->n + p.bn - 1) / p.bn;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0; cudaGetDevice(&dev);
@@ -776,7 +867,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     else if (!row7 && p.passes == 3) p.fold = 1;
   }
   if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
-  if (p.kxn) p.BN = 32;
+  if (p.kxn) p.BN = p.kxn == 1 ? 32 : KXW_COLS;
   else {
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes;
     p.BN = 0;
@@ -807,18 +898,19 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     const bool pair_b = (cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0;
     const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
     p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
+    p.pf_wide = (p.cta2 && p.fold == 1 && (cta2_env & 8)) ? 1 : 0;
   }
-  p.b_rows_total = p.kxn ? 32 : p.classes * a->cout;
+  p.b_rows_total = p.kxn ? p.BN : p.classes * a->cout;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
   const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes +
       (p.cta2 ? (uint32_t)p.BN * (p.fold ? 128u : 64u) : (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u)));
-  const uint32_t extra_smem = p.kxn ? 2u * 128u * 29u * 4u : 0u;
+  const uint32_t extra_smem = p.kxn == 1 ? 2u * 128u * 29u * 4u : (p.kxn ? 128u * (uint32_t)KXW_LD * 4u : 0u);
   const uint32_t ring_bytes = 200u * 1024u - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
   // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
   static int ksub_env = -1;
   if (ksub_env < 0) { const char* e = getenv("EAMM_TC_KSUB"); ksub_env = e ? atoi(e) : 0; }
-  const int kc_total = ((p.halo || p.kxn) ? 7 : p.taps) * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
+  const int kc_total = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
   int ksub = 1;
   for (int k = 4; k >= 2; --k)
     if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
@@ -836,7 +928,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
   p.num_stages = stages;
-  if (query) { query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub; return 0; }
+  if (query) {
+    query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub;
+    query[4] = p.cta2 | (p.pf_wide << 1); query[5] = p.num_stages;
+    return 0;
+  }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
   ActView dummy = make_view(in);
   p.out = p.has_out ? make_view(a->out) : dummy;
@@ -875,10 +971,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   {
     // halo mode: rows = (kx, cout), K = (ky, pass, channel); otherwise rows = (class, cout), K = (tap, pass, channel)
-    // kxn mode : rows = 32 (kx*4 + cout), K = (ky, pass, channel)
+    // kxn mode : rows = 32 (kx*4 + cout), K = (ky, pass, channel); kxn 2: rows = 112 (dr*28 + kx*4 + cout), K = (input
+    //            row j of 10, pass, channel); kxn 3: rows = 112 (kx*16 + cout), K = (ky, pass, channel)
     // fold mode: K = (tap, channel) only, rows = [hi block | lo block]
-    const cuuint64_t ktot = (cuuint64_t)((p.halo || p.kxn) ? 7 : p.taps) * (p.fold ? 1 : p.passes) * (row7 ? 64 : a->cin);
-    const cuuint64_t rows = (p.kxn ? 32 : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout) * (p.fold ? 2 : 1);
+    const cuuint64_t ktot = (cuuint64_t)p.ntap * (p.fold ? 1 : p.passes) * (row7 ? 64 : a->cin);
+    const cuuint64_t rows = (p.kxn ? (cuuint64_t)p.BN : (cuuint64_t)(p.halo ? 7 : p.classes) * a->cout) * (p.fold ? 2 : 1);
     cuuint64_t dims[2] = {ktot, rows};
     cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : (p.cta2 ? p.BN / 2 : p.BN))};

@@ -175,6 +175,39 @@ def pack_tc_weights_kxn(full, nchw_c, passes, fold=0):
     return packed.reshape(32, -1).contiguous()
 
 
+def _pack_rows_k(rows, passes, fold):
+    """[n rows][taps][cin] fp32 -> bf16 [n][passes * taps * cin] (K order (pass, tap, channel), planes lo, hi, hi)
+    or, folded, rows [n hi | n lo] with K = (tap, channel)."""
+    n = rows.shape[0]
+    hi = rows.to(torch.bfloat16)
+    if fold:
+        lo = (rows - hi.float()).to(torch.bfloat16)
+        return torch.cat([hi.reshape(n, -1), lo.reshape(n, -1)], dim=0).contiguous()
+    if passes == 1:
+        return hi.reshape(n, -1).contiguous()
+    lo = (rows - hi.float()).to(torch.bfloat16)
+    return torch.stack([lo, hi, hi], dim=1).reshape(n, -1).contiguous()
+
+
+def pack_tc_weights_kxn_rows(full, nchw_c, passes, fold=0):
+    """7x7 scheme 3 (kx-in-N, four output rows per tile): [49 taps][cout][cin] -> 112 rows (dr*28 + kx*4 + co),
+    K taps = the 10 input rows j of a tile; row block j of output row dr holds w[ky = j - dr] (zero outside 0..6)."""
+    _, cout, cin = full.shape
+    w = full.view(7, 7, cout, cin)[:, :, :nchw_c]                         # [ky][kx][co][cin]
+    rows = torch.zeros(4, 7, 4, 10, cin, dtype=torch.float32, device=full.device)   # [dr][kx][co][j][cin]
+    for dr in range(4):
+        rows[dr, :, :nchw_c, dr:dr + 7] = w.permute(1, 2, 0, 3)
+    return _pack_rows_k(rows.reshape(112, 10, cin), passes, fold)
+
+
+def pack_tc_weights_kxn_full(full, passes, fold=0):
+    """7x7 scheme 4 (kx-in-N, full-width tiles, 16 couts): [49 taps][16][cin] -> 112 rows (kx*16 + co), K taps = ky."""
+    _, cout, cin = full.shape
+    assert cout == 16
+    rows = full.view(7, 7, cout, cin).permute(1, 2, 0, 3)                 # [kx][co][ky][cin]
+    return _pack_rows_k(rows.reshape(112, 7, cin), passes, fold)
+
+
 def pack_tc_weights_row7(w, cout_pad, passes, fold=0):
     """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
 
@@ -269,16 +302,20 @@ class ConvLayer:
                    out_nhwc_f32 is not None)
             sel = self.plan_cache.get(key)
             if sel is None:
-                q = (C.c_int * 4)()
+                q = (C.c_int * 6)()
                 L.check(lib.eamm_conv_tc_query(C.byref(a), q), "conv %s (plan)" % self.name)
                 L.LAUNCHES -= 1                      # a query launches nothing
                 scheme, fold = q[1], q[2]
-                wkey = (scheme, fold, out_nchw_c if scheme == 2 else 0)
+                wkey = (scheme, fold, out_nchw_c if scheme in (2, 3) else 0)
                 if wkey not in self.weight_alt:
                     passes = 3 if self.impl == "tc3" else 1
                     classes = 4 if self.kind == L.CONV_UP2_3X3 else 1
                     if scheme == 2:
                         wt = pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes, fold)
+                    elif scheme == 3:
+                        wt = pack_tc_weights_kxn_rows(self.w_ref, out_nchw_c, passes, fold)
+                    elif scheme == 4:
+                        wt = pack_tc_weights_kxn_full(self.w_ref, passes, fold)
                     elif scheme == 1:
                         wt = pack_tc_weights_halo(self.w_ref, passes)
                     elif fold:
@@ -288,6 +325,7 @@ class ConvLayer:
                     self.weight_alt[wkey] = wt
                 sel = (self.weight_alt[wkey], fold)
                 self.plan_cache[key] = sel
+                self.last_plan = tuple(q)            # (N tile, scheme, fold, chunks/stage, pair bits, stages)
             a.weight = sel[0].data_ptr()
             a.weight_fold = sel[1]
         fn = lib.eamm_conv_simt if self.impl == "simt" else lib.eamm_conv_tc
@@ -355,7 +393,7 @@ class FirstConvTC:
         a.pack_passes = self.passes
         fold = self.plan_cache.get((nsrc, H, W))
         if fold is None:
-            q = (C.c_int * 4)()
+            q = (C.c_int * 6)()
             a.weight = self.bias.data_ptr()          # any valid pointer: the query does not read it
             L.check(lib.eamm_conv_tc_query(C.byref(a), q), "conv first (plan)")
             L.LAUNCHES -= 1

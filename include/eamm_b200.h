@@ -195,7 +195,12 @@ int eamm_conv_tc(const eamm_conv_args* args, void* stream);
  *   0  one TMA tile per tap           bf16 [cout][passes * 49 taps * cin]
  *   1  halo row, kx-shifted views     bf16 [7 kx * cout][passes * 7 ky * cin]      (w % 128 == 0, cout <= 32)
  *   2  kx taps in the GEMM N axis     bf16 [32 = kx*4 + co][passes * 7 ky * cin]   (w % 128 == 0, only
- *      out_nchw with <= 4 channels; out_nchw_c = 0 when the call has any NHWC output) */
+ *      out_nchw with <= 4 channels; out_nchw_c = 0 when the call has any NHWC output)
+ * eamm_conv_tc_query may also report (EAMM_TC_KXW switch, see conv_tc.cu):
+ *   3  as 2 with four output rows per tile: bf16 [112 = dr*28 + kx*4 + co][passes * 10 input rows * cin],
+ *      row block j of output row dr = w[ky = j - dr] (zero outside the filter)         (h % 4 == 0)
+ *   4  kx in N, full-width tiles      bf16 [112 = kx*16 + co][passes * 7 ky * cin]    (cout == 16, w <= 128,
+ *      only out_nhwc_f32, no flags) */
 int eamm_conv_tc_uses_halo(int kind, int w, int cout, int out_nchw_c);
 
 /* Split (hi/lo) layers with cout <= 128 (and the kx-in-N 7x7 scheme) stack the two weight planes along N:
@@ -208,7 +213,8 @@ int eamm_conv_tc_fold(int kind, int split, int cout, int halo_scheme);
 
 /* Planning dry run of eamm_conv_tc for `args` (weight_fold ignored, nothing launched):
  * out[0] = N tile, out[1] = 7x7 scheme (eamm_conv_tc_uses_halo), out[2] = fold (eamm_conv_tc_fold),
- * out[3] = K chunks per pipeline stage.  The host packs the weights for out[1]/out[2]. */
+ * out[3] = K chunks per pipeline stage, out[4] = bit 0 CTA pairs (cta_group::2), bit 1 wide folded step,
+ * out[5] = pipeline stages (`out` has room for 6 ints).  The host packs the weights for out[1]/out[2]. */
 int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
 
 /* ---- source image for EAMM_CONV_ROW7_PACKED: src [n,C<=3,H,W] fp32 NCHW -> dst bf16

@@ -75,6 +75,72 @@ def test_tc_weight_packing_order_and_split():
 
 
 # ------------------------------------------------------------------ sampler pins (index selection)
+def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
+    """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
+    D = torch.zeros(len(y_rows), B.shape[0], dtype=torch.float64)
+    for j in range(ntap):
+        zero = torch.zeros(cin, dtype=torch.float64)                 # TMA zero-fills out-of-range pixels
+        A = torch.stack([xpad[y + j - 3 + pad, x + pad] if 0 <= x + pad < xpad.shape[1] and
+                         0 <= y + j - 3 + pad < xpad.shape[0] else zero for y, x in zip(y_rows, x_cols)])    # [128][cin]
+        D += A @ B[:, j * cin:(j + 1) * cin].T
+    return D
+
+
+def test_kxn_wide_packings_reproduce_the_7x7_conv():
+    """Schemes 3 and 4 of eamm_conv_tc (112-column kx-in-N): the packed weight matrices plus the shift-sum
+    of the kernel's epilogue (conv_tc.cu epilogue_kxn_wide) equal a 7x7 / pad-3 convolution."""
+    g = torch.Generator().manual_seed(5)
+    cin, pad = 64, 16
+    # scheme 3: 3 NCHW channels, four output rows per tile, x tiles of 122 (+6 halo) pixels
+    H, W = 8, 130
+    w = torch.randn(3, cin, 7, 7, generator=g, dtype=torch.float64)
+    x = torch.randn(H, W, cin, generator=g, dtype=torch.float64)
+    want = F.conv2d(x.permute(2, 0, 1)[None], w, padding=3)[0]                     # [3][H][W]
+    full = torch.zeros(49, 16, cin, dtype=torch.float64)
+    full[:, :3] = w.permute(2, 3, 0, 1).reshape(49, 3, cin)
+    xpad = F.pad(x, (0, 0, pad, pad, pad, pad))
+    rows = torch.zeros(4, 7, 4, 10, cin, dtype=torch.float64)
+    for dr in range(4):
+        rows[dr, :, :3, dr:dr + 7] = full.view(7, 7, 16, cin)[:, :, :3].permute(1, 2, 0, 3)
+    B = rows.reshape(112, 10 * cin)
+    packed = engine.pack_tc_weights_kxn_rows(full.float(), 3, 1, 0).double()          # bf16-rounded copy of B
+    assert packed.shape == B.shape and (packed - B).abs().max() <= B.abs().max() * 2 ** -8
+    folded = engine.pack_tc_weights_kxn_rows(full.float(), 3, 3, 1).double()
+    assert folded.shape == (224, 10 * cin)
+    assert (folded[:112] + folded[112:] - B).abs().max() <= B.abs().max() * 2 ** -15
+    split3 = engine.pack_tc_weights_kxn_rows(full.float(), 3, 3, 0).double()
+    assert split3.shape == (112, 30 * cin) and torch.equal(split3[:, 10 * cin:20 * cin], folded[:112])
+    got = torch.zeros_like(want)
+    for y0 in range(0, H, 4):
+        for x0 in range(0, W, 122):
+            D = _emulate_kxn_tile_gemm(xpad, pad, [y0] * 128, [x0 - 3 + p for p in range(128)], B, cin, 10)
+            for dr in range(4):
+                for r in range(122):
+                    if x0 + r < W and y0 + dr < H:
+                        for co in range(3):
+                            got[co, y0 + dr, x0 + r] = sum(D[r + kx, dr * 28 + kx * 4 + co] for kx in range(7))
+    assert torch.allclose(got, want, atol=1e-9)
+    # scheme 4: 16 fp32 NHWC couts, W = 64, tile = two whole rows, zero padding instead of an x halo
+    H, W = 4, 64
+    w = torch.randn(16, cin, 7, 7, generator=g, dtype=torch.float64)
+    x = torch.randn(H, W, cin, generator=g, dtype=torch.float64)
+    want = F.conv2d(x.permute(2, 0, 1)[None], w, padding=3)[0]
+    full = w.permute(2, 3, 0, 1).reshape(49, 16, cin)
+    B = full.view(7, 7, 16, cin).permute(1, 2, 0, 3).reshape(112, 7 * cin)
+    packed = engine.pack_tc_weights_kxn_full(full.float(), 1, 0).double()
+    assert packed.shape == B.shape and (packed - B).abs().max() <= B.abs().max() * 2 ** -8
+    xpad = F.pad(x, (0, 0, pad, pad, pad, pad))
+    got = torch.zeros_like(want)
+    for y0 in range(0, H, 2):
+        px = [(y0 + p // W, p % W) for p in range(128)]
+        D = _emulate_kxn_tile_gemm(xpad, pad, [a for a, _ in px], [b for _, b in px], B, cin, 7)
+        for p in range(128):
+            yl, xl = p // W, p % W
+            for co in range(16):
+                got[co, y0 + yl, xl] = sum(D[p + kx - 3, kx * 16 + co] for kx in range(7) if 0 <= xl + kx - 3 < W)
+    assert torch.allclose(got, want, atol=1e-9)
+
+
 def test_numpy_sampler_matches_torch_grid_sample_and_corner_values():
     assert sampler_np.unnormalize(np.float32(-1.0), 64) == -0.5          # SURVEY.md §7 "hard parts"
     assert sampler_np.unnormalize(np.float32(1.0), 64) == 63.5

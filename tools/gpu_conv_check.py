@@ -44,6 +44,20 @@ CASES = [
     ("pair 3x3 64->64 64x64 N=8 pool", "3x3", "rp", 64, 64, 8, 64, 64, 1, 0, 0, ""),
     ("pair 3x3 256->512 8x8 N=32 pool x3", "3x3", "rp", 256, 512, 32, 8, 8, 2, 0, 0, ""),
     ("pair up2 512->256 4x4 N=32", "up2", "r", 512, 256, 32, 4, 4, 1, 0, 0, ""),
+    # EAMM_TC_KXW=3 (name prefix kxw): 112-column kx-in-N schemes 3 (rows) and 4 (full width)
+    ("kxw 7x7 128->16 64x64 N=2 logits", "7x7", "", 128, 16, 2, 64, 64, 1, 0, 0, "nhwc"),
+    ("kxw 7x7 128->16 64x64 N=5 logits x3", "7x7", "", 128, 16, 5, 64, 64, 2, 0, 0, "nhwc"),
+    ("kxw 7x7 64->16 32x32 N=3 logits x3", "7x7", "", 64, 16, 3, 32, 32, 2, 0, 0, "nhwc"),
+    ("kxw 7x7 64->16 128x128 N=2 logits", "7x7", "", 64, 16, 2, 128, 128, 1, 0, 0, "nhwc"),
+    ("kxw 7x7 64->16 256x256 N=2 sigmoid x3", "7x7", "s", 64, 16, 2, 256, 256, 2, 0, 0, "nchw"),
+    ("kxw 7x7 64->16 256x256 N=3 sigmoid", "7x7", "s", 64, 16, 3, 256, 256, 1, 0, 0, "nchw"),
+    ("kxw 7x7 128->16 128x128 N=2 sigmoid x3", "7x7", "s", 128, 16, 2, 128, 128, 2, 0, 0, "nchw"),
+    # EAMM_TC_CTA2=11 (name prefix pfwide): folded pairs with one N = 2*BN step per type-0 chunk
+    ("pfwide 3x3 64->128 256x256 N=2 pool x3", "3x3", "rp", 64, 128, 2, 256, 256, 2, 0, 0, ""),
+    ("pfwide up2 128->64 128x128 N=2 x3", "up2", "r", 128, 64, 2, 128, 128, 2, 0, 0, ""),
+    ("pfwide 3x3 128->128 32x32 N=3 r+o2 x3", "3x3", "", 128, 128, 3, 32, 32, 2, 1, 1, ""),
+    ("pfwide up2 256->128 64x64 N=5 x3", "up2", "r", 256, 128, 5, 64, 64, 2, 0, 0, ""),
+    ("pfwide 3x3 64->32 64x64 N=8 pool x3", "3x3", "rp", 64, 32, 8, 64, 64, 2, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
@@ -55,6 +69,10 @@ def run_case(idx):
     from eamm_b200 import _lib as L
     from eamm_b200.engine import ActBuf, ConvLayer, current_stream_ptr
     name, kind, fl, cin, cout, N, H, W, planes, has_res, has_out2, special = CASES[idx]
+    if name.startswith("kxw"):
+        os.environ["EAMM_TC_KXW"] = "3"
+    if name.startswith("pfwide"):
+        os.environ["EAMM_TC_CTA2"] = "11"
     dev = torch.device("cuda:0")
     lib = L.load()
     g = torch.Generator().manual_seed(100 + idx)
@@ -111,8 +129,13 @@ def run_case(idx):
             worst = float("inf")
     tol = 2e-4 if planes == 2 else 1e-2     # bf16 output rounding dominates in 1-plane mode
     status = "OK " if worst <= tol else "BAD"
-    print("%s case %2d %-34s rel_err %.3e" % (status, idx, name, worst), flush=True)
-    return 0 if worst <= tol else 1
+    plan = getattr(layer, "last_plan", ())
+    if name.startswith("kxw") and (not plan or plan[1] not in (3, 4)):
+        status, worst = "BAD", float("nan")          # the scheme under test was not selected
+    if name.startswith("pfwide") and (not plan or plan[4] != 3):
+        status, worst = "BAD", float("nan")
+    print("%s case %2d %-38s rel_err %.3e plan %s" % (status, idx, name, worst, plan), flush=True)
+    return 0 if status == "OK " else 1
 
 
 def run_first(idx):
