@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--shared-source", action="store_true", help="one source image for the whole batch")
     ap.add_argument("--ref-batch", type=int, default=16, help="frames per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-kernels", action="store_true", help="kernels_ms_per_step lists every kernel, not the top 12")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -297,7 +298,7 @@ def main():
         gbs = wo[2] / (wo[0] * 1e-3) / 1e9
         hbm = {"kernel": "warp_occlude_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": wo[2]}
-    kernels = {k: {"ms": round(v[0], 4), "launches": v[3]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:12]}
+    kernels = {k: {"ms": round(v[0], 4), "launches": v[3]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:(None if args.all_kernels else 12)]}
 
     frames = total * args.steps
     value = frames / (ms * 1e-3)

@@ -11,6 +11,7 @@ from . import build as _build
 EAMM_F32, EAMM_BF16 = 0, 1
 CONV_3X3, CONV_7X7, CONV_UP2_3X3, CONV_ROW7_PACKED = 0, 1, 2, 3
 EPI_RELU, EPI_POOL2, EPI_SIGMOID = 1, 2, 4
+SPLITK_WS_BYTES = 4096 + 160 * 128 * 256 * 4          # EAMM_SPLITK_WS_BYTES
 
 _ERR = {-1: "EAMM_ERR_ARG", -2: "EAMM_ERR_SHAPE", -3: "EAMM_ERR_DTYPE", -4: "EAMM_ERR_ALIGN",
         -5: "EAMM_ERR_UNSUPPORTED"}
@@ -42,7 +43,8 @@ class ConvArgs(C.Structure):
                 ("residual", C.POINTER(Act)), ("out", C.POINTER(Act)), ("out2", C.POINTER(Act)),
                 ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("out_nchw", C.c_void_p),
                 ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32),
-                ("weight_fold", C.c_int32), ("out_u8_nhwc", C.c_void_p)]
+                ("weight_fold", C.c_int32), ("out_u8_nhwc", C.c_void_p),
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/eamm_b200.h

@@ -19,9 +19,16 @@
 //               kx-in-N    7x7 -> <=4 NCHW channels: the 7 kx taps are GEMM columns, epilogue sums shifts
 //               row7       7x7 over a packed <=3-channel image: K window = 8 pixels x (hi,lo) channels
 //               fold       split mode, cout <= 128: weight planes stacked along N (2 A loads, not 3)
+//               kx-in-N x4 `final` with four output rows per tile: N = (dr, kx, co) = 112, K walks 10 input rows
+//               kx-in-N fw mask+occlusion logits (W <= 128, 16 couts): N = (kx, co) = 112, full-width tiles
+//               split-K    layers with too few N = 256 tiles for the chip (hourglass 8x8 ... 2x2): partial tiles through
+//                          an fp32 workspace, the last-arriving CTA reduces in split order and runs the epilogue
 //               CTA pair   N tile 256 and folded layers: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
-//               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step -- default 3), EAMM_TC_KSUB / _CTA2_KSUB force the
+//               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step (measured no faster: a pair MMA
+//               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 3),
+//               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4; default 3), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
+//               split-K / the 32-byte epilogue stores off, EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -61,7 +68,16 @@ struct ConvTcParams {
                        // N = (kx, co) = 7*16 = 112, tile = (128/W) whole rows, no x halo (it is the zero padding)
   int x_stride;        // pixels between consecutive x tiles (122 in kxn mode 1/2, else bw)
   int y_stride;        // rows between consecutive y tiles (4 for kxn == 2, else bh)
+  int st256;           // epilogue activation stores / residual loads as 32-byte pieces (every view 32-byte aligned)
   int ntap;            // K-loop taps: 7 (halo, kxn 1/3), 10 (kxn 2), else taps
+  int splitk;          // > 1: split-K.  `splitk` consecutive work items share one output tile, each runs 1/splitk of the
+                       // K loop (contiguous in the (pass, tap, chunk) order), publishes its fp32 partial tile to sk_ws
+                       // and bumps the tile's counter; the item that arrives last sums the partials in split order
+                       // (deterministic) and runs the normal epilogue.  For the 8x8 ... 2x2 hourglass layers, which
+                       // otherwise need N tiles of 32 columns to occupy the chip and then pay the per-MMA A-slab cost
+                       // 8x more often than an N = 256 tile would.
+  float* sk_ws;        // [out tile][split][128][BN] fp32 partials
+  unsigned int* sk_cnt;// [out tile] arrival counters, zero before and after every launch
   int fold;            // split mode with 2*BN <= 256: the weight planes are stacked along N.  Chunk type 0 =
                        // a_hi x [b_hi; b_lo] (N = 2*BN), type 1 = a_lo x b_hi (N = BN); the epilogue adds
                        // accumulator columns [BN, 2BN) (the a_hi*b_lo cross term) to [0, BN).  2 A loads and
@@ -217,9 +233,42 @@ template <> struct TmemLd<16> {
 };
 
 // bf16 vector store/load of CH consecutive channels (hi plane, and lo plane when planes == 2)
+// 256-bit global store / load (sm_100: STG.E.ENL2.256): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+// WIDE: every lane writes 32-byte pieces (a thread owns one pixel, so a warp store spans 32 pixels: 16-byte
+// pieces fill only half of each sector they touch)
 template <int CH>
-__device__ __forceinline__ void store_chunk(const ActView& v, long long off, const float* f) {
+__device__ __forceinline__ void store_chunk(const ActView& v, long long off, const float* f, bool wide) {
   __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
+  if (wide) {
+#pragma unroll
+    for (int g = 0; g < CH / 16; ++g) {
+      uint2 q[4];
+      float4 h[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        q[i] = float4_to_bf16x4(make_float4(f[16 * g + 4 * i], f[16 * g + 4 * i + 1], f[16 * g + 4 * i + 2], f[16 * g + 4 * i + 3]));
+        h[i] = bf16x4_to_float4(q[i]);
+      }
+      stg256(p + 16 * g, make_uint4(q[0].x, q[0].y, q[1].x, q[1].y), make_uint4(q[2].x, q[2].y, q[3].x, q[3].y));
+      if (v.planes == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          q[i] = float4_to_bf16x4(make_float4(f[16 * g + 4 * i] - h[i].x, f[16 * g + 4 * i + 1] - h[i].y,
+                                              f[16 * g + 4 * i + 2] - h[i].z, f[16 * g + 4 * i + 3] - h[i].w));
+        stg256(p + v.c_buf + 16 * g, make_uint4(q[0].x, q[0].y, q[1].x, q[1].y), make_uint4(q[2].x, q[2].y, q[3].x, q[3].y));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < CH / 8; ++g) {
     uint2 a = float4_to_bf16x4(make_float4(f[8 * g], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3]));
@@ -234,8 +283,23 @@ __device__ __forceinline__ void store_chunk(const ActView& v, long long off, con
   }
 }
 template <int CH>
-__device__ __forceinline__ void add_chunk(const ActView& v, long long off, float* f) {
+__device__ __forceinline__ void add_chunk(const ActView& v, long long off, float* f, bool wide) {
   const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(v.data) + off;
+  if (wide) {
+#pragma unroll
+    for (int g = 0; g < CH / 16; ++g) {
+      for (int pl = 0; pl < v.planes; ++pl) {
+        uint4 a, b;
+        ldg256(p + pl * v.c_buf + 16 * g, a, b);
+        const float4 x0 = bf16x4_to_float4(make_uint2(a.x, a.y)), x1 = bf16x4_to_float4(make_uint2(a.z, a.w));
+        const float4 x2 = bf16x4_to_float4(make_uint2(b.x, b.y)), x3 = bf16x4_to_float4(make_uint2(b.z, b.w));
+        float* o = f + 16 * g;
+        o[0] += x0.x; o[1] += x0.y; o[2] += x0.z; o[3] += x0.w; o[4] += x1.x; o[5] += x1.y; o[6] += x1.z; o[7] += x1.w;
+        o[8] += x2.x; o[9] += x2.y; o[10] += x2.z; o[11] += x2.w; o[12] += x3.x; o[13] += x3.y; o[14] += x3.z; o[15] += x3.w;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < CH / 8; ++g) {
     uint4 r = __ldg(reinterpret_cast<const uint4*>(p + 8 * g));
@@ -251,10 +315,13 @@ __device__ __forceinline__ void add_chunk(const ActView& v, long long off, float
   }
 }
 
-struct TileCoord { int x0, y0, n0, cls, nt; };
+struct TileCoord { int x0, y0, n0, cls, nt, split; uint32_t out_tile; };
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t tile) {
   TileCoord t;
+  t.split = 0;
+  if (p.splitk > 1) { const uint32_t q0 = tile / (uint32_t)p.splitk; t.split = (int)(tile - q0 * p.splitk); tile = q0; }
+  t.out_tile = tile;
   // CTA pairs: tiles 2i and 2i+1 are adjacent M tiles of the same (class, N tile) -- they share the weights
   const uint32_t rank = p.cta2 ? (tile & 1u) : 0u;
   if (p.cta2) tile >>= 1;
@@ -284,15 +351,36 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
   for (int c0 = half * CH; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * CH) {
     uint32_t raw[CH];
-    TmemLd<CH>::ld(taddr + c0, raw);
-    if (p.fold) {                                   // add the a_hi*b_lo columns kept at [BN, 2BN)
-      uint32_t raw2[CH];
-      TmemLd<CH>::ld(taddr + p.BN + c0, raw2);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (p.splitk > 1) {                             // reducer of a split-K tile: partials summed in split order
+      const float* src = p.sk_ws + (((size_t)tc.out_tile * p.splitk) * 128 + r) * p.BN + c0;
 #pragma unroll
-      for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      for (int g = 0; g < CH / 4; ++g) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + g);
+        raw[4 * g] = __float_as_uint(v.x); raw[4 * g + 1] = __float_as_uint(v.y);
+        raw[4 * g + 2] = __float_as_uint(v.z); raw[4 * g + 3] = __float_as_uint(v.w);
+      }
+      for (int s2 = 1; s2 < p.splitk; ++s2) {
+        src += 128 * p.BN;
+#pragma unroll
+        for (int g = 0; g < CH / 4; ++g) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + g);
+          raw[4 * g] = __float_as_uint(__uint_as_float(raw[4 * g]) + v.x);
+          raw[4 * g + 1] = __float_as_uint(__uint_as_float(raw[4 * g + 1]) + v.y);
+          raw[4 * g + 2] = __float_as_uint(__uint_as_float(raw[4 * g + 2]) + v.z);
+          raw[4 * g + 3] = __float_as_uint(__uint_as_float(raw[4 * g + 3]) + v.w);
+        }
+      }
+    } else {
+      TmemLd<CH>::ld(taddr + c0, raw);
+      if (p.fold) {                                   // add the a_hi*b_lo columns kept at [BN, 2BN)
+        uint32_t raw2[CH];
+        TmemLd<CH>::ld(taddr + p.BN + c0, raw2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     float f[CH];
     const int co = tc.nt * p.BN + c0;
 #pragma unroll
@@ -316,8 +404,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
       }
     }
     if (valid) {
-      if (p.has_res) add_chunk<CH>(p.res, act_offset(p.res, n, oy, ox, co), f);
-      if (p.has_out) store_chunk<CH>(p.out, act_offset(p.out, n, oy, ox, co), f);
+      if (p.has_res) add_chunk<CH>(p.res, act_offset(p.res, n, oy, ox, co), f, p.st256);
+      if (p.has_out) store_chunk<CH>(p.out, act_offset(p.out, n, oy, ox, co), f, p.st256);
       if (p.has_out2) {
         float g2[CH];
 #pragma unroll
@@ -329,7 +417,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
           g2[4 * g + 2] = fmaxf(fmaf(f[4 * g + 2], s.z, t.z), 0.f);
           g2[4 * g + 3] = fmaxf(fmaf(f[4 * g + 3], s.w, t.w), 0.f);
         }
-        store_chunk<CH>(p.out2, act_offset(p.out2, n, oy, ox, co), g2);
+        store_chunk<CH>(p.out2, act_offset(p.out2, n, oy, ox, co), g2, p.st256);
       }
       if (p.out_nhwc != nullptr) {
         float4* dst = reinterpret_cast<float4*>(p.out_nhwc + (((long long)n * OH + oy) * OW + ox) * p.cout + co);
@@ -349,6 +437,39 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
       }
     }
   }
+}
+
+// Split-K: publish this work item's fp32 partial accumulator tile and elect the reducer.  Returns true in the
+// CTA whose arrival completes the tile (all its epilogue threads): it then runs epilogue_tile, which sums the
+// partials.  Classic last-block pattern: data stores, __threadfence, CTA barrier, one atomicAdd on the tile's
+// counter; the reducer fences again and reads with ld.global.cg.  The counter is left at zero for the next launch.
+__device__ __forceinline__ bool splitk_publish(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                               int quadrant, int lane, int half, volatile uint32_t* flag) {
+  const int r = quadrant * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  float* dst = p.sk_ws + (((size_t)tc.out_tile * p.splitk + tc.split) * 128 + r) * p.BN;
+  for (int c0 = half * 32; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * 32) {
+    uint32_t raw[32];
+    TmemLd<32>::ld(taddr + (uint32_t)c0, raw);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      __stcg(reinterpret_cast<float4*>(dst + c0) + g,
+             make_float4(__uint_as_float(raw[4 * g]), __uint_as_float(raw[4 * g + 1]),
+                         __uint_as_float(raw[4 * g + 2]), __uint_as_float(raw[4 * g + 3])));
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(p.sk_cnt + tc.out_tile, 1u);
+    const bool last = old == (unsigned int)(p.splitk - 1);
+    if (last) p.sk_cnt[tc.out_tile] = 0u;
+    *flag = last ? 1u : 0u;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const bool last = *flag != 0u;
+  if (last) __threadfence();
+  return last;
 }
 
 // kx-in-N epilogue (7x7 -> <=4 channels, sigmoid, NCHW fp32): accumulator row p holds, for the input
@@ -456,6 +577,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 16 + 4];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t sk_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem is only guaranteed 16B-aligned by the ABI: align the ring to 1024 B by hand
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -501,7 +623,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CTA2) cluster_sync_all();          // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int KC = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
+  const int KC = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes)) / (p.splitk > 1 ? p.splitk : 1);
   const uint32_t total_tiles = (uint32_t)p.total_tiles;
   const int dbg = INSTR ? p.debug : 0;
   // tile walk: CTA i takes tiles i, i+grid, ...; a CTA pair takes adjacent M tiles (2c + rank), (2c + rank) + grid, ...
@@ -561,7 +683,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // (fold mode keeps a_hi*b_lo in its own accumulator columns instead.)
               const uint32_t kc = kc0 + sub;
               const uint32_t type1 = (fold == 1 && kc >= 1u && kc <= foldT) ? 1u : 0u;
-              const uint32_t kq = fold == 1 ? (kc == 0u ? 0u : (type1 ? kc - 1u : kc - foldT)) : kc;
+              const uint32_t kq = fold == 1 ? (kc == 0u ? 0u : (type1 ? kc - 1u : kc - foldT))
+                                            : kc + (uint32_t)tc.split * (uint32_t)KC;     // split-K: this item's K range
               const uint32_t cc = kq & chunk_mask, q = kq >> chunk_shift;          // q = pass * ntap + tap
               const uint32_t ps = q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u);
               const int t = (int)(q - ps * ntap);
@@ -707,6 +830,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (INSTR && dbg >= 5) {                     // 5: protocol only, 6: real main loop, no epilogue work
       } else if (p.kxn == 1) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
       else if (p.kxn) epilogue_kxn_wide(p, tc, tmem_acc, quadrant, lane, half, kxn_smem);
+      else if (p.splitk > 1) {
+        if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+      }
       else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
       tc_fence_before();
@@ -827,7 +953,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   // 112-column kx-in-N variants (EAMM_TC_KXW bit 0: scheme 3 = four output rows per tile for the <=4-channel
   // NCHW layer; bit 1: scheme 4 = full-width tiles for a <=128-wide map with 16 fp32 NHWC couts)
   static int kxw_env = -1;
-  if (kxw_env < 0) { const char* e = getenv("EAMM_TC_KXW"); kxw_env = e ? atoi(e) : 0; }
+  if (kxw_env < 0) { const char* e = getenv("EAMM_TC_KXW"); kxw_env = e ? atoi(e) : 3; }
   if (mode7 == 2 && (kxw_env & 1) && in->h % 4 == 0) mode7 = 3;
   if (halo_env > 0 && (kxw_env & 2) && a->kind == EAMM_CONV_7X7 && a->cout == 16 && a->flags == 0 && a->out_nhwc_f32 &&
       !(a->out || a->out2 || a->out_nchw || a->residual) && in->w <= 128 && in->w * in->h >= 128)
@@ -881,6 +1007,29 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
       else return EAMM_ERR_UNSUPPORTED;
     }
   }
+  // split-K (see ConvTcParams::splitk): unfolded layers whose N = 256 tiling leaves more than half of the SMs idle.
+  // S = the largest divisor of the K-chunk count that keeps tiles * S within the SM count (>= 8 chunks per item).
+  // The partial sums are added in split order, so a result is reproducible for a given batch size, but its last
+  // bits depend on S and hence on how many frames share the launch.
+  p.splitk = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  static int splitk_env = -1;
+  if (splitk_env < 0) { const char* e = getenv("EAMM_TC_SPLITK"); splitk_env = e ? atoi(e) : 1; }
+  if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && a->cout % 256 == 0 && (query || a->splitk_ws)) {
+    const long long t256 = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / 256);
+    const int kc_all = p.taps * p.cin_chunks * p.passes;
+    int S = 1;
+    for (int d = 2; d <= 32 && t256 * d <= num_sms; ++d)
+      if (kc_all % d == 0 && kc_all / d >= 8) S = d;
+    const long long need = 4096 + t256 * S * 128ll * 256 * 4;
+    if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && (query || a->splitk_ws_bytes >= need) &&
+        (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
+      p.BN = 256; p.splitk = S;
+      if (!query) {
+        p.sk_cnt = reinterpret_cast<unsigned int*>(a->splitk_ws);
+        p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(a->splitk_ws) + 4096);
+      }
+    }
+  }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   static int cta2_env = -1, prof_env = -1;
   if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 3; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256 (measured slower in
@@ -889,7 +1038,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
   {
     const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
-    const bool common = cta2_env && !instr && !p.halo && !p.kxn && !row7 && (num_sms % 2) == 0;
+    const bool common = cta2_env && !instr && !p.halo && !p.kxn && !row7 && p.splitk == 1 && (num_sms % 2) == 0;
     // (a) unfolded layers (3-pass cout > 128, every single-plane layer), (b) folded layers (split mode, cout <= 128); both
     // once they fill the chip and when a pair's two M tiles exist (even count).  The arithmetic (per-column
     // accumulation order) is the same as the single-CTA kernel's, so the choice may depend on the batch.
@@ -910,7 +1059,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
   static int ksub_env = -1;
   if (ksub_env < 0) { const char* e = getenv("EAMM_TC_KSUB"); ksub_env = e ? atoi(e) : 0; }
-  const int kc_total = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes));
+  const int kc_total = p.ntap * p.cin_chunks * (p.fold == 1 ? 2 : (p.fold == 2 ? 1 : p.passes)) / p.splitk;
   int ksub = 1;
   for (int k = 4; k >= 2; --k)
     if ((uint32_t)k * chunk_bytes * 4u <= ring_bytes && k <= kc_total) { ksub = k; break; }
@@ -930,7 +1079,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.num_stages = stages;
   if (query) {
     query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub;
-    query[4] = p.cta2 | (p.pf_wide << 1); query[5] = p.num_stages;
+    query[4] = p.cta2 | (p.pf_wide << 1) | (p.splitk << 8); query[5] = p.num_stages;
     return 0;
   }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
@@ -938,9 +1087,16 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.out = p.has_out ? make_view(a->out) : dummy;
   p.out2 = p.has_out2 ? make_view(a->out2) : dummy;
   p.res = p.has_res ? make_view(a->residual) : dummy;
+  static int st256_env = -1;
+  if (st256_env < 0) { const char* e = getenv("EAMM_TC_ST256"); st256_env = e ? atoi(e) : 1; }
+  p.st256 = st256_env ? 1 : 0;
+  for (int i = 0; i < 3; ++i)
+    if (views[i] && ((uintptr_t)views[i]->data % 32 || views[i]->c_off % 16 || views[i]->c_buf % 16 ||
+                     views[i]->n_stride % 16 || (views[i]->planes * views[i]->c_buf) % 16))
+      p.st256 = 0;
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
+  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles * p.splitk;
   if (p.total_tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
 
   EncodeTiledFn encode = get_encode_fn();

@@ -80,6 +80,20 @@ class ActBuf:
 # --------------------------------------------------------------------------------------------
 # weight packing
 # --------------------------------------------------------------------------------------------
+_SPLITK_WS = {}
+
+
+def splitk_workspace(device, stream):
+    """Split-K scratch of eamm_conv_tc (include/eamm_b200.h `splitk_ws`): one zero-initialised buffer per
+    (device, stream) -- launches on one stream are ordered, so they can share it; different streams cannot."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           int(getattr(stream, "value", stream) or 0))
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = torch.zeros(L.SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
 def fold_bn(w, b, bn):
     """conv -> eval BatchNorm  ==  conv with w*s, (b-mean)*s+beta   (batchnorm.py:50-53)."""
     s = bn["weight"] / torch.sqrt(bn["running_var"] + BN_EPS)
@@ -298,6 +312,8 @@ class ConvLayer:
         if out_u8 is not None:
             a.out_u8_nhwc = out_u8.data_ptr()
         if self.impl != "simt":
+            ws = splitk_workspace(self.bias.device, stream)
+            a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel()
             key = (inp.n, inp.h, inp.w, out_nchw_c if out_nchw is not None else -1, out is not None,
                    out_nhwc_f32 is not None)
             sel = self.plan_cache.get(key)

@@ -100,7 +100,13 @@ typedef struct {
   uint8_t* out_u8_nhwc;    /* optional, only together with out_nchw: [n, H, W, out_nchw_c] uint8 frames,
                               clip(rint(y * 255), 0, 255) of the value written to out_nchw -- skimage
                               img_as_ubyte of a float image in [0,1] (demo.py:281,507) */
+  void* splitk_ws;         /* optional, eamm_conv_tc only: device workspace for split-K on layers whose output has too
+                              few tiles to occupy the chip (hourglass 8x8 ... 2x2 maps).  The first 4 KiB are arrival
+                              counters: zero them ONCE after allocation, the kernel leaves them zero.  Launches that
+                              may run concurrently must not share a workspace.  NULL = never split                    */
+  int64_t splitk_ws_bytes; /* size of splitk_ws; EAMM_SPLITK_WS_BYTES always suffices                               */
 } eamm_conv_args;
+#define EAMM_SPLITK_WS_BYTES (4096 + 160ll * 128 * 256 * 4)
 
 /* ---- library info --------------------------------------------------------------------------- */
 int eamm_abi_version(void);
@@ -213,7 +219,8 @@ int eamm_conv_tc_fold(int kind, int split, int cout, int halo_scheme);
 
 /* Planning dry run of eamm_conv_tc for `args` (weight_fold ignored, nothing launched):
  * out[0] = N tile, out[1] = 7x7 scheme (eamm_conv_tc_uses_halo), out[2] = fold (eamm_conv_tc_fold),
- * out[3] = K chunks per pipeline stage, out[4] = bit 0 CTA pairs (cta_group::2), bit 1 wide folded step,
+ * out[3] = K chunks per pipeline stage, out[4] = bit 0 CTA pairs (cta_group::2), bit 1 wide folded step, bits 8.. =
+ * split-K factor (1 = none; planned as if a workspace were given),
  * out[5] = pipeline stages (`out` has room for 6 ints).  The host packs the weights for out[1]/out[2]. */
 int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
 

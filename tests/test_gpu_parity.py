@@ -116,8 +116,12 @@ def test_full_size_batch32_properties_and_batch_invariance(dev):
     i = 17
     one = run_ours("full", dev, "fp32", src[i:i + 1], {k: v[i:i + 1] for k, v in kpd.items()},
                    {k: v[i:i + 1] for k, v in kps.items()})
-    for k in ("prediction", "mask", "deformed"):
-        assert torch.allclose(one[k][0], got[k][i], atol=1e-6), k
+    # Not bit-equal by design: the 8x8 ... 2x2 hourglass layers run split-K with a split factor chosen from the number
+    # of frames in the launch (conv_tc.cu), so the fp32 summation grouping of those layers differs between B=32 and B=1.
+    for k, tol in (("prediction", 2e-5), ("mask", 2e-5), ("deformed", 3e-4)):
+        err = (one[k][0] - got[k][i]).abs().max().item()
+        print("batch invariance %s max-abs %.3e" % (k, err))
+        assert err <= tol, (k, err)
     # the oracle on two of the 32 frames (keeps the CPU cost of this test in seconds)
     from oracle import eamm_oracle as oracle
     sd = synth.make_state_dict(cfg, seed=0)

@@ -55,9 +55,17 @@ CASES = [
     # EAMM_TC_CTA2=11 (name prefix pfwide): folded pairs with one N = 2*BN step per type-0 chunk
     ("pfwide 3x3 64->128 256x256 N=2 pool x3", "3x3", "rp", 64, 128, 2, 256, 256, 2, 0, 0, ""),
     ("pfwide up2 128->64 128x128 N=2 x3", "up2", "r", 128, 64, 2, 128, 128, 2, 0, 0, ""),
-    ("pfwide 3x3 128->128 32x32 N=3 r+o2 x3", "3x3", "", 128, 128, 3, 32, 32, 2, 1, 1, ""),
+    ("pfwide 3x3 128->128 32x32 N=8 r+o2 x3", "3x3", "", 128, 128, 8, 32, 32, 2, 1, 1, ""),
     ("pfwide up2 256->128 64x64 N=5 x3", "up2", "r", 256, 128, 5, 64, 64, 2, 0, 0, ""),
     ("pfwide 3x3 64->32 64x64 N=8 pool x3", "3x3", "rp", 64, 32, 8, 64, 64, 2, 0, 0, ""),
+    # EAMM_TC_SPLITK=1 (name prefix splitk): split-K for the small hourglass maps
+    ("splitk 3x3 1024->1024 4x4 N=32 pool x3", "3x3", "rp", 1024, 1024, 32, 4, 4, 2, 0, 0, ""),
+    ("splitk up2 1024->1024 2x2 N=32 x3", "up2", "r", 1024, 1024, 32, 2, 2, 2, 0, 0, ""),
+    ("splitk up2 2048->512 4x4 N=32 x3", "up2", "r", 2048, 512, 32, 4, 4, 2, 0, 0, ""),
+    ("splitk 3x3 512->1024 8x8 N=32 pool", "3x3", "rp", 512, 1024, 32, 8, 8, 1, 0, 0, ""),
+    ("splitk up2 1024->256 8x8 N=32", "up2", "r", 1024, 256, 32, 8, 8, 1, 0, 0, ""),
+    ("splitk 3x3 256->256 8x8 N=3 r+o2 x3", "3x3", "", 256, 256, 3, 8, 8, 2, 1, 1, ""),
+    ("splitk 3x3 256->512 16x16 N=1 pool x3", "3x3", "rp", 256, 512, 1, 16, 16, 2, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
@@ -73,6 +81,8 @@ def run_case(idx):
         os.environ["EAMM_TC_KXW"] = "3"
     if name.startswith("pfwide"):
         os.environ["EAMM_TC_CTA2"] = "11"
+    if name.startswith("splitk"):
+        os.environ["EAMM_TC_SPLITK"] = "1"
     dev = torch.device("cuda:0")
     lib = L.load()
     g = torch.Generator().manual_seed(100 + idx)
@@ -115,8 +125,9 @@ def run_case(idx):
         o2 = ActBuf(N, OH, OW, cout, mode, dev) if has_out2 else None
         nhwc = torch.zeros(N, OH, OW, cout, device=dev) if special == "nhwc" else None
         nchw = torch.zeros(N, 3, OH, OW, device=dev) if special == "nchw" else None
-        layer.launch(lib, st, xin.act(), out=o.act() if o else None, out2=o2.act() if o2 else None,
-                     residual=res.act() if res else None, out_nchw=nchw, out_nchw_c=3, out_nhwc_f32=nhwc)
+        for _ in range(3 if name.startswith("splitk") else 1):       # relaunch: split-K counters must self-reset
+            layer.launch(lib, st, xin.act(), out=o.act() if o else None, out2=o2.act() if o2 else None,
+                         residual=res.act() if res else None, out_nchw=nchw, out_nchw_c=3, out_nhwc_f32=nhwc)
         torch.cuda.synchronize()
         outs[impl] = [t for t in (o.to_float() if o else None, o2.to_float() if o2 else None, nhwc, nchw)
                       if t is not None]
@@ -133,6 +144,8 @@ def run_case(idx):
     if name.startswith("kxw") and (not plan or plan[1] not in (3, 4)):
         status, worst = "BAD", float("nan")          # the scheme under test was not selected
     if name.startswith("pfwide") and (not plan or plan[4] != 3):
+        status, worst = "BAD", float("nan")
+    if name.startswith("splitk") and (not plan or (plan[4] >> 8) < 2):
         status, worst = "BAD", float("nan")
     print("%s case %2d %-38s rel_err %.3e plan %s" % (status, idx, name, worst, plan), flush=True)
     return 0 if status == "OK " else 1
@@ -179,13 +192,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", type=int, default=-1)
     ap.add_argument("--timeout", type=int, default=90)
-    ap.add_argument("--only", default="", help="substring filter on case names")
+    ap.add_argument("--only", default="", help="comma-separated substring filters on case names")
     args = ap.parse_args()
     if args.case >= 0:
         return run_case(args.case)
     bad = 0
     for i in range(len(CASES)):
-        if args.only and args.only not in CASES[i][0]:
+        if args.only and not any(k in CASES[i][0] for k in args.only.split(",")):
             continue
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", str(i)], timeout=args.timeout,
