@@ -27,7 +27,7 @@
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
 //               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step (measured no faster: a pair MMA
 //               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 3),
-//               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4; default 3), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
+//               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4, bit 2: compact scheme-3 epilogue buffer; default 7), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
 //               split-K / the 32-byte epilogue stores off, EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
@@ -69,6 +69,7 @@ struct ConvTcParams {
   int x_stride;        // pixels between consecutive x tiles (122 in kxn mode 1/2, else bw)
   int y_stride;        // rows between consecutive y tiles (4 for kxn == 2, else bh)
   int st256;           // epilogue activation stores / residual loads as 32-byte pieces (every view 32-byte aligned)
+  int s_nc;            // kxn == 2: channels kept per (dr, kx) group in the epilogue's smem buffer (4, or out_nchw_c: compact)
   int ntap;            // K-loop taps: 7 (halo, kxn 1/3), 10 (kxn 2), else taps
   int splitk;          // > 1: split-K.  `splitk` consecutive work items share one output tile, each runs 1/splitk of the
                        // K loop (contiguous in the (pass, tap, chunk) order), publishes its fp32 partial tile to sk_ws
@@ -513,6 +514,27 @@ __device__ __forceinline__ void epilogue_kxn_wide(const ConvTcParams& p, const T
                                                   int quadrant, int lane, int half, float* S) {
   const int r = quadrant * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  if (p.kxn == 2 && p.s_nc != 4) {
+    // compact rows: only the nc valid channels of every (dr, kx) group are kept, row stride 28*nc + 1 floats
+    // (odd): the smaller buffer buys a fourth pipeline stage.  A 32-column load per output row dr (28 used).
+    const int nc = p.s_nc, ld = 28 * nc + 1;
+    for (int dr = half; dr < 4; dr += 2) {
+      uint32_t raw[32];
+      TmemLd<32>::ld(taddr + (uint32_t)(dr * 28), raw);
+      if (p.fold) {
+        uint32_t raw2[32];
+        TmemLd<32>::ld(taddr + (uint32_t)(KXW_COLS + dr * 28), raw2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 28; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = S + r * ld + dr * 7 * nc;
+#pragma unroll
+      for (int j = 0; j < 28; ++j)
+        if ((j & 3) < nc) dst[(j >> 2) * nc + (j & 3)] = __uint_as_float(raw[j]);
+    }
+  } else
   for (int c0 = half * 16; c0 < KXW_COLS; c0 += 32) {
     uint32_t raw[16];
     TmemLd<16>::ld(taddr + (uint32_t)c0, raw);
@@ -530,7 +552,7 @@ __device__ __forceinline__ void epilogue_kxn_wide(const ConvTcParams& p, const T
   asm volatile("bar.sync 1, 256;" ::: "memory");
   const int tid = (half * 4 + quadrant) * 32 + lane;
   if (p.kxn == 2) {
-    const int nc = p.out_nchw_c;
+    const int nc = p.out_nchw_c, snc = p.s_nc, ld = 28 * snc + 1;
     for (int i = tid; i < 4 * nc * 128; i += 256) {
       const int rr = i & 127, q = i >> 7;
       const int dr = q / nc, co = q - dr * nc;
@@ -538,7 +560,7 @@ __device__ __forceinline__ void epilogue_kxn_wide(const ConvTcParams& p, const T
       if (rr < 122 && x < p.W && y < p.H && tc.n0 < p.N) {
         float acc = __ldg(p.bias + co);
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) acc += S[(rr + kx) * KXW_LD + dr * 28 + kx * 4 + co];
+        for (int kx = 0; kx < 7; ++kx) acc += S[(rr + kx) * ld + (dr * 7 + kx) * snc + co];
         if (p.flags & EAMM_EPI_SIGMOID) acc = 1.f / (1.f + expf(-acc));
         p.out_nchw[(((long long)tc.n0 * nc + co) * p.H + y) * p.W + x] = acc;
         if (p.out_u8 != nullptr) p.out_u8[(((long long)tc.n0 * p.H + y) * p.W + x) * nc + co] = to_ubyte(acc);
@@ -953,7 +975,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   // 112-column kx-in-N variants (EAMM_TC_KXW bit 0: scheme 3 = four output rows per tile for the <=4-channel
   // NCHW layer; bit 1: scheme 4 = full-width tiles for a <=128-wide map with 16 fp32 NHWC couts)
   static int kxw_env = -1;
-  if (kxw_env < 0) { const char* e = getenv("EAMM_TC_KXW"); kxw_env = e ? atoi(e) : 3; }
+  if (kxw_env < 0) { const char* e = getenv("EAMM_TC_KXW"); kxw_env = e ? atoi(e) : 7; }
   if (mode7 == 2 && (kxw_env & 1) && in->h % 4 == 0) mode7 = 3;
   if (halo_env > 0 && (kxw_env & 2) && a->kind == EAMM_CONV_7X7 && a->cout == 16 && a->flags == 0 && a->out_nhwc_f32 &&
       !(a->out || a->out2 || a->out_nchw || a->residual) && in->w <= 128 && in->w * in->h >= 128)
@@ -1053,8 +1075,12 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
   const uint32_t chunk_bytes = (uint32_t)p.a_slot_bytes +
       (p.cta2 ? (uint32_t)p.BN * (p.fold ? 128u : 64u) : (uint32_t)p.BN * 128u * (p.halo ? 7u : (p.fold ? 2u : 1u)));
-  const uint32_t extra_smem = p.kxn == 1 ? 2u * 128u * 29u * 4u : (p.kxn ? 128u * (uint32_t)KXW_LD * 4u : 0u);
-  const uint32_t ring_bytes = 200u * 1024u - extra_smem;
+  p.s_nc = (p.kxn == 2 && (kxw_env & 4) && a->out_nchw_c < 4) ? a->out_nchw_c : 4;
+  const uint32_t extra_smem = p.kxn == 1 ? 2u * 128u * 29u * 4u
+                            : p.kxn == 2 ? 128u * (28u * (uint32_t)p.s_nc + 1u) * 4u
+                            : (p.kxn ? 128u * (uint32_t)KXW_LD * 4u : 0u);
+  // (scheme 3 takes everything the SM has: with <= 3 NCHW channels that is a fourth 44 KB stage)
+  const uint32_t ring_bytes = (p.kxn == 2 ? 225u * 1024u : 200u * 1024u) - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
   // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
   static int ksub_env = -1;
