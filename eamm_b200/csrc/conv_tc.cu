@@ -244,6 +244,16 @@ __device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
                : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
+// L2-coherent (.cg) 256-bit variants for the split-K partial tiles (written by one CTA, read by another)
+__device__ __forceinline__ void stg256_cg(void* p, const uint32_t* v) {
+  asm volatile("st.global.cg.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg256_cg(const void* p, float* v) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+
 // WIDE: every lane writes 32-byte pieces (a thread owns one pixel, so a warp store spans 32 pixels: 16-byte
 // pieces fill only half of each sector they touch)
 template <int CH>
@@ -354,23 +364,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
     uint32_t raw[CH];
     if (p.splitk > 1) {                             // reducer of a split-K tile: partials summed in split order
       const float* src = p.sk_ws + (((size_t)tc.out_tile * p.splitk) * 128 + r) * p.BN + c0;
+      float acc[CH];
 #pragma unroll
-      for (int g = 0; g < CH / 4; ++g) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + g);
-        raw[4 * g] = __float_as_uint(v.x); raw[4 * g + 1] = __float_as_uint(v.y);
-        raw[4 * g + 2] = __float_as_uint(v.z); raw[4 * g + 3] = __float_as_uint(v.w);
-      }
+      for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, acc + 8 * g);
       for (int s2 = 1; s2 < p.splitk; ++s2) {
         src += 128 * p.BN;
+        float v[CH];
 #pragma unroll
-        for (int g = 0; g < CH / 4; ++g) {
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(src) + g);
-          raw[4 * g] = __float_as_uint(__uint_as_float(raw[4 * g]) + v.x);
-          raw[4 * g + 1] = __float_as_uint(__uint_as_float(raw[4 * g + 1]) + v.y);
-          raw[4 * g + 2] = __float_as_uint(__uint_as_float(raw[4 * g + 2]) + v.z);
-          raw[4 * g + 3] = __float_as_uint(__uint_as_float(raw[4 * g + 3]) + v.w);
-        }
+        for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, v + 8 * g);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[j] += v[j];
       }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(acc[j]);
     } else {
       TmemLd<CH>::ld(taddr + c0, raw);
       if (p.fold) {                                   // add the a_hi*b_lo columns kept at [BN, 2BN)
@@ -454,10 +460,7 @@ __device__ __forceinline__ bool splitk_publish(const ConvTcParams& p, const Tile
     TmemLd<32>::ld(taddr + (uint32_t)c0, raw);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      __stcg(reinterpret_cast<float4*>(dst + c0) + g,
-             make_float4(__uint_as_float(raw[4 * g]), __uint_as_float(raw[4 * g + 1]),
-                         __uint_as_float(raw[4 * g + 2]), __uint_as_float(raw[4 * g + 3])));
+    for (int g = 0; g < 4; ++g) stg256_cg(dst + c0 + 8 * g, raw + 8 * g);
   }
   __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1040,11 +1043,24 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     const long long t256 = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / 256);
     const int kc_all = p.taps * p.cin_chunks * p.passes;
     int S = 1;
-    for (int d = 2; d <= 32 && t256 * d <= num_sms; ++d)
+    static int splitk_max = -1;
+    if (splitk_max < 0) { const char* e = getenv("EAMM_TC_SPLITK_MAX"); splitk_max = e ? atoi(e) : 9; }
+    for (int d = 2; d <= splitk_max && t256 * d <= num_sms; ++d)
       if (kc_all % d == 0 && kc_all / d >= 8) S = d;
     const long long need = 4096 + t256 * S * 128ll * 256 * 4;
-    if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && (query || a->splitk_ws_bytes >= need) &&
-        (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
+    // Worth it?  Measured cycle model (EAMM_TC_PROF role counters, B200): one K=16 MMA step costs ~110 cycles up to
+    // N = 64, 124 at N = 128, 192 at N = 256 (the 128-row A slab is re-fetched per step whatever N is); publishing
+    // a partial tile and electing costs ~20k cycles, the reducer's reload + epilogue ~10k + 3k per split (the
+    // reducer walks the S partials one L2 round trip after the other, hence the cap: 27 splits of a batch-1 layer
+    // were measured slower than no split); a plain 128 x BN epilogue ~2k + 14k * BN/256.
+    // Split only when the model says >= 15 % faster: batch-1 bottleneck convs (one wave of N = 64 tiles) stay unsplit.
+    const long long tiles_plain = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / p.BN);
+    const long long waves = (tiles_plain + num_sms - 1) / num_sms;
+    const long long step_plain = p.BN >= 256 ? 192 : (p.BN >= 128 ? 124 : (p.BN >= 64 ? 114 : 110));
+    const long long cost_plain = waves * (4ll * kc_all * step_plain + 2000 + 14000ll * p.BN / 256);
+    const long long cost_split = 4ll * (kc_all / S) * 192 + 30000 + 3000ll * S;
+    if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && cost_split * 100 < cost_plain * 85 &&
+        (query || a->splitk_ws_bytes >= need) && (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
       p.BN = 256; p.splitk = S;
       if (!query) {
         p.sk_cnt = reinterpret_cast<unsigned int*>(a->splitk_ws);

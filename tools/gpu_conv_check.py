@@ -63,9 +63,9 @@ CASES = [
     ("splitk up2 1024->1024 2x2 N=32 x3", "up2", "r", 1024, 1024, 32, 2, 2, 2, 0, 0, ""),
     ("splitk up2 2048->512 4x4 N=32 x3", "up2", "r", 2048, 512, 32, 4, 4, 2, 0, 0, ""),
     ("splitk 3x3 512->1024 8x8 N=32 pool", "3x3", "rp", 512, 1024, 32, 8, 8, 1, 0, 0, ""),
-    ("splitk up2 1024->256 8x8 N=32", "up2", "r", 1024, 256, 32, 8, 8, 1, 0, 0, ""),
-    ("splitk 3x3 256->256 8x8 N=3 r+o2 x3", "3x3", "", 256, 256, 3, 8, 8, 2, 1, 1, ""),
-    ("splitk 3x3 256->512 16x16 N=1 pool x3", "3x3", "rp", 256, 512, 1, 16, 16, 2, 0, 0, ""),
+    ("splitk up2 1024->256 8x8 N=32 x3", "up2", "r", 1024, 256, 32, 8, 8, 2, 0, 0, ""),
+    ("splitk 3x3 1024->256 8x8 N=32 r+o2 x3", "3x3", "", 1024, 256, 32, 8, 8, 2, 1, 1, ""),
+    ("splitk 3x3 1024->512 4x4 N=2 pool x3", "3x3", "rp", 1024, 512, 2, 4, 4, 2, 0, 0, ""),
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
