@@ -282,7 +282,10 @@ def main():
     pipe.close()
 
     # per-kernel roofline pass: one extra step with every launch bracketed by CUDA events
+    # (the GPU is parked on a ~3 ms spin first, so that the host has queued the whole step before the first kernel
+    #  starts: otherwise the interval around a 20-100 us kernel also holds the host's launch latency)
     engine.PROFILE = []
+    torch.cuda._sleep(6_000_000)
     step_device()
     torch.cuda.synchronize()
     prof, engine.PROFILE = engine.PROFILE, None
@@ -305,8 +308,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks["source"] == "measured"
                 else "fallback (B200_PROFILING.md)",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the ncu --set full capture
-                # summarised in profiles/ (138.9 MB + 86.0 MB at B=32, fp32 mode); scales with the batch
-                "traffic": (138.91e6 + 85.99e6) * B / 32.0 if args.precision == "fp32" else None,
+                # summarised in profiles/r1b_ncu_summary.md (138.3 MB + 95.1 MB at B=32, fp32 mode); scales with the batch
+                "traffic": (138.35e6 + 95.15e6) * B / 32.0 if args.precision == "fp32" else None,
                 "share_of_step": dom_ms / step_ms_prof if step_ms_prof else None,
                 "all_convs_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                 "all_convs_share_of_step": conv_ms / step_ms_prof if step_ms_prof else None,
