@@ -1003,8 +1003,12 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.tiles_y = (in->h + p.y_stride - 1) / p.y_stride; p.tiles_n = (in->n + p.bn - 1) / p.bn;
   static int num_sms = 0;
   if (!num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("EAMM_TC_NUM_SMS");       // planning dry runs (eamm_conv_tc_query) on a host without a GPU
+    if (e && atoi(e) > 0) num_sms = atoi(e);
+    else {
+      int dev = 0; cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
   }
   // N tile: the widest UMMA N (<= 256) dividing cout that still yields at least one tile per SM;
   // small maps (hourglass 8x8 ... 2x2) prefer narrow N tiles so that more SMs stream the weights.
@@ -1024,6 +1028,28 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     p.BN = 0;
     const int cand[5] = {256, 128, 64, 32, 16};
     if (a->cout <= 256 && m_tiles >= num_sms) p.BN = a->cout;
+    // Layers that cannot give every SM a full-width tile: the N tile with the lowest modelled time (waves x MMA steps
+    // x per-step cycles, measured: ~110 up to N = 64, 124 at 128, 192 at 256, plus the epilogue) -- one wave of
+    // N = 64 tiles beats two waves of N = 32 tiles even though it leaves SMs idle.  EAMM_TC_BNCOST=0: the older rule
+    // (widest tile that still yields one tile per SM).  The choice never changes a result bit (same per-column order).
+    static int bncost_env = -1;
+    if (bncost_env < 0) { const char* e = getenv("EAMM_TC_BNCOST"); bncost_env = e ? atoi(e) : 1; }
+    if (!p.BN && bncost_env) {
+      auto step = [](int n) -> long long {
+        return n >= 256 ? 192 : (n >= 128 ? 124 + (n - 128) * 68 / 128 : (n >= 64 ? 114 + (n - 64) * 10 / 64 : 110));
+      };
+      const long long pairs = (long long)p.taps * p.cin_chunks;          // (tap, 64-channel chunk) pairs per tile
+      long long best = -1;
+      const int cands[6] = {a->cout <= 256 ? a->cout : 0, 256, 128, 64, 32, 16};
+      for (int i = 0; i < 6; ++i) {
+        const int c = cands[i];
+        if (c <= 0 || c > a->cout || a->cout % c != 0 || (p.fold && 2 * c > 256)) continue;
+        const long long waves = (m_tiles * (a->cout / c) + num_sms - 1) / num_sms;
+        const long long per_pair = p.fold == 1 ? step(2 * c) + step(c) : (p.fold == 2 ? step(2 * c) : (long long)p.passes * step(c));
+        const long long cost = waves * (4 * pairs * per_pair + 2000 + 14000ll * c / 256);
+        if (best < 0 || cost < best) { best = cost; p.BN = c; }
+      }
+    }
     for (int i = 0; i < 5 && !p.BN; ++i)
       if (cand[i] <= a->cout && a->cout % cand[i] == 0 && m_tiles * (a->cout / cand[i]) >= num_sms) p.BN = cand[i];
     if (!p.BN) {                       // cannot fill the chip: narrowest tile of at least 64 columns
