@@ -141,6 +141,76 @@ def test_kxn_wide_packings_reproduce_the_7x7_conv():
     assert torch.allclose(got, want, atol=1e-9)
 
 
+def _plan(lib, L, kind, cin, cout, n, h, w, planes, flags=0, nhwc=False, nchw_c=0):
+    """eamm_conv_tc_query on dummy pointers (nothing is dereferenced or launched by the dry run)."""
+    a = L.ConvArgs()
+    a.kind, a.flags, a.cin, a.cout = kind, flags, cin, cout
+    act = L.Act(data=4096, dtype=L.EAMM_BF16, n=n, h=h, w=w, c=cin, c_off=0, c_buf=cin, planes=planes,
+                n_stride=h * w * planes * cin)
+    oh, ow = (2 * h, 2 * w) if kind == L.CONV_UP2_3X3 else ((h // 2, w // 2) if flags & L.EPI_POOL2 else (h, w))
+    out = L.Act(data=4096, dtype=L.EAMM_BF16, n=n, h=oh, w=ow, c=cout, c_off=0, c_buf=cout, planes=planes,
+                n_stride=oh * ow * planes * cout)
+    a.inp, a.weight, a.bias = ctypes.pointer(act), 4096, 4096
+    if nhwc:
+        a.out_nhwc_f32 = 4096
+    elif nchw_c:
+        a.out_nchw, a.out_nchw_c = 4096, nchw_c
+    else:
+        a.out = ctypes.pointer(out)
+    a.splitk_ws, a.splitk_ws_bytes = 4096, L.SPLITK_WS_BYTES
+    q = (ctypes.c_int * 6)()
+    assert lib.eamm_conv_tc_query(ctypes.byref(a), q) == 0
+    return {"bn": q[0], "scheme": q[1], "fold": q[2], "ksub": q[3], "pair": q[4] & 1, "splitk": q[4] >> 8, "stages": q[5]}
+
+
+def test_conv_tc_planner_decisions_for_the_path_layers():
+    """Planning dry run of eamm_conv_tc for a 148-SM device (EAMM_TC_NUM_SMS, no GPU needed): the schemes DESIGN.md
+    describes are the ones chosen for the BASELINE configs[1] layers and for the batch-1 per-frame path."""
+    code = r"""
+import ctypes, json, os, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+os.environ["EAMM_TC_NUM_SMS"] = "148"
+for k in list(os.environ):
+    if k.startswith("EAMM_TC_") and k != "EAMM_TC_NUM_SMS":
+        del os.environ[k]
+from eamm_b200 import _lib as L
+from test_host_logic import _plan
+lib = L.load()
+P = lambda *a, **k: _plan(lib, L, *a, **k)
+out = {}
+for B in (1, 32):
+    out["res%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 2)
+    out["res_bf16_%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 1)
+    out["down0_%%d" %% B] = P(L.CONV_3X3, 64, 128, B, 256, 256, 2, flags=3)
+    out["enc4_%%d" %% B] = P(L.CONV_3X3, 1024, 1024, B, 4, 4, 2, flags=3)
+    out["dec1_%%d" %% B] = P(L.CONV_UP2_3X3, 2048, 512, B, 4, 4, 2, flags=1)
+    out["mask%%d" %% B] = P(L.CONV_7X7, 128, 16, B, 64, 64, 2, nhwc=True)
+    out["final%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 2, flags=4, nchw_c=3)
+    out["final_bf16_%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 1, flags=4, nchw_c=3)
+print(json.dumps(out))
+""" % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    p = json.loads(r.stdout.strip().splitlines()[-1])
+    # bottleneck convs at B=32: N = 256 CTA pairs, three passes unfolded, no split; at B=1 one wave of N = 64 tiles
+    assert (p["res32"]["bn"], p["res32"]["pair"], p["res32"]["fold"], p["res32"]["splitk"]) == (256, 1, 0, 1)
+    assert (p["res1"]["bn"], p["res1"]["pair"], p["res1"]["splitk"]) == (64, 0, 1)
+    assert p["res_bf16_1"]["bn"] == 64 and p["res_bf16_32"]["bn"] == 256
+    # cout <= 128 in split mode: weight planes folded into N, CTA pairs once the chip is filled
+    assert (p["down0_32"]["bn"], p["down0_32"]["fold"], p["down0_32"]["pair"]) == (128, 1, 1)
+    # small hourglass maps: N = 256 tiles with split-K (<= 9 splits, tiles * splits <= 148 SMs)
+    assert (p["enc4_32"]["bn"], p["enc4_32"]["splitk"]) == (256, 9) and (p["enc4_1"]["bn"], p["enc4_1"]["splitk"]) == (256, 9)
+    assert (p["dec1_32"]["bn"], p["dec1_32"]["splitk"]) == (256, 4)
+    # 7x7 layers: 112-column kx-in-N schemes (4 = full-width mask+occlusion, 3 = four output rows for `final`), folded
+    for B in (1, 32):
+        assert (p["mask%d" % B]["scheme"], p["mask%d" % B]["bn"], p["mask%d" % B]["fold"]) == (4, 112, 1)
+        assert (p["final%d" % B]["scheme"], p["final%d" % B]["bn"], p["final%d" % B]["fold"]) == (3, 112, 1)
+        assert p["final%d" % B]["stages"] == 4                    # compact epilogue buffer -> fourth pipeline stage
+        assert (p["final_bf16_%d" % B]["scheme"], p["final_bf16_%d" % B]["fold"]) == (3, 0)
+
+
 def test_numpy_sampler_matches_torch_grid_sample_and_corner_values():
     assert sampler_np.unnormalize(np.float32(-1.0), 64) == -0.5          # SURVEY.md §7 "hard parts"
     assert sampler_np.unnormalize(np.float32(1.0), 64) == 63.5
