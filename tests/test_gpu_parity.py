@@ -228,6 +228,11 @@ def test_cabi_conv_tc_matches_conv_simt_on_layer_shapes(dev):
     spec.loader.exec_module(mod)
     for idx in (1, 3, 5, 7, 8, 9, 10, 12, 13, 15, 17, 18, 19, 21, 22):
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]
+    # 112-column kx-in-N schemes and split-K: the case fails unless the planner really chose the scheme under test
+    new = [i for i, c in enumerate(mod.CASES) if c[0].startswith(("kxw", "splitk"))]
+    assert len(new) >= 14
+    for idx in new:
+        assert mod.run_case(idx) == 0, mod.CASES[idx][0]
 
 
 def test_cabi_rejects_bad_arguments_without_launching(dev):
