@@ -323,6 +323,11 @@ def main():
         gbs = wo[2] / (wo[0] * 1e-3) / 1e9
         hbm = {"kernel": "warp_occlude_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                "frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": wo[2]}
+    # every HBM-bound (non-conv) kernel of the step against the copy peak; the 12-45 us ones are latency-, not
+    # bandwidth-limited at this batch (algorithmic bytes per launch as in SURVEY 8(d), fp32-equivalent storage)
+    hbm_all = {k: {"ms": round(v[0], 4), "mbytes": round(v[2] / 1e6, 2), "gbs": round(v[2] / (v[0] * 1e-3) / 1e9, 1),
+                   "frac": round(v[2] / (v[0] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
+               for k, v in per.items() if not k.startswith("conv:") and v[0] > 0 and v[2] > 0}
     kernels = {k: {"ms": round(v[0], 4), "launches": v[3]} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:(None if args.all_kernels else 12)]}
 
     frames = total * args.steps
@@ -348,6 +353,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "roofline_hbm": hbm,
+        "hbm_kernels": hbm_all,
         "tensor_frac_whole_step": (ALG_GFLOP_PER_FRAME * 1e9 * frames / (ms * 1e-3) / 1e12) / peak / world,
         "kernels_ms_per_step": kernels,
     }
