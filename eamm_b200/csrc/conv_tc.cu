@@ -28,7 +28,9 @@
 //               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step (measured no faster: a pair MMA
 //               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 3),
 //               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4, bit 2: compact scheme-3 epilogue buffer; default 7), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
-//               split-K / the 32-byte epilogue stores off, EAMM_TC_KSUB / _CTA2_KSUB force the
+//               split-K / the 32-byte epilogue stores off, EAMM_TC_SPLITK_DIST = 1 selects the distributed split-K reduction
+//               (opt-in), EAMM_TC_SPLITK_MAX caps the split factor (9), EAMM_TC_BNCOST = 0 restores the older N-tile rule,
+//               EAMM_TC_NUM_SMS lets eamm_conv_tc_query plan on a host without a GPU, EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
 // Epilogues: folded-BN bias, ReLU, 2x2 avg-pool (DownBlock2d), parity scatter (UpBlock2d as four
@@ -77,8 +79,12 @@ struct ConvTcParams {
                        // (deterministic) and runs the normal epilogue.  For the 8x8 ... 2x2 hourglass layers, which
                        // otherwise need N tiles of 32 columns to occupy the chip and then pay the per-MMA A-slab cost
                        // 8x more often than an N = 256 tile would.
+  int sk_dist;         // distributed reduction: every CTA of a tile waits for all S partials (arrival counter spin; the S CTAs
+                       // are co-resident: cooperative launch, one item per CTA) and then reduces + finishes the
+                       // 32-column chunks j = split, split + S, ... of the tile, instead of the last arriver doing all 8
   float* sk_ws;        // [out tile][split][128][BN] fp32 partials
-  unsigned int* sk_cnt;// [out tile] arrival counters, zero before and after every launch
+  unsigned int* sk_cnt;// [out tile] arrival counters (+512: completion counters of the distributed mode), zero before and
+                       // after every launch
   int fold;            // split mode with 2*BN <= 256: the weight planes are stacked along N.  Chunk type 0 =
                        // a_hi x [b_hi; b_lo] (N = 2*BN), type 1 = a_lo x b_hi (N = BN); the epilogue adds
                        // accumulator columns [BN, 2BN) (the a_hi*b_lo cross term) to [0, BN).  2 A loads and
@@ -360,7 +366,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   if (pool) { oy = y >> 1; ox = x >> 1; OH = p.H >> 1; OW = p.W >> 1; valid = valid && !(xl & 1) && !(yl & 1); }
   else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); OH = 2 * p.H; OW = 2 * p.W; }
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
-  for (int c0 = half * CH; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * CH) {
+  // chunk walk: the two warps of a quadrant alternate over the CH-column chunks; in the distributed split-K mode a
+  // CTA owns the chunks j = split, split + S, ... only
+  const int dist = (p.splitk > 1 && p.sk_dist) ? 1 : 0;
+  const int cfirst = dist ? (tc.split + half * p.splitk) * CH : half * CH;
+  const int cstep = (dist ? p.splitk : 1) * (TC_EPI_WARPS / 4) * CH;
+  for (int c0 = cfirst; c0 < p.BN; c0 += cstep) {
     uint32_t raw[CH];
     if (p.splitk > 1) {                             // reducer of a split-K tile: partials summed in split order
       const float* src = p.sk_ws + (((size_t)tc.out_tile * p.splitk) * 128 + r) * p.BN + c0;
@@ -474,6 +485,43 @@ __device__ __forceinline__ bool splitk_publish(const ConvTcParams& p, const Tile
   const bool last = *flag != 0u;
   if (last) __threadfence();
   return last;
+}
+
+// Distributed variant: publish, arrive, then wait until all S partial tiles of the output tile are visible.  Safe because
+// the S CTAs run at the same time (cooperative launch, at most one work item per CTA); the wait is bounded and traps.
+__device__ __forceinline__ void splitk_publish_wait(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                                    int quadrant, int lane, int half) {
+  const int r = quadrant * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  float* dst = p.sk_ws + (((size_t)tc.out_tile * p.splitk + tc.split) * 128 + r) * p.BN;
+  for (int c0 = half * 32; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * 32) {
+    uint32_t raw[32];
+    TmemLd<32>::ld(taddr + (uint32_t)c0, raw);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int g = 0; g < 4; ++g) stg256_cg(dst + c0 + 8 * g, raw + 8 * g);
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    unsigned int* cnt = p.sk_cnt + tc.out_tile;
+    atomicAdd(cnt, 1u);
+    unsigned int seen = 0, it = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+      if (++it > (1u << 24)) __trap();
+    } while (seen < (unsigned int)p.splitk);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  __threadfence();
+}
+// ... and after the CTA's share of the epilogue: the CTA that finishes last zeroes both counters for the next launch
+__device__ __forceinline__ void splitk_done(const ConvTcParams& p, const TileCoord& tc) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(p.sk_cnt + 512 + tc.out_tile, 1u);
+    if (old == (unsigned int)(p.splitk - 1)) { p.sk_cnt[tc.out_tile] = 0u; p.sk_cnt[512 + tc.out_tile] = 0u; }
+  }
 }
 
 // kx-in-N epilogue (7x7 -> <=4 channels, sigmoid, NCHW fp32): accumulator row p holds, for the input
@@ -856,7 +904,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (p.kxn == 1) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
       else if (p.kxn) epilogue_kxn_wide(p, tc, tmem_acc, quadrant, lane, half, kxn_smem);
       else if (p.splitk > 1) {
-        if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+        if (p.sk_dist) {
+          splitk_publish_wait(p, tc, tmem_acc, quadrant, lane, half);
+          epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+          splitk_done(p, tc);
+        } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
       }
       else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
@@ -1062,7 +1114,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   // S = the largest divisor of the K-chunk count that keeps tiles * S within the SM count (>= 8 chunks per item).
   // The partial sums are added in split order, so a result is reproducible for a given batch size, but its last
   // bits depend on S and hence on how many frames share the launch.
-  p.splitk = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.splitk = 1; p.sk_dist = 0; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   static int splitk_env = -1;
   if (splitk_env < 0) { const char* e = getenv("EAMM_TC_SPLITK"); splitk_env = e ? atoi(e) : 1; }
   if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && a->cout % 256 == 0 && (query || a->splitk_ws)) {
@@ -1088,6 +1140,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && cost_split * 100 < cost_plain * 85 &&
         (query || a->splitk_ws_bytes >= need) && (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
       p.BN = 256; p.splitk = S;
+      static int dist_env = -1;
+      if (dist_env < 0) { const char* e = getenv("EAMM_TC_SPLITK_DIST"); dist_env = e ? atoi(e) : 0; }
+      p.sk_dist = (dist_env && t256 <= 512) ? 1 : 0;
       if (!query) {
         p.sk_cnt = reinterpret_cast<unsigned int*>(a->splitk_ws);
         p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(a->splitk_ws) + 4096);
@@ -1147,7 +1202,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.num_stages = stages;
   if (query) {
     query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub;
-    query[4] = p.cta2 | (p.pf_wide << 1) | (p.splitk << 8); query[5] = p.num_stages;
+    query[4] = p.cta2 | (p.pf_wide << 1) | (p.sk_dist << 2) | (p.splitk << 8); query[5] = p.num_stages;
     return 0;
   }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
@@ -1235,6 +1290,18 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, p);
+    if (e != cudaSuccess) return (int)e;
+  } else if (p.splitk > 1 && p.sk_dist && !instr) {
+    // the CTAs of a tile wait for each other: ask the runtime to guarantee that the whole grid is resident
+    if (grid != p.total_tiles) return EAMM_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, p);
     if (e != cudaSuccess) return (int)e;
   } else if (instr) conv_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   else conv_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
