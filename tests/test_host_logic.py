@@ -322,6 +322,32 @@ def test_shared_library_exports_every_declared_symbol():
 
 
 # ------------------------------------------------------------------ sharding (gloo, world_size 2)
+def test_ctypes_structs_mirror_the_header_layout(tmp_path):
+    """The ctypes mirrors in eamm_b200/_lib.py have the field offsets and sizes gcc gives include/eamm_b200.h."""
+    from eamm_b200 import _lib as L
+    structs = {"eamm_act": L.Act, "eamm_kp": L.Kp, "eamm_conv_args": L.ConvArgs, "eamm_one_euro": L.OneEuro}
+    rename = {"inp": "in"}                       # `in` is a Python keyword
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "eamm_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, rename.get(fname, fname)))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, cls in structs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    assert L.SPLITK_WS_BYTES == 4096 + 160 * 128 * 256 * 4
+    hdr = open(os.path.join(ROOT, "include", "eamm_b200.h")).read()
+    assert "#define EAMM_SPLITK_WS_BYTES (4096 + 160ll * 128 * 256 * 4)" in hdr
+
+
 def test_partition_covers_every_frame_once():
     for total in (0, 1, 7, 32, 1024):
         for world in (1, 2, 3, 8):
