@@ -285,7 +285,8 @@ def main():
     # (the GPU is parked on a ~3 ms spin first, so that the host has queued the whole step before the first kernel
     #  starts: otherwise the interval around a 20-100 us kernel also holds the host's launch latency)
     engine.PROFILE = []
-    torch.cuda._sleep(6_000_000)
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(6_000_000)
     step_device()
     torch.cuda.synchronize()
     prof, engine.PROFILE = engine.PROFILE, None

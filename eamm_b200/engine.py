@@ -90,6 +90,9 @@ def splitk_workspace(device, stream):
            int(getattr(stream, "value", stream) or 0))
     ws = _SPLITK_WS.get(key)
     if ws is None:
+        if len(_SPLITK_WS) >= 16:                 # callers that make a fresh stream per call: keep the table bounded
+            torch.cuda.synchronize(device)        # (nothing may still be using the buffers that are dropped)
+            _SPLITK_WS.clear()
         ws = _SPLITK_WS[key] = torch.zeros(L.SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
     return ws
 
