@@ -90,7 +90,8 @@ def splitk_workspace(device, stream):
            int(getattr(stream, "value", stream) or 0))
     ws = _SPLITK_WS.get(key)
     if ws is None:
-        if len(_SPLITK_WS) >= 16:                 # callers that make a fresh stream per call: keep the table bounded
+        if len(_SPLITK_WS) >= 16 and not torch.cuda.is_current_stream_capturing():
+            # callers that make a fresh stream per call: keep the table bounded (CUDA graphs keep their own reference)
             torch.cuda.synchronize(device)        # (nothing may still be using the buffers that are dropped)
             _SPLITK_WS.clear()
         ws = _SPLITK_WS[key] = torch.zeros(L.SPLITK_WS_BYTES, dtype=torch.uint8, device=device)

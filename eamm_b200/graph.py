@@ -39,6 +39,8 @@ class GraphedGenerator:
             generator.strict_errors = strict
             generator.cache_source = cache
         self._strict = strict
+        from . import engine
+        self._workspaces = list(engine._SPLITK_WS.values())     # the captured kernels point into these
 
     def __call__(self, source_image, kp_driving, kp_source, check=True):
         if not self.fixed_source and source_image is not self.s_src:
