@@ -322,6 +322,25 @@ def test_shared_library_exports_every_declared_symbol():
 
 
 # ------------------------------------------------------------------ sharding (gloo, world_size 2)
+def test_split_k_chunk_ownership_covers_every_column_chunk_once():
+    """Distributed split-K reduction of conv_tc.cu (epilogue_tile chunk walk): the S CTAs of a tile, two epilogue
+    warps per TMEM quadrant each, own the 32-column chunks j = split + k*S exactly once for every split factor."""
+    CH, BN, halves = 32, 256, 2
+    for S in range(2, 10):
+        seen = []
+        for split in range(S):
+            for half in range(halves):
+                c0 = (split + half * S) * CH                      # cfirst
+                while c0 < BN:
+                    seen.append(c0 // CH)
+                    c0 += S * halves * CH                         # cstep
+        assert sorted(seen) == list(range(BN // CH)), (S, seen)
+    # plain walk (no split, or last-arriver reduction): the two warps of a quadrant alternate over the chunks
+    for bn, ch in ((256, 32), (128, 32), (64, 32), (48, 16), (16, 16)):
+        seen = [c0 // ch for half in range(halves) for c0 in range(half * ch, bn, halves * ch)]
+        assert sorted(seen) == list(range(bn // ch))
+
+
 def test_ctypes_structs_mirror_the_header_layout(tmp_path):
     """The ctypes mirrors in eamm_b200/_lib.py have the field offsets and sizes gcc gives include/eamm_b200.h."""
     from eamm_b200 import _lib as L
