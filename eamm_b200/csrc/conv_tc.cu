@@ -1265,7 +1265,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem;
-  static size_t smem_set = 0;
+  // the attribute is per device: a process that drives several GPUs (nn.DataParallel replicas, train.py:53-60) must set it on each
+  static size_t smem_set_dev[64] = {0};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  size_t& smem_set = smem_set_dev[cur_dev & 63];
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
