@@ -319,96 +319,6 @@ warp_occlude_bf16_kernel(ActView feat, const float2* __restrict__ deform, const 
   }
 }
 
-// 16 channels (32 bytes) per thread with 256-bit global accesses (sm_100 LDG/STG.E.ENL2.256), 32-bit index
-// arithmetic, all eight tap loads of a thread issued before the first use.  A 256-channel pixel is 16 lanes, so
-// every tap of a half-warp is 512 contiguous bytes per plane.  Same tap order and FMA sequence as the kernel above.
-__device__ __forceinline__ void ldg256_nc(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, uint4 a, uint4 b) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
-template <int PLANES>
-__device__ __forceinline__ void bf16x16_store(const ActView& v, long long off, const float* f) {
-  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
-  uint2 q[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = float4_to_bf16x4(make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]));
-  stg256(p, make_uint4(q[0].x, q[0].y, q[1].x, q[1].y), make_uint4(q[2].x, q[2].y, q[3].x, q[3].y));
-  if (PLANES == 2) {
-    uint2 l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 h = bf16x4_to_float4(q[i]);
-      l[i] = float4_to_bf16x4(make_float4(f[4 * i] - h.x, f[4 * i + 1] - h.y, f[4 * i + 2] - h.z, f[4 * i + 3] - h.w));
-    }
-    stg256(p + v.c_buf, make_uint4(l[0].x, l[0].y, l[1].x, l[1].y), make_uint4(l[2].x, l[2].y, l[3].x, l[3].y));
-  }
-}
-
-template <int PLANES>
-__global__ void __launch_bounds__(256)
-warp_occlude_bf16x16_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
-                            ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
-                            const float* __restrict__ shift2, unsigned int total, unsigned int c16_log2) {
-  const __nv_bfloat16* fbase = static_cast<const __nv_bfloat16*>(feat.data);
-  const unsigned int W = (unsigned int)feat.w, HW = (unsigned int)(feat.w * feat.h);
-  for (unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int cg = (int)(idx & ((1u << c16_log2) - 1u));
-    const unsigned int pix = idx >> c16_log2;
-    const unsigned int n = pix / HW, rem = pix - n * HW;
-    const int y = (int)(rem / W), x = (int)(rem - (rem / W) * W);
-    const float2 d = __ldg(deform + pix);
-    const Bilinear b = bilinear_setup(d.x, d.y, feat.w, feat.h);
-    const float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
-    const bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
-    const bool yin0 = b.y0 >= 0 && b.y0 < feat.h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < feat.h;
-    const bool in[4] = {yin0 && xin0, yin0 && xin1, yin1 && xin0, yin1 && xin1};
-    const float q[4] = {wy0 * wx0, wy0 * b.wx1, b.wy1 * wx0, b.wy1 * b.wx1};
-    uint4 ra[4][PLANES], rb[4][PLANES];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (in[t]) {
-        const long long off = act_offset(feat, (int)n, b.y0 + (t >> 1), b.x0 + (t & 1), 16 * cg);
-#pragma unroll
-        for (int pl = 0; pl < PLANES; ++pl) ldg256_nc(fbase + off + pl * feat.c_buf, ra[t][pl], rb[t][pl]);
-      } else {
-#pragma unroll
-        for (int pl = 0; pl < PLANES; ++pl) { ra[t][pl] = make_uint4(0, 0, 0, 0); rb[t][pl] = make_uint4(0, 0, 0, 0); }
-      }
-    }
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (in[t]) {                                   // a skipped tap adds nothing (not even +0 * q)
-#pragma unroll
-        for (int pl = 0; pl < PLANES; ++pl) { bf16x8_fma(ra[t][pl], q[t], acc); bf16x8_fma(rb[t][pl], q[t], acc + 8); }
-      }
-    }
-    if (occ != nullptr) {
-      const float o = __ldg(occ + pix);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] *= o;
-    }
-    bf16x16_store<PLANES>(out, act_offset(out, (int)n, y, x, 16 * cg), acc);
-    if (has_out2) {
-      float r[16];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale2) + 4 * cg + g);
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(shift2) + 4 * cg + g);
-        r[4 * g] = fmaxf(fmaf(acc[4 * g], s4.x, t4.x), 0.f); r[4 * g + 1] = fmaxf(fmaf(acc[4 * g + 1], s4.y, t4.y), 0.f);
-        r[4 * g + 2] = fmaxf(fmaf(acc[4 * g + 2], s4.z, t4.z), 0.f); r[4 * g + 3] = fmaxf(fmaf(acc[4 * g + 3], s4.w, t4.w), 0.f);
-      }
-      bf16x16_store<PLANES>(out2, act_offset(out2, (int)n, y, x, 16 * cg), r);
-    }
-  }
-}
-
 // =============================================================================================
 // a9-ii  deformed = grid_sample(source, interpolate(deformation, (H,W), bilinear))  (generator.py:50-57,86)
 // The flow upsample (align_corners=False: src = (dst+0.5)*h/H - 0.5, clamped at 0, upper tap
@@ -791,30 +701,6 @@ extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation,
     return v.dtype == EAMM_BF16 && v.planes == planes && v.c % 8 == 0 && v.c_off % 8 == 0 && v.c_buf % 8 == 0 &&
            ((uintptr_t)v.data % 16) == 0 && v.n_stride % 8 == 0;
   };
-  auto wide_ok = [](const ActView& v) {
-    return v.c_off % 16 == 0 && v.c_buf % 16 == 0 && ((uintptr_t)v.data % 32) == 0 && v.n_stride % 16 == 0 &&
-           v.pix_stride % 16 == 0;
-  };
-  static int warp16_env = -1;
-  if (warp16_env < 0) { const char* e = getenv("EAMM_WARP16"); warp16_env = e ? atoi(e) : 0; }
-  if (f.dtype == EAMM_BF16 && vec_ok(f, f.planes) && vec_ok(o, f.planes) && (!has2 || vec_ok(o2, f.planes)) && warp16_env &&
-      f.c % 16 == 0 && ((f.c / 16) & (f.c / 16 - 1)) == 0 && wide_ok(f) && wide_ok(o) && (!has2 || wide_ok(o2)) &&
-      (long long)f.n * f.h * f.w * (f.c / 16) < 0x7fffffffLL) {
-    // 32 bytes per thread (see warp_occlude_bf16x16_kernel); channel groups per pixel must be a power of two
-    const unsigned int total = (unsigned int)((long long)f.n * f.h * f.w * (f.c / 16));
-    unsigned int lg = 0;
-    while ((1u << lg) < (unsigned int)(f.c / 16)) ++lg;
-    unsigned int blocks = (total + 255u) / 256u;
-    if (blocks > 148u * 8u) blocks = 148u * 8u;
-    if (f.planes == 2)
-      warp_occlude_bf16x16_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
-                                                                              has2, scale2, shift2, total, lg);
-    else
-      warp_occlude_bf16x16_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
-                                                                              has2, scale2, shift2, total, lg);
-    EAMM_LAUNCH_CHECK();
-    return 0;
-  }
   if (f.dtype == EAMM_BF16 && vec_ok(f, f.planes) && vec_ok(o, f.planes) && (!has2 || vec_ok(o2, f.planes))) {
     long long total = (long long)f.n * f.h * f.w * (f.c / 8);
     int blocks = (int)((total + 255) / 256);
