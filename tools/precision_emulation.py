@@ -56,6 +56,20 @@ def make(scheme):
             else:
                 x8, w8 = xh, wh
             y = real_conv(x8, wl, None, padding=padding) + real_conv(xl, w8, None, padding=padding) + real_conv(xh, wh, None, padding=padding)
+        elif scheme == "f16s+f8":
+            # the pre-scaled domain of DESIGN.md section 9: max|A'| ~ 2^13, lo8 = e4m3((A' - hi) * 2^6), hi8 = e4m3(hi * 2^-6)
+            def split(t):
+                m = t.abs().max().item()
+                sc = 1.0 if m == 0 else 2.0 ** math.floor(math.log2(2.0 ** 13 / m))
+                tp = t * sc
+                hi = tp.clamp(-65504, 65504).half().float()
+                lo8 = ((tp - hi) * 64.0).clamp(-448, 448).to(E4).float()
+                hi8 = (hi / 64.0).clamp(-448, 448).to(E4).float()
+                return hi, lo8, hi8, sc
+            xh, xl, x8, sx = split(x)
+            wh, wl, w8, sw = split(w)
+            y = (real_conv(x8, wl, None, padding=padding) + real_conv(xl, w8, None, padding=padding) +
+                 real_conv(xh, wh, None, padding=padding)) / (sx * sw)
         elif scheme == "f16+mxf8":
             xh = x.half().float(); wh = w.half().float()
             xl = mx8(x - xh, 1); wl = mx8(w - wh, 1)
