@@ -1,0 +1,202 @@
+// Round-2 experiment: can the two cross terms of the split-operand scheme run as fp8
+// MMAs (tcgen05.mma.kind::f8f6f4, e4m3, K = 32) into the SAME TMEM accumulator as the fp16 main term
+// (tcgen05.mma.kind::f16, K = 16), and how accurate is D = hi*hi + hi8*lo8 + lo8*hi8 in the pre-scaled domain?
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 tools/experiments/f16_f8_gemm.cu -o /tmp/f16_f8_gemm
+//   /tmp/f16_f8_gemm            (prints the error of mode 0 = main term only, mode 1 = main + cross terms)
+//
+// One CTA, D[128 x 128] = A[128 x 256] * B[128 x 256]^T.  Operands are prepared on the host exactly as a producing
+// epilogue would (A' = a * 2^ta with max ~2^13; hi = fp16(A'), lo8 = e4m3((A' - hi) * 64), hi8 = e4m3(hi / 64)), copied
+// into the canonical K-major SWIZZLE_128B shared-memory layout by plain stores (no TMA: this tests the MMA side only),
+// and consumed by 16 f16 steps + 8 + 8 fp8 steps.  Not part of the library; compiled and run by hand on a B200.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+constexpr int M = 128, N = 128, K = 256, KC = 128;      // KC: K elements per shared-memory refill
+constexpr int TILE16 = 128 * 128;                       // bytes of one [128 rows x 128 B] swizzled tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {      // K-major, SWIZZLE_128B, SBO = 1024 B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_f8(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done;
+}
+
+// copy a [rows x 128 B] slab (row pitch `pitch` bytes in global memory) into the SWIZZLE_128B K-major layout:
+// 16-byte chunk c of row r lands at (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16)
+__device__ __forceinline__ void fill_tile(uint8_t* dst, const uint8_t* src, size_t pitch, int rows) {
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)r * pitch + c * 16);
+    *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1)
+gemm_kernel(const __half* a_hi, const uint8_t* a_lo8, const uint8_t* a_hi8, const __half* b_hi, const uint8_t* b_lo8,
+            const uint8_t* b_hi8, float* D, int mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  // slab order: A hi16 tile 0, tile 1, B hi16 tile 0, tile 1, A lo8, A hi8, B lo8, B hi8
+  uint8_t* sA16 = sm; uint8_t* sB16 = sm + 2 * TILE16;
+  uint8_t* sAlo = sm + 4 * TILE16; uint8_t* sAh8 = sm + 5 * TILE16; uint8_t* sBlo = sm + 6 * TILE16; uint8_t* sBh8 = sm + 7 * TILE16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_smem;
+  // instruction descriptors: D = f32 (bits 4-5 = 1), K-major A/B, N >> 3 at bit 17, M >> 4 at bit 24;
+  // kind::f16: a/b format 0 = F16; kind::f8f6f4: a/b format 0 = E4M3
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  uint32_t first = 1;
+  for (int kc = 0; kc < K / KC; ++kc) {
+    if (kc > 0) {                               // the previous chunk's MMAs must have read their operands
+      while (!mbar_try_wait(smem_u32(&bar), (uint32_t)((kc - 1) & 1))) {}
+    }
+    // fp16 slabs: 128 K elements = two 64-element (128-byte) tiles per operand
+    for (int t = 0; t < 2; ++t) {
+      fill_tile(sA16 + t * TILE16, reinterpret_cast<const uint8_t*>(a_hi + kc * KC + t * 64), (size_t)K * 2, M);
+      fill_tile(sB16 + t * TILE16, reinterpret_cast<const uint8_t*>(b_hi + kc * KC + t * 64), (size_t)K * 2, N);
+    }
+    // fp8 slabs: 128 K elements = one 128-byte tile per operand
+    fill_tile(sAlo, a_lo8 + kc * KC, K, M); fill_tile(sAh8, a_hi8 + kc * KC, K, M);
+    fill_tile(sBlo, b_lo8 + kc * KC, K, N); fill_tile(sBh8, b_hi8 + kc * KC, K, N);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (mode & 1) {                           // small terms first (see conv_tc.cu: the accumulator truncates)
+        const uint64_t dAh8 = make_sw128_desc(smem_u32(sAh8)), dBlo = make_sw128_desc(smem_u32(sBlo));
+        const uint64_t dAlo = make_sw128_desc(smem_u32(sAlo)), dBh8 = make_sw128_desc(smem_u32(sBh8));
+        for (int k = 0; k < 4; ++k) { mma_f8(tmem, dAh8 + 2 * k, dBlo + 2 * k, idesc, first ? 0u : 1u); first = 0; }
+        for (int k = 0; k < 4; ++k) mma_f8(tmem, dAlo + 2 * k, dBh8 + 2 * k, idesc, 1u);
+      }
+      for (int t = 0; t < 2; ++t) {
+        const uint64_t dA = make_sw128_desc(smem_u32(sA16 + t * TILE16)), dB = make_sw128_desc(smem_u32(sB16 + t * TILE16));
+        for (int k = 0; k < 4; ++k) { mma_f16(tmem, dA + 2 * k, dB + 2 * k, idesc, first ? 0u : 1u); first = 0; }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    __syncthreads();
+  }
+  while (!mbar_try_wait(smem_u32(&bar), (uint32_t)((K / KC - 1) & 1))) {}
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+static float frand() { return (float)rand() / (float)RAND_MAX; }
+static float gauss() { return sqrtf(-2.f * logf(frand() + 1e-7f)) * cosf(6.2831853f * frand()); }
+
+struct Split { std::vector<__half> hi; std::vector<uint8_t> lo8, hi8; std::vector<double> hi_d, lo_d, h8_d; double scale; };
+static Split split(const std::vector<float>& x) {
+  Split s; const size_t n = x.size();
+  float m = 0.f; for (float v : x) m = fmaxf(m, fabsf(v));
+  s.scale = exp2(floor(log2(8192.0 / m)));                 // max|A'| in [2^12, 2^13)
+  s.hi.resize(n); s.lo8.resize(n); s.hi8.resize(n); s.hi_d.resize(n); s.lo_d.resize(n); s.h8_d.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float ap = (float)(x[i] * s.scale);
+    const __half h = __float2half_rn(ap);
+    const float hf = __half2float(h);
+    const __nv_fp8_e4m3 lo((ap - hf) * 64.f), h8(hf / 64.f);
+    s.hi[i] = h; s.lo8[i] = lo.__x; s.hi8[i] = h8.__x;
+    s.hi_d[i] = hf; s.lo_d[i] = (double)(float)lo; s.h8_d[i] = (double)(float)h8;
+  }
+  return s;
+}
+
+int main() {
+  srand(1);
+  std::vector<float> a((size_t)M * K), b((size_t)N * K);
+  for (auto& v : a) v = gauss() * expf(1.5f * gauss());    // wide dynamic range, like post-ReLU features
+  for (auto& v : b) v = 0.05f * gauss();
+  Split sa = split(a), sb = split(b);
+  std::vector<double> ref((size_t)M * N), emu0((size_t)M * N), emu1((size_t)M * N);
+  double refmax = 0;
+  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
+    double r = 0, e0 = 0, e1 = 0;
+    for (int k = 0; k < K; ++k) {
+      r += (double)a[(size_t)i * K + k] * (double)b[(size_t)j * K + k];
+      e0 += sa.hi_d[(size_t)i * K + k] * sb.hi_d[(size_t)j * K + k];
+      e1 += sa.h8_d[(size_t)i * K + k] * sb.lo_d[(size_t)j * K + k] + sa.lo_d[(size_t)i * K + k] * sb.h8_d[(size_t)j * K + k];
+    }
+    ref[(size_t)i * N + j] = r; emu0[(size_t)i * N + j] = e0; emu1[(size_t)i * N + j] = e0 + e1;
+    refmax = fmax(refmax, fabs(r));
+  }
+  __half *dAh, *dBh; uint8_t *dAl, *dA8, *dBl, *dB8; float* dD;
+  cudaMalloc(&dAh, a.size() * 2); cudaMalloc(&dBh, b.size() * 2);
+  cudaMalloc(&dAl, a.size()); cudaMalloc(&dA8, a.size()); cudaMalloc(&dBl, b.size()); cudaMalloc(&dB8, b.size());
+  cudaMalloc(&dD, (size_t)M * N * 4);
+  cudaMemcpy(dAh, sa.hi.data(), a.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dBh, sb.hi.data(), b.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dAl, sa.lo8.data(), a.size(), cudaMemcpyHostToDevice); cudaMemcpy(dA8, sa.hi8.data(), a.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(dBl, sb.lo8.data(), b.size(), cudaMemcpyHostToDevice); cudaMemcpy(dB8, sb.hi8.data(), b.size(), cudaMemcpyHostToDevice);
+  const int smem = 8 * TILE16 + 1024;
+  cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  std::vector<float> out((size_t)M * N);
+  const double inv = 1.0 / (sa.scale * sb.scale);
+  for (int mode = 0; mode < 2; ++mode) {
+    cudaMemset(dD, 0, (size_t)M * N * 4);
+    gemm_kernel<<<1, 128, smem>>>(dAh, dAl, dA8, dBh, dBl, dB8, dD, mode);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(out.data(), dD, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+    double err_ref = 0, err_emu = 0;
+    const std::vector<double>& emu = mode ? emu1 : emu0;
+    for (size_t i = 0; i < out.size(); ++i) {
+      err_ref = fmax(err_ref, fabs(out[i] * inv - ref[i]));
+      err_emu = fmax(err_emu, fabs((double)out[i] - emu[i]) * inv);
+    }
+    printf("mode %d (%s): max|D - exact| / max|exact| = %.3e   max|D - same operands in fp64| / max|exact| = %.3e\n", mode,
+           mode ? "fp16 main + fp8 cross terms" : "fp16 main term only", err_ref / refmax, err_emu / refmax);
+  }
+  printf("expected: mode 0 ~1e-4 (11-bit operands), mode 1 ~1e-5 or below; second column ~1e-6 (fp32 accumulation) in both\n");
+  return 0;
+}
