@@ -9,6 +9,7 @@
 // epilogue would (A' = a * 2^ta with max ~2^13; hi = fp16(A'), lo8 = e4m3((A' - hi) * 64), hi8 = e4m3(hi / 64)), copied
 // into the canonical K-major SWIZZLE_128B shared-memory layout by plain stores (no TMA: this tests the MMA side only),
 // and consumed by 16 f16 steps + 8 + 8 fp8 steps.  Not part of the library; compiled and run by hand on a B200.
+// Result on B200 (round 1): mode 0 2.523e-04 / 3.6e-07, mode 1 1.062e-05 / 5.0e-07 -- the mixed-kind accumulation works.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
