@@ -86,7 +86,7 @@ def test_tiny_config_matches_reference_golden(dev, precision, case, cfg_name):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", ["full_b2", "full_b3_shared"])
+@pytest.mark.parametrize("case", ["full_b2", "full_b3_shared", "full_b16_shared"])   # the last = BASELINE configs[0]
 def test_full_config_matches_reference_golden(dev, precision, case):
     blob = np.load(os.path.join(GOLD, case + ".npz"))
     batch, size, jac, shared = [int(v) for v in blob["meta"]]

@@ -11,7 +11,8 @@ from oracle import eamm_oracle as oracle
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
 CASES = [("tiny_b2", "tiny", True), ("tiny_b3_nojac", "tiny", True), ("full_b2", "full", False),
-         ("full_b3_shared", "full", False)]
+         ("full_b3_shared", "full", False),
+         ("full_b16_shared", "full", False)]       # BASELINE.json configs[0]: one source + 16 kp/jacobian frames
 
 
 def load_case(name, cfg_name):

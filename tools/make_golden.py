@@ -169,6 +169,8 @@ if __name__ == "__main__":
     run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
     run_case("full_b2", "full", 2, 256, full=False)
     run_case("full_b3_shared", "full", 3, 256, shared_source=True, full=False)
+    # BASELINE.json configs[0]: one 256x256 source + 16 synthetic kp/jacobian frames
+    run_case("full_b16_shared", "full", 16, 256, shared_source=True, full=False)
     run_kp_case("kp_tiny_b2", "tiny", 2, 64, audio=False)
     run_kp_case("kp_a_tiny_b3", "tiny", 3, 64, audio=True)
     run_kp_case("kp_full_b2", "full", 2, 256, audio=False)
