@@ -90,7 +90,8 @@ def make(scheme):
 
 cfg = get_config("full")
 sd = synth.make_state_dict(cfg, seed=0)
-src, kpd, kps = synth.make_inputs(2, cfg, size=256, seed=1)
+B = int(os.environ.get("EMU_BATCH", "2"))
+src, kpd, kps = synth.make_inputs(B, cfg, size=256, seed=1, shared_source=bool(int(os.environ.get("EMU_SHARED", "0"))))
 torch.set_num_threads(8)
 want = oracle.generator_forward(sd, cfg, src, kpd, kps)
 for scheme in sys.argv[1:]:
