@@ -8,6 +8,14 @@ A "step" is one pass of DenseMotionNetwork + OcclusionAwareGenerator over one ba
 256x256 frames (BASELINE.json configs[1]: batch 32, 10 keypoints; fp32-equivalent arithmetic by
 default).  One JSON line is printed by rank 0.  Work per GPU is fixed (weak scaling): with N ranks
 the job processes N*batch frames per step, frames block-partitioned, no data-path collective.
+
+Extra keys of the same line (each a separately timed leg after the headline region):
+  cudnn_baseline   the reference's own GPU path (demo.py:98-109, :279): the same algorithm as eager PyTorch-CUDA ops
+                   (cuDNN / ATen kernels, fp32, allow_tf32 off and on) on this GPU -- the stronger second bar next to
+                   the CPU arm (N = 1 only)
+  configs          BASELINE.json configs[2] (batch 256, one-pass reduced-precision convs / fp32 warp; N = 1) and
+                   configs[3] (1024 frames block-partitioned over the ranks, i.e. 128 per GPU at N = 8, plus the
+                   optional NCCL gather of the uint8 frames onto rank 0; N > 1)
 """
 import argparse
 import json
@@ -26,6 +34,8 @@ sys.path.insert(0, ROOT)
 from eamm_b200 import get_config, synth, sharding           # noqa: E402
 
 ALG_GFLOP_PER_FRAME = 107.286       # 30 convs, 2*MAC, per (source, kp) frame
+# ncu --set full DRAM traffic (read + write bytes) of ONE bottleneck-conv launch at B=32: (bytes, source file)
+TRAFFIC = {"fp32_bf16x3": (138.35e6 + 95.15e6, "profiles/r1b_ncu_summary.md")}
 METRIC = "256x256 frames/sec (DenseMotionNetwork + OcclusionAwareGenerator forward, 10 kp)"
 
 
@@ -151,6 +161,123 @@ def oracle_frames_per_sec(batch, repeats, warmup, threads=None):
     return batch / statistics.median(times), times
 
 
+def _time_steps(fn, steps, warmup, barrier=None):
+    """ms per step of fn(), CUDA events on the current stream, after warm-up, synchronised on both sides."""
+    for _ in range(warmup):
+        fn()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def cudnn_baseline(cfg, dev, B, d_src, d_kpd, d_kps, our_value):
+    """The reference's own GPU path (demo.py:98-109 `.cuda().eval()`, :279) on this GPU: the same algorithm as eager
+    PyTorch-CUDA ops -- cuDNN / ATen kernels, one per op, fp32 -- with torch.backends.cudnn.allow_tf32 off and on.
+    (The oracle functions are device-agnostic torch.nn.functional calls; here their tensors live on cuda:0.  This leg
+    is a reported baseline: none of our kernels run in it.)"""
+    from oracle import eamm_oracle as oracle          # baseline leg only
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(cfg, seed=0).items()}
+    src = d_src.contiguous()
+    out = {"unit": "frames/s", "batch": B, "what": "eager PyTorch-CUDA (cuDNN/ATen) run of the reference algorithm, fp32 storage"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        torch.backends.cudnn.benchmark = True
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ms = _time_steps(lambda: oracle.generator_forward(sd, cfg, src, d_kpd, d_kps), 10, 3)
+            out[name] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "allow_tf32": tf32,
+                         "ours_over_this": our_value / (B / (ms * 1e-3))}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def config2_leg(gen, cfg, dev, peaks, batch=256, steps=6):
+    """BASELINE.json configs[2]: batch 256, 256x256, one-pass reduced-precision convs / fp32 warp, 1 GPU."""
+    from eamm_b200 import engine
+    res = {"workload": "BASELINE configs[2]: batch %d frames, 256x256, reduced-precision conv / fp32 warp, 1 GPU" % batch}
+    src, kpd, kps = synth.make_inputs(batch, cfg, size=256, seed=2)
+    d_src = src.to(dev)
+    d_kpd = {k: v.to(dev) for k, v in kpd.items()}
+    d_kps = {k: v.to(dev) for k, v in kps.items()}
+    old = gen.precision
+    try:
+        for prec in ("fp16", "bf16"):
+            gen.precision = prec
+            ms = _time_steps(lambda: gen(d_src, kp_driving=d_kpd, kp_source=d_kps), steps, 3)
+            engine.PROFILE = []
+            if hasattr(torch.cuda, "_sleep"):
+                torch.cuda._sleep(20_000_000)
+            gen(d_src, kp_driving=d_kpd, kp_source=d_kps)
+            torch.cuda.synchronize()
+            prof, engine.PROFILE = engine.PROFILE, None
+            dom = [(fl, a.elapsed_time(b)) for name, fl, nb, a, b in prof if name.startswith("conv:res")]
+            wo = [(nb, a.elapsed_time(b)) for name, fl, nb, a, b in prof if name == "warp_occlude"]
+            tf = sum(f for f, _ in dom) / (sum(t for _, t in dom) * 1e-3) / 1e12
+            res[prec] = {"value": batch / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+                         "bottleneck_conv_tflops": tf, "bottleneck_conv_frac_of_peak": tf / peaks["bf16_tflops_sustained"],
+                         "warp_occlude_gbs": wo[0][0] / (wo[0][1] * 1e-3) / 1e9 if wo else None}
+            gen._eng.ws.clear(); gen._eng.dm.ws.clear()
+            torch.cuda.empty_cache()
+    finally:
+        gen.precision = old
+    return res
+
+
+def config3_leg(gen, cfg, dev, rank, world, total=1024, steps=5):
+    """BASELINE.json configs[3]: 1024 frames block-partitioned over the ranks (128 per GPU at N = 8), frames/s of the
+    whole job, plus the optional tail of SURVEY 8(e): NCCL gather of the uint8 frames onto rank 0."""
+    import torch.distributed as dist
+    start, stop = sharding.partition(total, world, rank)
+    n = stop - start
+    src_all, kpd_all, kps_all = synth.make_inputs(total, cfg, size=256, seed=3)
+    sl = slice(start, stop)
+    d_src = src_all[sl].contiguous().to(dev)
+    d_kpd = {k: v[sl].contiguous().to(dev) for k, v in kpd_all.items()}
+    d_kps = {k: v[sl].contiguous().to(dev) for k, v in kps_all.items()}
+    del src_all
+    gen.emit_u8 = True
+    try:
+        last = {}
+
+        def step():
+            last["out"] = gen(d_src, kp_driving=d_kpd, kp_source=d_kps)
+
+        ms = sharding.reduce_max(_time_steps(step, steps, 3, barrier=dist.barrier), device=dev)
+        frames_u8 = last["out"]["prediction_u8"]
+
+        def step_gather():
+            step()
+            last["gathered"] = sharding.gather_frames(last["out"]["prediction_u8"], total)
+
+        ms_g = sharding.reduce_max(_time_steps(step_gather, steps, 2, barrier=dist.barrier), device=dev)
+        ok = True
+        if rank == 0:
+            g = last["gathered"]
+            ok = tuple(g.shape) == (total, 256, 256, 3) and bool(torch.equal(g[start:stop], frames_u8))
+    finally:
+        gen.emit_u8 = False
+    gen._eng.ws.clear(); gen._eng.dm.ws.clear()
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[3]: %d frames sharded over %d GPUs (%d per GPU), precision %s" % (total, world, n, gen.precision),
+            "value": total / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "steps": steps, "frames_per_gpu": n,
+            "with_gather_u8": {"value": total / (ms_g * 1e-3), "ms_per_step": ms_g, "gather_ms": ms_g - ms,
+                               "bytes_to_root": (total - n) * 256 * 256 * 3, "root_has_all_frames": ok}}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -163,8 +290,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: DenseMotion+Generator 256x256, 10 kp (reference arm batch %d)"
-                               % args.ref_batch, "cpu": cpu_info()},
+        "config": {"workload": "BASELINE configs[1]: batch %d frames, 256x256, 10 kp, DenseMotion+Generator, distinct source "
+                               "per frame (reference arm: the oracle's torch-CPU ops)" % args.ref_batch, "cpu": cpu_info()},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -180,14 +307,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EAMM_B200_PRECISION", "fp32"),
-                    choices=["fp32", "bf16", "fp32_simt"])
+                    choices=["fp32", "fp32_bf16x3", "fp16", "bf16", "fp32_simt"])
     ap.add_argument("--shared-source", action="store_true", help="one source image for the whole batch")
-    ap.add_argument("--ref-batch", type=int, default=16, help="frames per step of the CPU reference arm")
+    ap.add_argument("--ref-batch", type=int, default=0, help="frames per step of the CPU reference arm (0 = --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cudnn_baseline and configs[2]/[3] legs")
     ap.add_argument("--all-kernels", action="store_true", help="kernels_ms_per_step lists every kernel, not the top 12")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.ref_batch <= 0:
+        args.ref_batch = args.batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -270,15 +400,15 @@ def main():
     launches = _lib.LAUNCHES - l0
     clocks = sampler.stop() if sampler else None
     from eamm_b200.modules.dense_motion import check_status
-    check_status(gen._eng.dm.last_status)
+    check_status(gen._eng.dm.status, clear=True)
 
     for _ in range(3):
         step_e2e()
     pipe.drain()
-    # two passes of K steps each, the faster one is reported (both are listed): the host<->device copies of a
-    # pass occasionally run at a fraction of PCIe speed for the whole pass (seen on ~1 run in 5 on the pool's boxes)
+    # two passes of K steps each; the MEAN is the headline and both are listed (the host<->device copies of a pass
+    # occasionally run at a fraction of PCIe speed for the whole pass, seen on ~1 run in 5 on the pool's boxes)
     e2e_passes = [timed(step_e2e, args.steps, finish=pipe.drain) for _ in range(2)]
-    ms_e2e = min(e2e_passes)
+    ms_e2e = sum(e2e_passes) / len(e2e_passes)
     pipe.close()
 
     # per-kernel roofline pass: one extra step with every launch bracketed by CUDA events
@@ -302,22 +432,30 @@ def main():
     dom = [(k, v) for k, v in per.items() if k.startswith("conv:res")]
     dom_ms = sum(v[0] for _, v in dom); dom_fl = sum(v[1] for _, v in dom); dom_n = sum(v[3] for _, v in dom)
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    passes = 3 if args.precision == "fp32" else 1
+    mixed = bool(getattr(gen._eng, "mixed", False))
+    # bf16-pass equivalents executed per algorithmic FLOP by the bottleneck convs: 3 bf16 passes (hi/lo planes), or one
+    # fp16 pass + two fp8 passes at twice the rate (mixed fp16 + 2 x e4m3 operands), or a single pass
+    passes = (2 if mixed else 3) if args.precision in ("fp32", "fp32_bf16x3") else 1
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<cta_group::2> (bottleneck 3x3 256->256, %d launches/step)" % dom_n,
+    traffic = TRAFFIC.get("mix" if mixed else args.precision)
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel<cta_group::2> (bottleneck 3x3 256->256, %d launches/step, %s operands)"
+                % (dom_n, "fp16 + 2 x e4m3" if mixed else {"fp32": "bf16 hi/lo", "fp32_bf16x3": "bf16 hi/lo"}.get(args.precision, args.precision)),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks["source"] == "measured"
                 else "fallback (B200_PROFILING.md)",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the ncu --set full capture
-                # summarised in profiles/r1b_ncu_summary.md (138.3 MB + 95.1 MB at B=32, fp32 mode); scales with the batch
-                "traffic": (138.35e6 + 95.15e6) * B / 32.0 if args.precision == "fp32" else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one such launch, NOT measured by this run: the figure of
+                # the ncu --set full capture named in traffic_source (at B=32), scaled with the batch
+                "traffic": traffic[0] * B / 32.0 if traffic else None,
+                "traffic_source": traffic[1] if traffic else None,
                 "share_of_step": dom_ms / step_ms_prof if step_ms_prof else None,
                 "all_convs_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                 "all_convs_share_of_step": conv_ms / step_ms_prof if step_ms_prof else None,
                 # what the tensor pipe actually runs: 3 bf16 MMA passes per algorithmic FLOP in fp32 mode
                 "executed_tflops": achieved * passes, "executed_frac": achieved * passes / peak,
-                "note": "achieved/frac count the ALGORITHMIC FLOPs of the reference conv (2*MAC); fp32 mode executes "
-                        "3 bf16 MMA passes per FLOP, so frac <= 1/3 there -- executed_frac is the tensor-pipe view"}
+                "pass_equivalents": passes,
+                "note": "achieved/frac count the ALGORITHMIC FLOPs of the reference conv (2*MAC); the fp32-equivalent modes "
+                        "execute 3 (bf16 hi/lo) or 2 (fp16 + fp8 cross terms) bf16-pass equivalents per FLOP, so frac <= 1/3 "
+                        "or 1/2 there -- executed_frac is the tensor-pipe view"}
     wo = per.get("warp_occlude")
     hbm = None
     if wo:
@@ -339,17 +477,21 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": {"fp32": "bf16x3 split (fp32-equivalent, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate, fp32 warp)",
+        "dtype": {"fp32": "fp32-equivalent split operands: fp16 + 2 x e4m3 (bottleneck) / bf16 hi+lo (other layers), fp32 accumulate"
+                  if mixed else "bf16x3 split (fp32-equivalent, fp32 accumulate)",
+                  "fp32_bf16x3": "bf16x3 split (fp32-equivalent, fp32 accumulate)",
+                  "fp16": "fp16 (fp32 accumulate, fp32 warp)", "bf16": "bf16 (fp32 accumulate, fp32 warp)",
                   "fp32_simt": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: batch %d frames/GPU, 256x256, 10 kp, DenseMotion+Generator, %s"
                                % (B, "one shared source" if args.shared_source else "distinct source per frame"),
                    "precision": args.precision, "global_batch": total, "parallelism": "frames block-partitioned x%d" % world,
                    "l2": "per-step working set (activations %.1f GB + weights) exceeds the 126 MB L2; no explicit flush"
-                         % (B * 0.085 if args.precision != "bf16" else B * 0.043)},
+                         % (B * 0.085 if args.precision not in ("bf16", "fp16") else B * 0.043)},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": h_outs[0].numel() * 4 * world, "ms_per_step": ms_e2e / args.steps,
-                "passes_ms_per_step": [round(t / args.steps, 4) for t in e2e_passes], "numa_local_cpus": numa_cpus},
+                "passes_ms_per_step": [round(t / args.steps, 4) for t in e2e_passes], "reported": "mean of the passes",
+                "numa_local_cpus": numa_cpus},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -358,6 +500,17 @@ def main():
         "tensor_frac_whole_step": (ALG_GFLOP_PER_FRAME * 1e9 * frames / (ms * 1e-3) / 1e12) / peak / world,
         "kernels_ms_per_step": kernels,
     }
+    if not args.no_extras:
+        del pipe, h_outs
+        gen._eng.ws.clear(); gen._eng.dm.ws.clear()
+        torch.cuda.empty_cache()
+        extras = {}
+        if world == 1:
+            line["cudnn_baseline"] = cudnn_baseline(cfg, dev, B, d_src, d_kpd, d_kps, value)
+            extras["configs[2]"] = config2_leg(gen, cfg, dev, peaks)
+        else:
+            extras["configs[3]"] = config3_leg(gen, cfg, dev, rank, world)
+        line["configs"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 64)
         fps, times = oracle_frames_per_sec(args.ref_batch, 3, 1, cores)

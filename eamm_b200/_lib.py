@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-EAMM_F32, EAMM_BF16 = 0, 1
+EAMM_F32, EAMM_BF16, EAMM_F16 = 0, 1, 2
 CONV_3X3, CONV_7X7, CONV_UP2_3X3, CONV_ROW7_PACKED = 0, 1, 2, 3
 EPI_RELU, EPI_POOL2, EPI_SIGMOID = 1, 2, 4
 SPLITK_WS_BYTES = 4096 + 160 * 128 * 256 * 4          # EAMM_SPLITK_WS_BYTES
@@ -21,7 +21,7 @@ class Act(C.Structure):
     """eamm_act (include/eamm_b200.h)."""
     _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("c", C.c_int32), ("c_off", C.c_int32), ("c_buf", C.c_int32),
-                ("planes", C.c_int32), ("n_stride", C.c_int64)]
+                ("planes", C.c_int32), ("n_stride", C.c_int64), ("scale_exp", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Kp(C.Structure):
@@ -44,6 +44,7 @@ class ConvArgs(C.Structure):
                 ("scale2", C.c_void_p), ("shift2", C.c_void_p), ("out_nchw", C.c_void_p),
                 ("out_nchw_c", C.c_int32), ("out_nhwc_f32", C.c_void_p), ("pack_passes", C.c_int32),
                 ("weight_fold", C.c_int32), ("out_u8_nhwc", C.c_void_p),
+                ("acc_scale", C.c_void_p), ("amax_out", C.c_void_p), ("amax_out2", C.c_void_p),
                 ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
@@ -66,7 +67,7 @@ _PROTOS = {
     "eamm_flow_combine": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_warp_occlude": (C.c_int, [C.POINTER(Act), C.c_void_p, C.c_void_p, C.POINTER(Act), C.POINTER(Act),
-                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_warp_image": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_nchw_to_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Act), C.c_void_p]),
@@ -102,7 +103,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.eamm_abi_version() != 1:
+    if lib.eamm_abi_version() != 2:
         raise RuntimeError("libeamm_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -16,7 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .engine import ActBuf, ConvLayer, _launch, _round_up, current_stream_ptr, fold_bn, bn_affine
+from .engine import ActBuf, ConvLayer, WorkspaceCache, _launch, _round_up, current_stream_ptr, fold_bn, bn_affine
 
 
 def _bn(sd_mod):
@@ -108,7 +108,7 @@ class ATNet2Engine:
                             w.permute(1, 0, 2, 3), b, w.shape[0], 4, "simt", parity=convT_parity_weights(w))
             lay.flops_per_in_pixel = 2.0 * w.shape[0] * w.shape[1] * 16
             self.dec.append(lay)
-        self.ws = {}
+        self.ws = WorkspaceCache()
 
     def workspace(self, B, T, H, W):
         key = (B, T, H, W)

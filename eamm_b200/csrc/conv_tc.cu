@@ -106,6 +106,12 @@ struct ConvTcParams {
   const float* bias; const float* scale2; const float* shift2;
   float* out_nchw; int out_nchw_c; float* out_nhwc; unsigned char* out_u8;
   long long total_tiles;
+  int f16in;           // the A/B operands are fp16 (EAMM_F16 input): tensor-map coordinates are BYTES (uint8 maps)
+  int mix;             // EAMM_F16 two-plane input: K loop = [a_hi8 x w_lo8 | a_lo8 x w_hi8] as kind::f8f6f4 steps over 128-channel
+                       // chunks (n8 = ntap * cin/128 chunks each), then a_hi x w_hi as kind::f16 steps over 64-channel chunks
+  int n8;              // mix: chunks per fp8 pass
+  const float* acc_scale;   // [cout] accumulator multiplier (undoes the operand pre-scales), or null
+  float* amax_out; float* amax_out2;   // running max |value| of out / out2 (calibration statistic), or null
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -186,6 +192,20 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t da, uint6
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 
+// kind::f8f6f4 (e4m3 x e4m3, K = 32 per instruction): the cross terms of the fp16 + fp8 scheme
+__device__ __forceinline__ void tc2_mma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -260,10 +280,74 @@ __device__ __forceinline__ void ldg256_cg(const void* p, float* v) {
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
 }
 
+// EAMM_F16 views (one fp16 plane, or fp16 + e4m3 lo8 + e4m3 hi8): stored = value * v.mul, saturating packs.
+// The mixed format needs the 32-byte path with CH == 32 (one 32-byte store per e4m3 plane and chunk).
+template <int CH>
+__device__ __forceinline__ void store_chunk_f16(const ActView& v, long long off, int ch, const float* f, bool wide) {
+  __half* p = static_cast<__half*>(v.data) + off;
+  uint32_t h[CH / 2];
+#pragma unroll
+  for (int j = 0; j < CH / 2; ++j) h[j] = f32x2_to_f16x2_sat(f[2 * j] * v.mul, f[2 * j + 1] * v.mul);
+  if (wide) {
+#pragma unroll
+    for (int g = 0; g < CH / 16; ++g)
+      stg256(p + 16 * g, make_uint4(h[8 * g], h[8 * g + 1], h[8 * g + 2], h[8 * g + 3]),
+             make_uint4(h[8 * g + 4], h[8 * g + 5], h[8 * g + 6], h[8 * g + 7]));
+  } else {
+#pragma unroll
+    for (int g = 0; g < CH / 8; ++g)
+      *reinterpret_cast<uint4*>(p + 8 * g) = make_uint4(h[4 * g], h[4 * g + 1], h[4 * g + 2], h[4 * g + 3]);
+  }
+  if (v.planes == 2 && CH == 32) {
+    uint32_t lo8[CH / 4], hi8[CH / 4];
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+      const float2 a = f16x2_to_f32x2(h[2 * j]), b = f16x2_to_f32x2(h[2 * j + 1]);
+      lo8[j] = f32x4_to_e4m3x4_sat((f[4 * j] * v.mul - a.x) * MIX_LO_GAIN, (f[4 * j + 1] * v.mul - a.y) * MIX_LO_GAIN,
+                                   (f[4 * j + 2] * v.mul - b.x) * MIX_LO_GAIN, (f[4 * j + 3] * v.mul - b.y) * MIX_LO_GAIN);
+      hi8[j] = f32x4_to_e4m3x4_sat(a.x * MIX_HI_GAIN, a.y * MIX_HI_GAIN, b.x * MIX_HI_GAIN, b.y * MIX_HI_GAIN);
+    }
+    // plane 1 of the pixel starts 2*c_buf bytes after plane 0 and holds [c_buf lo8 bytes | c_buf hi8 bytes]:
+    // p points at fp16 element (c_off + ch) of plane 0, i.e. 2*(c_off + ch) bytes into the pixel
+    uint8_t* q = reinterpret_cast<uint8_t*>(p) + 2 * v.c_buf - (v.c_off + ch);
+    stg256(q, make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]), make_uint4(lo8[4], lo8[5], lo8[6], lo8[7]));
+    stg256(q + v.c_buf, make_uint4(hi8[0], hi8[1], hi8[2], hi8[3]), make_uint4(hi8[4], hi8[5], hi8[6], hi8[7]));
+  }
+}
+template <int CH>
+__device__ __forceinline__ void add_chunk_f16(const ActView& v, long long off, float* f, bool wide) {   // single plane only
+  const __half* p = static_cast<const __half*>(v.data) + off;
+  if (wide) {
+#pragma unroll
+    for (int g = 0; g < CH / 16; ++g) {
+      uint4 a, b;
+      ldg256(p + 16 * g, a, b);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 x = f16x2_to_f32x2(w[j]);
+        f[16 * g + 2 * j] += x.x * v.inv_mul; f[16 * g + 2 * j + 1] += x.y * v.inv_mul;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int g = 0; g < CH / 8; ++g) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p + 8 * g));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = f16x2_to_f32x2(w[j]);
+      f[8 * g + 2 * j] += x.x * v.inv_mul; f[8 * g + 2 * j + 1] += x.y * v.inv_mul;
+    }
+  }
+}
+
 // WIDE: every lane writes 32-byte pieces (a thread owns one pixel, so a warp store spans 32 pixels: 16-byte
 // pieces fill only half of each sector they touch)
 template <int CH>
-__device__ __forceinline__ void store_chunk(const ActView& v, long long off, const float* f, bool wide) {
+__device__ __forceinline__ void store_chunk(const ActView& v, long long off, int ch, const float* f, bool wide) {
+  if (v.dtype == EAMM_F16) { store_chunk_f16<CH>(v, off, ch, f, wide); return; }
   __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
   if (wide) {
 #pragma unroll
@@ -301,6 +385,7 @@ __device__ __forceinline__ void store_chunk(const ActView& v, long long off, con
 }
 template <int CH>
 __device__ __forceinline__ void add_chunk(const ActView& v, long long off, float* f, bool wide) {
+  if (v.dtype == EAMM_F16) { add_chunk_f16<CH>(v, off, f, wide); return; }
   const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(v.data) + off;
   if (wide) {
 #pragma unroll
@@ -354,7 +439,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
 // Epilogue for one accumulator tile, CH columns at a time.
 template <int CH>
 __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
-                                              int quadrant, int lane, int half) {
+                                              int quadrant, int lane, int half, float& amax1, float& amax2) {
   const int r = quadrant * 32 + lane;
   const int xl = r & (p.bw - 1);
   const int yl = (r >> p.bw_log2) & (p.bh - 1);
@@ -401,6 +486,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
     }
     float f[CH];
     const int co = tc.nt * p.BN + c0;
+    if (p.acc_scale != nullptr) {                     // pre-scaled operands: undo 2^(e_in + e_w[co]) before the bias
+#pragma unroll
+      for (int g = 0; g < CH / 4; ++g) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co) + g);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(p.acc_scale + co) + g);
+        f[4 * g] = fmaf(__uint_as_float(raw[4 * g]), s.x, b.x);
+        f[4 * g + 1] = fmaf(__uint_as_float(raw[4 * g + 1]), s.y, b.y);
+        f[4 * g + 2] = fmaf(__uint_as_float(raw[4 * g + 2]), s.z, b.z);
+        f[4 * g + 3] = fmaf(__uint_as_float(raw[4 * g + 3]), s.w, b.w);
+      }
+    } else {
 #pragma unroll
     for (int g = 0; g < CH / 4; ++g) {
       float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co) + g);
@@ -408,6 +504,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
       f[4 * g + 1] = __uint_as_float(raw[4 * g + 1]) + b.y;
       f[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + b.z;
       f[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + b.w;
+    }
     }
     if (p.flags & EAMM_EPI_RELU) {
 #pragma unroll
@@ -423,7 +520,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
     }
     if (valid) {
       if (p.has_res) add_chunk<CH>(p.res, act_offset(p.res, n, oy, ox, co), f, p.st256);
-      if (p.has_out) store_chunk<CH>(p.out, act_offset(p.out, n, oy, ox, co), f, p.st256);
+      if (p.has_out) {
+        store_chunk<CH>(p.out, act_offset(p.out, n, oy, ox, co), co, f, p.st256);
+        if (p.amax_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) amax1 = fmaxf(amax1, fabsf(f[j]));
+        }
+      }
       if (p.has_out2) {
         float g2[CH];
 #pragma unroll
@@ -435,7 +538,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
           g2[4 * g + 2] = fmaxf(fmaf(f[4 * g + 2], s.z, t.z), 0.f);
           g2[4 * g + 3] = fmaxf(fmaf(f[4 * g + 3], s.w, t.w), 0.f);
         }
-        store_chunk<CH>(p.out2, act_offset(p.out2, n, oy, ox, co), g2, p.st256);
+        store_chunk<CH>(p.out2, act_offset(p.out2, n, oy, ox, co), co, g2, p.st256);
+        if (p.amax_out2 != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) amax2 = fmaxf(amax2, g2[j]);          // post-ReLU: non-negative
+        }
       }
       if (p.out_nhwc != nullptr) {
         float4* dst = reinterpret_cast<float4*>(p.out_nhwc + (((long long)n * OH + oy) * OW + ox) * p.cout + co);
@@ -758,10 +865,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t type1 = (fold == 1 && kc >= 1u && kc <= foldT) ? 1u : 0u;
               const uint32_t kq = fold == 1 ? (kc == 0u ? 0u : (type1 ? kc - 1u : kc - foldT))
                                             : kc + (uint32_t)tc.split * (uint32_t)KC;     // split-K: this item's K range
-              const uint32_t cc = kq & chunk_mask, q = kq >> chunk_shift;          // q = pass * ntap + tap
-              const uint32_t ps = q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u);
+              uint32_t cc, q;
+              int cbase, bcol;
+              if (p.f16in) {
+                // byte coordinates (uint8 tensor maps).  mix: chunks [0, n8) = a_hi8 (plane 1, second half) x w_lo8,
+                // [n8, 2 n8) = a_lo8 x w_hi8, 128 channels each; then a_hi x w_hi, 64 fp16 channels each
+                const uint32_t n8 = (uint32_t)p.n8;
+                if (kq < 2u * n8) {
+                  const uint32_t second = kq >= n8 ? 1u : 0u, i8 = kq - second * n8;
+                  cc = i8 & (chunk_mask >> 1); q = i8 >> (chunk_shift - 1u);
+                  cbase = 2 * p.a_c_buf + (second ? 0 : p.a_c_buf) + p.a_c_off + (int)cc * 128;
+                } else {
+                  const uint32_t i16 = kq - 2u * n8;
+                  cc = i16 & chunk_mask; q = i16 >> chunk_shift;
+                  cbase = 2 * (p.a_c_off + (int)cc * 64);
+                }
+                bcol = (int)kq * 128;
+              } else {
+                cc = kq & chunk_mask; q = kq >> chunk_shift;                        // q = pass * ntap + tap
+                const uint32_t psb = q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u);
+                cbase = p.a_c_off + (((passes == 3 && psb == 1u) || type1) ? p.a_c_buf : 0) + (int)cc * 64;
+                bcol = (int)kq * 64;
+              }
+              const uint32_t ps = p.f16in ? 0u : (q >= 2u * ntap ? 2u : (q >= ntap ? 1u : 0u));
               const int t = (int)(q - ps * ntap);
-              int cbase = p.a_c_off + (((passes == 3 && ps == 1u) || type1) ? p.a_c_buf : 0);
               int dy, dx;
               if (haloish) { dy = t - 3; dx = p.kxn == 3 ? 0 : -3; }
               else if (kind == EAMM_CONV_ROW7_PACKED) { dy = t; dx = 0; cbase = 0; }   // both planes inside the K window
@@ -770,20 +897,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else { const int ty = (t * 37) >> 8; dy = ty - 3; dx = t - 7 * ty - 3; }   // 7x7 per-tap
               const uint32_t sB = sa + KS * a_slot + sub * b_bytes;
               if (CTA2) {
-                tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
+                tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase, tc.x0 + dx, tc.y0 + dy, tc.n0);
                 if (fold && !type1 && p.pf_wide) {
                   // wide step: this CTA stages every row of ONE weight plane of the N tile (rank 0: hi, rank 1: lo)
                   const int prow = tc.cls * p.cout + tc.nt * p.BN + (int)cta_rank * p.b_rows_total;
-                  tma2_load_2d(sB, &tmB, fb, (int)kq * 64, prow);
-                  tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, prow + (p.BN >> 1));
+                  tma2_load_2d(sB, &tmB, fb, bcol, prow);
+                  tma2_load_2d(sB + b_half, &tmB, fb, bcol, prow + (p.BN >> 1));
                 } else {
-                  tma2_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
-                  if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+                  tma2_load_2d(sB, &tmB, fb, bcol, brow);
+                  if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
                 }
               } else {
-                tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase + (int)cc * 64, tc.x0 + dx, tc.y0 + dy, tc.n0);
-                tma_load_2d(sB, &tmB, fb, (int)kq * 64, brow);
-                if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, (int)kq * 64, brow + p.b_rows_total);
+                tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase, tc.x0 + dx, tc.y0 + dy, tc.n0);
+                tma_load_2d(sB, &tmB, fb, bcol, brow);
+                if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
               }
             }
           }
@@ -800,8 +927,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == TC_MMA_WARP && (!CTA2 || cta_rank == 0u)) {
     // ================================================================ MMA issuer (leader CTA of a pair)
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
-    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 2) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);   // N = 2*BN
+    // (a/b format code 0 is F16 under kind::f16 and E4M3 under kind::f8f6f4: fp16 and mixed inputs use one descriptor for both)
+    const uint32_t fmt = p.f16in ? 0u : ((1u << 7) | (1u << 10));
+    const uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 2) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);   // N = 2*BN
+    const uint32_t n8x2 = p.mix ? 2u * (uint32_t)p.n8 : 0u;      // mixed input: K chunks [0, 2 n8) are the fp8 cross terms
     const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
@@ -814,6 +944,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (INSTR) pm0 += clock64() - t0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * 256u;
+      const uint32_t kbase = (n8x2 && p.splitk > 1) ? (uint32_t)decode_tile(p, tile).split * (uint32_t)KC : 0u;
       for (int kc = 0; kc < KC; kc += (int)KS) {
         const uint32_t nsub = (uint32_t)(KC - kc) < KS ? (uint32_t)(KC - kc) : KS;
         if (INSTR) t0 = clock64();
@@ -840,6 +971,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   tc_mma_bf16(tmem_acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first | (uint32_t)kx | (uint32_t)k) ? 1u : 0u);
+              }
+            } else if (kbase + kcs < n8x2) {
+              // fp8 cross-term chunk (128 e4m3 channels = one 128-byte row): four K = 32 steps, 32 bytes apart
+              const uint64_t da = make_sw128_desc(sA), db = make_sw128_desc(sB);
+              if (CTA2) {
+                tc2_mma_f8(tmem_acc, da, db, idesc1, first);
+                tc2_mma_f8(tmem_acc, da + 2, db + 2, idesc1, 1u);
+                tc2_mma_f8(tmem_acc, da + 4, db + 4, idesc1, 1u);
+                tc2_mma_f8(tmem_acc, da + 6, db + 6, idesc1, 1u);
+              } else {
+                tc_mma_f8(tmem_acc, da, db, idesc1, first);
+                tc_mma_f8(tmem_acc, da + 2, db + 2, idesc1, 1u);
+                tc_mma_f8(tmem_acc, da + 4, db + 4, idesc1, 1u);
+                tc_mma_f8(tmem_acc, da + 6, db + 6, idesc1, 1u);
               }
             } else {
               const uint64_t da = make_sw128_desc(sA), db = make_sw128_desc(sB);
@@ -889,6 +1034,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quadrant = warp & 3, half = warp >> 2;
     int as = 0; uint32_t aphase = 0;
     long long pe = 0, pstart = 0;
+    float amax1 = 0.f, amax2 = 0.f;              // running max |out|, |out2| of this thread (calibration statistic)
     if (INSTR) pstart = clock64();
     float* kxn_smem = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
                                                (size_t)p.num_stages * stage_bytes);
@@ -906,12 +1052,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else if (p.splitk > 1) {
         if (p.sk_dist) {
           splitk_publish_wait(p, tc, tmem_acc, quadrant, lane, half);
-          epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+          epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
           splitk_done(p, tc);
-        } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
+        } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
       }
-      else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half);
-      else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half);
+      else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
+      else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -919,6 +1065,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (p.amax_out != nullptr || p.amax_out2 != nullptr) {
+      // values are non-negative: the integer order of their bit patterns is the float order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        amax1 = fmaxf(amax1, __shfl_xor_sync(0xffffffffu, amax1, o));
+        amax2 = fmaxf(amax2, __shfl_xor_sync(0xffffffffu, amax2, o));
+      }
+      if (lane == 0) {
+        if (p.amax_out != nullptr) atomicMax(reinterpret_cast<int*>(p.amax_out), __float_as_int(amax1));
+        if (p.amax_out2 != nullptr) atomicMax(reinterpret_cast<int*>(p.amax_out2), __float_as_int(amax2));
+      }
     }
     if (INSTR && p.prof && warp == 0 && lane == 0) {
       p.prof[blockIdx.x * 8 + 5] = pe;                             // epilogue warp 0: waiting for an accumulator
@@ -998,7 +1156,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (rc) return rc;
   const eamm_act* in = a->in;
   const bool row7 = a->kind == EAMM_CONV_ROW7_PACKED;
-  if (in->dtype != EAMM_BF16) return EAMM_ERR_DTYPE;
+  if (in->dtype != EAMM_BF16 && in->dtype != EAMM_F16) return EAMM_ERR_DTYPE;
+  const bool f16in = in->dtype == EAMM_F16, mix = f16in && in->planes == 2;
+  if (mix && (row7 || a->kind == EAMM_CONV_7X7 || a->cin % 128)) return EAMM_ERR_UNSUPPORTED;
   if (row7) {
     if (in->c != 8 || in->c_buf != 8 || in->c_off != 0 || in->planes != 1 || a->cin != 8) return EAMM_ERR_SHAPE;
     if (a->pack_passes != 1 && a->pack_passes != 2) return EAMM_ERR_ARG;
@@ -1007,7 +1167,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   const eamm_act* views[3] = {a->out, a->out2, a->residual};
   for (int i = 0; i < 3; ++i)
-    if (views[i] && (views[i]->dtype != EAMM_BF16 || views[i]->c_off % 8 || views[i]->c_buf % 8)) return EAMM_ERR_DTYPE;
+    if (views[i] && ((views[i]->dtype != EAMM_BF16 && views[i]->dtype != EAMM_F16) || views[i]->c_off % 8 || views[i]->c_buf % 8))
+      return EAMM_ERR_DTYPE;
+  if (a->residual && a->residual->dtype == EAMM_F16 && a->residual->planes != 1) return EAMM_ERR_UNSUPPORTED;
   if ((uintptr_t)in->data % 16 || (uintptr_t)a->weight % 16) return EAMM_ERR_ALIGN;
 
   ConvTcParams p;
@@ -1021,7 +1183,10 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.cin_chunks = row7 ? 1 : a->cin / 64;
   p.chunk_shift = ilog2_exact(p.cin_chunks);
   if (p.chunk_shift < 0) return EAMM_ERR_UNSUPPORTED;          // cin/64 must be a power of two
-  p.passes = row7 ? a->pack_passes : (in->planes == 2 ? 3 : 1);
+  // (mixed input: the two fp8 passes over 128-channel chunks count as one pass of 64-channel chunks)
+  p.passes = row7 ? a->pack_passes : (mix ? 2 : (in->planes == 2 ? 3 : 1));
+  p.f16in = f16in ? 1 : 0; p.mix = mix ? 1 : 0;
+  if (f16in && row7 && a->pack_passes != 1) return EAMM_ERR_UNSUPPORTED;
   p.a_c_off = in->c_off; p.a_c_buf = in->c_buf;
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("EAMM_TC_HALO"); halo_env = e ? atoi(e) : 1; }
@@ -1217,6 +1382,13 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (views[i] && ((uintptr_t)views[i]->data % 32 || views[i]->c_off % 16 || views[i]->c_buf % 16 ||
                      views[i]->n_stride % 16 || (views[i]->planes * views[i]->c_buf) % 16))
       p.st256 = 0;
+  // mixed-format outputs: one 32-byte store per e4m3 plane and 32-channel chunk
+  for (int i = 0; i < 2; ++i)
+    if (views[i] && views[i]->dtype == EAMM_F16 && views[i]->planes == 2 &&
+        (!p.st256 || p.BN % 32 || views[i]->c_off % 32 || views[i]->c_buf % 32 || p.kxn))
+      return EAMM_ERR_UNSUPPORTED;
+  p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
+  p.n8 = mix ? p.ntap * p.cin_chunks / 2 : 0;
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles * p.splitk;
@@ -1243,7 +1415,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
       strides[0] = pix * 2; strides[1] = pix * 2 * in->w; strides[2] = pix * 2 * in->w * in->h;
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, es,
+    if (f16in) { dims[0] *= 2; box[0] = 128; }            // byte units: fp16 and e4m3 planes are addressed through one uint8 map
+    CUresult r = encode(&tmA, f16in ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 100 - (int)r;      // distinguishable in bring-up logs
@@ -1259,7 +1432,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(p.halo ? 7 * p.BN : (p.cta2 ? p.BN / 2 : p.BN))};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), dims, strides, box, es,
+    if (f16in) {                                          // bytes; mixed: (tap, channel) x [lo8 | hi8 | fp16 hi] = 4 bytes each
+      dims[0] = mix ? (cuuint64_t)p.ntap * a->cin * 4 : ktot * 2;
+      strides[0] = dims[0]; box[0] = 128;
+    }
+    CUresult r = encode(&tmB, f16in ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a->weight), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;

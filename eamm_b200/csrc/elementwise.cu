@@ -250,39 +250,83 @@ warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float
   }
 }
 
-// bf16 fast path of a9-i: 8 channels (one 16-byte vector per plane) per thread, so the per-pixel
-// sampling setup is amortised over twice the data and every access is a 128-bit transaction.
+// Vector fast path of a9-i: 8 channels per thread, so the per-pixel sampling setup is amortised over twice the
+// data and every access is a 128-bit transaction.  Storage formats (template parameters): 0 = bf16, 1 = bf16 hi/lo
+// planes, 2 = fp16, 3 = fp16 + e4m3 lo8 + e4m3 hi8 (mixed operand format, include/eamm_b200.h); feat and out
+// share FIN, out2 (the next conv's A operand) has its own FOUT2.
+constexpr int FMT_BF16 = 0, FMT_BF16X2 = 1, FMT_F16 = 2, FMT_MIX = 3;
+
 __device__ __forceinline__ void bf16x8_fma(uint4 r, float q, float* acc) {
   float4 a = bf16x4_to_float4(make_uint2(r.x, r.y)), b = bf16x4_to_float4(make_uint2(r.z, r.w));
   acc[0] = fmaf(a.x, q, acc[0]); acc[1] = fmaf(a.y, q, acc[1]); acc[2] = fmaf(a.z, q, acc[2]); acc[3] = fmaf(a.w, q, acc[3]);
   acc[4] = fmaf(b.x, q, acc[4]); acc[5] = fmaf(b.y, q, acc[5]); acc[6] = fmaf(b.z, q, acc[6]); acc[7] = fmaf(b.w, q, acc[7]);
 }
-template <int PLANES>
-__device__ __forceinline__ void bf16x8_tap(const __nv_bfloat16* base, long long off, int c_buf, float q, float* acc) {
-  bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off)), q, acc);
-  if (PLANES == 2) bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off + c_buf)), q, acc);
+__device__ __forceinline__ void f16x8_fma(uint4 r, float q, float* acc) {
+  const float2 a = f16x2_to_f32x2(r.x), b = f16x2_to_f32x2(r.y), c = f16x2_to_f32x2(r.z), d = f16x2_to_f32x2(r.w);
+  acc[0] = fmaf(a.x, q, acc[0]); acc[1] = fmaf(a.y, q, acc[1]); acc[2] = fmaf(b.x, q, acc[2]); acc[3] = fmaf(b.y, q, acc[3]);
+  acc[4] = fmaf(c.x, q, acc[4]); acc[5] = fmaf(c.y, q, acc[5]); acc[6] = fmaf(d.x, q, acc[6]); acc[7] = fmaf(d.y, q, acc[7]);
 }
-template <int PLANES>
-__device__ __forceinline__ void bf16x8_store(const ActView& v, long long off, const float* f) {
-  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
-  uint2 a = float4_to_bf16x4(make_float4(f[0], f[1], f[2], f[3]));
-  uint2 b = float4_to_bf16x4(make_float4(f[4], f[5], f[6], f[7]));
-  *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b.x, b.y);
-  if (PLANES == 2) {
-    float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
-    uint2 la = float4_to_bf16x4(make_float4(f[0] - ha.x, f[1] - ha.y, f[2] - ha.z, f[3] - ha.w));
-    uint2 lb = float4_to_bf16x4(make_float4(f[4] - hb.x, f[5] - hb.y, f[6] - hb.z, f[7] - hb.w));
-    *reinterpret_cast<uint4*>(p + v.c_buf) = make_uint4(la.x, la.y, lb.x, lb.y);
+// acc += q * (8 channels starting at channel `ch` of the view at plane-0 element offset `off`)
+template <int FMT>
+__device__ __forceinline__ void vec8_tap(const ActView& v, long long off, int ch, float q, float* acc) {
+  if (FMT == FMT_BF16 || FMT == FMT_BF16X2) {
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(v.data);
+    bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off)), q, acc);
+    if (FMT == FMT_BF16X2) bf16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off + v.c_buf)), q, acc);
+  } else {
+    const __half* base = static_cast<const __half*>(v.data);
+    const float qs = q * v.inv_mul;
+    f16x8_fma(__ldg(reinterpret_cast<const uint4*>(base + off)), qs, acc);
+    if (FMT == FMT_MIX) {
+      const uint2 r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(base + off) + 2 * v.c_buf - (v.c_off + ch)));
+      const float4 a = e4m3x4_to_f32x4(r.x), b = e4m3x4_to_f32x4(r.y);
+      const float ql = qs * MIX_HI_GAIN;                       // lo8 / 64
+      acc[0] = fmaf(a.x, ql, acc[0]); acc[1] = fmaf(a.y, ql, acc[1]); acc[2] = fmaf(a.z, ql, acc[2]); acc[3] = fmaf(a.w, ql, acc[3]);
+      acc[4] = fmaf(b.x, ql, acc[4]); acc[5] = fmaf(b.y, ql, acc[5]); acc[6] = fmaf(b.z, ql, acc[6]); acc[7] = fmaf(b.w, ql, acc[7]);
+    }
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void vec8_store(const ActView& v, long long off, int ch, const float* f) {
+  if (FMT == FMT_BF16 || FMT == FMT_BF16X2) {
+    __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
+    uint2 a = float4_to_bf16x4(make_float4(f[0], f[1], f[2], f[3]));
+    uint2 b = float4_to_bf16x4(make_float4(f[4], f[5], f[6], f[7]));
+    *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b.x, b.y);
+    if (FMT == FMT_BF16X2) {
+      float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+      uint2 la = float4_to_bf16x4(make_float4(f[0] - ha.x, f[1] - ha.y, f[2] - ha.z, f[3] - ha.w));
+      uint2 lb = float4_to_bf16x4(make_float4(f[4] - hb.x, f[5] - hb.y, f[6] - hb.z, f[7] - hb.w));
+      *reinterpret_cast<uint4*>(p + v.c_buf) = make_uint4(la.x, la.y, lb.x, lb.y);
+    }
+  } else {
+    __half* p = static_cast<__half*>(v.data) + off;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = f[j] * v.mul;
+    const uint4 h = make_uint4(f32x2_to_f16x2_sat(s[0], s[1]), f32x2_to_f16x2_sat(s[2], s[3]),
+                               f32x2_to_f16x2_sat(s[4], s[5]), f32x2_to_f16x2_sat(s[6], s[7]));
+    *reinterpret_cast<uint4*>(p) = h;
+    if (FMT == FMT_MIX) {
+      const float2 a = f16x2_to_f32x2(h.x), b = f16x2_to_f32x2(h.y), c = f16x2_to_f32x2(h.z), d = f16x2_to_f32x2(h.w);
+      uint8_t* q = reinterpret_cast<uint8_t*>(p) + 2 * v.c_buf - (v.c_off + ch);
+      *reinterpret_cast<uint2*>(q) = make_uint2(
+          f32x4_to_e4m3x4_sat((s[0] - a.x) * MIX_LO_GAIN, (s[1] - a.y) * MIX_LO_GAIN, (s[2] - b.x) * MIX_LO_GAIN, (s[3] - b.y) * MIX_LO_GAIN),
+          f32x4_to_e4m3x4_sat((s[4] - c.x) * MIX_LO_GAIN, (s[5] - c.y) * MIX_LO_GAIN, (s[6] - d.x) * MIX_LO_GAIN, (s[7] - d.y) * MIX_LO_GAIN));
+      *reinterpret_cast<uint2*>(q + v.c_buf) = make_uint2(
+          f32x4_to_e4m3x4_sat(a.x * MIX_HI_GAIN, a.y * MIX_HI_GAIN, b.x * MIX_HI_GAIN, b.y * MIX_HI_GAIN),
+          f32x4_to_e4m3x4_sat(c.x * MIX_HI_GAIN, c.y * MIX_HI_GAIN, d.x * MIX_HI_GAIN, d.y * MIX_HI_GAIN));
+    }
   }
 }
 
-template <int PLANES>
+template <int FIN, int FOUT2>
 __global__ void __launch_bounds__(256)
-warp_occlude_bf16_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
-                         ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
-                         const float* __restrict__ shift2, long long total) {
+warp_occlude_vec_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
+                        ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
+                        const float* __restrict__ shift2, float* __restrict__ amax_out2, long long total) {
   const int c8 = feat.c >> 3;
-  const __nv_bfloat16* fbase = static_cast<const __nv_bfloat16*>(feat.data);
+  float amax = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % c8);
@@ -296,16 +340,16 @@ warp_occlude_bf16_kernel(ActView feat, const float2* __restrict__ deform, const 
     const bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
     const bool yin0 = b.y0 >= 0 && b.y0 < feat.h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < feat.h;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (yin0 && xin0) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0, b.x0, 8 * cg), feat.c_buf, wy0 * wx0, acc);
-    if (yin0 && xin1) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0, b.x0 + 1, 8 * cg), feat.c_buf, wy0 * b.wx1, acc);
-    if (yin1 && xin0) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0 + 1, b.x0, 8 * cg), feat.c_buf, b.wy1 * wx0, acc);
-    if (yin1 && xin1) bf16x8_tap<PLANES>(fbase, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 8 * cg), feat.c_buf, b.wy1 * b.wx1, acc);
+    if (yin0 && xin0) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0, b.x0, 8 * cg), 8 * cg, wy0 * wx0, acc);
+    if (yin0 && xin1) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0, b.x0 + 1, 8 * cg), 8 * cg, wy0 * b.wx1, acc);
+    if (yin1 && xin0) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0 + 1, b.x0, 8 * cg), 8 * cg, b.wy1 * wx0, acc);
+    if (yin1 && xin1) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 8 * cg), 8 * cg, b.wy1 * b.wx1, acc);
     if (occ != nullptr) {
       const float o = __ldg(occ + pix);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] *= o;
     }
-    bf16x8_store<PLANES>(out, act_offset(out, n, y, x, 8 * cg), acc);
+    vec8_store<FIN == FMT_MIX ? FMT_BF16X2 : FIN>(out, act_offset(out, n, y, x, 8 * cg), 8 * cg, acc);
     if (has_out2) {
       const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale2) + 2 * cg), s1 = __ldg(reinterpret_cast<const float4*>(scale2) + 2 * cg + 1);
       const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift2) + 2 * cg), t1 = __ldg(reinterpret_cast<const float4*>(shift2) + 2 * cg + 1);
@@ -314,8 +358,15 @@ warp_occlude_bf16_kernel(ActView feat, const float2* __restrict__ deform, const 
       r[2] = fmaxf(fmaf(acc[2], s0.z, t0.z), 0.f); r[3] = fmaxf(fmaf(acc[3], s0.w, t0.w), 0.f);
       r[4] = fmaxf(fmaf(acc[4], s1.x, t1.x), 0.f); r[5] = fmaxf(fmaf(acc[5], s1.y, t1.y), 0.f);
       r[6] = fmaxf(fmaf(acc[6], s1.z, t1.z), 0.f); r[7] = fmaxf(fmaf(acc[7], s1.w, t1.w), 0.f);
-      bf16x8_store<PLANES>(out2, act_offset(out2, n, y, x, 8 * cg), r);
+      vec8_store<FOUT2>(out2, act_offset(out2, n, y, x, 8 * cg), 8 * cg, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) amax = fmaxf(amax, r[j]);
     }
+  }
+  if (amax_out2 != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax_out2), __float_as_int(amax));   // non-negative floats
   }
 }
 
@@ -405,7 +456,8 @@ pack_image_kernel(const float* __restrict__ src, int C, int H, int W, int split,
     for (int c = 0; c < C; ++c) v[c] = __ldg(src + (((long long)n * C + c) * H + y) * W + x);
     uint2 hi = float4_to_bf16x4(make_float4(v[0], v[1], v[2], 0.f));
     uint2 lo = make_uint2(0u, 0u);
-    if (split) {
+    if (split == 2) hi = make_uint2(f32x2_to_f16x2_sat(v[0], v[1]), f32x2_to_f16x2_sat(v[2], 0.f));     // fp16, single plane
+    else if (split) {
       float4 h = bf16x4_to_float4(hi);
       lo = float4_to_bf16x4(make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, 0.f));
     }
@@ -682,9 +734,15 @@ extern "C" int eamm_flow_combine(const float* logits, int ldl, const eamm_kp* kp
   return 0;
 }
 
+static int view_fmt(const ActView& v) {
+  if (v.dtype == EAMM_BF16) return v.planes == 2 ? FMT_BF16X2 : FMT_BF16;
+  if (v.dtype == EAMM_F16) return v.planes == 2 ? FMT_MIX : FMT_F16;
+  return -1;
+}
+
 extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
                                  const eamm_act* out, const eamm_act* out2, const float* scale2,
-                                 const float* shift2, void* stream) {
+                                 const float* shift2, float* amax_out2, void* stream) {
   int rc = check_view(feat); if (rc) return rc;
   rc = check_view(out); if (rc) return rc;
   if (!deformation) return EAMM_ERR_ARG;
@@ -697,23 +755,32 @@ extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation,
     if (out2->n != feat->n || out2->h != feat->h || out2->w != feat->w || out2->c != feat->c) return EAMM_ERR_SHAPE;
     o2 = make_view(out2); has2 = 1;
   }
-  auto vec_ok = [](const ActView& v, int planes) {
-    return v.dtype == EAMM_BF16 && v.planes == planes && v.c % 8 == 0 && v.c_off % 8 == 0 && v.c_buf % 8 == 0 &&
+  auto vec_ok = [](const ActView& v) {
+    return v.dtype != EAMM_F32 && v.c % 8 == 0 && v.c_off % 8 == 0 && v.c_buf % 8 == 0 &&
            ((uintptr_t)v.data % 16) == 0 && v.n_stride % 8 == 0;
   };
-  if (f.dtype == EAMM_BF16 && vec_ok(f, f.planes) && vec_ok(o, f.planes) && (!has2 || vec_ok(o2, f.planes))) {
+  const int fin = view_fmt(f), fo = view_fmt(o), fo2 = has2 ? view_fmt(o2) : fin;
+  // the vector kernel's format pairs: out has feat's format (a mixed feat writes bf16 hi/lo); out2 the same or mixed
+  const bool pair_ok = fin >= 0 && fo == (fin == FMT_MIX ? FMT_BF16X2 : fin) && (fo2 == fo || fo2 == FMT_MIX) &&
+                       !(fo2 == FMT_MIX && fin != FMT_BF16X2 && fin != FMT_MIX);
+  if (pair_ok && vec_ok(f) && vec_ok(o) && (!has2 || vec_ok(o2))) {
     long long total = (long long)f.n * f.h * f.w * (f.c / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    if (f.planes == 2)
-      warp_occlude_bf16_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
-                                                                           has2, scale2, shift2, total);
-    else
-      warp_occlude_bf16_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2,
-                                                                           has2, scale2, shift2, total);
+    const float2* dp = (const float2*)deformation;
+    cudaStream_t st = (cudaStream_t)stream;
+#define EAMM_WO(FI, FO2) warp_occlude_vec_kernel<FI, FO2><<<blocks, 256, 0, st>>>(f, dp, occlusion, o, o2, has2, scale2, shift2, amax_out2, total)
+    if (fin == FMT_BF16) EAMM_WO(FMT_BF16, FMT_BF16);
+    else if (fin == FMT_F16) EAMM_WO(FMT_F16, FMT_F16);
+    else if (fin == FMT_BF16X2 && fo2 == FMT_MIX) EAMM_WO(FMT_BF16X2, FMT_MIX);
+    else if (fin == FMT_BF16X2) EAMM_WO(FMT_BF16X2, FMT_BF16X2);
+    else if (fo2 == FMT_MIX) EAMM_WO(FMT_MIX, FMT_MIX);
+    else EAMM_WO(FMT_MIX, FMT_BF16X2);
+#undef EAMM_WO
     EAMM_LAUNCH_CHECK();
     return 0;
   }
+  if (amax_out2 != nullptr) return EAMM_ERR_UNSUPPORTED;          // the statistic is only kept by the vector kernel
   long long total = (long long)f.n * f.h * f.w * (f.c / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
@@ -746,7 +813,7 @@ extern "C" int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, co
 }
 
 extern "C" int eamm_pack_image(const float* src, int n, int C, int H, int W, int split, void* dst, void* stream) {
-  if (!src || !dst || n <= 0 || C <= 0 || C > 3 || H <= 0 || W <= 0) return EAMM_ERR_ARG;
+  if (!src || !dst || n <= 0 || C <= 0 || C > 3 || H <= 0 || W <= 0 || split < 0 || split > 2) return EAMM_ERR_ARG;
   if ((uintptr_t)dst % 16) return EAMM_ERR_ALIGN;
   long long total = (long long)n * H * W;
   int blocks = (int)((total + 255) / 256);

@@ -5,9 +5,14 @@ device memory, streams and the one-off weight repacking (BatchNorm folding etc.)
 follows /root/reference/modules/generator.py:59-97 and dense_motion.py:81-113.
 
 Precision modes (``precision`` attribute of the drop-in modules):
-  "fp32_simt" fp32 activations, fp32 CUDA-core convs              -- exact-fp32 parity path
-  "fp32"      bf16 hi/lo planes (16 mantissa bits) + 3-pass bf16 tensor-core convs, fp32 accumulate
-  "bf16"      single bf16 plane, 1-pass tensor-core convs, fp32 accumulate; warp/flow math fp32
+  "fp32_simt"   fp32 activations, fp32 CUDA-core convs              -- exact-fp32 parity path
+  "fp32"        fp32-equivalent tensor-core mode (the default): bf16 hi/lo planes + 3-pass bf16 convs, and for
+                the bottleneck ResBlocks the mixed fp16 + 2 x e4m3 operand format: one fp16 pass + two fp8
+                cross-term passes (2 pass-equivalents), per-tensor power-of-two pre-scales from a calibration pass
+  "fp32_bf16x3" the 3-pass bf16 hi/lo scheme on every layer (round-1 "fp32" mode; no calibration state)
+  "fp16"        single fp16 plane, 1-pass tensor-core convs, fp32 accumulate; warp/flow math fp32
+                (BASELINE configs[2] "reduced-precision conv / fp32 warp": 7x more accurate than bf16 at equal cost)
+  "bf16"        the same with bf16 operands (the literal BASELINE wording; 8 significant bits)
 """
 import ctypes as C
 import math
@@ -18,7 +23,7 @@ from . import _lib as L
 
 BN_EPS = 1e-5  # /root/reference/sync_batchnorm/batchnorm.py:39
 
-PRECISIONS = ("fp32_simt", "fp32", "bf16")
+PRECISIONS = ("fp32_simt", "fp32", "fp32_bf16x3", "fp16", "bf16")
 
 
 def _round_up(x, m):
@@ -49,17 +54,62 @@ def _launch(name, fn, flops=0.0, nbytes=0.0):
     PROFILE.append((name, flops, nbytes, e0, e1))
 
 
+class WorkspaceCache:
+    """Bounded cache of per-shape workspaces (a few GB each at the bench batch): the `limit` most recently used shapes
+    stay allocated, older ones are dropped (PyTorch's allocator is stream-ordered, so work already queued on the
+    allocating stream still sees valid memory).  A service with ragged batches or varying clip lengths therefore does
+    not accumulate one workspace per shape it has ever seen.  CUDA graphs keep their own references (graph.py)."""
+
+    def __init__(self, limit=2):
+        import collections
+        self.limit = limit
+        self._d = collections.OrderedDict()
+
+    def get(self, key):
+        ws = self._d.get(key)
+        if ws is not None:
+            self._d.move_to_end(key)
+        return ws
+
+    def __getitem__(self, key):
+        return self._d[key]
+
+    def __setitem__(self, key, ws):
+        self._d[key] = ws
+        self._d.move_to_end(key)
+        while len(self._d) > self.limit:
+            self._d.popitem(last=False)
+
+    def __contains__(self, key):
+        return key in self._d
+
+    def __len__(self):
+        return len(self._d)
+
+    def values(self):
+        return self._d.values()
+
+    def clear(self):
+        self._d.clear()
+
+
 class ActBuf:
-    """A zero-initialised NHWC activation buffer [n, h, w, planes*c_buf] and its eamm_act views."""
+    """A zero-initialised NHWC activation buffer [n, h, w, planes*c_buf] and its eamm_act views.
+
+    modes: "f32" | "bf16" | "bf16x2" (hi/lo planes) | "f16" | "mix" (fp16 + e4m3 lo8 + e4m3 hi8, include/eamm_b200.h);
+    `exp` is the power-of-two pre-scale of an fp16 / mixed buffer (stored = value * 2^exp)."""
 
     def __init__(self, n, h, w, c_buf, mode, device):
-        self.n, self.h, self.w, self.c_buf = n, h, w, c_buf
-        self.planes = 2 if mode == "bf16x2" else 1
-        self.dtype = L.EAMM_F32 if mode == "f32" else L.EAMM_BF16
-        tdt = torch.float32 if mode == "f32" else torch.bfloat16
+        self.n, self.h, self.w, self.c_buf, self.mode = n, h, w, c_buf, mode
+        self.planes = 2 if mode in ("bf16x2", "mix") else 1
+        self.dtype = {"f32": L.EAMM_F32, "bf16": L.EAMM_BF16, "bf16x2": L.EAMM_BF16, "f16": L.EAMM_F16,
+                      "mix": L.EAMM_F16}[mode]
+        tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "bf16x2": torch.bfloat16, "f16": torch.float16,
+               "mix": torch.float16}[mode]
+        self.exp = 0
         self.t = torch.zeros(n, h, w, self.planes * c_buf, dtype=tdt, device=device)
 
-    def act(self, c_off=0, c=None, n=None, broadcast=False):
+    def act(self, c_off=0, c=None, n=None, broadcast=False, exp=None):
         a = L.Act()
         a.data = self.t.data_ptr()
         a.dtype = self.dtype
@@ -68,12 +118,42 @@ class ActBuf:
         a.c = self.c_buf - c_off if c is None else c
         a.c_off, a.c_buf, a.planes = c_off, self.c_buf, self.planes
         a.n_stride = 0 if broadcast else self.h * self.w * self.planes * self.c_buf
+        a.scale_exp = (self.exp if exp is None else exp) if self.dtype == L.EAMM_F16 else 0
         return a
 
-    def to_float(self, c_off=0, c=None):
-        """Debug/test helper: the view as an fp32 NCHW tensor (sums the planes)."""
+    def store_float(self, x, exp=None):
+        """Debug/test helper: encode an fp32 NHWC tensor [n,h,w,c_buf] into the buffer's storage format (the same
+        roundings as the kernels' epilogues: RN, saturating)."""
+        if exp is not None:
+            self.exp = exp
+        x = x.to(self.t.device, torch.float32)
+        if self.mode == "f32":
+            self.t.copy_(x)
+        elif self.mode in ("bf16", "bf16x2"):
+            hi = x.bfloat16()
+            self.t.copy_(hi if self.mode == "bf16" else torch.cat([hi, (x - hi.float()).bfloat16()], dim=-1))
+        else:
+            s = (x * 2.0 ** self.exp).clamp(-65504, 65504)
+            hi = s.half()
+            if self.mode == "f16":
+                self.t.copy_(hi)
+            else:
+                lo8 = ((s - hi.float()) * 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
+                hi8 = (hi.float() / 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
+                plane1 = torch.cat([lo8.view(torch.uint8), hi8.view(torch.uint8)], dim=-1).view(torch.float16)
+                self.t.copy_(torch.cat([hi, plane1], dim=-1))
+
+    def to_float(self, c_off=0, c=None, exp=None):
+        """Debug/test helper: the view as an fp32 NCHW tensor (sums the planes, undoes the pre-scale)."""
         c = self.c_buf - c_off if c is None else c
-        t = self.t.view(self.n, self.h, self.w, self.planes, self.c_buf).float().sum(3)
+        if self.mode == "mix":
+            hi = self.t[..., :self.c_buf].float()
+            lo8 = self.t[..., self.c_buf:].contiguous().view(torch.uint8)[..., :self.c_buf].view(torch.float8_e4m3fn).float()
+            t = (hi + lo8 / 64.0) * 2.0 ** -(self.exp if exp is None else exp)
+        else:
+            t = self.t.view(self.n, self.h, self.w, self.planes, self.c_buf).float().sum(3)
+            if self.mode == "f16":
+                t = t * 2.0 ** -(self.exp if exp is None else exp)
         return t[..., c_off:c_off + c].permute(0, 3, 1, 2).contiguous()
 
 
@@ -132,7 +212,7 @@ def up2_parity_weights(w):
     return torch.stack(classes, 0)
 
 
-def pack_tc_weights(full, classes, passes):
+def pack_tc_weights(full, classes, passes, dt=torch.bfloat16):
     """[classes*taps][cout][cin] fp32 -> bf16 [classes*cout][taps*passes*cin] for eamm_conv_tc.
 
     K order is (pass, tap, channel).  passes == 3 is the split-bf16 scheme: the weight planes
@@ -142,13 +222,41 @@ def pack_tc_weights(full, classes, passes):
     ct, cout, cin = full.shape
     taps = ct // classes
     w = full.view(classes, taps, cout, cin).permute(0, 2, 1, 3)          # [cls][cout][taps][cin]
-    hi = w.to(torch.bfloat16)
+    hi = w.to(dt)
     if passes == 1:
         packed = hi
     else:
-        lo = (w - hi.float()).to(torch.bfloat16)
+        lo = (w - hi.float()).to(dt)
         packed = torch.stack([lo, hi, hi], dim=2)                         # [cls][cout][3][taps][cin]
     return packed.reshape(classes * cout, -1).contiguous()
+
+
+MIX_TOP = 13.4      # log2 of the largest stored weight magnitude (fp16 hi < 2^14; lo8 = (w' - hi) * 64 <= 256 < 448)
+ACT_TOP = 11.5      # log2 target of a stored activation maximum: 4x headroom before lo8 saturates, 22x before fp16 does
+
+
+def pack_tc_weights_mix(full, classes):
+    """Mixed fp16 + 2 x e4m3 weight matrix of eamm_conv_tc (EAMM_F16 two-plane inputs; include/eamm_b200.h).
+
+    [classes*taps][cout][cin] fp32 -> (uint8 [classes*cout][taps*cin*4], int exponents [cout]).  Row co is scaled by
+    2^e[co] (one exponent per output channel, shared by the UP2 parity classes) so that its largest entry sits just
+    below 2^13.4; K bytes = e4m3 lo8 [tap][cin] | e4m3 hi8 [tap][cin] | fp16 hi [tap][cin], where
+    hi = fp16(w'), lo8 = e4m3((w' - hi) * 64), hi8 = e4m3(hi / 64)."""
+    ct, cout, cin = full.shape
+    taps = ct // classes
+    w = full.view(classes, taps, cout, cin).permute(0, 2, 1, 3)          # [cls][cout][taps][cin]
+    amax = w.abs().amax(dim=(0, 2, 3))
+    e = torch.where(amax > 0, torch.floor(MIX_TOP - torch.log2(amax.clamp_min(1e-30))), torch.zeros_like(amax))
+    e = e.clamp(-60, 60)
+    ws = w * torch.exp2(e).view(1, cout, 1, 1)
+    hi = ws.to(torch.float16)
+    hif = hi.float()
+    lo8 = ((ws - hif) * 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
+    hi8 = (hif / 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
+    rows = classes * cout
+    packed = torch.cat([lo8.reshape(rows, -1).view(torch.uint8), hi8.reshape(rows, -1).view(torch.uint8),
+                        hi.reshape(rows, -1).view(torch.uint8)], dim=1).contiguous()
+    return packed, e.to(torch.int32)
 
 
 def pack_tc_weights_fold(full, classes):
@@ -161,53 +269,53 @@ def pack_tc_weights_fold(full, classes):
     return torch.cat([hi, lo], dim=0).contiguous()
 
 
-def pack_tc_weights_halo(full, passes):
+def pack_tc_weights_halo(full, passes, dt=torch.bfloat16):
     """7x7 halo-row scheme of eamm_conv_tc: [49 taps][cout][cin] -> bf16 [7 kx * cout][passes * 7 ky * cin]."""
     _, cout, cin = full.shape
     w = full.view(7, 7, cout, cin).permute(1, 2, 0, 3)                   # [kx][cout][ky][cin]
-    hi = w.to(torch.bfloat16)
+    hi = w.to(dt)
     if passes == 1:
         packed = hi
     else:
-        lo = (w - hi.float()).to(torch.bfloat16)
+        lo = (w - hi.float()).to(dt)
         packed = torch.stack([lo, hi, hi], dim=2)                         # [kx][cout][3][ky][cin]
     return packed.reshape(7 * cout, -1).contiguous()
 
 
-def pack_tc_weights_kxn(full, nchw_c, passes, fold=0):
+def pack_tc_weights_kxn(full, nchw_c, passes, fold=0, dt=torch.bfloat16):
     """7x7 kx-in-N scheme: [49 taps][cout][cin] -> bf16 [32 rows = kx*4 + co][passes * 7 ky * cin]
     (fold: rows [32 hi | 32 lo], K = (ky, channel))."""
     _, cout, cin = full.shape
     w = full.view(7, 7, cout, cin)[:, :, :nchw_c]                         # [ky][kx][co][cin]
     rows = torch.zeros(8, 4, 7, cin, dtype=torch.float32, device=full.device)   # [kx(8)][co(4)][ky][cin]
     rows[:7, :nchw_c] = w.permute(1, 2, 0, 3)
-    hi = rows.to(torch.bfloat16)
+    hi = rows.to(dt)
     if fold:
-        lo = (rows - hi.float()).to(torch.bfloat16)
+        lo = (rows - hi.float()).to(dt)
         return torch.cat([hi.reshape(32, -1), lo.reshape(32, -1)], dim=0).contiguous()
     if passes == 1:
         packed = hi
     else:
-        lo = (rows - hi.float()).to(torch.bfloat16)
+        lo = (rows - hi.float()).to(dt)
         packed = torch.stack([lo, hi, hi], dim=2)                         # [kx][co][3][ky][cin]
     return packed.reshape(32, -1).contiguous()
 
 
-def _pack_rows_k(rows, passes, fold):
+def _pack_rows_k(rows, passes, fold, dt=torch.bfloat16):
     """[n rows][taps][cin] fp32 -> bf16 [n][passes * taps * cin] (K order (pass, tap, channel), planes lo, hi, hi)
     or, folded, rows [n hi | n lo] with K = (tap, channel)."""
     n = rows.shape[0]
-    hi = rows.to(torch.bfloat16)
+    hi = rows.to(dt)
     if fold:
-        lo = (rows - hi.float()).to(torch.bfloat16)
+        lo = (rows - hi.float()).to(dt)
         return torch.cat([hi.reshape(n, -1), lo.reshape(n, -1)], dim=0).contiguous()
     if passes == 1:
         return hi.reshape(n, -1).contiguous()
-    lo = (rows - hi.float()).to(torch.bfloat16)
+    lo = (rows - hi.float()).to(dt)
     return torch.stack([lo, hi, hi], dim=1).reshape(n, -1).contiguous()
 
 
-def pack_tc_weights_kxn_rows(full, nchw_c, passes, fold=0):
+def pack_tc_weights_kxn_rows(full, nchw_c, passes, fold=0, dt=torch.bfloat16):
     """7x7 scheme 3 (kx-in-N, four output rows per tile): [49 taps][cout][cin] -> 112 rows (dr*28 + kx*4 + co),
     K taps = the 10 input rows j of a tile; row block j of output row dr holds w[ky = j - dr] (zero outside 0..6)."""
     _, cout, cin = full.shape
@@ -215,18 +323,18 @@ def pack_tc_weights_kxn_rows(full, nchw_c, passes, fold=0):
     rows = torch.zeros(4, 7, 4, 10, cin, dtype=torch.float32, device=full.device)   # [dr][kx][co][j][cin]
     for dr in range(4):
         rows[dr, :, :nchw_c, dr:dr + 7] = w.permute(1, 2, 0, 3)
-    return _pack_rows_k(rows.reshape(112, 10, cin), passes, fold)
+    return _pack_rows_k(rows.reshape(112, 10, cin), passes, fold, dt)
 
 
-def pack_tc_weights_kxn_full(full, passes, fold=0):
+def pack_tc_weights_kxn_full(full, passes, fold=0, dt=torch.bfloat16):
     """7x7 scheme 4 (kx-in-N, full-width tiles, 16 couts): [49 taps][16][cin] -> 112 rows (kx*16 + co), K taps = ky."""
     _, cout, cin = full.shape
     assert cout == 16
     rows = full.view(7, 7, cout, cin).permute(1, 2, 0, 3)                 # [kx][co][ky][cin]
-    return _pack_rows_k(rows.reshape(112, 7, cin), passes, fold)
+    return _pack_rows_k(rows.reshape(112, 7, cin), passes, fold, dt)
 
 
-def pack_tc_weights_row7(w, cout_pad, passes, fold=0):
+def pack_tc_weights_row7(w, cout_pad, passes, fold=0, dt=torch.bfloat16):
     """EAMM_CONV_ROW7_PACKED: w [cout][C<=3][7][7] -> bf16 [cout_pad][7 ky * passes * 64].
 
     K window of one ky = 8 pixels x 8 channels (hi0..2, 0, lo0..2, 0); k = kx*8 + channel, kx = 7 is
@@ -234,15 +342,15 @@ def pack_tc_weights_row7(w, cout_pad, passes, fold=0):
     last pass holds w_hi against both the hi and the lo channels: a_hi*b_lo, then a_hi*b_hi + a_lo*b_hi.
     """
     cout, C = w.shape[0], w.shape[1]
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
+    hi = w.to(dt)
+    lo = (w - hi.float()).to(dt)
     if fold:     # rows [w_hi vs (a_hi, a_lo) | w_lo vs a_hi], K = (ky, kx, channel)
-        out = torch.zeros(2, cout_pad, 7, 8, 8, dtype=torch.bfloat16, device=w.device)
+        out = torch.zeros(2, cout_pad, 7, 8, 8, dtype=dt, device=w.device)
         out[0, :cout, :, :7, :C] = hi.permute(0, 2, 3, 1)
         out[0, :cout, :, :7, 4:4 + C] = hi.permute(0, 2, 3, 1)
         out[1, :cout, :, :7, :C] = lo.permute(0, 2, 3, 1)
         return out.reshape(2 * cout_pad, -1).contiguous()
-    out = torch.zeros(cout_pad, passes, 7, 8, 8, dtype=torch.bfloat16, device=w.device)   # [co][pass][ky][kx][ch]
+    out = torch.zeros(cout_pad, passes, 7, 8, 8, dtype=dt, device=w.device)   # [co][pass][ky][kx][ch]
     main = passes - 1                                    # the pass holding w_hi runs last
     out[:cout, main, :, :7, :C] = hi.permute(0, 2, 3, 1)
     if passes == 2:
@@ -257,10 +365,10 @@ def impl_for(precision):
     forced = os.environ.get("EAMM_B200_CONV", "")
     if precision == "fp32_simt":
         return "simt", "f32", 4, 4
-    mode = "bf16x2" if precision == "fp32" else "bf16"
+    mode = {"fp32": "bf16x2", "fp32_bf16x3": "bf16x2", "fp16": "f16", "bf16": "bf16"}[precision]
     if forced == "simt":
         return "simt", mode, 4, 4
-    return ("tc3" if precision == "fp32" else "tc"), mode, 64, 16
+    return {"bf16x2": "tc3", "f16": "tc16", "bf16": "tc"}[mode], mode, 64, 16
 
 
 class ConvLayer:
@@ -290,12 +398,17 @@ class ConvLayer:
         self.w_ref = full                                               # [taps][cout][cin] fp32
         self.bias = torch.zeros(self.cout, dtype=torch.float32, device=dev)
         self.bias[:cout] = b
+        self.wdt = torch.float16 if impl == "tc16" else torch.bfloat16
         if impl == "simt":
             self.weight = full.permute(0, 2, 1).contiguous()            # [taps][cin][cout]
-        elif impl in ("tc", "tc3"):
-            self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1)
+        elif impl in ("tc", "tc3", "tc16"):
+            self.weight = pack_tc_weights(full, 4 if kind == L.CONV_UP2_3X3 else 1, 3 if impl == "tc3" else 1, self.wdt)
             self.weight_alt = {}             # other packings eamm_conv_tc may ask for (7x7 schemes, fold)
             self.plan_cache = {}             # (input shape, outputs) -> (weight tensor, fold)
+        elif impl == "mix":
+            # fp16 + 2 x e4m3 operands: one byte matrix and one power-of-two exponent per output channel
+            self.weight, self.w_exp = pack_tc_weights_mix(full, 4 if kind == L.CONV_UP2_3X3 else 1)
+            self.acc_scales = {}             # input exponent -> [cout] fp32 accumulator multipliers 2^-(e_in + e_w)
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -305,8 +418,14 @@ class ConvLayer:
             self.scale2[:cout] = scale2
             self.shift2[:cout] = shift2
 
+    def acc_scale(self, in_exp):
+        t = self.acc_scales.get(in_exp)
+        if t is None:
+            t = self.acc_scales[in_exp] = torch.exp2(-(self.w_exp.float() + float(in_exp))).contiguous()
+        return t
+
     def launch(self, lib, stream, inp, out=None, out2=None, residual=None, out_nchw=None, out_nchw_c=0,
-               out_nhwc_f32=None, out_u8=None):
+               out_nhwc_f32=None, out_u8=None, amax_out=None, amax_out2=None):
         a = L.ConvArgs()
         a.kind, a.flags, a.cin, a.cout = self.kind, self.flags, self.cin, self.cout
         a.inp = C.pointer(inp)
@@ -315,7 +434,15 @@ class ConvLayer:
         self._fill_outputs(a, out, out2, residual, out_nchw, out_nchw_c, out_nhwc_f32)
         if out_u8 is not None:
             a.out_u8_nhwc = out_u8.data_ptr()
-        if self.impl != "simt":
+        if amax_out is not None:
+            a.amax_out = amax_out
+        if amax_out2 is not None:
+            a.amax_out2 = amax_out2
+        if self.impl == "mix":
+            ws = splitk_workspace(self.bias.device, stream)
+            a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel()
+            a.acc_scale = self.acc_scale(inp.scale_exp).data_ptr()
+        elif self.impl != "simt":
             ws = splitk_workspace(self.bias.device, stream)
             a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel()
             key = (inp.n, inp.h, inp.w, out_nchw_c if out_nchw is not None else -1, out is not None,
@@ -331,13 +458,13 @@ class ConvLayer:
                     passes = 3 if self.impl == "tc3" else 1
                     classes = 4 if self.kind == L.CONV_UP2_3X3 else 1
                     if scheme == 2:
-                        wt = pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes, fold)
+                        wt = pack_tc_weights_kxn(self.w_ref, out_nchw_c, passes, fold, self.wdt)
                     elif scheme == 3:
-                        wt = pack_tc_weights_kxn_rows(self.w_ref, out_nchw_c, passes, fold)
+                        wt = pack_tc_weights_kxn_rows(self.w_ref, out_nchw_c, passes, fold, self.wdt)
                     elif scheme == 4:
-                        wt = pack_tc_weights_kxn_full(self.w_ref, passes, fold)
+                        wt = pack_tc_weights_kxn_full(self.w_ref, passes, fold, self.wdt)
                     elif scheme == 1:
-                        wt = pack_tc_weights_halo(self.w_ref, passes)
+                        wt = pack_tc_weights_halo(self.w_ref, passes, self.wdt)
                     elif fold:
                         wt = pack_tc_weights_fold(self.w_ref, classes)
                     else:
@@ -377,7 +504,8 @@ class FirstConvTC:
     overlapping-stride TMA map, so the whole 7x7x3 filter is 7 K-chunks instead of 49.
     """
 
-    def __init__(self, w, b, nalign, split):
+    def __init__(self, w, b, nalign, split, f16=False):
+        self.f16 = f16                       # fp16 single plane (split must be False)
         cout, cin = w.shape[0], w.shape[1]
         if cin > 3:
             raise RuntimeError("eamm_b200: the packed first conv supports at most 3 input channels")
@@ -394,15 +522,16 @@ class FirstConvTC:
         self.cin = 8
 
     def buffer(self, n, H, W, device):
-        return torch.zeros(n, H + 6, W + 8, 8, dtype=torch.bfloat16, device=device)
+        return torch.zeros(n, H + 6, W + 8, 8, dtype=torch.float16 if self.f16 else torch.bfloat16, device=device)
 
     def launch(self, lib, stream, src, nsrc, C_, H, W, packed, out):
         _launch("pack_image", lambda: L.check(
-            lib.eamm_pack_image(src.data_ptr(), nsrc, C_, H, W, 1 if self.split else 0, packed.data_ptr(), stream),
+            lib.eamm_pack_image(src.data_ptr(), nsrc, C_, H, W, 2 if self.f16 else (1 if self.split else 0),
+                                packed.data_ptr(), stream),
             "pack_image"), nbytes=nsrc * H * W * (C_ * 4 + 16))
         inp = L.Act()
         inp.data = packed.data_ptr()
-        inp.dtype, inp.n, inp.h, inp.w = L.EAMM_BF16, nsrc, H, W
+        inp.dtype, inp.n, inp.h, inp.w = (L.EAMM_F16 if self.f16 else L.EAMM_BF16), nsrc, H, W
         inp.c, inp.c_off, inp.c_buf, inp.planes = 8, 0, 8, 1
         inp.n_stride = (H + 6) * (W + 8) * 8
         a = L.ConvArgs()
@@ -419,7 +548,8 @@ class FirstConvTC:
             L.LAUNCHES -= 1
             fold = self.plan_cache[(nsrc, H, W)] = q[2]
         if fold not in self.weights:
-            self.weights[fold] = pack_tc_weights_row7(self.w_src, self.cout, self.passes, fold)
+            self.weights[fold] = pack_tc_weights_row7(self.w_src, self.cout, self.passes, fold,
+                                                      torch.float16 if self.f16 else torch.bfloat16)
         a.weight = self.weights[fold].data_ptr()
         a.weight_fold = fold
         _launch("conv:first", lambda: L.check(lib.eamm_conv_tc(C.byref(a), stream), "conv first (packed)"),
@@ -530,7 +660,7 @@ class DenseMotionEngine:
         self.precision = precision
         self.lib = L.load()
         self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
-        self.ws = {}
+        self.ws = WorkspaceCache()
         self._pack()
 
     # ---- weights
@@ -538,6 +668,13 @@ class DenseMotionEngine:
         m = self.m
         dev = m.mask.weight.device
         self.device = dev
+        if m.num_channels != 3:
+            # eamm_aa_downsample / eamm_kp_stage hard-wire RGB (float4 R,G,B,0 pixels, 4 channels per keypoint slot)
+            raise RuntimeError("eamm_b200: the B200 dense-motion path supports num_channels == 3 only")
+        # device flag of the forward (bit 0: singular driving Jacobian).  Strict mode clears it before every forward and
+        # checks it after; otherwise it is STICKY until check_status(..., clear=True) reads it (FramePipeline.drain,
+        # GraphedGenerator, bench.py), so an error in any queued batch is still reported
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         K1 = m.num_kp + 1
         cin0 = K1 * (m.num_channels + 1)
         ca = self.calign
@@ -580,13 +717,14 @@ class DenseMotionEngine:
         ws.cat, ws.bott = self.hg.buffers(B, h, w, self.mode, dev)
         K1 = self.m.num_kp + 1
         ws.logits = torch.empty(B, h, w, self.head.cout, dtype=torch.float32, device=dev)
-        ws.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws.status = self.status
         self.ws[key] = ws
         return ws
 
-    def run(self, source_image, kp_driving, kp_source, src_n_stride=None, reuse_small=False):
+    def run(self, source_image, kp_driving, kp_source, src_n_stride=None, reuse_small=False, sticky=False):
         """Launch the dense-motion kernels on the current stream; returns the reference's out_dict.
-        reuse_small: the anti-aliased source of the previous call is still valid (generator source cache)."""
+        reuse_small: the anti-aliased source of the previous call is still valid (generator source cache).
+        sticky: leave the error flag of earlier forwards set (non-strict callers check it later)."""
         m, lib = self.m, self.lib
         B, Cc, H, W = source_image.shape
         ws = self.workspace(B, H, W)
@@ -620,8 +758,9 @@ class DenseMotionEngine:
         sparse_deformed = torch.empty(B, K1, Cc, h, w, dtype=torch.float32, device=dev)
         cat0 = ws.cat[0]
         hg_in = cat0.act(c_off=cat0.s_up, c=cat0.s_sk)
-        ws.status.zero_()
-        esz = 4 if self.mode != "bf16" else 2
+        if not sticky:
+            ws.status.zero_()
+        esz = 2 if self.mode in ("bf16", "f16") else 4
         _launch("kp_stage", lambda: L.check(
             lib.eamm_kp_stage(ws.small.data_ptr(), small_stride, C.byref(kd), C.byref(ks), K,
                               float(m.kp_variance), C.byref(hg_in), sparse_deformed.data_ptr(),
@@ -662,9 +801,18 @@ class GeneratorEngine:
         self.precision = precision
         self.lib = L.load()
         self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
-        self.ws = {}
+        self.ws = WorkspaceCache()
         self.dm = DenseMotionEngine(module.dense_motion_network, precision) \
             if module.dense_motion_network is not None else None
+        # "fp32": the bottleneck ResBlocks run the fp16 + fp8 mixed scheme (needs 128-channel K chunks)
+        import os
+        blocks = list(module.bottleneck.children())
+        c_bott = _round_up(blocks[0].conv1.in_channels, self.calign) if blocks else 0
+        self.mixed = (precision == "fp32" and self.impl == "tc3" and bool(blocks) and c_bott % 128 == 0 and
+                      os.environ.get("EAMM_B200_MIX", "1") != "0")
+        self.calibrated = False
+        self._tracked = False
+        self.exps = {}                       # tensor name ("a0", "t0", ...) -> power-of-two pre-scale exponent
         self._pack()
 
     def _pack(self):
@@ -678,7 +826,7 @@ class GeneratorEngine:
         import os
         self.first_packed = impl != "simt" and m.num_channels <= 3 and os.environ.get("EAMM_TC_ROW7", "1") != "0"
         if self.first_packed:
-            self.first = FirstConvTC(w, b, na, split=(impl == "tc3"))
+            self.first = FirstConvTC(w, b, na, split=(impl == "tc3"), f16=(impl == "tc16"))
         else:
             self.first = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, _round_up(m.num_channels, ca), na, impl)
         self.down = []
@@ -691,11 +839,17 @@ class GeneratorEngine:
         for i, blk in enumerate(blocks):
             w1, b1 = fold_bn(blk.conv1.weight.detach().float(), blk.conv1.bias.detach().float(), _bn_dict(blk.norm2))
             c = blk.conv1.in_channels
-            l1 = ConvLayer("res%d.conv1" % i, L.CONV_3X3, L.EPI_RELU, w1, b1, _round_up(c, ca), na, impl)
+            rimpl = "mix" if self.mixed else impl
+            l1 = ConvLayer("res%d.conv1" % i, L.CONV_3X3, L.EPI_RELU, w1, b1, _round_up(c, ca), na, rimpl)
             nxt = bn_affine(_bn_dict(blocks[i + 1].norm1)) if i + 1 < len(blocks) else (None, None)
             l2 = ConvLayer("res%d.conv2" % i, L.CONV_3X3, 0, blk.conv2.weight.detach().float(),
-                           blk.conv2.bias.detach().float(), _round_up(c, ca), na, impl, scale2=nxt[0], shift2=nxt[1])
+                           blk.conv2.bias.detach().float(), _round_up(c, ca), na, rimpl, scale2=nxt[0], shift2=nxt[1])
             self.res.append((l1, l2))
+        if self.mixed:
+            # calibration statistics: running max of a_i = relu(bn1(x_i)) (slot 2i) and t_i = relu(bn2(conv1(a_i))) (2i+1)
+            self.amax = torch.zeros(2 * len(blocks), dtype=torch.float32, device=self.device)
+            for i in range(len(blocks)):
+                self.exps["a%d" % i] = self.exps["t%d" % i] = 0
         self.pre = None
         if blocks:
             s, t = bn_affine(_bn_dict(blocks[0].norm1))
@@ -731,8 +885,8 @@ class GeneratorEngine:
         fh, fw = H >> nd, W >> nd
         cb = ws.enc[-1].c_buf
         ws.x = [ActBuf(B, fh, fw, cb, mode, dev), ActBuf(B, fh, fw, cb, mode, dev)]
-        ws.a = ActBuf(B, fh, fw, cb, mode, dev)
-        ws.t = ActBuf(B, fh, fw, cb, mode, dev)
+        ws.a = ActBuf(B, fh, fw, cb, "mix" if self.mixed else mode, dev)
+        ws.t = ActBuf(B, fh, fw, cb, "mix" if self.mixed else mode, dev)
         ws.dec = []
         for i, blk in enumerate(m.up_blocks):
             ws.dec.append(ActBuf(B, fh << (i + 1), fw << (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
@@ -753,8 +907,62 @@ class GeneratorEngine:
         self.dm.last_status = torch.zeros(1, dtype=torch.int32, device=dev)
         return out
 
-    def run(self, source_image, kp_driving, kp_source):
+    # ---- calibration of the mixed-format pre-scales -------------------------------------------------------------
+    def _amax_ptr(self, slot):
+        return self.amax.data_ptr() + 4 * slot
+
+    def _exps_from_amax(self, force):
+        """New exponents from the running maxima of the last tracked forward.  force: re-centre every tensor;
+        otherwise only tensors whose stored maximum left the window [2^9, 2^13.2] move (hysteresis)."""
+        amax = self.amax.cpu().tolist()
+        new = dict(self.exps)
+        for i in range(len(self.res)):
+            for nm, v in (("a%d" % i, amax[2 * i]), ("t%d" % i, amax[2 * i + 1])):
+                if not (v > 0.0) or not math.isfinite(v):
+                    continue                               # never written (last block's a) or all zero: keep
+                stored = math.log2(v) + self.exps[nm]
+                if force or stored > 13.2 or stored < 9.0:
+                    new[nm] = max(-60, min(60, int(math.floor(ACT_TOP - math.log2(v) + 0.5))))
+        return new
+
+    def needs_recalibration(self):
+        """After a tracked forward (strict mode): True when an activation maximum drifted out of its window; the
+        exponents are then updated and the caller runs the forward again."""
+        if not self.mixed or not self._tracked:
+            return False
+        new = self._exps_from_amax(force=False)
+        if new == self.exps:
+            return False
+        self.exps = new
+        return True
+
+    def run(self, source_image, kp_driving, kp_source, track=None):
+        """track: keep the calibration statistics of this forward (default: in strict mode, where the module checks
+        them right after the call).  The first call calibrates: forward, read the maxima, set the exponents, repeat
+        until they stop moving (normally two forwards)."""
+        if not self.mixed:
+            return self._forward(source_image, kp_driving, kp_source, False)
+        if source_image.dim() == 4 and source_image.shape[0] == 0:
+            return self._forward(source_image, kp_driving, kp_source, False)
+        if not self.calibrated:
+            out = None
+            for it in range(4):
+                out = self._forward(source_image, kp_driving, kp_source, True)
+                new = self._exps_from_amax(force=(it == 0))
+                if new == self.exps:
+                    break
+                self.exps = new
+            self.calibrated = True
+            return out
+        if track is None:
+            track = bool(getattr(self.m, "strict_errors", True)) and not torch.cuda.is_current_stream_capturing()
+        return self._forward(source_image, kp_driving, kp_source, track)
+
+    def _forward(self, source_image, kp_driving, kp_source, track):
         m, lib = self.m, self.lib
+        self._tracked = track
+        if track:
+            self.amax.zero_()
         if source_image.dim() != 4 or source_image.shape[1] != m.num_channels:
             raise RuntimeError("eamm_b200: source_image must be [B,%d,H,W]" % m.num_channels)
         B, Cc, H, W = source_image.shape
@@ -775,8 +983,10 @@ class GeneratorEngine:
         if getattr(m, "cache_source", False):
             src_key = (source_image.data_ptr(), source_image._version, tuple(source_image.shape),
                        tuple(source_image.stride()), B, H, W)
+        # (the workspace keeps a strong reference to the cached source: its storage cannot be freed and handed to a
+        #  different tensor with the same address / version while the key is alive)
         reuse = src_key is not None and getattr(ws, "src_key", None) == src_key
-        esz = 4 if self.mode != "bf16" else 2
+        esz = 2 if self.mode in ("bf16", "f16") else 4
         if not reuse:
             if self.first_packed:
                 self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed, ws.enc[0].act(c=self.first.cout, n=nsrc))
@@ -789,12 +999,14 @@ class GeneratorEngine:
             for i, layer in enumerate(self.down):
                 layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
         ws.src_key = src_key
+        ws.src_ref = source_image if src_key is not None else None
         result = {}
         feat = ws.enc[-1]
         blocks = self.res
         if self.dm is not None:
             dmo, dws = self.dm.run(src.expand(B, -1, -1, -1) if shared else src, kp_driving, kp_source,
-                                   src_n_stride=src_n_stride, reuse_small=reuse)
+                                   src_n_stride=src_n_stride, reuse_small=reuse,
+                                   sticky=not getattr(m, "strict_errors", True))
             self.last_dm = dmo
             result["mask"] = dmo["mask"]
             result["sparse_deformed"] = dmo["sparse_deformed"]
@@ -807,13 +1019,15 @@ class GeneratorEngine:
                                    "(scale_factor == 2**-num_down_blocks)" % (tuple(deformation.shape[1:3]), feat.h, feat.w))
             # a9-i feature warp x occlusion (+ fused norm1/relu of the first ResBlock)
             fa = feat.act(n=B, broadcast=shared)
-            out2 = ws.a.act() if blocks else None
+            mx = self.mixed
+            out2 = ws.a.act(exp=self.exps["a0"] if mx else None) if blocks else None
             x0 = ws.x[0].act()
+            am0 = C.c_void_p(self._amax_ptr(0)) if (mx and track) else None
             _launch("warp_occlude", lambda: L.check(
                 lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(x0),
                                       C.byref(out2) if out2 is not None else None,
                                       _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
-                                      st), "warp_occlude"),
+                                      am0, st), "warp_occlude"),
                 nbytes=B * feat.h * feat.w * (feat.c_buf * esz * (3 if blocks else 2) + 12))
             # a9-ii deformed image
             deformed = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
@@ -827,12 +1041,18 @@ class GeneratorEngine:
             raise RuntimeError("eamm_b200: dense_motion_params=None is not supported by the B200 path")
         # bottleneck (generator.py:89): t = relu(bn2(conv1(a))); x' = conv2(t) + x; a' = relu(bn1'(x'))
         cur = 0
+        mx = self.mixed
         for i, (l1, l2) in enumerate(blocks):
-            l1.launch(lib, st, ws.a.act(), out=ws.t.act(c=l1.cout))
+            ea = self.exps["a%d" % i] if mx else None
+            et = self.exps["t%d" % i] if mx else None
+            en = self.exps.get("a%d" % (i + 1)) if mx else None
+            l1.launch(lib, st, ws.a.act(exp=ea), out=ws.t.act(c=l1.cout, exp=et),
+                      amax_out=self._amax_ptr(2 * i + 1) if (mx and track) else None)
             nxt = ws.x[1 - cur]
             last = i + 1 == len(blocks)
-            l2.launch(lib, st, ws.t.act(), out=nxt.act(c=l2.cout), residual=ws.x[cur].act(c=l2.cout),
-                      out2=None if last else ws.a.act(c=l2.cout))
+            l2.launch(lib, st, ws.t.act(exp=et), out=nxt.act(c=l2.cout), residual=ws.x[cur].act(c=l2.cout),
+                      out2=None if last else ws.a.act(c=l2.cout, exp=en),
+                      amax_out2=self._amax_ptr(2 * i + 2) if (mx and track and not last) else None)
             cur = 1 - cur
         x = ws.x[cur]
         # decoder (generator.py:90-91)

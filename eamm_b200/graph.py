@@ -23,8 +23,10 @@ class GraphedGenerator:
         cache = getattr(generator, "cache_source", False)
         self.fixed_source = fixed_source
         generator.strict_errors = False                  # no host read inside a capture
-        if fixed_source:
-            generator.cache_source = True                # warm-up fills the cache, the capture then hits it
+        # fixed source: warm-up fills the encoder cache and the capture hits it (the graph holds no encoder kernels);
+        # otherwise the cache must be OFF while capturing, or a caller that had enabled it would get a graph without
+        # the encoder and stale features after `s_src.copy_(new_source)`
+        generator.cache_source = bool(fixed_source)
         try:
             side = torch.cuda.Stream(p.device)
             side.wait_stream(torch.cuda.current_stream(p.device))
@@ -41,6 +43,8 @@ class GraphedGenerator:
         self._strict = strict
         from . import engine
         self._workspaces = list(engine._SPLITK_WS.values())     # the captured kernels point into these
+        eng = generator._eng                                    # ... and into the per-shape workspaces (bounded caches)
+        self._ws_refs = list(eng.ws.values()) + (list(eng.dm.ws.values()) if eng.dm is not None else [])
 
     def __call__(self, source_image, kp_driving, kp_source, check=True):
         if not self.fixed_source and source_image is not self.s_src:
@@ -52,5 +56,5 @@ class GraphedGenerator:
         self.graph.replay()
         if check and self._strict:
             from .modules.dense_motion import check_status
-            check_status(self.gen._eng.dm.last_status)
+            check_status(self.gen._eng.dm.status, clear=True)
         return self.out

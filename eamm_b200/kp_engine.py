@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib as L
-from .engine import (ActBuf, ConvLayer, HourglassPlan, _launch, _round_up, current_stream_ptr, impl_for)
+from .engine import (ActBuf, ConvLayer, HourglassPlan, WorkspaceCache, _launch, _round_up, current_stream_ptr, impl_for)
 
 
 class KPDetectorEngine:
@@ -23,6 +23,8 @@ class KPDetectorEngine:
         self.hg = None
         if m.uses_predictor:
             cin0 = m.predictor.encoder.down_blocks[0].conv.in_channels
+            if cin0 != 3:
+                raise RuntimeError("eamm_b200: the B200 keypoint detector supports num_channels == 3 only")
             self.hg = HourglassPlan(m.predictor, cin0, ca, self.nalign, self.impl, prefix="kp.hg")
             wk, cin_slot = self.hg.split_cat_weights(wk, self.hg.dec_ch[-1], cin0)
             self.step = int(1 / m.scale_factor) if m.scale_factor != 1 else 1
@@ -33,7 +35,7 @@ class KPDetectorEngine:
         else:
             cin_slot = _round_up(feat, ca)
         self.head = ConvLayer("kp_head", L.CONV_7X7, 0, wk, bk, cin_slot, self.nalign, self.impl, cin_valid=feat)
-        self.ws = {}
+        self.ws = WorkspaceCache()
 
     def workspace(self, B, h, w):
         ws = self.ws.get((B, h, w))

@@ -42,11 +42,14 @@ class _EngineMixin:
         return super()._apply(fn, *args, **kwargs)
 
     def _engine(self, ref_param):
-        if self.training and torch.is_grad_enabled():
+        if self.training:
+            # (train mode would need batch statistics in every BatchNorm; the kernels fold the running statistics)
             raise RuntimeError("eamm_b200 implements the inference path only: call .eval() and run under "
-                               "torch.no_grad() (the reference's demo.py:195 does)")
+                               "torch.no_grad() (the reference's demo.py:105,195 does)")
         if ref_param.device.type != "cuda":
             raise RuntimeError("eamm_b200 has no CPU path: move the module to a CUDA (sm_100) device")
+        if self._eng is not None and getattr(self._eng, "device", ref_param.device) != ref_param.device:
+            self._eng = None            # e.g. an nn.DataParallel replica that inherited the original's engine
         if self._eng is None:
             with torch.no_grad(), torch.cuda.device(ref_param.device):
                 self._eng = self._engine_cls(self, self._precision)
@@ -92,8 +95,12 @@ class DenseMotionNetwork(_EngineMixin, nn.Module):
         return out
 
 
-def check_status(status):
-    """Raise like torch.inverse does (dense_motion.py:56) if a driving Jacobian was singular."""
-    if int(status.item()) & 1:
+def check_status(status, clear=False):
+    """Raise like torch.inverse does (dense_motion.py:56) if a driving Jacobian was singular.  clear: reset the flag
+    after reading it (callers that run non-strict forwards and check once, e.g. FramePipeline.drain)."""
+    flag = int(status.item())
+    if clear and flag:
+        status.zero_()
+    if flag & 1:
         raise torch.linalg.LinAlgError("eamm_b200: kp_driving['jacobian'] contains a singular matrix "
                                        "(torch.inverse in the reference raises here)")

@@ -59,4 +59,8 @@ class OcclusionAwareGenerator(_EngineMixin, nn.Module):
             out = eng.run(source_image, kp_driving, kp_source)
             if self.strict_errors and eng.dm is not None:
                 check_status(eng.dm.last_status)
+            if self.strict_errors and eng.needs_recalibration():
+                # an activation maximum left the window its fp16 + fp8 pre-scale was calibrated for: the exponents
+                # have been re-centred on this batch, run it again (rare: the window spans 4 octaves)
+                out = eng.run(source_image, kp_driving, kp_source)
         return out

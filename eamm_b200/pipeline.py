@@ -62,8 +62,10 @@ class FramePipeline:
         self.s_run.synchronize()
         eng = getattr(self.gen, "_eng", None)
         if self._strict and eng is not None and getattr(eng, "dm", None) is not None:
+            # the flag is sticky across the non-strict forwards queued since the last drain: a singular driving
+            # Jacobian in ANY of those batches is reported here (the reference raises from torch.inverse)
             from .modules.dense_motion import check_status
-            check_status(eng.dm.last_status)
+            check_status(eng.dm.status, clear=True)
 
     def close(self):
         self.drain()

@@ -12,6 +12,10 @@
  *
  * Activation layout ("eamm_act"): NHWC with the channel axis optionally holding 2 bf16 planes
  * (hi, lo) so that value = hi + lo carries 16 mantissa bits; see DESIGN.md "Data layout in HBM".
+ * EAMM_F16 with planes == 2 is the mixed operand format of the fp16 + fp8 convolution scheme: plane 0 holds
+ * c_buf fp16 values hi = fp16(v * 2^scale_exp), plane 1 (the same 2*c_buf bytes) holds c_buf e4m3 bytes
+ * lo8 = e4m3((v * 2^scale_exp - hi) * 64) followed by c_buf e4m3 bytes hi8 = e4m3(hi / 64);
+ * value = (hi + lo8 / 64) * 2^-scale_exp (15-16 significant bits inside a 13-octave window below the maximum).
  */
 #ifndef EAMM_B200_H
 #define EAMM_B200_H
@@ -22,9 +26,9 @@
 extern "C" {
 #endif
 
-#define EAMM_ABI_VERSION 1
+#define EAMM_ABI_VERSION 2
 
-enum { EAMM_F32 = 0, EAMM_BF16 = 1 };
+enum { EAMM_F32 = 0, EAMM_BF16 = 1, EAMM_F16 = 2 };
 
 enum {
   EAMM_ERR_ARG = -1,       /* null pointer / non-positive size */
@@ -41,13 +45,16 @@ enum {
  * over the whole batch (shared source). */
 typedef struct {
   void* data;
-  int32_t dtype;     /* EAMM_F32 (planes must be 1) or EAMM_BF16 (planes 1 or 2) */
+  int32_t dtype;     /* EAMM_F32 (planes must be 1), EAMM_BF16 (planes 1 or 2) or EAMM_F16 (planes 1, or 2 = fp16 + 2 x e4m3) */
   int32_t n, h, w;
   int32_t c;
   int32_t c_off;
   int32_t c_buf;
   int32_t planes;
   int64_t n_stride;
+  int32_t scale_exp; /* EAMM_F16 only: stored = value * 2^scale_exp (per-tensor power-of-two pre-scale chosen by the host
+                        from a calibration pass so that the e4m3 planes sit inside their exponent range); 0 otherwise */
+  int32_t reserved;
 } eamm_act;
 
 /* Keypoints of one side (driving or source): value [n,K,2] fp32 (x,y) and optionally
@@ -100,6 +107,12 @@ typedef struct {
   uint8_t* out_u8_nhwc;    /* optional, only together with out_nchw: [n, H, W, out_nchw_c] uint8 frames,
                               clip(rint(y * 255), 0, 255) of the value written to out_nchw -- skimage
                               img_as_ubyte of a float image in [0,1] (demo.py:281,507) */
+  const float* acc_scale;  /* optional [cout] fp32, eamm_conv_tc only: the accumulator is multiplied by acc_scale[co] before the
+                              bias is added.  With EAMM_F16 operands the host passes 2^-(in.scale_exp + weight exponent of
+                              row co); NULL = 1                                                                          */
+  float* amax_out;         /* optional device float, eamm_conv_tc only: atomically raised to max |value| written to `out`
+                              (the value before the 2^scale_exp pre-scale): the host's running calibration statistic   */
+  float* amax_out2;        /* same for `out2`                                                                          */
   void* splitk_ws;         /* optional, eamm_conv_tc only: device workspace for split-K on layers whose output has too
                               few tiles to occupy the chip (hourglass 8x8 ... 2x2 maps).  The first 4 KiB are arrival
                               counters: zero them ONCE after allocation, the kernel leaves them zero.  Launches that
@@ -170,10 +183,11 @@ int eamm_flow_combine(const float* logits, int ldl, const eamm_kp* kp_driving, c
 
 /* ---- a9-i: grid_sample(features, deformation) * occlusion (generator.py:57,79-84), fused with
  * the first ResBlock2d's norm1+relu (out2, optional).  feat/out/out2 are NHWC views with equal
- * h,w,c; deformation [n,h,w,2]; occlusion [n,1,h,w] or NULL. */
+ * h,w,c; deformation [n,h,w,2]; occlusion [n,1,h,w] or NULL.  amax_out2 (device float, may be NULL) is atomically
+ * raised to max |out2 value|: the calibration statistic of an EAMM_F16 second output (see eamm_act.scale_exp). */
 int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
                       const eamm_act* out, const eamm_act* out2, const float* scale2,
-                      const float* shift2, void* stream);
+                      const float* shift2, float* amax_out2, void* stream);
 
 /* ---- a9-ii: 'deformed' = grid_sample(source, bilinear_upsample(deformation)) (generator.py:50-57,86)
  * src [n,C,H,W] fp32 NCHW, deformation [n,h,w,2] fp32 -> dst [n,C,H,W] fp32 NCHW. */
@@ -188,13 +202,21 @@ int eamm_nchw_to_act(const float* src, int n, int C, int H, int W, const eamm_ac
  *                 Accepts F32 and BF16 (1 or 2 planes) activations.  Exact-fp32 parity path. */
 int eamm_conv_simt(const eamm_conv_args* args, void* stream);
 
-/* eamm_conv_tc:   tcgen05/TMEM/TMA implicit GEMM (bf16 operands, fp32 accumulate).  Activations must
- *                 be EAMM_BF16 with c_buf, c_off and cin multiples of 64 and power-of-two h, w; cout a
+/* eamm_conv_tc:   tcgen05/TMEM/TMA implicit GEMM (bf16 / fp16 / fp16+fp8 operands, fp32 accumulate).  Activations
+ *                 must be EAMM_BF16 or EAMM_F16 with c_buf, c_off and cin multiples of 64 and power-of-two h, w; cout a
  *                 multiple of 16.  weight is bf16 [classes*cout][passes*taps*cin] (K contiguous),
  *                 K ordered (pass, tap, channel); passes = 1 for single-plane inputs, 3 for hi/lo
  *                 inputs (weight planes lo, hi, hi against activation planes hi, lo, hi: the two
  *                 cross terms first, the dominant hi*hi term last).  UP2 has
- *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout). */
+ *                 4 classes of 4 taps, class c occupying rows [c*cout, (c+1)*cout).
+ *                 EAMM_F16 single-plane inputs: the same with fp16 weights (one pass).
+ *                 EAMM_F16 two-plane (mixed) inputs, cin a multiple of 128: `weight` is a byte matrix
+ *                 [classes*cout][taps*cin*4]: e4m3 lo8 [tap][cin] | e4m3 hi8 [tap][cin] | fp16 hi [tap][cin], of
+ *                 w * 2^e_row split like the activations (include/eamm_b200.h top).  The K loop runs
+ *                 a_hi8 x w_lo8 and a_lo8 x w_hi8 as tcgen05.mma.kind::f8f6f4 steps (K = 32, twice the fp16 rate) and
+ *                 a_hi x w_hi as kind::f16 steps into one TMEM accumulator: two pass-equivalents instead of the three
+ *                 bf16 passes of hi/lo inputs.  acc_scale[co] = 2^-(in.scale_exp + e_row) undoes the pre-scales.
+ *                 3x3 / UP2 kinds only (no 7x7 schemes, no fold). */
 int eamm_conv_tc(const eamm_conv_args* args, void* stream);
 
 /* Which scheme eamm_conv_tc uses for a 7x7 layer, i.e. which weight matrix it expects:
@@ -226,7 +248,7 @@ int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
 
 /* ---- source image for EAMM_CONV_ROW7_PACKED: src [n,C<=3,H,W] fp32 NCHW -> dst bf16
  * [n][H+6][W+8][8] with channels [hi0,hi1,hi2,0,lo0,lo1,lo2,0] (lo = bf16(v-hi); zero when
- * split == 0).  The zero border (3 rows top/bottom, 3 columns left, 5 right) must already be
+ * split == 0; split == 2 writes fp16 values instead of bf16, lo zero: the EAMM_F16 single-plane path).  The zero border (3 rows top/bottom, 3 columns left, 5 right) must already be
  * zero in dst (allocate it zeroed once); only the interior is written. */
 int eamm_pack_image(const float* src, int n, int C, int H, int W, int split, void* dst, void* stream);
 

@@ -66,10 +66,11 @@ def res_block(x, sd, p):
     return out + x
 
 
-def make_coordinate_grid(h, w):
-    """util.py:839-855: x = 2*i/(w-1)-1, y = 2*j/(h-1)-1, last dim (x, y)."""
-    x = torch.arange(w).type(torch.float32)
-    y = torch.arange(h).type(torch.float32)
+def make_coordinate_grid(h, w, device=None):
+    """util.py:839-855: x = 2*i/(w-1)-1, y = 2*j/(h-1)-1, last dim (x, y).  (`device`: the reference builds the grid
+    with `.type(kp.type())`, i.e. on the keypoints' device; bench.py's eager-CUDA baseline leg uses that.)"""
+    x = torch.arange(w, device=device).type(torch.float32)
+    y = torch.arange(h, device=device).type(torch.float32)
     x = (2 * (x / (w - 1)) - 1)
     y = (2 * (y / (h - 1)) - 1)
     yy = y.view(-1, 1).repeat(1, w)
@@ -79,7 +80,7 @@ def make_coordinate_grid(h, w):
 
 def kp2gaussian(value, h, w, kp_variance):
     """util.py:815-836."""
-    grid = make_coordinate_grid(h, w).view(1, 1, h, w, 2)
+    grid = make_coordinate_grid(h, w, value.device).view(1, 1, h, w, 2)
     mean_sub = grid - value.view(value.shape[0], value.shape[1], 1, 1, 2)
     return torch.exp(-0.5 * (mean_sub ** 2).sum(-1) / kp_variance)
 
@@ -101,14 +102,14 @@ def anti_alias_down(x, weight, scale):
 def heatmap_representation(kp_driving, kp_source, h, w, kp_variance):
     """create_heatmap_representations, dense_motion.py:32-45 -> [B, K+1, 1, h, w]."""
     hm = kp2gaussian(kp_driving["value"], h, w, kp_variance) - kp2gaussian(kp_source["value"], h, w, kp_variance)
-    zeros = torch.zeros(hm.shape[0], 1, h, w, dtype=hm.dtype)
+    zeros = torch.zeros(hm.shape[0], 1, h, w, dtype=hm.dtype, device=hm.device)
     return torch.cat([zeros, hm], dim=1).unsqueeze(2)
 
 
 def sparse_motions(kp_driving, kp_source, h, w):
     """create_sparse_motions, dense_motion.py:47-67 -> [B, K+1, h, w, 2]."""
     bs, nkp = kp_driving["value"].shape[:2]
-    identity = make_coordinate_grid(h, w).view(1, 1, h, w, 2)
+    identity = make_coordinate_grid(h, w, kp_driving["value"].device).view(1, 1, h, w, 2)
     grid = identity - kp_driving["value"].view(bs, nkp, 1, 1, 2)
     if "jacobian" in kp_driving:
         jac = torch.matmul(kp_source["jacobian"], torch.inverse(kp_driving["jacobian"]))

@@ -3,9 +3,14 @@ modules and directly through the C ABI, against the CPU oracle and the committed
 
 Tolerances (max-abs):
   fp32_simt : 2e-5 everywhere (true fp32 CUDA-core convs), warped images 2e-4
-  fp32      : prediction/mask/occlusion/deformation 1e-4, sparse_deformed 1e-4, deformed 3e-3
-              (split-bf16 tensor cores; `deformed` samples a white-noise image, DESIGN.md "Numerics")
-  bf16      : prediction 3e-2, mask/occlusion 3e-2 (bf16 convs; flow-sensitive outputs are not pinned)
+  fp32      : prediction/mask/occlusion/deformation 1e-4, sparse_deformed 1e-4, deformed 3e-3 on the synthetic
+              white-noise source (it turns a 1e-5 flow error into 1e-3 of intensity, DESIGN.md "Numerics") and the
+              survey's 1e-3 on natural images (test_natural_images_match_reference_golden); the same bounds for
+              fp32_bf16x3 (every layer on the 3-pass bf16 hi/lo scheme instead of fp16 + fp8 in the bottleneck)
+  fp16      : prediction/mask/occlusion 1e-2 and PSNR >= 50 dB (SURVEY 8(c)'s reduced-precision bound: one-pass
+              convs with fp16 operands; flow-sensitive outputs are not pinned)
+  bf16      : prediction 3e-2, mask/occlusion 3e-2 (the literal "bf16 conv" wording of BASELINE configs[2]: 8
+              significant bits, measured 1.1e-2 on the white-noise source -- kept as a mode, not the recommended one)
 """
 import ctypes as C
 import os
@@ -24,8 +29,10 @@ TOL = {
                   "sparse_deformed": 2e-5, "deformed": 2e-4},
     "fp32": {"prediction": 1e-4, "mask": 1e-4, "occlusion_map": 1e-4, "deformation": 1e-4,
              "sparse_deformed": 1e-4, "deformed": 3e-3},
+    "fp16": {"prediction": 1e-2, "mask": 1e-2, "occlusion_map": 1e-2, "sparse_deformed": 1e-4},
     "bf16": {"prediction": 3e-2, "mask": 3e-2, "occlusion_map": 3e-2, "sparse_deformed": 1e-4},
 }
+TOL["fp32_bf16x3"] = TOL["fp32"]
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
 
 
@@ -72,7 +79,7 @@ def test_native_library_is_the_in_tree_build_and_device_is_sm100(dev):
     assert lib.eamm_device_ok(0) == 1
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("case,cfg_name", [("tiny_b2", "tiny"), ("tiny_b3_nojac", "tiny")])
 def test_tiny_config_matches_reference_golden(dev, precision, case, cfg_name):
     blob = np.load(os.path.join(GOLD, case + ".npz"))
@@ -85,7 +92,7 @@ def test_tiny_config_matches_reference_golden(dev, precision, case, cfg_name):
         assert err <= tol, "%s %s %s: max-abs %.3e > %.1e" % (case, precision, k, err, tol)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32_bf16x3", "fp16", "bf16"])
 @pytest.mark.parametrize("case", ["full_b2", "full_b3_shared", "full_b16_shared"])   # the last = BASELINE configs[0]
 def test_full_config_matches_reference_golden(dev, precision, case):
     blob = np.load(os.path.join(GOLD, case + ".npz"))
@@ -98,10 +105,41 @@ def test_full_config_matches_reference_golden(dev, precision, case):
         s = STRIDES[k]
         sub = a[:, ::s, ::s, :] if k == "deformation" else a[..., ::s, ::s]
         err = np.abs(sub - blob[k]).max()
+        print("%s %s %-16s max-abs %.3e (tol %.1e)" % (case, precision, k, err, tol))
         assert err <= tol, "%s %s %s: max-abs %.3e > %.1e" % (case, precision, k, err, tol)
-        if precision == "fp32":   # checksum of the whole tensor, not just the stored sub-sample
+        if precision == "fp16" and k == "prediction":
+            assert psnr(torch.from_numpy(sub), torch.from_numpy(blob[k])) >= 50.0
+        if precision.startswith("fp32"):   # checksum of the whole tensor, not just the stored sub-sample
             tot = a.astype(np.float64).sum()
             assert abs(tot - blob["sum_" + k][0]) <= tol * a.size * 0.3 + 1e-3, k
+
+
+def psnr(a, b):
+    return float(-10.0 * torch.log10(((a.double() - b.double()) ** 2).mean()))
+
+
+# Natural source images (the reference's own demo assets; pixels carried by the fixture).  Here the survey's tolerance
+# for the warped outputs holds as stated (deformed / sparse_deformed <= 1e-3): a natural image has none of
+# the white-noise gradient that turns a 1e-5 flow error into 1e-3 of intensity in the synthetic cases.
+NATURAL_TOL = {
+    "fp32": {"prediction": 1e-4, "mask": 1e-4, "occlusion_map": 1e-4, "deformation": 1e-4, "sparse_deformed": 1e-4,
+             "deformed": 1e-3},
+    "fp16": {"prediction": 1e-2, "mask": 1e-2, "occlusion_map": 1e-2, "sparse_deformed": 1e-4},
+}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_natural_images_match_reference_golden(dev, precision):
+    from test_oracle_golden import natural_case, natural_subsample
+    blob, cfg, src, kpd, kps = natural_case()
+    got = run_ours("full", dev, precision, src, kpd, kps)
+    for k, tol in NATURAL_TOL[precision].items():
+        err = np.abs(natural_subsample(k, got[k].numpy()) - blob[k]).max()
+        print("natural images %s %-16s max-abs %.3e (tol %.1e)" % (precision, k, err, tol))
+        assert err <= tol, (precision, k, err)
+    p = psnr(torch.from_numpy(natural_subsample("prediction", got["prediction"].numpy())), torch.from_numpy(blob["prediction"]))
+    print("natural images %s prediction PSNR %.1f dB" % (precision, p))
+    assert p >= (50.0 if precision == "fp16" else 80.0)
 
 
 def test_full_size_batch32_properties_and_batch_invariance(dev):
@@ -124,13 +162,16 @@ def test_full_size_batch32_properties_and_batch_invariance(dev):
         err = (one[k][0] - got[k][i]).abs().max().item()
         print("batch invariance %s max-abs %.3e" % (k, err))
         assert err <= tol, (k, err)
-    # the oracle on two of the 32 frames (keeps the CPU cost of this test in seconds)
+    # the oracle on ALL 32 frames and all outputs (the headline configuration; ~3 s of CPU on the bench box)
     from oracle import eamm_oracle as oracle
     sd = synth.make_state_dict(cfg, seed=0)
-    idx = [3, 29]
-    want = oracle.generator_forward(sd, cfg, src[idx], {k: v[idx] for k, v in kpd.items()}, {k: v[idx] for k, v in kps.items()})
-    for k, tol in (("prediction", 1e-4), ("mask", 1e-4), ("occlusion_map", 1e-4), ("deformed", 3e-3)):
-        assert (got[k][idx] - want[k]).abs().max() <= tol, k
+    taps = {}
+    want = oracle.generator_forward(sd, cfg, src, kpd, kps, taps=taps)
+    want["deformation"] = taps["deformation"]
+    for k, tol in TOL["fp32"].items():
+        err = (got[k] - want[k]).abs().max().item()
+        print("configs[1] B=32 fp32 mode vs oracle: %-16s max-abs %.3e (tol %.1e)" % (k, err, tol))
+        assert err <= tol, (k, err)
 
 
 def test_shared_source_broadcast_equals_distinct_copies(dev):
@@ -184,13 +225,23 @@ def test_cabi_warp_occlude_matches_grid_sample_times_occlusion(dev):
     fout = ActBuf(n, h, w, c, "f32", dev)
     gd, od = grid.to(dev), occ.to(dev)
     L.check(lib.eamm_warp_occlude(C.byref(fin.act()), gd.data_ptr(), od.data_ptr(), C.byref(fout.act()), None, None, None,
-                                  current_stream_ptr()), "warp_occlude")
+                                  None, current_stream_ptr()), "warp_occlude")
     torch.cuda.synchronize()
     assert (fout.to_float().cpu() - want).abs().max() <= 2e-6
+    # NaN / inf flow coordinates give NaN like F.grid_sample (weights inf - inf); huge finite ones sample zeros
+    grid3 = grid.clone()
+    grid3[1, 2, 3, 0] = float("nan"); grid3[1, 2, 4, 1] = float("inf"); grid3[1, 2, 5, 0] = 1e30
+    want3 = F.grid_sample(feat, grid3, align_corners=False) * occ
+    L.check(lib.eamm_warp_occlude(C.byref(fin.act()), grid3.to(dev).data_ptr(), od.data_ptr(), C.byref(fout.act()), None, None,
+                                  None, None, current_stream_ptr()), "warp_occlude")
+    torch.cuda.synchronize()
+    got3 = fout.to_float().cpu()
+    assert torch.equal(torch.isnan(got3), torch.isnan(want3)) and torch.isnan(got3).sum() == 2 * c
+    assert (torch.nan_to_num(got3) - torch.nan_to_num(want3)).abs().max() <= 2e-6
     # zero padding is bit-exact: a sample fully outside the image reads exactly 0
     grid2 = torch.full((n, h, w, 2), 3.0)
     L.check(lib.eamm_warp_occlude(C.byref(fin.act()), grid2.to(dev).data_ptr(), None, C.byref(fout.act()), None, None, None,
-                                  current_stream_ptr()), "warp_occlude")
+                                  None, current_stream_ptr()), "warp_occlude")
     torch.cuda.synchronize()
     assert fout.t.abs().max().item() == 0.0
 
@@ -229,8 +280,8 @@ def test_cabi_conv_tc_matches_conv_simt_on_layer_shapes(dev):
     for idx in (1, 3, 5, 7, 8, 9, 10, 12, 13, 15, 17, 18, 19, 21, 22):
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]
     # 112-column kx-in-N schemes and split-K: the case fails unless the planner really chose the scheme under test
-    new = [i for i, c in enumerate(mod.CASES) if c[0].startswith(("kxw", "splitk"))]
-    assert len(new) >= 14
+    new = [i for i, c in enumerate(mod.CASES) if c[0].startswith(("kxw", "splitk", "f16", "mix"))]
+    assert len(new) >= 29
     for idx in new:
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]
 
@@ -271,6 +322,58 @@ def test_frame_pipeline_equals_direct_forward(dev):
     pipe.close()
     for o, w in zip(outs, want):
         assert torch.equal(o, w)
+
+
+def test_frame_pipeline_reports_a_singular_jacobian_of_any_queued_batch(dev):
+    """The device error flag is sticky across the non-strict forwards of a pipeline: a singular driving Jacobian in an
+    EARLY batch still raises from drain() (the reference raises from torch.inverse, dense_motion.py:56)."""
+    from eamm_b200.pipeline import FramePipeline
+    gen, cfg = generator("tiny", dev)
+    gen.precision = "fp32"
+    batches = [synth.make_inputs(2, cfg, size=64, seed=90 + i) for i in range(4)]
+    batches[1][1]["jacobian"][0, 1] = 0.0                  # batch 1 of 4 is the bad one
+    pinned = [(s.pin_memory(), {k: v.pin_memory() for k, v in kd.items()}, {k: v.pin_memory() for k, v in ks.items()})
+              for s, kd, ks in batches]
+    outs = [torch.empty(2, 3, 64, 64).pin_memory() for _ in batches]
+    pipe = FramePipeline(gen, depth=2)
+    for (s, kd, ks), o in zip(pinned, outs):
+        pipe.submit(s, kd, ks, o)
+    with pytest.raises(torch.linalg.LinAlgError):
+        pipe.drain()
+    pipe.close()                                           # the flag was cleared by the failed drain
+    assert gen.strict_errors
+    out = run_ours("tiny", dev, "fp32", *batches[0])       # and the generator is usable afterwards
+    assert torch.isfinite(out["prediction"]).all()
+
+
+def test_graph_without_fixed_source_ignores_a_warm_source_cache(dev):
+    """a caller that had `cache_source = True` must still get a graph that contains the encoder, so that a
+    replay with a new source image renders the new identity."""
+    from eamm_b200.graph import GraphedGenerator
+    gen, cfg = generator("tiny", dev)
+    gen.precision = "fp32"
+    src_a, kpd, kps = synth.make_inputs(1, cfg, size=64, seed=95)
+    src_b = synth.make_inputs(1, cfg, size=64, seed=96)[0]
+    want_b = run_ours("tiny", dev, "fp32", src_b, kpd, kps)["prediction"]
+    gen.cache_source = True
+    try:
+        sa = src_a.to(dev)
+        gen(sa, kp_driving=to_dev(kpd, dev), kp_source=to_dev(kps, dev))          # warms the cache for src_a
+        graphed = GraphedGenerator(gen, sa, to_dev(kpd, dev), to_dev(kps, dev), fixed_source=False)
+        assert gen.cache_source is True                                          # restored for the caller
+        got = graphed(src_b.to(dev), to_dev(kpd, dev), to_dev(kps, dev))["prediction"]
+        torch.cuda.synchronize()
+    finally:
+        gen.cache_source = False
+    assert torch.equal(got.cpu(), want_b)
+
+
+def test_workspace_cache_is_bounded(dev):
+    gen, cfg = generator("tiny", dev)
+    gen.precision = "fp32"
+    for b in (1, 2, 3, 4, 5):
+        run_ours("tiny", dev, "fp32", *synth.make_inputs(b, cfg, size=64, seed=97))
+    assert len(gen._eng.ws) <= 2 and len(gen._eng.dm.ws) <= 2
 
 
 @pytest.mark.parametrize("size,batch", [(128, 3), (512, 1), (256, 5)])

@@ -141,14 +141,16 @@ def test_kxn_wide_packings_reproduce_the_7x7_conv():
     assert torch.allclose(got, want, atol=1e-9)
 
 
-def _plan(lib, L, kind, cin, cout, n, h, w, planes, flags=0, nhwc=False, nchw_c=0):
-    """eamm_conv_tc_query on dummy pointers (nothing is dereferenced or launched by the dry run)."""
+def _plan(lib, L, kind, cin, cout, n, h, w, planes, flags=0, nhwc=False, nchw_c=0, f16=False):
+    """eamm_conv_tc_query on dummy pointers (nothing is dereferenced or launched by the dry run).
+    f16: EAMM_F16 operands (planes 1 = fp16, 2 = mixed fp16 + 2 x e4m3)."""
     a = L.ConvArgs()
     a.kind, a.flags, a.cin, a.cout = kind, flags, cin, cout
-    act = L.Act(data=4096, dtype=L.EAMM_BF16, n=n, h=h, w=w, c=cin, c_off=0, c_buf=cin, planes=planes,
+    dt = L.EAMM_F16 if f16 else L.EAMM_BF16
+    act = L.Act(data=4096, dtype=dt, n=n, h=h, w=w, c=cin, c_off=0, c_buf=cin, planes=planes,
                 n_stride=h * w * planes * cin)
     oh, ow = (2 * h, 2 * w) if kind == L.CONV_UP2_3X3 else ((h // 2, w // 2) if flags & L.EPI_POOL2 else (h, w))
-    out = L.Act(data=4096, dtype=L.EAMM_BF16, n=n, h=oh, w=ow, c=cout, c_off=0, c_buf=cout, planes=planes,
+    out = L.Act(data=4096, dtype=dt, n=n, h=oh, w=ow, c=cout, c_off=0, c_buf=cout, planes=planes,
                 n_stride=oh * ow * planes * cout)
     a.inp, a.weight, a.bias = ctypes.pointer(act), 4096, 4096
     if nhwc:
@@ -188,6 +190,9 @@ for B in (1, 32):
     out["mask%%d" %% B] = P(L.CONV_7X7, 128, 16, B, 64, 64, 2, nhwc=True)
     out["final%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 2, flags=4, nchw_c=3)
     out["final_bf16_%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 1, flags=4, nchw_c=3)
+    out["res_mix_%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 2, f16=True)
+    out["res_f16_%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 1, f16=True)
+    out["final_f16_%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 1, flags=4, nchw_c=3, f16=True)
 print(json.dumps(out))
 """ % (ROOT, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
@@ -209,6 +214,61 @@ print(json.dumps(out))
         assert (p["final%d" % B]["scheme"], p["final%d" % B]["bn"], p["final%d" % B]["fold"]) == (3, 112, 1)
         assert p["final%d" % B]["stages"] == 4                    # compact epilogue buffer -> fourth pipeline stage
         assert (p["final_bf16_%d" % B]["scheme"], p["final_bf16_%d" % B]["fold"]) == (3, 0)
+        assert (p["final_f16_%d" % B]["scheme"], p["final_f16_%d" % B]["fold"]) == (3, 0)
+    # mixed fp16 + fp8 bottleneck convs: N = 256 CTA pairs like the bf16 hi/lo scheme, never folded, no split at B = 32
+    assert (p["res_mix_32"]["bn"], p["res_mix_32"]["pair"], p["res_mix_32"]["fold"], p["res_mix_32"]["splitk"]) == (256, 1, 0, 1)
+    assert p["res_mix_1"]["fold"] == 0 and p["res_f16_32"]["bn"] == 256 and p["res_f16_32"]["pair"] == 1
+
+
+def _decode_mix_act(buf):
+    """ActBuf in "mix" mode -> (hi, lo8, hi8) fp32 NHWC tensors in the stored (pre-scaled) domain, straight from the bytes."""
+    c = buf.c_buf
+    hi = buf.t[..., :c].float()
+    p1 = buf.t[..., c:].contiguous().view(torch.uint8)
+    lo8 = p1[..., :c].view(torch.float8_e4m3fn).float()
+    hi8 = p1[..., c:].view(torch.float8_e4m3fn).float()
+    return hi, lo8, hi8
+
+
+def test_mixed_fp16_fp8_operand_format_reproduces_the_conv_on_cpu():
+    """The fp16 + 2 x e4m3 operand format (include/eamm_b200.h; conv_tc.cu `mix`): decode the packed weight bytes and an
+    encoded activation buffer exactly as the kernel's K loop addresses them (e4m3 lo8 [tap][cin] | e4m3 hi8 [tap][cin] |
+    fp16 hi [tap][cin]; a_hi8 x w_lo8 + a_lo8 x w_hi8 + a_hi x w_hi in one accumulator, times acc_scale) and compare with
+    the fp32 convolution.  Pins the byte layout, the power-of-two bookkeeping and the accuracy claim (~1e-5 of the output
+    scale, against 2.5e-4 for the fp16 term alone)."""
+    from eamm_b200 import engine
+    g = torch.Generator().manual_seed(3)
+    cin, cout, N, H, W = 128, 32, 1, 8, 8
+    w = (torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) * (3.0 / (cin * 9)) ** 0.5
+    w = w * torch.exp(torch.randn(cout, 1, 1, 1, generator=g))               # rows of very different magnitude
+    x = torch.randn(N, H, W, cin, generator=g).relu() * torch.exp(0.8 * torch.randn(N, H, W, cin, generator=g))
+    full = w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()
+    packed, w_exp = engine.pack_tc_weights_mix(full, 1)
+    assert packed.shape == (cout, 9 * cin * 4) and packed.dtype == torch.uint8
+    assert int((full.abs().amax(dim=(0, 2)) * torch.exp2(w_exp.float())).log2().floor().max()) == 13
+    n8 = 9 * cin
+    w_lo8 = packed[:, :n8].contiguous().view(torch.float8_e4m3fn).float().view(cout, 9, cin)
+    w_hi8 = packed[:, n8:2 * n8].contiguous().view(torch.float8_e4m3fn).float().view(cout, 9, cin)
+    w_hi = packed[:, 2 * n8:].contiguous().view(torch.float16).float().view(cout, 9, cin)
+    buf = engine.ActBuf(N, H, W, cin, "mix", torch.device("cpu"))
+    in_exp = int(engine.ACT_TOP - float(x.abs().max().log2()))
+    buf.store_float(x, exp=in_exp)
+    assert (buf.to_float().permute(0, 2, 3, 1) - x).abs().max() <= 2.0 ** -15 * x.abs().max()     # ~16 significant bits
+    a_hi, a_lo8, a_hi8 = _decode_mix_act(buf)
+    assert a_hi.abs().max() < 2.0 ** 12 and a_lo8.abs().max() <= 448 and a_hi8.abs().max() <= 448
+
+    def conv(a, wt):                                   # a NHWC, wt [cout][tap][cin] -> [N,cout,H,W] in fp64
+        wk = wt.view(cout, 3, 3, cin).permute(0, 3, 1, 2).double()
+        return F.conv2d(a.permute(0, 3, 1, 2).double(), wk, padding=1)
+
+    acc_scale = torch.exp2(-(w_exp.float() + in_exp)).view(1, cout, 1, 1).double()
+    main = conv(a_hi, w_hi) * acc_scale
+    cross = (conv(a_hi8, w_lo8) + conv(a_lo8, w_hi8)) * acc_scale
+    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1)
+    scale = want.abs().amax(dim=(0, 2, 3), keepdim=True)                    # per output channel (rows differ by e^3)
+    err_main = ((main - want).abs() / scale).max().item()
+    err_full = ((main + cross - want).abs() / scale).max().item()
+    assert err_full <= 3e-5 and err_main >= 5 * err_full, (err_main, err_full)
 
 
 def test_numpy_sampler_matches_torch_grid_sample_and_corner_values():
@@ -315,7 +375,7 @@ def test_shared_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.eamm_abi_version.restype = ctypes.c_int
-    assert lib.eamm_abi_version() == 1
+    assert lib.eamm_abi_version() == 2
     null = ctypes.c_void_p(0)
     lib.eamm_warp_image.restype = ctypes.c_int
     assert lib.eamm_warp_image(null, 0, null, null, 1, 3, 8, 8, 2, 2, null) == -1      # EAMM_ERR_ARG, no launch

@@ -47,6 +47,36 @@ def test_oracle_reproduces_reference_golden(name, cfg_name, full):
         np.testing.assert_allclose(s, blob["sum_" + k], rtol=1e-6, err_msg="checksum " + k)
 
 
+NATURAL_STRIDES = {"mask": 2, "sparse_deformed": 2, "occlusion_map": 2, "deformed": 4, "prediction": 4, "deformation": 2}
+
+
+def natural_case():
+    """Natural source images (pixels carried by the fixture, tools/make_golden.py run_natural_case) + seeded keypoints."""
+    blob = np.load(os.path.join(GOLD, "natural_b4.npz"))
+    cfg = get_config("full")
+    src = (torch.from_numpy(blob["pixels_u8"]).float() / 255.0).permute(0, 3, 1, 2).contiguous()
+    _, kpd, kps = synth.make_inputs(src.shape[0], cfg, size=256, seed=1)
+    return blob, cfg, src, kpd, kps
+
+
+def natural_subsample(k, a):
+    s = NATURAL_STRIDES[k]
+    return a[:, ::s, ::s, :] if k == "deformation" else a[..., ::s, ::s]
+
+
+def test_oracle_reproduces_reference_golden_on_natural_images():
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    blob, cfg, src, kpd, kps = natural_case()
+    taps = {}
+    got = oracle.generator_forward(synth.make_state_dict(cfg, seed=0), cfg, src, kpd, kps, taps=taps)
+    got["deformation"] = taps["deformation"]
+    for k, v in got.items():
+        a = v.numpy()
+        np.testing.assert_allclose(natural_subsample(k, a), blob[k], rtol=0, atol=2e-6, err_msg=k)
+        s = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+        np.testing.assert_allclose(s, blob["sum_" + k], rtol=1e-6, err_msg="checksum " + k)
+
+
 def test_structural_known_answers():
     """mask sums to 1, occlusion/prediction in (0,1), identity keypoints give identity flows."""
     cfg = get_config("tiny")

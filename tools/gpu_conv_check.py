@@ -69,6 +69,23 @@ CASES = [
     ("first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 1, 0, 0, ""),
     ("first row7 3->64 256x256 x3", "first", "r", 3, 64, 2, 256, 256, 2, 0, 0, ""),
     ("first row7 3->16 32x32 x3", "first", "r", 3, 16, 3, 32, 32, 2, 0, 0, ""),
+    # planes code 3 = fp16 single plane (name prefix f16), 4 = mixed fp16 + 2 x e4m3 operands (name prefix mix: the
+    # input, `out` without a residual and `out2` are mixed-format buffers, residual / `out` with a residual bf16 hi/lo)
+    ("f16 3x3 64->64 16x16 relu", "3x3", "r", 64, 64, 2, 16, 16, 3, 0, 0, ""),
+    ("f16 cta2 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 3, 1, 1, ""),
+    ("f16 3x3 64->128 64x64 relu pool", "3x3", "rp", 64, 128, 3, 64, 64, 3, 0, 0, ""),
+    ("f16 up2 256->128 16x16", "up2", "r", 256, 128, 2, 16, 16, 3, 0, 0, ""),
+    ("f16 kxw 7x7 128->16 64x64 N=2 logits", "7x7", "", 128, 16, 2, 64, 64, 3, 0, 0, "nhwc"),
+    ("f16 kxw 7x7 64->16 256x256 N=3 sigmoid", "7x7", "s", 64, 16, 3, 256, 256, 3, 0, 0, "nchw"),
+    ("f16 splitk 3x3 2048->1024 4x4 N=8 pool", "3x3", "rp", 2048, 1024, 8, 4, 4, 3, 0, 0, ""),
+    ("f16 first row7 3->64 64x64", "first", "r", 3, 64, 2, 64, 64, 3, 0, 0, ""),
+    ("mix 3x3 128->128 16x16 N=2 relu", "3x3", "r", 128, 128, 2, 16, 16, 4, 0, 0, ""),
+    ("mix cta2 3x3 256->256 64x64 N=8 relu", "3x3", "r", 256, 256, 8, 64, 64, 4, 0, 0, ""),
+    ("mix cta2 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 4, 1, 1, ""),
+    ("mix 3x3 256->256 64x64 N=1 res+out2", "3x3", "", 256, 256, 1, 64, 64, 4, 1, 1, ""),
+    ("mix up2 256->128 32x32 N=4 relu", "up2", "r", 256, 128, 4, 32, 32, 4, 0, 0, ""),
+    ("mix 3x3 128->256 128x128 N=2 pool", "3x3", "rp", 128, 256, 2, 128, 128, 4, 0, 0, ""),
+    ("mix splitk 3x3 1024->1024 4x4 N=32 pool", "3x3", "rp", 1024, 1024, 32, 4, 4, 4, 0, 0, ""),
 ]
 
 
@@ -89,17 +106,17 @@ def run_case(idx):
     flags = (L.EPI_RELU if "r" in fl else 0) | (L.EPI_POOL2 if "p" in fl else 0) | (L.EPI_SIGMOID if "s" in fl else 0)
     w = ((torch.rand(cout, cin, ks, ks, generator=g) * 2 - 1) * (3.0 / (cin * ks * ks)) ** 0.5).to(dev)
     b = ((torch.rand(cout, generator=g) * 2 - 1) * 0.1).to(dev)
-    mode = "bf16x2" if planes == 2 else "bf16"
+    mode = {1: "bf16", 2: "bf16x2", 3: "f16", 4: "mix"}[planes]
+    omode = "bf16x2" if planes == 4 else mode         # mixed cases: residual stream and `out` next to a residual
     if planes == 1:
         w = w.bfloat16().float()                      # same operand values for both kernels
+    if planes == 3:
+        w = w.half().float()
     x = torch.randn(N, H, W, cin, generator=g).to(dev)
+    if planes == 4:
+        x = x.relu() * torch.exp(0.8 * torch.randn(N, H, W, cin, generator=g)).to(dev)    # post-ReLU-like dynamic range
     xin = ActBuf(N, H, W, cin, mode, dev)
-    hi = x.bfloat16()
-    if planes == 2:
-        lo = (x - hi.float()).bfloat16()
-        xin.t.copy_(torch.cat([hi, lo], dim=-1))
-    else:
-        xin.t.copy_(hi)
+    xin.store_float(x, exp=int(11.5 - float(x.abs().max().log2())) if planes == 4 else 0)
     s2 = (torch.rand(cout, generator=g) + 0.5).to(dev) if has_out2 else None
     t2 = (torch.randn(cout, generator=g) * 0.1).to(dev) if has_out2 else None
     OH, OW = H, W
@@ -109,24 +126,39 @@ def run_case(idx):
         OH, OW = 2 * H, 2 * W
     res = None
     if has_res:
-        res = ActBuf(N, OH, OW, cout, mode, dev)
-        r = torch.randn(N, OH, OW, cout, generator=g).to(dev)
-        rh = r.bfloat16()
-        res.t.copy_(torch.cat([rh, (r - rh.float()).bfloat16()], -1) if planes == 2 else rh)
+        res = ActBuf(N, OH, OW, cout, omode, dev)
+        res.store_float(torch.randn(N, OH, OW, cout, generator=g))
     st = current_stream_ptr()
     outs = {}
-    for impl in ("simt", "tc3" if planes == 2 else "tc"):
+    amax = torch.zeros(2, device=dev)
+    exps = [0, 0]
+    for impl in ("simt", {1: "tc", 2: "tc3", 3: "tc16", 4: "mix"}[planes]):
         layer = ConvLayer(name, kk, flags, w, b, cin, 16, impl, scale2=s2, shift2=t2)
-        o = ActBuf(N, OH, OW, cout, mode, dev) if not special else None
-        o2 = ActBuf(N, OH, OW, cout, mode, dev) if has_out2 else None
-        nhwc = torch.zeros(N, OH, OW, cout, device=dev) if special == "nhwc" else None
-        nchw = torch.zeros(N, 3, OH, OW, device=dev) if special == "nchw" else None
-        for _ in range(3 if name.startswith("splitk") else 1):       # relaunch: split-K counters must self-reset
-            layer.launch(lib, st, xin.act(), out=o.act() if o else None, out2=o2.act() if o2 else None,
-                         residual=res.act() if res else None, out_nchw=nchw, out_nchw_c=3, out_nhwc_f32=nhwc)
-        torch.cuda.synchronize()
-        outs[impl] = [t for t in (o.to_float() if o else None, o2.to_float() if o2 else None, nhwc, nchw)
-                      if t is not None]
+        for rep in range(2 if (planes == 4 and impl == "simt") else 1):
+            o = ActBuf(N, OH, OW, cout, omode if has_res else mode, dev) if not special else None
+            o2 = ActBuf(N, OH, OW, cout, mode, dev) if has_out2 else None
+            if planes == 4:
+                if o and not has_res:
+                    o.exp = exps[0]
+                if o2:
+                    o2.exp = exps[1]
+            nhwc = torch.zeros(N, OH, OW, cout, device=dev) if special == "nhwc" else None
+            nchw = torch.zeros(N, 3, OH, OW, device=dev) if special == "nchw" else None
+            track = planes == 4 and impl == "mix"
+            for _ in range(3 if "splitk" in name else 1):       # relaunch: split-K counters must self-reset
+                layer.launch(lib, st, xin.act(), out=o.act() if o else None, out2=o2.act() if o2 else None,
+                             residual=res.act() if res else None, out_nchw=nchw, out_nchw_c=3, out_nhwc_f32=nhwc,
+                             amax_out=amax.data_ptr() if track else None, amax_out2=amax.data_ptr() + 4 if track else None)
+            torch.cuda.synchronize()
+            res_list = [t for t in (o.to_float() if o else None, o2.to_float() if o2 else None, nhwc, nchw)
+                        if t is not None]
+            if planes == 4 and impl == "simt" and rep == 0:
+                # output pre-scales from the reference's own result (what the engine's calibration pass does)
+                if o and not has_res:
+                    exps[0] = int(11.5 - float(res_list[0].abs().max().clamp_min(1e-20).log2()))
+                if o2:
+                    exps[1] = int(11.5 - float(res_list[1 if o else 0].abs().max().clamp_min(1e-20).log2()))
+        outs[impl] = res_list
     a, c = list(outs.values())
     worst = 0.0
     for u, v in zip(a, c):
@@ -134,14 +166,21 @@ def run_case(idx):
         worst = max(worst, d / max(1e-6, u.abs().max().item()))
         if not torch.isfinite(v).all():
             worst = float("inf")
-    tol = 2e-4 if planes == 2 else 1e-2     # bf16 output rounding dominates in 1-plane mode
+    tol = {1: 1e-2, 2: 2e-4, 3: 2e-3, 4: 2e-4}[planes]     # output rounding dominates in the 1-plane modes
     status = "OK " if worst <= tol else "BAD"
+    if planes == 4:
+        # the running-max statistic must equal the maximum of what was written
+        want = [a[0].abs().max().item() if not has_res else 0.0, a[1].abs().max().item() if has_out2 else 0.0]
+        got = amax.tolist()
+        for wv, gv in zip(want, got):
+            if wv > 0 and abs(gv - wv) > 2e-3 * wv:
+                status, worst = "BAD", float("nan")
     plan = getattr(layer, "last_plan", ())
-    if name.startswith("kxw") and (not plan or plan[1] not in (3, 4)):
+    if "kxw" in name and (not plan or plan[1] not in (3, 4)):
         status, worst = "BAD", float("nan")          # the scheme under test was not selected
     if name.startswith("pfwide") and (not plan or plan[4] != 3):
         status, worst = "BAD", float("nan")
-    if name.startswith("splitk") and (not plan or (plan[4] >> 8) < 2):
+    if "splitk" in name and planes != 4 and (not plan or (plan[4] >> 8) < 2):
         status, worst = "BAD", float("nan")
     print("%s case %2d %-38s rel_err %.3e plan %s" % (status, idx, name, worst, plan), flush=True)
     return 0 if status == "OK " else 1
@@ -161,8 +200,10 @@ def run_first(idx):
     b = ((torch.rand(cout, generator=g) * 2 - 1) * 0.1).to(dev)
     if planes == 1:
         w = w.bfloat16().float()
+    if planes == 3:
+        w = w.half().float()
     img = torch.rand(N, cin, H, W, generator=g).to(dev)
-    mode = "bf16x2" if planes == 2 else "bf16"
+    mode = {1: "bf16", 2: "bf16x2", 3: "f16"}[planes]
     st = current_stream_ptr()
     # reference: NHWC activation (4-channel slot) + SIMT 7x7
     xin = ActBuf(N, H, W, 4, mode, dev)
@@ -170,7 +211,7 @@ def run_first(idx):
     ref_layer = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, 4, 16, "simt")
     o_ref = ActBuf(N, H, W, ref_layer.cout, mode, dev)
     ref_layer.launch(lib, st, xin.act(), out=o_ref.act())
-    tc = FirstConvTC(w, b, 16, split=(planes == 2))
+    tc = FirstConvTC(w, b, 16, split=(planes == 2), f16=(planes == 3))
     packed = tc.buffer(N, H, W, dev)
     o_tc = ActBuf(N, H, W, tc.cout, mode, dev)
     tc.launch(lib, st, img, N, cin, H, W, packed, o_tc.act())
@@ -179,7 +220,7 @@ def run_first(idx):
     worst = (u - v).abs().max().item() / max(1e-6, u.abs().max().item())
     if not torch.isfinite(v).all():
         worst = float("inf")
-    tol = 2e-4 if planes == 2 else 1e-2
+    tol = {1: 1e-2, 2: 2e-4, 3: 2e-3}[planes]
     print("%s case %2d %-34s rel_err %.3e" % ("OK " if worst <= tol else "BAD", idx, name, worst), flush=True)
     return 0 if worst <= tol else 1
 

@@ -71,6 +71,48 @@ def run_case(name, cfg_name, batch, size, with_jacobian=True, shared_source=Fals
         print("   ", k, "min/max/mean = %.4f %.4f %.4f" % s)
 
 
+NATURAL = ["anne.png", "mona.png", "14.png", "jake4.png"]
+NATURAL_STRIDES = {"mask": 2, "sparse_deformed": 2, "occlusion_map": 2, "deformed": 4, "prediction": 4, "deformation": 2}
+
+
+def run_natural_case(name):
+    """Natural 256x256 source images (the reference's own demo assets, /root/reference/test/image/*.png, read the way
+    demo.py:476-478 feeds them: RGB / 255 as float32) with the synthetic keypoint recipe.  On a natural image the flow
+    error -> intensity amplification of `deformed` is what a real run sees (warped outputs <= 1e-3).
+    The fixture carries the uint8 pixels, so the GPU box needs nothing from the reference tree."""
+    import cv2
+    cfg = get_config("full")
+    sd = synth.make_state_dict(cfg, seed=0)
+    ref = OcclusionAwareGenerator(**cfg).eval()
+    ref.load_state_dict(sd, strict=True)
+    px = np.stack([cv2.cvtColor(cv2.imread("/root/reference/test/image/" + f, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+                   for f in NATURAL])                                  # [B,256,256,3] uint8
+    src = natural_source(px)
+    _, kpd, kps = synth.make_inputs(len(NATURAL), cfg, size=256, seed=1)
+    with torch.no_grad():
+        want = dict(ref(src, kp_driving=kpd, kp_source=kps))
+        want["deformation"] = ref.dense_motion_network(source_image=src, kp_driving=kpd, kp_source=kps)["deformation"]
+    taps = {}
+    got = oracle.generator_forward(sd, cfg, src, kpd, kps, taps=taps)
+    for k in KEYS:
+        assert torch.equal(want[k], got[k]), f"{name}: oracle != reference on {k}"
+    assert torch.equal(want["deformation"], taps["deformation"])
+    blob = {"meta": np.array([len(NATURAL), 256, 1, 0], dtype=np.int64), "pixels_u8": px}
+    for k, v in want.items():
+        a = v.numpy()
+        blob["sum_" + k] = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+        s = NATURAL_STRIDES[k]                                         # denser than the synthetic cases: 4 frames only
+        blob[k] = a[..., ::s, ::s].copy() if k != "deformation" else a[:, ::s, ::s, :].copy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **blob)
+    print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def natural_source(px):
+    """uint8 [B,H,W,3] RGB -> float32 [B,3,H,W] in [0,1] (skimage img_as_float32 = x / 255, demo.py:476-478, :198)."""
+    return (torch.from_numpy(px).float() / 255.0).permute(0, 3, 1, 2).contiguous()
+
+
 def run_kp_case(name, cfg_name, batch, size, audio):
     cfg = get_kp_config(cfg_name, audio=audio)
     sd = synth.make_kp_state_dict(cfg, seed=3 if audio else 2)
@@ -165,6 +207,13 @@ def run_at_case(name, B, T):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = sys.argv[1:]
+    if only:                                   # python tools/make_golden.py natural_b4 ...  (regenerate selected fixtures)
+        table = {"natural_b4": lambda: run_natural_case("natural_b4")}
+        for nm in only:
+            table[nm]()
+        sys.exit(0)
+    run_natural_case("natural_b4")
     run_case("tiny_b2", "tiny", 2, 64)
     run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
     run_case("full_b2", "full", 2, 256, full=False)
