@@ -17,6 +17,26 @@ KP_FILTER = (0.05, 8.0, 1.0, 100.0, 10.0)                 # mincutoff, beta, dcu
 EMO_FILTER = (1.0, 0.2, 1.0, 100.0, 100.0)                # demo.py:231-236
 
 
+def clip_inputs_from_windows(mfcc13, pose7, T=None):
+    """Host-side input preparation of `test_auido` (demo.py:286-343) for pre-windowed MFCC such as the LRW samples
+    (/root/reference/dataset/LRW/MFCC/*/*.npy, [n,28,13]): drop cepstral coefficient 0 (`[:, :, 1:]`, demo.py:329),
+    tile the windows to T frames; pose [m,7] -> first six columns (demo.py:297), mirrored and tiled until it covers
+    the clip, then cut to T rows (demo.py:334-340).  Returns (mfcc [1,T,28,12], pose [1,T,6]) fp32 CPU tensors."""
+    mfcc13 = np.asarray(mfcc13)
+    pose = np.asarray(pose7)[:, :6]
+    T = mfcc13.shape[0] if T is None else T
+    mfcc = np.tile(mfcc13[:, :, 1:], (-(-T // mfcc13.shape[0]), 1, 1))[:T]
+    if len(pose) == 1:
+        pose = np.repeat(pose, 100, 0)                                   # demo.py:298-299
+    if len(pose) < T:
+        gap = T - len(pose)
+        n = int((gap / len(pose) / 2)) + 2
+        pose = np.tile(np.concatenate((pose, pose[::-1, :]), axis=0), (n, 1))
+    pose = pose[:T]
+    return (torch.from_numpy(mfcc.astype(np.float32)).unsqueeze(0).contiguous(),
+            torch.from_numpy(pose.astype(np.float32)).unsqueeze(0).contiguous())
+
+
 def movement_scale(kp_source, kp_driving_initial):
     """sqrt(area(source hull)) / sqrt(area(initial driving hull)), demo.py:114-117 (host side, once per clip)."""
     from scipy.spatial import ConvexHull

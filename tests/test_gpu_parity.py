@@ -286,6 +286,48 @@ def test_cabi_conv_tc_matches_conv_simt_on_layer_shapes(dev):
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]
 
 
+@pytest.mark.parametrize("kind,cin,cout,N,H,W,flags", [
+    ("3x3", 64, 128, 2, 32, 32, "rp"),      # DownBlock2d (util.py:915-920)
+    ("3x3", 256, 256, 1, 16, 16, ""),       # ResBlock2d conv (util.py:876-878)
+    ("up2", 256, 128, 2, 8, 8, "r"),        # UpBlock2d (util.py:895-900)
+    ("up2", 44, 20, 1, 5, 7, "r"),          # odd map, ragged channels
+    ("7x7", 4, 64, 1, 32, 32, "r"),         # `first` (generator.py:25)
+    ("7x7", 108, 12, 2, 16, 16, ""),        # mask + occlusion logits (dense_motion.py:98,110)
+    ("3x3", 1024, 1024, 3, 2, 2, "rp"),     # deepest hourglass encoder block
+])
+def test_conv_simt_anchor_matches_torch_conv2d(dev, kind, cin, cout, N, H, W, flags):
+    """The fp32 CUDA-core convolution is the on-device anchor the tensor-core kernel is checked against
+    (tools/gpu_conv_check.py); here the anchor itself meets F.conv2d (fp32, CPU) on every layer shape family."""
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, ConvLayer, current_stream_ptr
+    lib = L.load()
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    ks = 7 if kind == "7x7" else 3
+    w = (torch.rand(cout, cin, ks, ks, generator=g) * 2 - 1) * (3.0 / (cin * ks * ks)) ** 0.5
+    b = (torch.rand(cout, generator=g) * 2 - 1) * 0.1
+    x = torch.randn(N, cin, H, W, generator=g)
+    xin = x
+    if kind == "up2":
+        xin = F.interpolate(x, scale_factor=2)
+    want = F.conv2d(xin, w, b, padding=ks // 2)
+    if "r" in flags:
+        want = F.relu(want)
+    if "p" in flags:
+        want = F.avg_pool2d(want, 2)
+    cs, co = (cin + 3) // 4 * 4, (cout + 3) // 4 * 4
+    kk = {"3x3": L.CONV_3X3, "up2": L.CONV_UP2_3X3, "7x7": L.CONV_7X7}[kind]
+    fl = (L.EPI_RELU if "r" in flags else 0) | (L.EPI_POOL2 if "p" in flags else 0)
+    layer = ConvLayer("anchor", kk, fl, w.to(dev), b.to(dev), cs, 4, "simt")
+    inb = ActBuf(N, H, W, cs, "f32", dev)
+    inb.t[..., :cin].copy_(x.permute(0, 2, 3, 1))
+    out = ActBuf(N, want.shape[2], want.shape[3], co, "f32", dev)
+    layer.launch(lib, current_stream_ptr(), inb.act(), out=out.act())
+    torch.cuda.synchronize()
+    got = out.to_float(c=cout).cpu()
+    err = (got - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, want.abs().max().item()), (kind, cin, cout, err)
+
+
 def test_cabi_rejects_bad_arguments_without_launching(dev):
     from eamm_b200 import _lib as L
     from eamm_b200.engine import ActBuf, current_stream_ptr
@@ -635,3 +677,38 @@ def test_audio_to_frames_chain_psnr(dev):
     frames = clip.animate_audio_clip(at_net(dev), det, det_a, gen, s, mfcc.to(dev), pose.to(dev), 1.6, chunk=4)
     assert frames.shape == (T, 256, 256, 3) and frames.dtype == torch.uint8
     assert (frames.cpu().int() - oracle.frames_u8(o_out["prediction"]).int()).abs().max() <= 2
+
+
+def test_config4_real_mfcc_clip_300_frames_psnr(dev):
+    """BASELINE.json configs[4]: the demo.py path on the reference's LRW sample (real MFCC windows [:, :, 1:] tiled to
+    300 frames, demo.py:318-346) -> AT_net2 -> KPDetector_a -> One-Euro + normalize_kp -> generator, one call, uint8
+    frames; against the frames the reference's own modules rendered (tests/golden/clip_lrw_t300.npz).  Stated
+    tolerance: per-frame PSNR >= 50 dB on the uint8 frames, keypoints within 1e-3."""
+    from test_oracle_golden import lrw_clip_case
+    from eamm_b200 import clip
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    blob, T, img, mfcc, pose = lrw_clip_case()
+    kcfg, acfg = get_kp_config("full"), get_kp_config("full", audio=True)
+    gen, _ = generator("full", dev)
+    gen.precision = "fp32"
+    det = KPDetector(**kcfg).eval(); det.load_state_dict(synth.make_kp_state_dict(kcfg, seed=2)); det = det.to(dev)
+    det_a = KPDetector_a(**acfg).eval(); det_a.load_state_dict(synth.make_kp_state_dict(acfg, seed=3)); det_a = det_a.to(dev)
+    det.precision = det_a.precision = "fp32_simt"
+    s = img.to(dev)
+    frames = clip.animate_audio_clip(at_net(dev), det, det_a, gen, s, mfcc.to(dev), pose.to(dev), 1.6, chunk=60)
+    torch.cuda.synchronize()
+    assert frames.shape == (T, 256, 256, 3) and frames.dtype == torch.uint8
+    got = frames[:, ::8, ::8].cpu().float()
+    want = torch.from_numpy(blob["frames_u8_s8"]).float()
+    mse = ((got - want) ** 2).mean(dim=(1, 2, 3))
+    worst = float(10 * torch.log10(255.0 ** 2 / mse.clamp_min(1e-12)).min())
+    print("configs[4] clip: worst per-frame PSNR %.1f dB, max |diff| %d grey levels, %.2f%% of sampled bytes identical"
+          % (worst, int((got - want).abs().max()), 100 * float((got == want).float().mean())))
+    assert worst >= 50.0
+    # the keypoints that drove it (recomputed: animate_audio_clip returns frames only)
+    deco = at_net(dev)(s, mfcc.to(dev), pose.to(dev), "cnn", 1.6)
+    k_src, k_drv = det(s), det_a(deco[0])
+    k_init = {k: k_drv[k][:1] for k in ("value", "jacobian")}
+    k_norm = clip.smooth_and_normalize(k_drv, k_src, k_init, relative=True, scale=clip.movement_scale(k_src, k_init))
+    assert np.abs(k_norm["value"].cpu().numpy() - blob["kp_value"]).max() <= 1e-3

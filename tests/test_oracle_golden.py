@@ -157,3 +157,43 @@ def test_at_net2_oracle_reproduces_reference_golden(name):
     assert float((got[:, 0] - got[:, 1]).abs().mean()) > 1e-2
     head = oracle.at_net2_forward(sd, img, mfcc[:, :1], pose[:, :1], 1.6)
     np.testing.assert_allclose(head[:, 0].numpy(), got[:, 0].numpy(), rtol=0, atol=5e-6)
+
+
+def lrw_clip_case():
+    """BASELINE.json configs[4] fixture: real MFCC / pose / source frame of the reference's LRW sample, tiled to 300 windows."""
+    from eamm_b200.clip import clip_inputs_from_windows
+    blob = np.load(os.path.join(GOLD, "clip_lrw_t300.npz"))
+    T = int(blob["meta"][0])
+    img = (torch.from_numpy(blob["pixels_u8"]).float() / 255.0).permute(2, 0, 1).unsqueeze(0).contiguous()
+    mfcc, pose = clip_inputs_from_windows(blob["mfcc13"], blob["pose7"], T)
+    return blob, T, img, mfcc, pose
+
+
+def test_oracle_chain_reproduces_the_reference_demo_path_on_real_mfcc():
+    """configs[4]: AT_net2 -> KPDetector_a -> One-Euro + normalize_kp -> generator on the LRW sample, against the
+    fixture the reference's own modules produced (tools/make_golden.py run_clip_case).  All 300 frames of keypoints;
+    three generator frames (the CPU generator costs ~0.2 s per frame)."""
+    from eamm_b200 import clip
+    from eamm_b200.config import get_kp_config
+    from oracle import kp_glue
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    blob, T, img, mfcc, pose = lrw_clip_case()
+    assert mfcc.shape == (1, 300, 28, 12) and pose.shape == (1, 300, 6)
+    cfg, kcfg, acfg = get_config("full"), get_kp_config("full"), get_kp_config("full", audio=True)
+    deco = oracle.at_net2_forward(synth.make_at_state_dict(), img, mfcc, pose, 1.6)
+    assert abs(float(deco.abs().mean()) - float(blob["deco_absmean"][0])) <= 1e-6
+    src = oracle.kp_detector_forward(synth.make_kp_state_dict(kcfg, seed=2), kcfg, img)
+    drv = oracle.kp_detector_a_forward(synth.make_kp_state_dict(acfg, seed=3), acfg, deco[0])
+    init = {k: drv[k][:1] for k in ("value", "jacobian")}
+    scale = clip.movement_scale(src, init)
+    assert abs(scale - float(blob["scale"][0])) <= 1e-6
+    nv, nj = kp_glue.clip_glue(drv["value"], drv["jacobian"], None, None, src, init, movement_scale=scale)
+    np.testing.assert_allclose(nv.numpy(), blob["kp_value"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(nj.numpy(), blob["kp_jacobian"], rtol=0, atol=1e-5)
+    idx = [0, 137, 299]
+    out = oracle.generator_forward(synth.make_state_dict(cfg, seed=0), cfg, img.expand(3, -1, -1, -1).contiguous(),
+                                   {"value": nv[idx], "jacobian": nj[idx]},
+                                   {k: src[k].expand(3, *src[k].shape[1:]).contiguous() for k in ("value", "jacobian")})
+    frames = oracle.frames_u8(out["prediction"])[:, ::8, ::8].numpy()
+    assert np.abs(frames.astype(int) - blob["frames_u8_s8"][idx].astype(int)).max() <= 1      # batch-of-3 vs batch-of-1 rounding
+    np.testing.assert_allclose(out["prediction"].double().sum((1, 2, 3)).numpy(), blob["frame_sums"][idx], rtol=1e-6)

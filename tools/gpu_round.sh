@@ -12,10 +12,10 @@ if [ -n "$ONLY" ]; then
   if [ "$ONLY" = all ]; then timeout 900 python tools/gpu_conv_check.py 2>&1 | grep -v -i warn | tail -60 | tee $OUT/conv_$TAG.log
   else timeout 900 python tools/gpu_conv_check.py --only "$ONLY" 2>&1 | grep -v -i warn | tail -30 | tee $OUT/conv_$TAG.log; fi
 fi
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests/ -q -m gpu 2>&1 | tail -8 | tee $OUT/pytest_$TAG.log
+echo "== pytest -m gpu"; timeout 1200 python -m pytest tests/ -q -m gpu -s 2>&1 | grep -v -i warn | tail -80 | tee $OUT/pytest_$TAG.log
 echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | grep -v -i warn | tail -5 | tee $OUT/smoke_$TAG.log
 echo "== bench fp32 B=32"; timeout 600 python bench.py --warmup 3 --all-kernels 2>&1 | grep -v -i warn | tee $OUT/bench_fp32_$TAG.json | python tools/bench_summary.py
-echo "== bench bf16 B=32"; timeout 600 python bench.py --warmup 3 --precision bf16 --no-cpu-baseline --all-kernels 2>&1 | grep -v -i warn | tee $OUT/bench_bf16_$TAG.json | python tools/bench_summary.py
+echo "== bench fp16 B=32"; timeout 600 python bench.py --warmup 3 --precision fp16 --no-cpu-baseline --no-extras --all-kernels 2>&1 | grep -v -i warn | tee $OUT/bench_fp16_$TAG.json | python tools/bench_summary.py
 echo "== per-frame latency"; timeout 200 python tools/bench_latency.py 2>&1 | grep -v -i warn | tail -4 | tee $OUT/latency_$TAG.log
 echo "== keypoint heads"; timeout 200 python tools/bench_kp.py 2>&1 | grep -v -i warn | tail -6 | tee $OUT/kp_$TAG.log
 echo "== AT_net2 per-clip time, config-5 clip (no oracle leg)"; timeout 200 python tools/bench_at.py 300 1 2>&1 | grep -v -i warn | tee $OUT/at_$TAG.log | head -3

@@ -205,15 +205,88 @@ def run_at_case(name, B, T):
     print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB", "abs mean %.4f" % np.abs(a).mean())
 
 
+def run_clip_case(name, T=300):
+    """BASELINE.json configs[4]: the demo.py path on REAL MFCC -- the in-tree LRW sample
+    (/root/reference/dataset/LRW/{MFCC,Pose,Image}/ABOUT/ABOUT_00001*) -> AT_net2 -> KPDetector_a per frame -> One-Euro
+    + normalize_kp -> generator per frame (demo.py:345, :206-281), every stage being the reference's own module or
+    source text, with the seeded synthetic weights (no checkpoint ships).  The fixture carries the raw MFCC / pose /
+    source pixels, the normalised keypoints and the frames as uint8 (stride-8 sub-sample) + per-frame checksums."""
+    import cv2
+    from scipy.spatial import ConvexHull
+    from modules.util import AT_net2
+    torch.Tensor.cuda = lambda self, *a, **k: self                       # AT_net2.forward hard-codes .cuda() (util.py:581)
+    cfg, kcfg, acfg = get_config("full"), get_kp_config("full"), get_kp_config("full", audio=True)
+    sd, ksd, asd, atsd = (synth.make_state_dict(cfg, seed=0), synth.make_kp_state_dict(kcfg, seed=2),
+                          synth.make_kp_state_dict(acfg, seed=3), synth.make_at_state_dict())
+    gen = OcclusionAwareGenerator(**cfg).eval(); gen.load_state_dict(sd, strict=True)
+    det = KPDetector(**kcfg).eval(); det.load_state_dict(ksd, strict=True)
+    det_a = KPDetector_a(**acfg).eval(); det_a.load_state_dict(asd, strict=True)
+    at = AT_net2().eval(); at.load_state_dict(atsd, strict=False)
+    base = "/root/reference/dataset/LRW/"
+    mfcc13 = np.load(base + "MFCC/ABOUT/ABOUT_00001.npy")              # (30, 28, 13) float64
+    pose7 = np.load(base + "Pose/ABOUT/ABOUT_00001.npy")               # (29, 7) float64
+    px = cv2.cvtColor(cv2.imread(base + "Image/ABOUT/ABOUT_00001/0.png", cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    img = natural_source(px[None])
+    from eamm_b200.clip import clip_inputs_from_windows
+    mfcc, pose = clip_inputs_from_windows(mfcc13, pose7, T)
+    txt = open("/root/reference/filter1.py").read()
+    ns = {"np": np}
+    exec(txt[txt.index("class LowPassFilter"):], ns)
+    demo = open("/root/reference/demo.py").read()
+    a = demo.index("def normalize_kp(")
+    ns2 = {"np": np, "torch": torch, "ConvexHull": ConvexHull}
+    exec(demo[a:demo.index("\ndef ", a + 10)], ns2)
+    with torch.no_grad():
+        deco = at(img, mfcc, pose, "cnn", 1.6)                           # demo.py:345
+        kp_source = det(img)                                             # demo.py:206
+        kp_init = det_a(deco[:, 0])
+        kp_all = [det_a(deco[:, t]) for t in range(T)]                   # demo.py:219
+        fv = ns["OneEuroFilter"](mincutoff=0.05, beta=8, dcutoff=1.0, freq=100)
+        fj = ns["OneEuroFilter"](mincutoff=0.05, beta=8, dcutoff=1.0, freq=100)
+        for j in range(T):                                               # demo.py:241-248
+            kp_all[j]["value"] = fv.process(kp_all[j]["value"] * 10) / 10
+            kp_all[j]["jacobian"] = fj.process(kp_all[j]["jacobian"] * 10) / 10
+        nv, nj, frames, sums = [], [], [], []
+        for t in range(T):                                               # demo.py:251-281
+            kn = ns2["normalize_kp"](kp_source=kp_source, kp_driving=kp_all[t], kp_driving_initial=kp_init,
+                                     use_relative_movement=True, use_relative_jacobian=True, adapt_movement_scale=True)
+            out = gen(img, kp_source=kp_source, kp_driving=kn)
+            nv.append(kn["value"]); nj.append(kn["jacobian"])
+            p = out["prediction"]
+            frames.append(oracle.frames_u8(p)[0, ::8, ::8].numpy())
+            sums.append(float(p.double().sum()))
+            if t % 50 == 0:
+                print("  frame", t, flush=True)
+    nv, nj = torch.cat(nv).numpy(), torch.cat(nj).numpy()
+    # the oracle chain (what the GPU box can re-run) reproduces the reference chain
+    from oracle import kp_glue
+    o_deco = oracle.at_net2_forward(atsd, img, mfcc, pose, 1.6)
+    assert torch.equal(o_deco, deco)
+    o_src = oracle.kp_detector_forward(ksd, kcfg, img)
+    o_drv = oracle.kp_detector_a_forward(asd, acfg, o_deco[0])
+    o_init = {k: o_drv[k][:1] for k in ("value", "jacobian")}
+    scale = float(np.sqrt(ConvexHull(o_src["value"][0].numpy()).volume) / np.sqrt(ConvexHull(o_init["value"][0].numpy()).volume))
+    ov, oj = kp_glue.clip_glue(o_drv["value"], o_drv["jacobian"], None, None, o_src, o_init, movement_scale=scale)
+    assert np.abs(ov.numpy() - nv).max() <= 1e-6 and np.abs(oj.numpy() - nj).max() <= 1e-5, "oracle chain != reference chain"
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, meta=np.array([T]), mfcc13=mfcc13.astype(np.float32), pose7=pose7.astype(np.float32),
+                        pixels_u8=px, kp_value=nv, kp_jacobian=nj, frames_u8_s8=np.stack(frames),
+                        frame_sums=np.array(sums), scale=np.array([scale]),
+                        deco_absmean=np.array([float(deco.abs().mean())]))
+    print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB; kp motion over the clip: value std %.4f" %
+          float(nv.std(axis=0).mean()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
     if only:                                   # python tools/make_golden.py natural_b4 ...  (regenerate selected fixtures)
-        table = {"natural_b4": lambda: run_natural_case("natural_b4")}
+        table = {"natural_b4": lambda: run_natural_case("natural_b4"), "clip_lrw_t300": lambda: run_clip_case("clip_lrw_t300")}
         for nm in only:
             table[nm]()
         sys.exit(0)
     run_natural_case("natural_b4")
+    run_clip_case("clip_lrw_t300")
     run_case("tiny_b2", "tiny", 2, 64)
     run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
     run_case("full_b2", "full", 2, 256, full=False)
