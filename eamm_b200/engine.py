@@ -93,6 +93,55 @@ class WorkspaceCache:
         self._d.clear()
 
 
+class MixCalib:
+    """Calibration state of the mixed-format (fp16 + 2 x e4m3) tensors of one engine: a power-of-two pre-scale
+    exponent per tensor and a device array of running maxima that the producing kernels raise atomically."""
+
+    def __init__(self):
+        self.slots, self.exps = {}, {}
+        self.amax = None
+        self.track = False           # the forward in flight keeps statistics
+        self.calibrated = False
+
+    def register(self, name):
+        if name not in self.slots:
+            self.slots[name] = len(self.slots)
+            self.exps[name] = 0
+        return name
+
+    def alloc(self, device):
+        self.amax = torch.zeros(max(1, len(self.slots)), dtype=torch.float32, device=device)
+
+    def begin(self, track):
+        self.track = bool(track) and bool(self.slots)
+        if self.track:
+            self.amax.zero_()
+
+    def ptr(self, name):
+        return self.amax.data_ptr() + 4 * self.slots[name] if self.track else None
+
+    def proposal(self, force):
+        """Exponents from the running maxima of the last tracked forward.  force: re-centre every tensor; otherwise
+        only tensors whose stored maximum left the window [2^9, 2^13.2] move (hysteresis)."""
+        amax = self.amax.cpu().tolist()
+        new = dict(self.exps)
+        for nm, i in self.slots.items():
+            v = amax[i]
+            if not (v > 0.0) or not math.isfinite(v):
+                continue                                   # never written or all zero: keep
+            stored = math.log2(v) + self.exps[nm]
+            if force or stored > 13.2 or stored < 9.0:
+                new[nm] = max(-60, min(60, int(math.floor(ACT_TOP - math.log2(v) + 0.5))))
+        return new
+
+
+def _bexp(buf, calib):
+    """(scale exponent, running-max pointer) of an activation buffer: (None, None) unless it is a mixed-format buffer."""
+    if calib is None or buf.mode != "mix":
+        return None, None
+    return calib.exps[buf.cname], calib.ptr(buf.cname)
+
+
 class ActBuf:
     """A zero-initialised NHWC activation buffer [n, h, w, planes*c_buf] and its eamm_act views.
 
@@ -589,28 +638,47 @@ class HourglassPlan:
     the keypoint detector.  Level L owns one buffer [up-block output | encoder map e_L]; the skip
     `torch.cat`s of util.py:982-987 are channel-slot views of those buffers."""
 
-    def __init__(self, hourglass, cin0, calign, nalign, impl, prefix="hg"):
+    def __init__(self, hourglass, cin0, calign, nalign, impl, prefix="hg", calib=None):
+        """calib (a MixCalib): buffers whose every consumer can take 128-channel K chunks and whose producers write
+        32-channel-aligned couts are kept in the mixed fp16 + 2 x e4m3 format and their convs run the fp16 + fp8 scheme."""
         enc, dec = hourglass.encoder.down_blocks, hourglass.decoder.up_blocks
-        dev = enc[0].conv.weight.device
         nb = len(enc)
-        self.nb, self.calign = nb, calign
+        self.nb, self.calign, self.prefix = nb, calign, prefix
         self.enc_ch = [cin0] + [blk.conv.out_channels for blk in enc]       # e_0 .. e_nb
         self.dec_ch = [blk.conv.out_channels for blk in dec]                # up_j output channels
+        ru = lambda c: _round_up(c, calign)
+        co = lambda c: _round_up(c, nalign)
+        # level L buffer = [up_{nb-1-L} output | e_L]; producers: enc_{L-1} (skip slot), dec_{nb-1-L} (up slot);
+        # consumers: enc_L (skip slot), dec_{nb-L} (whole buffer); level 0 also feeds the caller's 7x7 head: never mixed
+        self.cat_mix = [False] * nb
+        self.bott_mix = False
+        if calib is not None and impl == "tc3":
+            for lvl in range(1, nb):
+                s_up, s_sk = ru(self.dec_ch[nb - 1 - lvl]), ru(self.enc_ch[lvl])
+                self.cat_mix[lvl] = (s_sk % 128 == 0 and (s_up + s_sk) % 128 == 0 and co(self.enc_ch[lvl]) % 32 == 0 and
+                                     co(self.dec_ch[nb - 1 - lvl]) % 32 == 0)
+                if self.cat_mix[lvl]:
+                    calib.register("%s.cat%d" % (prefix, lvl))
+            self.bott_mix = ru(self.enc_ch[nb]) % 128 == 0 and co(self.enc_ch[nb]) % 32 == 0
+            if self.bott_mix:
+                calib.register("%s.bott" % prefix)
         self.enc_layers, self.dec_layers = [], []
         for i, blk in enumerate(enc):
             w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
             self.enc_layers.append(ConvLayer("%s.enc%d" % (prefix, i), L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
-                                             _round_up(self.enc_ch[i], calign), nalign, impl))
+                                             ru(self.enc_ch[i]), nalign, "mix" if self.cat_mix[i] else impl))
         for j, blk in enumerate(dec):
             w, b = fold_bn(blk.conv.weight.detach().float(), blk.conv.bias.detach().float(), _bn_dict(blk.norm))
             # input of up_block j: e_nb for j == 0, else cat(up_{j-1} out, e_{nb-j}) with padded slots
             if j == 0:
-                cin_slot = _round_up(self.enc_ch[nb], calign)
+                cin_slot = ru(self.enc_ch[nb])
                 wp = w
+                mixed_in = self.bott_mix
             else:
                 wp, cin_slot = self.split_cat_weights(w, self.dec_ch[j - 1], self.enc_ch[nb - j])
+                mixed_in = self.cat_mix[nb - j]
             self.dec_layers.append(ConvLayer("%s.dec%d" % (prefix, j), L.CONV_UP2_3X3, L.EPI_RELU, wp, b, cin_slot,
-                                             nalign, impl, cin_valid=w.shape[1]))
+                                             nalign, "mix" if mixed_in else impl, cin_valid=w.shape[1]))
 
     def split_cat_weights(self, w, c_up, c_sk):
         """Re-index a conv over cat(up, skip) channels to the padded two-slot buffer layout."""
@@ -628,38 +696,42 @@ class HourglassPlan:
         for lvl in range(nb):
             s_up = _round_up(self.dec_ch[nb - 1 - lvl], ca)
             s_sk = _round_up(self.enc_ch[lvl], ca)
-            buf = ActBuf(B, h >> lvl, w >> lvl, s_up + s_sk, mode, dev)
+            buf = ActBuf(B, h >> lvl, w >> lvl, s_up + s_sk, "mix" if self.cat_mix[lvl] else mode, dev)
             buf.s_up, buf.s_sk = s_up, s_sk
+            buf.cname = "%s.cat%d" % (self.prefix, lvl)
             cat.append(buf)
-        bott = ActBuf(B, h >> nb, w >> nb, _round_up(self.enc_ch[nb], ca), mode, dev)
+        bott = ActBuf(B, h >> nb, w >> nb, _round_up(self.enc_ch[nb], ca), "mix" if self.bott_mix else mode, dev)
+        bott.cname = "%s.bott" % self.prefix
         return cat, bott
 
-    def run(self, lib, st, cat, bott):
+    def run(self, lib, st, cat, bott, calib=None):
         """cat[0]'s skip slot holds the input; afterwards cat[0] holds [decoder output | input]."""
         nb = self.nb
         for i, layer in enumerate(self.enc_layers):          # e_{i+1} = down_block_i(e_i)
             src_buf = cat[i]
-            inp = src_buf.act(c_off=src_buf.s_up, c=src_buf.s_sk)
-            if i + 1 < nb:
-                dst_buf = cat[i + 1]
-                dst = dst_buf.act(c_off=dst_buf.s_up, c=layer.cout)
-            else:
-                dst = bott.act(c_off=0, c=layer.cout)
-            layer.launch(lib, st, inp, out=dst)
+            inp = src_buf.act(c_off=src_buf.s_up, c=src_buf.s_sk, exp=_bexp(src_buf, calib)[0])
+            dst_buf = cat[i + 1] if i + 1 < nb else bott
+            e, am = _bexp(dst_buf, calib)
+            dst = dst_buf.act(c_off=dst_buf.s_up if i + 1 < nb else 0, c=layer.cout, exp=e)
+            layer.launch(lib, st, inp, out=dst, amax_out=am)
         for j, layer in enumerate(self.dec_layers):          # up_block_j reads e_nb / cat_{nb-j}, fills cat_{nb-1-j}
-            inp = bott.act() if j == 0 else cat[nb - j].act()
+            src_buf = bott if j == 0 else cat[nb - j]
             dst_buf = cat[nb - 1 - j]
-            layer.launch(lib, st, inp, out=dst_buf.act(c_off=0, c=layer.cout))
+            e, am = _bexp(dst_buf, calib)
+            layer.launch(lib, st, src_buf.act(exp=_bexp(src_buf, calib)[0]), out=dst_buf.act(c_off=0, c=layer.cout, exp=e),
+                         amax_out=am)
 
 
 class DenseMotionEngine:
     """Executor for DenseMotionNetwork.forward (dense_motion.py:81-113)."""
 
-    def __init__(self, module, precision):
+    def __init__(self, module, precision, calib=None):
+        """calib: the owning generator's MixCalib (mixed-format hourglass layers); None = no mixed-format layers."""
         self.m = module
         self.precision = precision
         self.lib = L.load()
         self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
+        self.calib = calib
         self.ws = WorkspaceCache()
         self._pack()
 
@@ -678,7 +750,7 @@ class DenseMotionEngine:
         K1 = m.num_kp + 1
         cin0 = K1 * (m.num_channels + 1)
         ca = self.calign
-        self.hg = HourglassPlan(m.hourglass, cin0, ca, self.nalign, self.impl)
+        self.hg = HourglassPlan(m.hourglass, cin0, ca, self.nalign, self.impl, calib=self.calib)
         nb = self.nb = self.hg.nb
         self.enc_ch, self.dec_ch = self.hg.enc_ch, self.hg.dec_ch
         # mask (+ occlusion) merged into one 7x7 conv over cat(up_{nb-1} out, e_0)
@@ -768,7 +840,7 @@ class DenseMotionEngine:
             nbytes=B * h * w * (16 + K1 * 4 * esz + K1 * Cc * 4))
         out["sparse_deformed"] = sparse_deformed
         # a7 hourglass
-        self.hg.run(lib, st, ws.cat, ws.bott)
+        self.hg.run(lib, st, ws.cat, ws.bott, self.calib)
         # a8: mask/occlusion 7x7 conv -> logits; softmax + flow combine + sigmoid
         self.head.launch(lib, st, ws.cat[0].act(), out_nhwc_f32=ws.logits)
         mask = torch.empty(B, K1, h, w, dtype=torch.float32, device=dev)
@@ -802,18 +874,19 @@ class GeneratorEngine:
         self.lib = L.load()
         self.impl, self.mode, self.calign, self.nalign = impl_for(precision)
         self.ws = WorkspaceCache()
-        self.dm = DenseMotionEngine(module.dense_motion_network, precision) \
-            if module.dense_motion_network is not None else None
-        # "fp32": the bottleneck ResBlocks run the fp16 + fp8 mixed scheme (needs 128-channel K chunks)
+        # "fp32": every 3x3 / UP2 conv whose input has 128-channel K chunks runs the fp16 + fp8 mixed scheme
         import os
-        blocks = list(module.bottleneck.children())
-        c_bott = _round_up(blocks[0].conv1.in_channels, self.calign) if blocks else 0
-        self.mixed = (precision == "fp32" and self.impl == "tc3" and bool(blocks) and c_bott % 128 == 0 and
-                      os.environ.get("EAMM_B200_MIX", "1") != "0")
-        self.calibrated = False
-        self._tracked = False
-        self.exps = {}                       # tensor name ("a0", "t0", ...) -> power-of-two pre-scale exponent
+        self.mixed = precision == "fp32" and self.impl == "tc3" and os.environ.get("EAMM_B200_MIX", "1") != "0"
+        # EAMM_B200_MIX=res: only the bottleneck ResBlocks (the first cut); default: every eligible layer
+        self.mix_scope = os.environ.get("EAMM_B200_MIX", "1")
+        self.calib = MixCalib() if self.mixed else None
+        self.dm = DenseMotionEngine(module.dense_motion_network, precision,
+                                    calib=self.calib if self.mix_scope != "res" else None) \
+            if module.dense_motion_network is not None else None
         self._pack()
+        if self.mixed:
+            self.mixed = bool(self.calib.slots)
+            self.calib.alloc(self.device)
 
     def _pack(self):
         m, ca, na, impl = self.m, self.calign, self.nalign, self.impl
@@ -829,27 +902,51 @@ class GeneratorEngine:
             self.first = FirstConvTC(w, b, na, split=(impl == "tc3"), f16=(impl == "tc16"))
         else:
             self.first = ConvLayer("first", L.CONV_7X7, L.EPI_RELU, w, b, _round_up(m.num_channels, ca), na, impl)
+        # which activation buffers are kept in the mixed format: every consumer must take 128-channel K chunks (3x3 / UP2
+        # conv, or the warp kernel) and every producer must write 32-channel-aligned couts
+        nd = len(m.down_blocks)
+        blocks = list(m.bottleneck.children())
+        cal, wide = self.calib, self.mixed and self.mix_scope != "res"
+        ru = lambda c: _round_up(c, ca)
+        co = lambda c: _round_up(c, na)
+        c_bott = ru(blocks[0].conv1.in_channels) if blocks else 0
+        res_mix = self.mixed and bool(blocks) and c_bott % 128 == 0 and co(c_bott) % 32 == 0
+        self.enc_mix = [False] * (nd + 1)
+        for i in range(1, nd + 1):
+            cons_ok = ru(m.down_blocks[i].conv.in_channels) % 128 == 0 if i < nd else (self.dm is not None)
+            self.enc_mix[i] = wide and cons_ok and co(m.down_blocks[i - 1].conv.out_channels) % 32 == 0
+        self.xf_mix = wide and res_mix and nd > 0 and ru(m.up_blocks[0].conv.in_channels) % 128 == 0
+        self.dec_mix = [wide and i + 1 < nd and ru(m.up_blocks[i + 1].conv.in_channels) % 128 == 0 and
+                        co(m.up_blocks[i].conv.out_channels) % 32 == 0 for i in range(nd)]
+        if self.mixed:
+            for i in range(1, nd + 1):
+                if self.enc_mix[i]:
+                    cal.register("enc%d" % i)
+            if res_mix:
+                for i in range(len(blocks)):
+                    cal.register("a%d" % i)
+                    cal.register("t%d" % i)
+            if self.xf_mix:
+                cal.register("xf")
+            for i in range(nd):
+                if self.dec_mix[i]:
+                    cal.register("dec%d" % i)
+        self.res_mix = res_mix
         self.down = []
         for i, blk in enumerate(m.down_blocks):
             w, b = folded(blk)
             self.down.append(ConvLayer("down%d" % i, L.CONV_3X3, L.EPI_RELU | L.EPI_POOL2, w, b,
-                                       _round_up(blk.conv.in_channels, ca), na, impl))
+                                       ru(blk.conv.in_channels), na, "mix" if self.enc_mix[i] else impl))
         self.res = []
-        blocks = list(m.bottleneck.children())
         for i, blk in enumerate(blocks):
             w1, b1 = fold_bn(blk.conv1.weight.detach().float(), blk.conv1.bias.detach().float(), _bn_dict(blk.norm2))
             c = blk.conv1.in_channels
-            rimpl = "mix" if self.mixed else impl
-            l1 = ConvLayer("res%d.conv1" % i, L.CONV_3X3, L.EPI_RELU, w1, b1, _round_up(c, ca), na, rimpl)
+            rimpl = "mix" if res_mix else impl
+            l1 = ConvLayer("res%d.conv1" % i, L.CONV_3X3, L.EPI_RELU, w1, b1, ru(c), na, rimpl)
             nxt = bn_affine(_bn_dict(blocks[i + 1].norm1)) if i + 1 < len(blocks) else (None, None)
             l2 = ConvLayer("res%d.conv2" % i, L.CONV_3X3, 0, blk.conv2.weight.detach().float(),
-                           blk.conv2.bias.detach().float(), _round_up(c, ca), na, rimpl, scale2=nxt[0], shift2=nxt[1])
+                           blk.conv2.bias.detach().float(), ru(c), na, rimpl, scale2=nxt[0], shift2=nxt[1])
             self.res.append((l1, l2))
-        if self.mixed:
-            # calibration statistics: running max of a_i = relu(bn1(x_i)) (slot 2i) and t_i = relu(bn2(conv1(a_i))) (2i+1)
-            self.amax = torch.zeros(2 * len(blocks), dtype=torch.float32, device=self.device)
-            for i in range(len(blocks)):
-                self.exps["a%d" % i] = self.exps["t%d" % i] = 0
         self.pre = None
         if blocks:
             s, t = bn_affine(_bn_dict(blocks[0].norm1))
@@ -860,8 +957,9 @@ class GeneratorEngine:
         self.up = []
         for i, blk in enumerate(m.up_blocks):
             w, b = folded(blk)
+            mixed_in = (self.xf_mix if blocks else self.enc_mix[nd]) if i == 0 else self.dec_mix[i - 1]
             self.up.append(ConvLayer("up%d" % i, L.CONV_UP2_3X3, L.EPI_RELU, w, b,
-                                     _round_up(blk.conv.in_channels, ca), na, impl))
+                                     ru(blk.conv.in_channels), na, "mix" if mixed_in else impl))
         self.final = ConvLayer("final", L.CONV_7X7, L.EPI_SIGMOID, m.final.weight.detach().float(),
                                m.final.bias.detach().float(), _round_up(m.final.in_channels, ca), na, impl)
 
@@ -881,15 +979,22 @@ class GeneratorEngine:
             ws.src = ActBuf(B, H, W, self.first.cin, mode, dev)
         ws.enc = [ActBuf(B, H, W, _round_up(m.first.conv.out_channels, ca), mode, dev)]
         for i, blk in enumerate(m.down_blocks):
-            ws.enc.append(ActBuf(B, H >> (i + 1), W >> (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
+            ws.enc.append(ActBuf(B, H >> (i + 1), W >> (i + 1), _round_up(blk.conv.out_channels, ca),
+                                 "mix" if self.enc_mix[i + 1] else mode, dev))
+            ws.enc[-1].cname = "enc%d" % (i + 1)
         fh, fw = H >> nd, W >> nd
         cb = ws.enc[-1].c_buf
         ws.x = [ActBuf(B, fh, fw, cb, mode, dev), ActBuf(B, fh, fw, cb, mode, dev)]
-        ws.a = ActBuf(B, fh, fw, cb, "mix" if self.mixed else mode, dev)
-        ws.t = ActBuf(B, fh, fw, cb, "mix" if self.mixed else mode, dev)
+        ws.a = ActBuf(B, fh, fw, cb, "mix" if self.res_mix else mode, dev)
+        ws.t = ActBuf(B, fh, fw, cb, "mix" if self.res_mix else mode, dev)
+        ws.xf = ActBuf(B, fh, fw, cb, "mix", dev) if self.xf_mix else None      # the bottleneck's output as up0's operand
+        if ws.xf is not None:
+            ws.xf.cname = "xf"
         ws.dec = []
         for i, blk in enumerate(m.up_blocks):
-            ws.dec.append(ActBuf(B, fh << (i + 1), fw << (i + 1), _round_up(blk.conv.out_channels, ca), mode, dev))
+            ws.dec.append(ActBuf(B, fh << (i + 1), fw << (i + 1), _round_up(blk.conv.out_channels, ca),
+                                 "mix" if self.dec_mix[i] else mode, dev))
+            ws.dec[-1].cname = "dec%d" % i
         self.ws[key] = ws
         return ws
 
@@ -908,51 +1013,35 @@ class GeneratorEngine:
         return out
 
     # ---- calibration of the mixed-format pre-scales -------------------------------------------------------------
-    def _amax_ptr(self, slot):
-        return self.amax.data_ptr() + 4 * slot
-
-    def _exps_from_amax(self, force):
-        """New exponents from the running maxima of the last tracked forward.  force: re-centre every tensor;
-        otherwise only tensors whose stored maximum left the window [2^9, 2^13.2] move (hysteresis)."""
-        amax = self.amax.cpu().tolist()
-        new = dict(self.exps)
-        for i in range(len(self.res)):
-            for nm, v in (("a%d" % i, amax[2 * i]), ("t%d" % i, amax[2 * i + 1])):
-                if not (v > 0.0) or not math.isfinite(v):
-                    continue                               # never written (last block's a) or all zero: keep
-                stored = math.log2(v) + self.exps[nm]
-                if force or stored > 13.2 or stored < 9.0:
-                    new[nm] = max(-60, min(60, int(math.floor(ACT_TOP - math.log2(v) + 0.5))))
-        return new
-
     def needs_recalibration(self):
         """After a tracked forward (strict mode): True when an activation maximum drifted out of its window; the
         exponents are then updated and the caller runs the forward again."""
-        if not self.mixed or not self._tracked:
+        if not self.mixed or not self.calib.track:
             return False
-        new = self._exps_from_amax(force=False)
-        if new == self.exps:
+        new = self.calib.proposal(force=False)
+        if new == self.calib.exps:
             return False
-        self.exps = new
+        self.calib.exps = new
         return True
 
     def run(self, source_image, kp_driving, kp_source, track=None):
         """track: keep the calibration statistics of this forward (default: in strict mode, where the module checks
         them right after the call).  The first call calibrates: forward, read the maxima, set the exponents, repeat
-        until they stop moving (normally two forwards)."""
+        until they stop moving (normally two or three forwards)."""
         if not self.mixed:
             return self._forward(source_image, kp_driving, kp_source, False)
         if source_image.dim() == 4 and source_image.shape[0] == 0:
             return self._forward(source_image, kp_driving, kp_source, False)
-        if not self.calibrated:
+        cal = self.calib
+        if not cal.calibrated:
             out = None
-            for it in range(4):
+            for it in range(5):
                 out = self._forward(source_image, kp_driving, kp_source, True)
-                new = self._exps_from_amax(force=(it == 0))
-                if new == self.exps:
+                new = cal.proposal(force=(it == 0))
+                if new == cal.exps:
                     break
-                self.exps = new
-            self.calibrated = True
+                cal.exps = new
+            cal.calibrated = True
             return out
         if track is None:
             track = bool(getattr(self.m, "strict_errors", True)) and not torch.cuda.is_current_stream_capturing()
@@ -960,9 +1049,9 @@ class GeneratorEngine:
 
     def _forward(self, source_image, kp_driving, kp_source, track):
         m, lib = self.m, self.lib
-        self._tracked = track
-        if track:
-            self.amax.zero_()
+        cal = self.calib
+        if cal is not None:
+            cal.begin(track)
         if source_image.dim() != 4 or source_image.shape[1] != m.num_channels:
             raise RuntimeError("eamm_b200: source_image must be [B,%d,H,W]" % m.num_channels)
         B, Cc, H, W = source_image.shape
@@ -997,7 +1086,9 @@ class GeneratorEngine:
                     nbytes=nsrc * H * W * (Cc * 4 + ws.src.c_buf * esz))
                 self.first.launch(lib, st, ws.src.act(n=nsrc), out=ws.enc[0].act(c=self.first.cout, n=nsrc))
             for i, layer in enumerate(self.down):
-                layer.launch(lib, st, ws.enc[i].act(n=nsrc), out=ws.enc[i + 1].act(c=layer.cout, n=nsrc))
+                e, am = _bexp(ws.enc[i + 1], cal)
+                layer.launch(lib, st, ws.enc[i].act(n=nsrc, exp=_bexp(ws.enc[i], cal)[0]),
+                             out=ws.enc[i + 1].act(c=layer.cout, n=nsrc, exp=e), amax_out=am)
         ws.src_key = src_key
         ws.src_ref = source_image if src_key is not None else None
         result = {}
@@ -1018,11 +1109,11 @@ class GeneratorEngine:
                 raise RuntimeError("eamm_b200: motion grid %s must match the encoder feature map %dx%d "
                                    "(scale_factor == 2**-num_down_blocks)" % (tuple(deformation.shape[1:3]), feat.h, feat.w))
             # a9-i feature warp x occlusion (+ fused norm1/relu of the first ResBlock)
-            fa = feat.act(n=B, broadcast=shared)
-            mx = self.mixed
-            out2 = ws.a.act(exp=self.exps["a0"] if mx else None) if blocks else None
+            fa = feat.act(n=B, broadcast=shared, exp=_bexp(feat, cal)[0])
+            mx = self.res_mix
+            out2 = ws.a.act(exp=cal.exps["a0"] if mx else None) if blocks else None
             x0 = ws.x[0].act()
-            am0 = C.c_void_p(self._amax_ptr(0)) if (mx and track) else None
+            am0 = C.c_void_p(cal.ptr("a0")) if (mx and cal.track) else None
             _launch("warp_occlude", lambda: L.check(
                 lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(x0),
                                       C.byref(out2) if out2 is not None else None,
@@ -1041,23 +1132,32 @@ class GeneratorEngine:
             raise RuntimeError("eamm_b200: dense_motion_params=None is not supported by the B200 path")
         # bottleneck (generator.py:89): t = relu(bn2(conv1(a))); x' = conv2(t) + x; a' = relu(bn1'(x'))
         cur = 0
-        mx = self.mixed
+        mx = self.res_mix
+        x = ws.x[0]
         for i, (l1, l2) in enumerate(blocks):
-            ea = self.exps["a%d" % i] if mx else None
-            et = self.exps["t%d" % i] if mx else None
-            en = self.exps.get("a%d" % (i + 1)) if mx else None
+            ea = cal.exps["a%d" % i] if mx else None
+            et = cal.exps["t%d" % i] if mx else None
             l1.launch(lib, st, ws.a.act(exp=ea), out=ws.t.act(c=l1.cout, exp=et),
-                      amax_out=self._amax_ptr(2 * i + 1) if (mx and track) else None)
-            nxt = ws.x[1 - cur]
+                      amax_out=cal.ptr("t%d" % i) if mx else None)
             last = i + 1 == len(blocks)
-            l2.launch(lib, st, ws.t.act(exp=et), out=nxt.act(c=l2.cout), residual=ws.x[cur].act(c=l2.cout),
-                      out2=None if last else ws.a.act(c=l2.cout, exp=en),
-                      amax_out2=self._amax_ptr(2 * i + 2) if (mx and track and not last) else None)
-            cur = 1 - cur
-        x = ws.x[cur]
+            if last and ws.xf is not None:
+                nxt = ws.xf                          # the last block's sum is only read by up0: write its operand format
+                e, am = _bexp(nxt, cal)
+                l2.launch(lib, st, ws.t.act(exp=et), out=nxt.act(c=l2.cout, exp=e), residual=ws.x[cur].act(c=l2.cout),
+                          amax_out=am)
+                x = nxt
+            else:
+                nxt = ws.x[1 - cur]
+                en = cal.exps["a%d" % (i + 1)] if (mx and not last) else None
+                l2.launch(lib, st, ws.t.act(exp=et), out=nxt.act(c=l2.cout), residual=ws.x[cur].act(c=l2.cout),
+                          out2=None if last else ws.a.act(c=l2.cout, exp=en),
+                          amax_out2=cal.ptr("a%d" % (i + 1)) if (mx and not last) else None)
+                cur = 1 - cur
+                x = ws.x[cur]
         # decoder (generator.py:90-91)
         for i, layer in enumerate(self.up):
-            layer.launch(lib, st, x.act(), out=ws.dec[i].act(c=layer.cout))
+            e, am = _bexp(ws.dec[i], cal)
+            layer.launch(lib, st, x.act(exp=_bexp(x, cal)[0]), out=ws.dec[i].act(c=layer.cout, exp=e), amax_out=am)
             x = ws.dec[i]
         # final conv + sigmoid (generator.py:92-93)
         pred = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev)
