@@ -53,9 +53,9 @@ _PROTOS = {
     "eamm_abi_version": (C.c_int, []),
     "eamm_device_ok": (C.c_int, [C.c_int]),
     "eamm_aa_downsample": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_int, C.c_void_p]),
     "eamm_aa_downsample_act": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                         C.POINTER(Act), C.c_void_p]),
+                                         C.c_int, C.POINTER(Act), C.c_void_p]),
     "eamm_kp_head": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_kp_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -66,8 +66,8 @@ _PROTOS = {
                                 C.POINTER(Act), C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_flow_combine": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Kp), C.POINTER(Kp), C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "eamm_warp_occlude": (C.c_int, [C.POINTER(Act), C.c_void_p, C.c_void_p, C.POINTER(Act), C.POINTER(Act),
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eamm_warp_occlude": (C.c_int, [C.POINTER(Act), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Act),
+                                    C.POINTER(Act), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eamm_warp_image": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_nchw_to_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Act), C.c_void_p]),

@@ -64,4 +64,20 @@ def get_kp_config(name="full", audio=False):
 
 
 def get_config(name="full"):
-    return copy.deepcopy({"full": FULL_CONFIG, "tiny": TINY_CONFIG}[name])
+    """"full" / "tiny", or a constructor corner of the tiny config no shipped YAML uses but the reference's code
+    supports: "tiny_sf05" (motion grid 2x the encoder feature grid: generator.py:53-56, :82-83 resize flow and
+    occlusion), "tiny_sf1" (dense_motion.py:82: no anti-alias module), "tiny_nodm" (generator.py:20-24,67:
+    dense_motion_params=None)."""
+    if name in ("full", "tiny"):
+        return copy.deepcopy({"full": FULL_CONFIG, "tiny": TINY_CONFIG}[name])
+    cfg = copy.deepcopy(TINY_CONFIG)
+    if name == "tiny_sf05":
+        cfg["dense_motion_params"]["scale_factor"] = 0.5
+    elif name == "tiny_sf1":
+        cfg["dense_motion_params"]["scale_factor"] = 1
+    elif name == "tiny_nodm":
+        cfg["dense_motion_params"] = None
+        cfg["estimate_occlusion_map"] = False
+    else:
+        raise KeyError(name)
+    return cfg

@@ -190,6 +190,39 @@ __device__ __forceinline__ Bilinear bilinear_setup(float gx, float gy, int W, in
   return b;
 }
 
+// F.interpolate(mode='bilinear', align_corners=False) source taps for destination index d (ATen
+// area_pixel_compute_source_index: src = scale * (d + 0.5) - 0.5 clamped at 0, upper tap clamped to in - 1);
+// call sites generator.py:55 (flow -> feature / image grid) and generator.py:83 (occlusion map).
+struct Resize1D { int i0, i1; float w1; };
+__device__ __forceinline__ Resize1D resize_taps(int d, int in, int out) {
+  const float scale = (float)in / (float)out;
+  float f = scale * ((float)d + 0.5f) - 0.5f;
+  if (f < 0.f) f = 0.f;
+  Resize1D r;
+  r.i0 = (int)f;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.w1 = f - (float)r.i0;
+  return r;
+}
+// bilinear resize of a [h,w] map of float2 / float at destination pixel (y, x) of an [H,W] grid (same op order as ATen:
+// w0 * (wx0 * a + wx1 * b) + w1 * (wx0 * c + wx1 * d))
+__device__ __forceinline__ float2 resize_flow(const float2* __restrict__ dp, int h, int w, int y, int x, int H, int W) {
+  const Resize1D ry = resize_taps(y, h, H), rx = resize_taps(x, w, W);
+  const float ly0 = 1.f - ry.w1, lx0 = 1.f - rx.w1;
+  const float2 d00 = __ldg(dp + ry.i0 * w + rx.i0), d01 = __ldg(dp + ry.i0 * w + rx.i1);
+  const float2 d10 = __ldg(dp + ry.i1 * w + rx.i0), d11 = __ldg(dp + ry.i1 * w + rx.i1);
+  float2 g;
+  g.x = ly0 * (lx0 * d00.x + rx.w1 * d01.x) + ry.w1 * (lx0 * d10.x + rx.w1 * d11.x);
+  g.y = ly0 * (lx0 * d00.y + rx.w1 * d01.y) + ry.w1 * (lx0 * d10.y + rx.w1 * d11.y);
+  return g;
+}
+__device__ __forceinline__ float resize_scalar(const float* __restrict__ p, int h, int w, int y, int x, int H, int W) {
+  const Resize1D ry = resize_taps(y, h, H), rx = resize_taps(x, w, W);
+  const float ly0 = 1.f - ry.w1, lx0 = 1.f - rx.w1;
+  return ly0 * (lx0 * __ldg(p + ry.i0 * w + rx.i0) + rx.w1 * __ldg(p + ry.i0 * w + rx.i1)) +
+         ry.w1 * (lx0 * __ldg(p + ry.i1 * w + rx.i0) + rx.w1 * __ldg(p + ry.i1 * w + rx.i1));
+}
+
 // skimage.img_as_ubyte of a float32 image value in [0,1]: rint(v * 255) (round half to even), clipped to [0,255]
 __device__ __forceinline__ unsigned char to_ubyte(float v) {
   return (unsigned char)fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f);

@@ -26,7 +26,7 @@
 //               CTA pair   N tile 256 and folded layers: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
 //               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step (measured no faster: a pair MMA
-//               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 3),
+//               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 19; bit 4 = 16: pairs for mixed fp16+fp8 layers with N < 256),
 //               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4, bit 2: compact scheme-3 epilogue buffer; default 7), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
 //               split-K / the 32-byte epilogue stores off, EAMM_TC_SPLITK_DIST = 1 selects the distributed split-K reduction
 //               (opt-in), EAMM_TC_SPLITK_MAX caps the split factor (9), EAMM_TC_BNCOST = 0 restores the older N-tile rule,
@@ -109,7 +109,9 @@ struct ConvTcParams {
   int f16in;           // the A/B operands are fp16 (EAMM_F16 input): tensor-map coordinates are BYTES (uint8 maps)
   int mix;             // EAMM_F16 two-plane input: K loop = [a_hi8 x w_lo8 | a_lo8 x w_hi8] as kind::f8f6f4 steps over 128-channel
                        // chunks (n8 = ntap * cin/128 chunks each), then a_hi x w_hi as kind::f16 steps over 64-channel chunks
-  int n8;              // mix: chunks per fp8 pass
+  int nf8;             // mix: fp8 chunks at the head of the K loop (2 * ntap * cin/128, or ntap for mix64)
+  int mix64;           // mix with cin == c_buf == 64: plane 1 of a pixel, [lo8 x 64 | hi8 x 64], is ONE 128-byte K chunk that
+                       // meets the weight row [w_hi8 x 64 | w_lo8 x 64]: both cross terms in one fp8 chunk per tap
   const float* acc_scale;   // [cout] accumulator multiplier (undoes the operand pre-scales), or null
   float* amax_out; float* amax_out2;   // running max |value| of out / out2 (calibration statistic), or null
 };
@@ -869,14 +871,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               int cbase, bcol;
               if (p.f16in) {
                 // byte coordinates (uint8 tensor maps).  mix: chunks [0, n8) = a_hi8 (plane 1, second half) x w_lo8,
-                // [n8, 2 n8) = a_lo8 x w_hi8, 128 channels each; then a_hi x w_hi, 64 fp16 channels each
-                const uint32_t n8 = (uint32_t)p.n8;
-                if (kq < 2u * n8) {
+                // [n8, 2 n8) = a_lo8 x w_hi8, 128 channels each (mix64: [0, ntap) = [a_lo8 | a_hi8] x [w_hi8 | w_lo8], 64
+                // channels of both); then a_hi x w_hi, 64 fp16 channels each
+                const uint32_t nf8 = (uint32_t)p.nf8;
+                if (kq < nf8 && p.mix64) {
+                  cc = 0u; q = kq;
+                  cbase = 2 * p.a_c_buf;                       // (c_off == 0: the whole 64-channel pixel)
+                } else if (kq < nf8) {
+                  const uint32_t n8 = nf8 >> 1;
                   const uint32_t second = kq >= n8 ? 1u : 0u, i8 = kq - second * n8;
                   cc = i8 & (chunk_mask >> 1); q = i8 >> (chunk_shift - 1u);
                   cbase = 2 * p.a_c_buf + (second ? 0 : p.a_c_buf) + p.a_c_off + (int)cc * 128;
                 } else {
-                  const uint32_t i16 = kq - 2u * n8;
+                  const uint32_t i16 = kq - nf8;
                   cc = i16 & chunk_mask; q = i16 >> chunk_shift;
                   cbase = 2 * (p.a_c_off + (int)cc * 64);
                 }
@@ -931,7 +938,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t fmt = p.f16in ? 0u : ((1u << 7) | (1u << 10));
     const uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 2) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);   // N = 2*BN
-    const uint32_t n8x2 = p.mix ? 2u * (uint32_t)p.n8 : 0u;      // mixed input: K chunks [0, 2 n8) are the fp8 cross terms
+    const uint32_t n8x2 = p.mix ? (uint32_t)p.nf8 : 0u;          // mixed input: K chunks [0, nf8) are the fp8 cross terms
     const int nstages = p.num_stages, halo = p.halo, BN = p.BN;
     int stage = 0; uint32_t phase = 0; uint32_t as = 0, aphase = 0;
     uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
@@ -1158,7 +1165,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   const bool row7 = a->kind == EAMM_CONV_ROW7_PACKED;
   if (in->dtype != EAMM_BF16 && in->dtype != EAMM_F16) return EAMM_ERR_DTYPE;
   const bool f16in = in->dtype == EAMM_F16, mix = f16in && in->planes == 2;
-  if (mix && (row7 || a->kind == EAMM_CONV_7X7 || a->cin % 128)) return EAMM_ERR_UNSUPPORTED;
+  const bool mix64 = mix && a->cin == 64 && in->c_buf == 64 && in->c_off == 0;
+  if (mix && (row7 || a->kind == EAMM_CONV_7X7 || (a->cin % 128 && !mix64))) return EAMM_ERR_UNSUPPORTED;
   if (row7) {
     if (in->c != 8 || in->c_buf != 8 || in->c_off != 0 || in->planes != 1 || a->cin != 8) return EAMM_ERR_SHAPE;
     if (a->pack_passes != 1 && a->pack_passes != 2) return EAMM_ERR_ARG;
@@ -1239,11 +1247,16 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     else if (!row7 && p.passes == 3) p.fold = 1;
   }
   if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
+  // mixed-format outputs are written 32 channels at a time (one 32-byte store per e4m3 plane): N tiles of 32+ columns
+  bool need32 = false;
+  for (int i = 0; i < 2; ++i)
+    if (views[i] && views[i]->dtype == EAMM_F16 && views[i]->planes == 2) need32 = true;
+  if (need32 && a->cout % 32) return EAMM_ERR_UNSUPPORTED;
   if (p.kxn) p.BN = p.kxn == 1 ? 32 : KXW_COLS;
   else {
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes;
     p.BN = 0;
-    const int cand[5] = {256, 128, 64, 32, 16};
+    const int cand[5] = {256, 128, 64, 32, need32 ? 32 : 16};
     if (a->cout <= 256 && m_tiles >= num_sms) p.BN = a->cout;
     // Layers that cannot give every SM a full-width tile: the N tile with the lowest modelled time (waves x MMA steps
     // x per-step cycles, measured: ~110 up to N = 64, 124 at 128, 192 at 256, plus the epilogue) -- one wave of
@@ -1260,7 +1273,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
       const int cands[6] = {a->cout <= 256 ? a->cout : 0, 256, 128, 64, 32, 16};
       for (int i = 0; i < 6; ++i) {
         const int c = cands[i];
-        if (c <= 0 || c > a->cout || a->cout % c != 0 || (p.fold && 2 * c > 256)) continue;
+        if (c <= 0 || c > a->cout || a->cout % c != 0 || (p.fold && 2 * c > 256) || (need32 && c % 32)) continue;
         const long long waves = (m_tiles * (a->cout / c) + num_sms - 1) / num_sms;
         const long long per_pair = p.fold == 1 ? step(2 * c) + step(c) : (p.fold == 2 ? step(2 * c) : (long long)p.passes * step(c));
         const long long cost = waves * (4 * pairs * per_pair + 2000 + 14000ll * c / 256);
@@ -1316,7 +1329,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
   static int cta2_env = -1, prof_env = -1;
-  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 3; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256 (measured slower in
+  if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 19; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256 (measured slower in
                                                                                              // single-plane mode: the leader's one MMA warp issues for both CTAs; off by default)
   if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
   const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
@@ -1328,7 +1341,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     // accumulation order) is the same as the single-CTA kernel's, so the choice may depend on the batch.
     const long long m_tiles_pc = (long long)p.tiles_x * p.tiles_y * p.tiles_n;     // M tiles per (class, N tile)
     const bool pair_a = !p.fold && (p.BN == 256 || ((cta2_env & 4) && p.BN % 32 == 0));
-    const bool pair_b = (cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0;
+    const bool pair_b = ((cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0) ||
+                        ((cta2_env & 16) && p.mix && p.BN % 32 == 0);       // mixed operands: 8 steps per (tap, 64 ch) like a folded layer
     const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
     p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
     p.pf_wide = (p.cta2 && p.fold == 1 && (cta2_env & 8)) ? 1 : 0;
@@ -1388,7 +1402,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
         (!p.st256 || p.BN % 32 || views[i]->c_off % 32 || views[i]->c_buf % 32 || p.kxn))
       return EAMM_ERR_UNSUPPORTED;
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
-  p.n8 = mix ? p.ntap * p.cin_chunks / 2 : 0;
+  p.mix64 = mix64 ? 1 : 0;
+  p.nf8 = mix64 ? p.ntap : (mix ? p.ntap * p.cin_chunks : 0);
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles * p.splitk;

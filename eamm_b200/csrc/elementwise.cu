@@ -7,22 +7,23 @@ namespace eamm {
 
 // =============================================================================================
 // a3  AntiAliasInterpolation2d  (util.py:1044-1052)
-//   out[c][i][j] = sum_{u,v} k2[u][v] * src[c][step*i+u-6][step*j+v-6],  k2 = outer(g1,g1) (sum 1)
+//   out[c][i][j] = sum_{u,v} k2[u][v] * src[c][step*i+u-pad][step*j+v-pad],  k2 = outer(g1,g1) (sum 1), pad = taps/2
 // Block = (batch item, TR output rows).  Phase 1: horizontal 13-tap filter at the subsampled
 // columns for every needed input row (global reads, L1 absorbs the 13/step overlap); phase 2:
 // vertical 13-tap filter from shared memory; one float4 (R,G,B,0) store per output pixel.
 // =============================================================================================
-constexpr int AA_TAPS = 13;
-constexpr int AA_PAD = 6;
+constexpr int AA_MAX_TAPS = 13;   // the reference hard-codes sigma = 1.5 -> 13 taps (util.py:1011-1013); 1 tap = plain copy (scale 1)
 constexpr int AA_TR = 4;  // output rows per block
 
 __global__ void __launch_bounds__(256)
 aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, float4* __restrict__ dst,
-                     int H, int W, int Ho, int Wo, int step, const float* __restrict__ g1, ActView act, int to_act) {
+                     int H, int W, int Ho, int Wo, int step, int AA_TAPS, const float* __restrict__ g1, ActView act,
+                     int to_act) {
   extern __shared__ float tmp[];  // [3][rows][Wo]
-  __shared__ float g[AA_TAPS];
+  __shared__ float g[AA_MAX_TAPS];
   const int n = blockIdx.y;
   const int r0 = blockIdx.x * AA_TR;
+  const int AA_PAD = AA_TAPS >> 1;          // util.py:1044-1047: ka = ks // 2 on every side (ks is odd)
   const int rows = (AA_TR - 1) * step + AA_TAPS;
   if (threadIdx.x < AA_TAPS) g[threadIdx.x] = g1[threadIdx.x];
   __syncthreads();
@@ -37,7 +38,6 @@ aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, floa
     if (y >= 0 && y < H) {
       const float* rowp = img + ((long long)c * H + y) * W;
       int x0 = j * step - AA_PAD;
-#pragma unroll
       for (int v = 0; v < AA_TAPS; ++v) {
         int x = x0 + v;
         float s = (x >= 0 && x < W) ? __ldg(rowp + x) : 0.f;
@@ -55,7 +55,6 @@ aa_downsample_kernel(const float* __restrict__ src, long long src_n_stride, floa
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc = 0.f;
-#pragma unroll
       for (int u = 0; u < AA_TAPS; ++u) acc = fmaf(g[u], tmp[(c * rows + i * step + u) * Wo + j], acc);
       o[c] = acc;
     }
@@ -210,11 +209,23 @@ flow_combine_kernel(const float* __restrict__ logits, int ldl, KpDev kd, KpDev k
 // NHWC: each thread owns 4 channels of one pixel, so the 4 bilinear taps are four fully
 // coalesced channel-vector reads.  Algorithmic traffic: one read + one (or two) writes of the map.
 // =============================================================================================
+// flow and occlusion of feature pixel (n, y, x): read directly when the motion grid equals the feature grid, else
+// bilinearly resized on the fly (generator.py:53-56 and :82-83: F.interpolate(..., mode='bilinear'))
+__device__ __forceinline__ float2 flow_at(const float2* __restrict__ deform, int fh, int fw, int n, int y, int x, int H, int W) {
+  if (fh == H && fw == W) return __ldg(deform + ((long long)n * H + y) * W + x);
+  return resize_flow(deform + (long long)n * fh * fw, fh, fw, y, x, H, W);
+}
+__device__ __forceinline__ float occ_at(const float* __restrict__ occ, int fh, int fw, int n, int y, int x, int H, int W) {
+  if (fh == H && fw == W) return __ldg(occ + ((long long)n * H + y) * W + x);
+  return resize_scalar(occ + (long long)n * fh * fw, fh, fw, y, x, H, W);
+}
+
 __global__ void __launch_bounds__(256)
-warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
+warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ, int fh, int fw,
                     ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
-                    const float* __restrict__ shift2, long long total) {
+                    const float* __restrict__ shift2, float* __restrict__ amax_out2, long long total) {
   const int c4 = feat.c >> 2;
+  float amax = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int cg = (int)(idx % c4);
@@ -222,18 +233,22 @@ warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float
     int x = (int)(pix % feat.w);
     int y = (int)((pix / feat.w) % feat.h);
     int n = (int)(pix / ((long long)feat.w * feat.h));
-    float2 d = __ldg(deform + pix);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (deform != nullptr) {
+    float2 d = flow_at(deform, fh, fw, n, y, x, feat.h, feat.w);
     Bilinear b = bilinear_setup(d.x, d.y, feat.w, feat.h);
     float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
     bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
     bool yin0 = b.y0 >= 0 && b.y0 < feat.h, yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < feat.h;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yin0 && xin0) { float4 t = act_load4(feat, act_offset(feat, n, b.y0, b.x0, 4 * cg)); float q = wy0 * wx0; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
     if (yin0 && xin1) { float4 t = act_load4(feat, act_offset(feat, n, b.y0, b.x0 + 1, 4 * cg)); float q = wy0 * b.wx1; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
     if (yin1 && xin0) { float4 t = act_load4(feat, act_offset(feat, n, b.y0 + 1, b.x0, 4 * cg)); float q = b.wy1 * wx0; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
     if (yin1 && xin1) { float4 t = act_load4(feat, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 4 * cg)); float q = b.wy1 * b.wx1; acc.x += t.x * q; acc.y += t.y * q; acc.z += t.z * q; acc.w += t.w * q; }
+    } else {
+      acc = act_load4(feat, act_offset(feat, n, y, x, 4 * cg));     // no dense-motion network (generator.py:67): no warp
+    }
     if (occ != nullptr) {
-      float o = __ldg(occ + pix);
+      float o = occ_at(occ, fh, fw, n, y, x, feat.h, feat.w);
       acc.x *= o; acc.y *= o; acc.z *= o; acc.w *= o;
     }
     act_store4(out, act_offset(out, n, y, x, 4 * cg), acc);
@@ -246,7 +261,13 @@ warp_occlude_kernel(ActView feat, const float2* __restrict__ deform, const float
       r.z = fmaxf(fmaf(acc.z, s.z, t.z), 0.f);
       r.w = fmaxf(fmaf(acc.w, s.w, t.w), 0.f);
       act_store4(out2, act_offset(out2, n, y, x, 4 * cg), r);
+      amax = fmaxf(fmaxf(amax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
     }
+  }
+  if (amax_out2 != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax_out2), __float_as_int(amax));   // non-negative floats
   }
 }
 
@@ -322,7 +343,7 @@ __device__ __forceinline__ void vec8_store(const ActView& v, long long off, int 
 
 template <int FIN, int FOUT2>
 __global__ void __launch_bounds__(256)
-warp_occlude_vec_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ,
+warp_occlude_vec_kernel(ActView feat, const float2* __restrict__ deform, const float* __restrict__ occ, int fh, int fw,
                         ActView out, ActView out2, int has_out2, const float* __restrict__ scale2,
                         const float* __restrict__ shift2, float* __restrict__ amax_out2, long long total) {
   const int c8 = feat.c >> 3;
@@ -334,7 +355,7 @@ warp_occlude_vec_kernel(ActView feat, const float2* __restrict__ deform, const f
     const int x = (int)(pix % feat.w);
     const int y = (int)((pix / feat.w) % feat.h);
     const int n = (int)(pix / ((long long)feat.w * feat.h));
-    const float2 d = __ldg(deform + pix);
+    const float2 d = flow_at(deform, fh, fw, n, y, x, feat.h, feat.w);
     const Bilinear b = bilinear_setup(d.x, d.y, feat.w, feat.h);
     const float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
     const bool xin0 = b.x0 >= 0 && b.x0 < feat.w, xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < feat.w;
@@ -345,7 +366,7 @@ warp_occlude_vec_kernel(ActView feat, const float2* __restrict__ deform, const f
     if (yin1 && xin0) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0 + 1, b.x0, 8 * cg), 8 * cg, b.wy1 * wx0, acc);
     if (yin1 && xin1) vec8_tap<FIN>(feat, act_offset(feat, n, b.y0 + 1, b.x0 + 1, 8 * cg), 8 * cg, b.wy1 * b.wx1, acc);
     if (occ != nullptr) {
-      const float o = __ldg(occ + pix);
+      const float o = occ_at(occ, fh, fw, n, y, x, feat.h, feat.w);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] *= o;
     }
@@ -387,18 +408,8 @@ warp_image_kernel(const float* __restrict__ src, long long src_n_stride, const f
     float2 d = __ldg(deform + ((long long)n * h + y) * w + x);
     gx = d.x; gy = d.y;
   } else {
-    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-    float fy = sy * ((float)y + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
-    float fx = sx * ((float)x + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
-    int y0 = (int)fy, x0 = (int)fx;
-    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    float ly1 = fy - (float)y0, lx1 = fx - (float)x0;
-    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const float2* dp = deform + (long long)n * h * w;
-    float2 d00 = __ldg(dp + y0 * w + x0), d01 = __ldg(dp + y0 * w + x1);
-    float2 d10 = __ldg(dp + y1 * w + x0), d11 = __ldg(dp + y1 * w + x1);
-    gx = ly0 * (lx0 * d00.x + lx1 * d01.x) + ly1 * (lx0 * d10.x + lx1 * d11.x);
-    gy = ly0 * (lx0 * d00.y + lx1 * d01.y) + ly1 * (lx0 * d10.y + lx1 * d11.y);
+    const float2 g = resize_flow(deform + (long long)n * h * w, h, w, y, x, H, W);
+    gx = g.x; gy = g.y;
   }
   Bilinear b = bilinear_setup(gx, gy, W, H);
   float wx0 = 1.f - b.wx1, wy0 = 1.f - b.wy1;
@@ -664,8 +675,10 @@ extern "C" int eamm_device_ok(int device) {
 }
 
 extern "C" int eamm_aa_downsample(const float* src, int64_t src_n_stride, float* dst, int n, int H, int W,
-                                  int step, const float* g1, void* stream) {
+                                  int step, const float* g1, int taps, void* stream) {
+  const int AA_TAPS = taps;
   if (!src || !dst || !g1 || n <= 0 || H <= 0 || W <= 0 || step <= 0) return EAMM_ERR_ARG;
+  if (taps < 1 || taps > AA_MAX_TAPS || !(taps & 1)) return EAMM_ERR_UNSUPPORTED;
   if (H % step || W % step) return EAMM_ERR_SHAPE;
   if ((uintptr_t)dst % 16) return EAMM_ERR_ALIGN;
   int Ho = H / step, Wo = W / step;
@@ -676,14 +689,16 @@ extern "C" int eamm_aa_downsample(const float* src, int64_t src_n_stride, float*
     cudaFuncSetAttribute(aa_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((Ho + AA_TR - 1) / AA_TR, n);
   ActView none = {};
-  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, (float4*)dst, H, W, Ho, Wo, step, g1, none, 0);
+  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, (float4*)dst, H, W, Ho, Wo, step, taps, g1, none, 0);
   EAMM_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, int n, int H, int W, int step,
-                                      const float* g1, const eamm_act* dst, void* stream) {
+                                      const float* g1, int taps, const eamm_act* dst, void* stream) {
+  const int AA_TAPS = taps;
   if (!src || !g1 || n <= 0 || H <= 0 || W <= 0 || step <= 0) return EAMM_ERR_ARG;
+  if (taps < 1 || taps > AA_MAX_TAPS || !(taps & 1)) return EAMM_ERR_UNSUPPORTED;
   if (H % step || W % step) return EAMM_ERR_SHAPE;
   int rc = check_view(dst); if (rc) return rc;
   int Ho = H / step, Wo = W / step;
@@ -694,7 +709,7 @@ extern "C" int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, in
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(aa_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((Ho + AA_TR - 1) / AA_TR, n);
-  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, nullptr, H, W, Ho, Wo, step, g1,
+  aa_downsample_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, src_n_stride, nullptr, H, W, Ho, Wo, step, taps, g1,
                                                                  make_view(dst), 1);
   EAMM_LAUNCH_CHECK();
   return 0;
@@ -740,12 +755,13 @@ static int view_fmt(const ActView& v) {
   return -1;
 }
 
-extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
+extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion, int fh, int fw,
                                  const eamm_act* out, const eamm_act* out2, const float* scale2,
                                  const float* shift2, float* amax_out2, void* stream) {
   int rc = check_view(feat); if (rc) return rc;
   rc = check_view(out); if (rc) return rc;
-  if (!deformation) return EAMM_ERR_ARG;
+  if (fh <= 0 || fw <= 0) { fh = feat->h; fw = feat->w; }
+  if (!deformation && occlusion) return EAMM_ERR_ARG;         // an occlusion map only exists next to a flow
   if (out->n != feat->n || out->h != feat->h || out->w != feat->w || out->c != feat->c) return EAMM_ERR_SHAPE;
   ActView f = make_view(feat), o = make_view(out), o2 = o;
   int has2 = 0;
@@ -763,13 +779,13 @@ extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation,
   // the vector kernel's format pairs: out has feat's format (a mixed feat writes bf16 hi/lo); out2 the same or mixed
   const bool pair_ok = fin >= 0 && fo == (fin == FMT_MIX ? FMT_BF16X2 : fin) && (fo2 == fo || fo2 == FMT_MIX) &&
                        !(fo2 == FMT_MIX && fin != FMT_BF16X2 && fin != FMT_MIX);
-  if (pair_ok && vec_ok(f) && vec_ok(o) && (!has2 || vec_ok(o2))) {
+  if (deformation && pair_ok && vec_ok(f) && vec_ok(o) && (!has2 || vec_ok(o2))) {
     long long total = (long long)f.n * f.h * f.w * (f.c / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     const float2* dp = (const float2*)deformation;
     cudaStream_t st = (cudaStream_t)stream;
-#define EAMM_WO(FI, FO2) warp_occlude_vec_kernel<FI, FO2><<<blocks, 256, 0, st>>>(f, dp, occlusion, o, o2, has2, scale2, shift2, amax_out2, total)
+#define EAMM_WO(FI, FO2) warp_occlude_vec_kernel<FI, FO2><<<blocks, 256, 0, st>>>(f, dp, occlusion, fh, fw, o, o2, has2, scale2, shift2, amax_out2, total)
     if (fin == FMT_BF16) EAMM_WO(FMT_BF16, FMT_BF16);
     else if (fin == FMT_F16) EAMM_WO(FMT_F16, FMT_F16);
     else if (fin == FMT_BF16X2 && fo2 == FMT_MIX) EAMM_WO(FMT_BF16X2, FMT_MIX);
@@ -780,12 +796,11 @@ extern "C" int eamm_warp_occlude(const eamm_act* feat, const float* deformation,
     EAMM_LAUNCH_CHECK();
     return 0;
   }
-  if (amax_out2 != nullptr) return EAMM_ERR_UNSUPPORTED;          // the statistic is only kept by the vector kernel
   long long total = (long long)f.n * f.h * f.w * (f.c / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  warp_occlude_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, o, o2, has2,
-                                                               scale2, shift2, total);
+  warp_occlude_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f, (const float2*)deformation, occlusion, fh, fw, o, o2, has2,
+                                                               scale2, shift2, amax_out2, total);
   EAMM_LAUNCH_CHECK();
   return 0;
 }

@@ -290,7 +290,7 @@ def pack_tc_weights_mix(full, classes):
     [classes*taps][cout][cin] fp32 -> (uint8 [classes*cout][taps*cin*4], int exponents [cout]).  Row co is scaled by
     2^e[co] (one exponent per output channel, shared by the UP2 parity classes) so that its largest entry sits just
     below 2^13.4; K bytes = e4m3 lo8 [tap][cin] | e4m3 hi8 [tap][cin] | fp16 hi [tap][cin], where
-    hi = fp16(w'), lo8 = e4m3((w' - hi) * 64), hi8 = e4m3(hi / 64)."""
+    hi = fp16(w'), lo8 = e4m3((w' - hi) * 64), hi8 = e4m3(hi / 64).  cin == 64: e4m3 [tap][hi8 x 64 | lo8 x 64] | fp16 hi."""
     ct, cout, cin = full.shape
     taps = ct // classes
     w = full.view(classes, taps, cout, cin).permute(0, 2, 1, 3)          # [cls][cout][taps][cin]
@@ -303,8 +303,13 @@ def pack_tc_weights_mix(full, classes):
     lo8 = ((ws - hif) * 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
     hi8 = (hif / 64.0).clamp(-448, 448).to(torch.float8_e4m3fn)
     rows = classes * cout
-    packed = torch.cat([lo8.reshape(rows, -1).view(torch.uint8), hi8.reshape(rows, -1).view(torch.uint8),
-                        hi.reshape(rows, -1).view(torch.uint8)], dim=1).contiguous()
+    if cin == 64:
+        # one 128-byte fp8 chunk per tap: [w_hi8 x 64 | w_lo8 x 64] against the pixel's [a_lo8 x 64 | a_hi8 x 64]
+        x8 = torch.cat([hi8.view(torch.uint8), lo8.view(torch.uint8)], dim=-1)          # [cls][cout][taps][128]
+        packed = torch.cat([x8.reshape(rows, -1), hi.reshape(rows, -1).view(torch.uint8)], dim=1).contiguous()
+    else:
+        packed = torch.cat([lo8.reshape(rows, -1).view(torch.uint8), hi8.reshape(rows, -1).view(torch.uint8),
+                            hi.reshape(rows, -1).view(torch.uint8)], dim=1).contiguous()
     return packed, e.to(torch.int32)
 
 
@@ -573,7 +578,7 @@ class FirstConvTC:
     def buffer(self, n, H, W, device):
         return torch.zeros(n, H + 6, W + 8, 8, dtype=torch.float16 if self.f16 else torch.bfloat16, device=device)
 
-    def launch(self, lib, stream, src, nsrc, C_, H, W, packed, out):
+    def launch(self, lib, stream, src, nsrc, C_, H, W, packed, out, amax_out=None):
         _launch("pack_image", lambda: L.check(
             lib.eamm_pack_image(src.data_ptr(), nsrc, C_, H, W, 2 if self.f16 else (1 if self.split else 0),
                                 packed.data_ptr(), stream),
@@ -588,6 +593,8 @@ class FirstConvTC:
         a.inp = C.pointer(inp)
         a.bias = self.bias.data_ptr()
         a.out = C.pointer(out)
+        if amax_out is not None:
+            a.amax_out = amax_out
         a.pack_passes = self.passes
         fold = self.plan_cache.get((nsrc, H, W))
         if fold is None:
@@ -764,16 +771,20 @@ class DenseMotionEngine:
         wp, cin_slot = self.hg.split_cat_weights(wm, c_up, c_sk)
         self.head = ConvLayer("mask_occ", L.CONV_7X7, 0, wp, bm, cin_slot, self.nalign, self.impl,
                               cin_valid=wm.shape[1])
-        # 1-D factor of the anti-alias kernel: k2 = outer(g1, g1) with sum 1 (util.py:1012-1033)
-        self.step = 1
-        self.g1 = None
+        # 1-D factor of the anti-alias kernel: k2 = outer(g1, g1) with sum 1 (util.py:1011-1033: sigma hard-coded to 1.5,
+        # 13 taps at every scale).  scale_factor == 1 has no `down` module (dense_motion.py:28-30,82): a 1-tap identity
+        # filter turns the same kernel into the NCHW -> RGB0 copy.
+        self.step, self.taps = 1, 1
+        self.g1 = torch.ones(1, dtype=torch.float32, device=dev)
         if m.scale_factor != 1:
             self.step = int(1 / m.scale_factor)
             k2 = m.down.weight.detach().float()[0, 0]
-            if k2.shape != (13, 13):
-                raise RuntimeError("eamm_b200: anti-alias kernel must be 13x13 (sigma 1.5, util.py:1012)")
+            ks = k2.shape[0]
+            if k2.shape != (ks, ks) or ks > 13 or ks % 2 == 0:
+                raise RuntimeError("eamm_b200: anti-alias kernel must be odd and at most 13x13 (util.py:1012-1013)")
             g1 = k2.sum(1)                    # rows of an outer product with total sum 1
             self.g1 = (g1 / g1.sum()).contiguous()
+            self.taps = ks
 
     # ---- workspace for a batch size / image size
     def workspace(self, B, H, W):
@@ -816,15 +827,11 @@ class DenseMotionEngine:
         # a3 anti-alias downsample -> small [B,h,w,4]
         n_small = 1 if (src_n_stride == 0 and B > 1) else B
         small_stride = 0 if n_small == 1 and B > 1 else h * w * 4
-        if self.step != 1 and reuse_small:
-            pass
-        elif self.step != 1:
+        if not reuse_small:
             _launch("aa_downsample", lambda: L.check(
                 lib.eamm_aa_downsample(source_image.data_ptr(), src_n_stride, ws.small.data_ptr(), n_small, H, W,
-                                       self.step, self.g1.data_ptr(), st), "aa_downsample"),
+                                       self.step, self.g1.data_ptr(), self.taps, st), "aa_downsample"),
                 nbytes=n_small * (Cc * H * W * 4 + h * w * 16))
-        else:
-            raise RuntimeError("eamm_b200: scale_factor == 1 is not supported by the B200 path")
         # a4-a6 keypoint stage -> hourglass input (slot e_0 of cat_0) + sparse_deformed
         out = {}
         sparse_deformed = torch.empty(B, K1, Cc, h, w, dtype=torch.float32, device=dev)
@@ -912,6 +919,10 @@ class GeneratorEngine:
         c_bott = ru(blocks[0].conv1.in_channels) if blocks else 0
         res_mix = self.mixed and bool(blocks) and c_bott % 128 == 0 and co(c_bott) % 32 == 0
         self.enc_mix = [False] * (nd + 1)
+        # `first`'s output: a 64-channel buffer read whole by down0 (the cin == 64 variant of the mixed scheme)
+        c0 = ru(m.first.conv.out_channels)
+        self.enc_mix[0] = (wide and self.first_packed and nd > 0 and c0 == 64 and ru(m.down_blocks[0].conv.in_channels) == 64 and
+                           os.environ.get("EAMM_B200_MIX64", "1") != "0")
         for i in range(1, nd + 1):
             cons_ok = ru(m.down_blocks[i].conv.in_channels) % 128 == 0 if i < nd else (self.dm is not None)
             self.enc_mix[i] = wide and cons_ok and co(m.down_blocks[i - 1].conv.out_channels) % 32 == 0
@@ -919,7 +930,7 @@ class GeneratorEngine:
         self.dec_mix = [wide and i + 1 < nd and ru(m.up_blocks[i + 1].conv.in_channels) % 128 == 0 and
                         co(m.up_blocks[i].conv.out_channels) % 32 == 0 for i in range(nd)]
         if self.mixed:
-            for i in range(1, nd + 1):
+            for i in range(0, nd + 1):
                 if self.enc_mix[i]:
                     cal.register("enc%d" % i)
             if res_mix:
@@ -977,7 +988,8 @@ class GeneratorEngine:
             ws.src_packed = self.first.buffer(B, H, W, dev)
         else:
             ws.src = ActBuf(B, H, W, self.first.cin, mode, dev)
-        ws.enc = [ActBuf(B, H, W, _round_up(m.first.conv.out_channels, ca), mode, dev)]
+        ws.enc = [ActBuf(B, H, W, _round_up(m.first.conv.out_channels, ca), "mix" if self.enc_mix[0] else mode, dev)]
+        ws.enc[0].cname = "enc0"
         for i, blk in enumerate(m.down_blocks):
             ws.enc.append(ActBuf(B, H >> (i + 1), W >> (i + 1), _round_up(blk.conv.out_channels, ca),
                                  "mix" if self.enc_mix[i + 1] else mode, dev))
@@ -1001,6 +1013,8 @@ class GeneratorEngine:
     def _empty_result(self, source_image, kp_driving):
         m = self.m
         _, Cc, H, W = source_image.shape
+        if self.dm is None:
+            return {"prediction": torch.empty(0, Cc, H, W, dtype=torch.float32, device=source_image.device)}
         dev, K1 = source_image.device, m.dense_motion_network.num_kp + 1
         h, w = H // self.dm.step, W // self.dm.step
         z = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
@@ -1078,7 +1092,9 @@ class GeneratorEngine:
         esz = 2 if self.mode in ("bf16", "f16") else 4
         if not reuse:
             if self.first_packed:
-                self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed, ws.enc[0].act(c=self.first.cout, n=nsrc))
+                e0, am0e = _bexp(ws.enc[0], cal)
+                self.first.launch(lib, st, src, nsrc, Cc, H, W, ws.src_packed,
+                                  ws.enc[0].act(c=self.first.cout, n=nsrc, exp=e0), amax_out=am0e)
             else:
                 src_act = ws.src.act(n=nsrc)
                 _launch("nchw_to_act", lambda: L.check(
@@ -1105,9 +1121,9 @@ class GeneratorEngine:
             if occ is not None:
                 result["occlusion_map"] = occ
             deformation = dmo["deformation"]
-            if deformation.shape[1] != feat.h or deformation.shape[2] != feat.w:
-                raise RuntimeError("eamm_b200: motion grid %s must match the encoder feature map %dx%d "
-                                   "(scale_factor == 2**-num_down_blocks)" % (tuple(deformation.shape[1:3]), feat.h, feat.w))
+            # (a motion grid that differs from the encoder feature grid -- scale_factor != 2**-num_down_blocks -- is
+            #  resized inside the warp kernels: generator.py:53-56, :82-83)
+            fh, fw = deformation.shape[1], deformation.shape[2]
             # a9-i feature warp x occlusion (+ fused norm1/relu of the first ResBlock)
             fa = feat.act(n=B, broadcast=shared, exp=_bexp(feat, cal)[0])
             mx = self.res_mix
@@ -1115,7 +1131,7 @@ class GeneratorEngine:
             x0 = ws.x[0].act()
             am0 = C.c_void_p(cal.ptr("a0")) if (mx and cal.track) else None
             _launch("warp_occlude", lambda: L.check(
-                lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), C.byref(x0),
+                lib.eamm_warp_occlude(C.byref(fa), deformation.data_ptr(), _ptr(occ), fh, fw, C.byref(x0),
                                       C.byref(out2) if out2 is not None else None,
                                       _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
                                       am0, st), "warp_occlude"),
@@ -1129,7 +1145,20 @@ class GeneratorEngine:
             result["deformed"] = deformed
             x = ws.x[0]
         else:
-            raise RuntimeError("eamm_b200: dense_motion_params=None is not supported by the B200 path")
+            # no dense-motion network (dense_motion_params=None, generator.py:20-24,67): the encoder output goes straight
+            # into the bottleneck; the warp kernel without a flow is the copy + first norm1/ReLU
+            fa = feat.act(n=B, broadcast=shared, exp=_bexp(feat, cal)[0])
+            mx = self.res_mix
+            out2 = ws.a.act(exp=cal.exps["a0"] if mx else None) if blocks else None
+            x0 = ws.x[0].act()
+            am0 = C.c_void_p(cal.ptr("a0")) if (mx and cal.track) else None
+            _launch("warp_occlude", lambda: L.check(
+                lib.eamm_warp_occlude(C.byref(fa), None, None, 0, 0, C.byref(x0),
+                                      C.byref(out2) if out2 is not None else None,
+                                      _ptr(self.pre[0]) if blocks else None, _ptr(self.pre[1]) if blocks else None,
+                                      am0, st), "copy + norm1"),
+                nbytes=B * feat.h * feat.w * feat.c_buf * esz * (3 if blocks else 2))
+            x = ws.x[0]
         # bottleneck (generator.py:89): t = relu(bn2(conv1(a))); x' = conv2(t) + x; a' = relu(bn1'(x'))
         cur = 0
         mx = self.res_mix

@@ -28,10 +28,14 @@ class KPDetectorEngine:
             self.hg = HourglassPlan(m.predictor, cin0, ca, self.nalign, self.impl, prefix="kp.hg")
             wk, cin_slot = self.hg.split_cat_weights(wk, self.hg.dec_ch[-1], cin0)
             self.step = int(1 / m.scale_factor) if m.scale_factor != 1 else 1
+            self.taps, self.g1 = 1, torch.ones(1, dtype=torch.float32, device=dev)
             if self.step != 1:
                 k2 = m.down.weight.detach().float()[0, 0]
+                if k2.shape[0] > 13 or k2.shape[0] % 2 == 0:
+                    raise RuntimeError("eamm_b200: anti-alias kernel must be odd and at most 13x13")
                 g1 = k2.sum(1)
                 self.g1 = (g1 / g1.sum()).contiguous()
+                self.taps = k2.shape[0]
         else:
             cin_slot = _round_up(feat, ca)
         self.head = ConvLayer("kp_head", L.CONV_7X7, 0, wk, bk, cin_slot, self.nalign, self.impl, cin_valid=feat)
@@ -55,14 +59,12 @@ class KPDetectorEngine:
         B, Cc, H, W = x.shape
         K, J = m.num_kp, m.num_jacobian_maps
         if self.hg is not None:
-            if self.step == 1:
-                raise RuntimeError("eamm_b200: KPDetector with scale_factor == 1 is not supported")
             h, w = H // self.step, W // self.step
             ws = self.workspace(B, h, w)
             cat0 = ws.cat[0]
             dst = cat0.act(c_off=cat0.s_up, c=cat0.s_sk)
             _launch("kp.aa_downsample", lambda: L.check(
-                lib.eamm_aa_downsample_act(x.data_ptr(), Cc * H * W, B, H, W, self.step, self.g1.data_ptr(),
+                lib.eamm_aa_downsample_act(x.data_ptr(), Cc * H * W, B, H, W, self.step, self.g1.data_ptr(), self.taps,
                                            C.byref(dst), st), "aa_downsample_act"), nbytes=B * Cc * H * W * 4)
             self.hg.run(lib, st, ws.cat, ws.bott)
             feat = cat0.act()

@@ -127,16 +127,18 @@ int eamm_abi_version(void);
 int eamm_device_ok(int device);
 
 /* ---- a3: AntiAliasInterpolation2d (util.py:1044-1052; call site dense_motion.py:83) ---------
- * src [n,3,H,W] fp32 NCHW -> dst [n,H/step,W/step,4] fp32 (RGB0 per pixel).  Zero pad 6, 13x13
- * Gaussian (sigma 1.5, normalised), subsample ::step (step = int(1/scale_factor), 4 here).  g1 is the 13-tap 1-D factor (the 2-D buffer of the
- * reference is its normalised outer product). */
+ * src [n,3,H,W] fp32 NCHW -> dst [n,H/step,W/step,4] fp32 (RGB0 per pixel).  Zero pad taps/2, taps x taps
+ * Gaussian (normalised), subsample ::step (step = int(1/scale_factor)).  g1 is the `taps`-tap 1-D factor (the 2-D
+ * buffer of the reference is its normalised outer product); the reference hard-codes sigma = 1.5, i.e. 13 taps, at
+ * every scale (util.py:1011-1013); any odd taps <= 13 is accepted.  taps = 1, g1 = {1}, step = 1 is the plain
+ * NCHW -> RGB0 copy used when scale_factor == 1 (dense_motion.py:28-30,82: no `down` module then). */
 int eamm_aa_downsample(const float* src, int64_t src_n_stride, float* dst, int n, int H, int W,
-                       int step, const float* g1, void* stream);
+                       int step, const float* g1, int taps, void* stream);
 
 /* Same filter, written as channels [0,4) = (R,G,B,0) of an NHWC activation view (the keypoint detector's
  * hourglass input, keypoint_detector.py:78-79); remaining channels of the view are left untouched. */
 int eamm_aa_downsample_act(const float* src, int64_t src_n_stride, int n, int H, int W, int step,
-                           const float* g1, const eamm_act* dst, void* stream);
+                           const float* g1, int taps, const eamm_act* dst, void* stream);
 
 /* ---- keypoint heads (keypoint_detector.py:40-50, 82-103, 183-203) --------
  * logits [n,h,w,ldl] fp32 NHWC of a SAME-padded 7x7 conv over the detector's feature map: channels [0,K) =
@@ -183,9 +185,12 @@ int eamm_flow_combine(const float* logits, int ldl, const eamm_kp* kp_driving, c
 
 /* ---- a9-i: grid_sample(features, deformation) * occlusion (generator.py:57,79-84), fused with
  * the first ResBlock2d's norm1+relu (out2, optional).  feat/out/out2 are NHWC views with equal
- * h,w,c; deformation [n,h,w,2]; occlusion [n,1,h,w] or NULL.  amax_out2 (device float, may be NULL) is atomically
+ * h,w,c; deformation [n,fh,fw,2]; occlusion [n,1,fh,fw] or NULL.  When the motion grid (fh, fw) differs from the
+ * feature grid, flow and occlusion are resized on the fly exactly as generator.py:53-56 / :82-83 do
+ * (F.interpolate bilinear, align_corners=False); fh = fw = 0 means "same as feat".  deformation == NULL (a generator
+ * built with dense_motion_params=None, generator.py:67): no warp, out = feat.  amax_out2 (device float, may be NULL) is atomically
  * raised to max |out2 value|: the calibration statistic of an EAMM_F16 second output (see eamm_act.scale_exp). */
-int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion,
+int eamm_warp_occlude(const eamm_act* feat, const float* deformation, const float* occlusion, int fh, int fw,
                       const eamm_act* out, const eamm_act* out2, const float* scale2,
                       const float* shift2, float* amax_out2, void* stream);
 
@@ -216,6 +221,9 @@ int eamm_conv_simt(const eamm_conv_args* args, void* stream);
  *                 a_hi8 x w_lo8 and a_lo8 x w_hi8 as tcgen05.mma.kind::f8f6f4 steps (K = 32, twice the fp16 rate) and
  *                 a_hi x w_hi as kind::f16 steps into one TMEM accumulator: two pass-equivalents instead of the three
  *                 bf16 passes of hi/lo inputs.  acc_scale[co] = 2^-(in.scale_exp + e_row) undoes the pre-scales.
+ *                 cin == 64 is accepted when the view is the whole 64-channel buffer (c_off 0, c_buf 64): the pixel's
+ *                 [lo8 | hi8] bytes are then one 128-byte K chunk and the weight bytes of a tap are
+ *                 e4m3 [hi8 x 64 | lo8 x 64], all taps, followed by fp16 hi [tap][64].
  *                 3x3 / UP2 kinds only (no 7x7 schemes, no fold). */
 int eamm_conv_tc(const eamm_conv_args* args, void* stream);
 

@@ -269,6 +269,28 @@ def test_mixed_fp16_fp8_operand_format_reproduces_the_conv_on_cpu():
     err_main = ((main - want).abs() / scale).max().item()
     err_full = ((main + cross - want).abs() / scale).max().item()
     assert err_full <= 3e-5 and err_main >= 5 * err_full, (err_main, err_full)
+    # cin == 64: one fp8 chunk per tap holds both cross terms -- weight bytes [w_hi8 x 64 | w_lo8 x 64] meet the pixel's
+    # plane 1 = [a_lo8 x 64 | a_hi8 x 64]
+    full64 = full[:, :, :64].contiguous()
+    p64, e64 = engine.pack_tc_weights_mix(full64, 1)
+    assert p64.shape == (cout, 9 * 64 * 4)
+    x8 = p64[:, :9 * 128].contiguous().view(torch.float8_e4m3fn).float().view(cout, 9, 128)
+    f16 = p64[:, 9 * 128:].contiguous().view(torch.float16).float().view(cout, 9, 64)
+    buf64 = engine.ActBuf(N, H, W, 64, "mix", torch.device("cpu"))
+    buf64.store_float(x[..., :64].contiguous(), exp=in_exp)
+    a_hi, a_lo8, a_hi8 = _decode_mix_act(buf64)
+    plane1 = buf64.t[..., 64:].contiguous().view(torch.uint8).view(torch.float8_e4m3fn).float()       # [.., 128] as the TMA box sees it
+    assert torch.equal(plane1[..., :64], a_lo8) and torch.equal(plane1[..., 64:], a_hi8)
+
+    def conv_k(a, wt, k):
+        wk = wt.view(cout, 3, 3, k).permute(0, 3, 1, 2).double()
+        return F.conv2d(a.permute(0, 3, 1, 2).double(), wk, padding=1)
+
+    sc64 = torch.exp2(-(e64.float() + in_exp)).view(1, cout, 1, 1).double()
+    got64 = (conv_k(plane1, x8, 128) + conv_k(a_hi, f16, 64)) * sc64
+    want64 = F.conv2d(x[..., :64].permute(0, 3, 1, 2).double(), w[:, :64].double(), padding=1)
+    s64 = want64.abs().amax(dim=(0, 2, 3), keepdim=True)
+    assert ((got64 - want64).abs() / s64).max().item() <= 3e-5
 
 
 def test_numpy_sampler_matches_torch_grid_sample_and_corner_values():

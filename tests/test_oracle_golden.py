@@ -10,7 +10,10 @@ from oracle import eamm_oracle as oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
-CASES = [("tiny_b2", "tiny", True), ("tiny_b3_nojac", "tiny", True), ("full_b2", "full", False),
+CASES = [("tiny_b2", "tiny", True), ("tiny_b3_nojac", "tiny", True),
+         # constructor corners (flow/occlusion resize, no anti-alias module, no dense-motion network)
+         ("tiny_sf05_b2", "tiny_sf05", True), ("tiny_sf1_b2", "tiny_sf1", True), ("tiny_nodm_b2", "tiny_nodm", True),
+         ("full_b2", "full", False),
          ("full_b3_shared", "full", False),
          ("full_b16_shared", "full", False)]       # BASELINE.json configs[0]: one source + 16 kp/jacobian frames
 
@@ -38,7 +41,10 @@ def test_oracle_reproduces_reference_golden(name, cfg_name, full):
     chk = np.array([src.double().sum(), kpd["value"].double().sum(), kps["value"].double().sum()])
     np.testing.assert_allclose(chk, blob["in_checksum"], rtol=0, atol=0)      # seeded inputs are reproducible
     got = oracle.generator_forward(sd, cfg, src, kpd, kps)
-    got["deformation"] = oracle.dense_motion_forward(sd, cfg, src, kpd, kps)["deformation"]
+    if cfg.get("dense_motion_params") is not None:
+        got["deformation"] = oracle.dense_motion_forward(sd, cfg, src, kpd, kps)["deformation"]
+    else:
+        assert set(got) == {"prediction"}                                     # generator.py:66-95 without a motion network
     for k, v in got.items():
         a = v.numpy()
         # same torch build on both boxes -> bit-exact; the tolerance only absorbs a different BLAS thread split

@@ -86,6 +86,9 @@ CASES = [
     ("mix up2 256->128 32x32 N=4 relu", "up2", "r", 256, 128, 4, 32, 32, 4, 0, 0, ""),
     ("mix 3x3 128->256 128x128 N=2 pool", "3x3", "rp", 128, 256, 2, 128, 128, 4, 0, 0, ""),
     ("mix splitk 3x3 1024->1024 4x4 N=32 pool", "3x3", "rp", 1024, 1024, 32, 4, 4, 4, 0, 0, ""),
+    ("mix64 3x3 64->128 64x64 N=3 pool", "3x3", "rp", 64, 128, 3, 64, 64, 4, 0, 0, ""),
+    ("mix64 cta2 3x3 64->128 256x256 N=2 pool", "3x3", "rp", 64, 128, 2, 256, 256, 4, 0, 0, ""),
+    ("mix64 up2 64->64 32x32 N=2 relu", "up2", "r", 64, 64, 2, 32, 32, 4, 0, 0, ""),
 ]
 
 

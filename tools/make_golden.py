@@ -42,17 +42,20 @@ def run_case(name, cfg_name, batch, size, with_jacobian=True, shared_source=Fals
     assert not missing.missing_keys and not missing.unexpected_keys
     src, kpd, kps = synth.make_inputs(batch, cfg, size=size, seed=1, with_jacobian=with_jacobian,
                                       shared_source=shared_source)
+    has_dm = ref.dense_motion_network is not None
     with torch.no_grad():
         want = ref(src, kp_driving=kpd, kp_source=kps)
-        want_dm = ref.dense_motion_network(source_image=src, kp_driving=kpd, kp_source=kps)
+        want_dm = ref.dense_motion_network(source_image=src, kp_driving=kpd, kp_source=kps) if has_dm else {}
     got = oracle.generator_forward(sd, cfg, src, kpd, kps)
-    got_dm = oracle.dense_motion_forward(sd, cfg, src, kpd, kps)
-    for k in KEYS:
+    got_dm = oracle.dense_motion_forward(sd, cfg, src, kpd, kps) if has_dm else {}
+    assert set(want) == set(got), (sorted(want), sorted(got))
+    for k in want:
         assert torch.equal(want[k], got[k]), f"{name}: oracle != reference on {k}"
-    for k in ["deformation", "mask", "occlusion_map", "sparse_deformed"]:
+    for k in want_dm:
         assert torch.equal(want_dm[k], got_dm[k]), f"{name}: oracle != reference on dense_motion.{k}"
     want = dict(want)
-    want["deformation"] = want_dm["deformation"]
+    if has_dm:
+        want["deformation"] = want_dm["deformation"]
     blob = {"meta": np.array([batch, size, int(with_jacobian), int(shared_source)], dtype=np.int64)}
     blob["in_checksum"] = np.array([src.double().sum(), kpd["value"].double().sum(), kps["value"].double().sum()])
     for k, v in want.items():
@@ -281,7 +284,10 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     only = sys.argv[1:]
     if only:                                   # python tools/make_golden.py natural_b4 ...  (regenerate selected fixtures)
-        table = {"natural_b4": lambda: run_natural_case("natural_b4"), "clip_lrw_t300": lambda: run_clip_case("clip_lrw_t300")}
+        table = {"natural_b4": lambda: run_natural_case("natural_b4"), "clip_lrw_t300": lambda: run_clip_case("clip_lrw_t300"),
+                 "tiny_sf05_b2": lambda: run_case("tiny_sf05_b2", "tiny_sf05", 2, 64),
+                 "tiny_sf1_b2": lambda: run_case("tiny_sf1_b2", "tiny_sf1", 2, 64),
+                 "tiny_nodm_b2": lambda: run_case("tiny_nodm_b2", "tiny_nodm", 2, 64)}
         for nm in only:
             table[nm]()
         sys.exit(0)
@@ -289,6 +295,10 @@ if __name__ == "__main__":
     run_clip_case("clip_lrw_t300")
     run_case("tiny_b2", "tiny", 2, 64)
     run_case("tiny_b3_nojac", "tiny", 3, 64, with_jacobian=False)
+    # constructor corners no shipped config uses: flow / occlusion resize, no anti-alias module, no dense-motion network
+    run_case("tiny_sf05_b2", "tiny_sf05", 2, 64)
+    run_case("tiny_sf1_b2", "tiny_sf1", 2, 64)
+    run_case("tiny_nodm_b2", "tiny_nodm", 2, 64)
     run_case("full_b2", "full", 2, 256, full=False)
     run_case("full_b3_shared", "full", 3, 256, shared_source=True, full=False)
     # BASELINE.json configs[0]: one 256x256 source + 16 synthetic kp/jacobian frames
