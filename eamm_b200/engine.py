@@ -886,9 +886,11 @@ class GeneratorEngine:
         self.mixed = precision == "fp32" and self.impl == "tc3" and os.environ.get("EAMM_B200_MIX", "1") != "0"
         # EAMM_B200_MIX=res: only the bottleneck ResBlocks (the first cut); default: every eligible layer
         self.mix_scope = os.environ.get("EAMM_B200_MIX", "1")
+        # EAMM_B200_MIX_SKIP: comma list of layer groups kept on the 3-pass bf16 scheme (hg, down, enc0, res, up): A/B tool
+        self.mix_skip = set(filter(None, os.environ.get("EAMM_B200_MIX_SKIP", "").split(",")))
         self.calib = MixCalib() if self.mixed else None
         self.dm = DenseMotionEngine(module.dense_motion_network, precision,
-                                    calib=self.calib if self.mix_scope != "res" else None) \
+                                    calib=self.calib if (self.mix_scope != "res" and "hg" not in self.mix_skip) else None) \
             if module.dense_motion_network is not None else None
         self._pack()
         if self.mixed:
@@ -917,18 +919,21 @@ class GeneratorEngine:
         ru = lambda c: _round_up(c, ca)
         co = lambda c: _round_up(c, na)
         c_bott = ru(blocks[0].conv1.in_channels) if blocks else 0
-        res_mix = self.mixed and bool(blocks) and c_bott % 128 == 0 and co(c_bott) % 32 == 0
+        skip = self.mix_skip
+        res_mix = self.mixed and bool(blocks) and c_bott % 128 == 0 and co(c_bott) % 32 == 0 and "res" not in skip
         self.enc_mix = [False] * (nd + 1)
         # `first`'s output: a 64-channel buffer read whole by down0 (the cin == 64 variant of the mixed scheme)
         c0 = ru(m.first.conv.out_channels)
         self.enc_mix[0] = (wide and self.first_packed and nd > 0 and c0 == 64 and ru(m.down_blocks[0].conv.in_channels) == 64 and
-                           os.environ.get("EAMM_B200_MIX64", "1") != "0")
+                           co(m.first.conv.out_channels) % 32 == 0 and os.environ.get("EAMM_B200_MIX64", "1") != "0" and
+                           "enc0" not in skip)
         for i in range(1, nd + 1):
             cons_ok = ru(m.down_blocks[i].conv.in_channels) % 128 == 0 if i < nd else (self.dm is not None)
-            self.enc_mix[i] = wide and cons_ok and co(m.down_blocks[i - 1].conv.out_channels) % 32 == 0
-        self.xf_mix = wide and res_mix and nd > 0 and ru(m.up_blocks[0].conv.in_channels) % 128 == 0
+            self.enc_mix[i] = (wide and cons_ok and co(m.down_blocks[i - 1].conv.out_channels) % 32 == 0 and
+                               not (i < nd and "down" in skip))
+        self.xf_mix = wide and res_mix and nd > 0 and ru(m.up_blocks[0].conv.in_channels) % 128 == 0 and "up" not in skip
         self.dec_mix = [wide and i + 1 < nd and ru(m.up_blocks[i + 1].conv.in_channels) % 128 == 0 and
-                        co(m.up_blocks[i].conv.out_channels) % 32 == 0 for i in range(nd)]
+                        co(m.up_blocks[i].conv.out_channels) % 32 == 0 and "up" not in skip for i in range(nd)]
         if self.mixed:
             for i in range(0, nd + 1):
                 if self.enc_mix[i]:
