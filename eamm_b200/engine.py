@@ -889,8 +889,11 @@ class GeneratorEngine:
         # EAMM_B200_MIX_SKIP: comma list of layer groups kept on the 3-pass bf16 scheme (hg, down, enc0, res, up): A/B tool
         self.mix_skip = set(filter(None, os.environ.get("EAMM_B200_MIX_SKIP", "").split(",")))
         self.calib = MixCalib() if self.mixed else None
-        self.dm = DenseMotionEngine(module.dense_motion_network, precision,
-                                    calib=self.calib if (self.mix_scope != "res" and "hg" not in self.mix_skip) else None) \
+        # The dense-motion Hourglass stays on the 3-pass bf16 scheme unless EAMM_B200_MIX_HG=1: measured on B200
+        # (profiles/r2_mix_error_by_scope.txt) the mixed scheme there is what moves the flow-sensitive outputs
+        # (512 px B=1: prediction 1.30e-4 vs 5.7e-5, deformed 3.9e-3 vs 2.4e-3) for 0.13 ms of a 6.6 ms step.
+        hg_mix = os.environ.get("EAMM_B200_MIX_HG", "0") == "1" and self.mix_scope != "res" and "hg" not in self.mix_skip
+        self.dm = DenseMotionEngine(module.dense_motion_network, precision, calib=self.calib if hg_mix else None) \
             if module.dense_motion_network is not None else None
         self._pack()
         if self.mixed:

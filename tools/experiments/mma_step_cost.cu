@@ -35,12 +35,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 
-// mode: 0 = all f16, 1 = all f8, 2 = alternate every 4 steps (chunk-wise), 3 = f8 for the first half then f16,
-//       4 = f16 with two independent accumulators (TMEM columns 0 and 256) alternating step by step: are back-to-back
-//           steps into ONE accumulator latency-bound (dependent chain) rather than throughput-bound?
-//       5 = f16, alternating accumulators per 4-step chunk
-template <int CG>
-__global__ void __launch_bounds__(128, 1) step_kernel(int N, int mode, int steps, long long* out) {
+// MODE: 0 = all f16, 1 = all f8, 2 = kinds alternate every 4-step chunk, 4 = f16 with two independent accumulators (TMEM
+// columns 0 / 256) alternating step by step, 5 = the same alternating per chunk.  The issue loop is fully unrolled over
+// 16 steps (4 ring stages x 4 K slices) with every descriptor precomputed in registers, so the elected thread spends
+// ~2 instructions per MMA: what is measured is the tensor core's step time, not the issue overhead.
+// (A first version of this tool computed descriptors inside the loop and measured ~215 cycles for EVERY shape: a lone
+// thread retires a dependent instruction every ~10 cycles, i.e. it was issue-bound -- which is itself the lesson for
+// conv_tc.cu's narrow-N layers.)
+template <int CG, int MODE>
+__global__ void __launch_bounds__(128, 1) step_kernel(int N, int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_smem;
@@ -69,19 +72,25 @@ __global__ void __launch_bounds__(128, 1) step_kernel(int N, int mode, int steps
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_smem;
   if (threadIdx.x == 0 && rank == 0) {
-    const uint32_t idesc16 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((CG == 2 ? 256 : 128) >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((CG == 2 ? 256 : 128) >> 4) << 24);
+    uint64_t da[16], db[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      da[j] = make_sw128_desc(base + (j >> 2) * 48 * 1024) + 2 * (j & 3);             // A: 16 KB, B: up to 32 KB per stage
+      db[j] = make_sw128_desc(base + (j >> 2) * 48 * 1024 + 16 * 1024) + 2 * (j & 3);
+    }
+    mma<CG, 0>(tmem, da[0], db[0], idesc, 0u);
+    mma<CG, 0>(tmem + 256u, da[0], db[0], idesc, 0u);
     const long long t0 = clock64();
-    for (int s = 0; s < steps; ++s) {
-      const int stage = (s >> 2) & 3, k = s & 3;
-      const uint64_t da = make_sw128_desc(base + stage * 48 * 1024) + 2 * k;            // A: 16 KB, B: up to 32 KB per stage
-      const uint64_t db = make_sw128_desc(base + stage * 48 * 1024 + 16 * 1024) + 2 * k;
-      const int chunk = s >> 2;
-      const bool f8 = mode == 1 || (mode == 2 && (chunk & 1)) || (mode == 3 && s < steps / 2);
-      const uint32_t acc_sel = mode == 4 ? (uint32_t)(s & 1) : (mode == 5 ? (uint32_t)(chunk & 1) : 0u);
-      const uint32_t d = tmem + acc_sel * 256u;
-      const uint32_t accum = (mode >= 4 ? s >= 8 : s > 0) ? 1u : 0u;
-      if (f8) mma<CG, 1>(d, da, db, idesc16, accum);
-      else mma<CG, 0>(d, da, db, idesc16, accum);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const bool f8 = MODE == 1 || (MODE == 2 && ((j >> 2) & 1));
+        const uint32_t d = tmem + ((MODE == 4 ? (j & 1) : (MODE == 5 ? ((j >> 2) & 1) : 0)) ? 256u : 0u);
+        if (f8) mma<CG, 1>(d, da[j], db[j], idesc, 1u);
+        else mma<CG, 0>(d, da[j], db[j], idesc, 1u);
+      }
     }
     if (CG == 2) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "h"((uint16_t)1) : "memory");
     else asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -98,24 +107,31 @@ __global__ void __launch_bounds__(128, 1) step_kernel(int N, int mode, int steps
   }
 }
 
-template <int CG>
-static void run(int N, int mode, int grid, long long* d_out) {
-  const int steps = 4096, smem = 4 * 48 * 1024 + 1024;
-  cudaFuncSetAttribute(step_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <int CG, int MODE>
+static void run(int N, int grid, long long* d_out) {
+  const int iters = 256, smem = 4 * 48 * 1024 + 1024;
+  cudaFuncSetAttribute(step_kernel<CG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, step_kernel<CG>, N, mode, steps, d_out);
+  for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, step_kernel<CG, MODE>, N, iters, d_out);
   cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { printf("CG=%d N=%d mode=%d: CUDA error %s\n", CG, N, mode, cudaGetErrorString(e)); return; }
+  if (e != cudaSuccess) { printf("CG=%d N=%d mode=%d: CUDA error %s\n", CG, N, MODE, cudaGetErrorString(e)); return; }
   long long h[2] = {0, 0};
   cudaMemcpy(h, d_out, sizeof(long long) * (CG == 2 ? 2 : 1), cudaMemcpyDeviceToHost);
-  const char* names[6] = {"f16 K=16", "f8 K=32", "alternating kinds per 4-step chunk", "f8 half then f16 half",
+  const char* names[6] = {"f16 K=16", "f8 K=32", "alternating kinds per 4-step chunk", "-",
                           "f16, 2 accumulators per step", "f16, 2 accumulators per chunk"};
-  printf("cta_group::%d grid %3d M=%d N=%3d %-36s %7.1f cycles/step\n", CG, grid, CG == 2 ? 256 : 128, N, names[mode], (double)h[0] / steps);
+  printf("cta_group::%d grid %3d M=%d N=%3d %-36s %7.1f cycles/step\n", CG, grid, CG == 2 ? 256 : 128, N, names[MODE],
+         (double)h[0] / (iters * 16.0));
+}
+
+template <int CG>
+static void run_all(int N, int grid, long long* d_out) {
+  run<CG, 0>(N, grid, d_out); run<CG, 1>(N, grid, d_out); run<CG, 2>(N, grid, d_out);
+  if (N <= 256) { run<CG, 4>(N, grid, d_out); run<CG, 5>(N, grid, d_out); }
 }
 
 int main() {
@@ -123,10 +139,8 @@ int main() {
   cudaMalloc(&d_out, 1024 * sizeof(long long));
   cudaMemset(d_out, 0, 1024 * sizeof(long long));
   for (int grid : {1, 148}) {
-    for (int N : {64, 128, 256})
-      for (int mode = 0; mode < 6; ++mode) run<1>(N, mode, grid, d_out);
-    for (int N : {64, 128, 256})
-      for (int mode = 0; mode < 6; ++mode) run<2>(N, mode, grid == 1 ? 2 : 148, d_out);
+    for (int N : {16, 32, 64, 128, 256}) run_all<1>(N, grid, d_out);
+    for (int N : {32, 64, 128, 256}) run_all<2>(N, grid == 1 ? 2 : 148, d_out);
   }
   return 0;
 }

@@ -17,8 +17,8 @@ from oracle import eamm_oracle as oracle                                   # noq
 
 VARIANTS = [("bf16x3 (MIX=0)", {"EAMM_B200_MIX": "0"}),
             ("bottleneck only (MIX=res)", {"EAMM_B200_MIX": "res"}),
-            ("all eligible layers", {"EAMM_B200_MIX": "1"}),
-            ("all but hourglass", {"EAMM_B200_MIX": "1", "EAMM_B200_MIX_SKIP": "hg"}),
+            ("all eligible layers", {"EAMM_B200_MIX": "1", "EAMM_B200_MIX_HG": "1"}),
+            ("all but hourglass (default)", {"EAMM_B200_MIX": "1"}),
             ("all but decoder", {"EAMM_B200_MIX": "1", "EAMM_B200_MIX_SKIP": "up"}),
             ("all but encoder", {"EAMM_B200_MIX": "1", "EAMM_B200_MIX_SKIP": "down,enc0", "EAMM_B200_MIX64": "0"})]
 CASES = [(256, 8, 7), (512, 1, 562), (512, 2, 11), (128, 3, 178)]
@@ -36,7 +36,7 @@ def main():
         wants[(size, batch)] = oracle.generator_forward(sd, cfg, *inputs[(size, batch)])
     print("%-28s %-12s" % ("variant", "case") + "".join("%14s" % k for k in KEYS))
     for name, env in VARIANTS:
-        for k in ("EAMM_B200_MIX", "EAMM_B200_MIX64", "EAMM_B200_MIX_SKIP"):
+        for k in ("EAMM_B200_MIX", "EAMM_B200_MIX64", "EAMM_B200_MIX_SKIP", "EAMM_B200_MIX_HG"):
             os.environ.pop(k, None)
         os.environ.update(env)
         gen = OcclusionAwareGenerator(**cfg).eval()
