@@ -106,6 +106,7 @@ struct ConvTcParams {
   const float* bias; const float* scale2; const float* shift2;
   float* out_nchw; int out_nchw_c; float* out_nhwc; unsigned char* out_u8;
   long long total_tiles;
+  int lean;            // the specialised MMA issue loop (mma_issuer_lean); 0 = the generic loop (EAMM_TC_LEAN=0, halo, pf_wide, INSTR)
   int f16in;           // the A/B operands are fp16 (EAMM_F16 input): tensor-map coordinates are BYTES (uint8 maps)
   int mix;             // EAMM_F16 two-plane input: K loop = [a_hi8 x w_lo8 | a_lo8 x w_hi8] as kind::f8f6f4 steps over 128-channel
                        // chunks (n8 = ntap * cin/128 chunks each), then a_hi x w_hi as kind::f16 steps over 64-channel chunks
@@ -234,6 +235,34 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// The same descriptor from a pre-shifted address (smem byte address >> 4; the ring lives below 256 KB, so no masking):
+// what the lean MMA issuer keeps as running 32-bit counters instead of re-deriving descriptors from byte addresses.
+constexpr uint64_t SW128_DESC_BITS = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t sw128_desc16(uint32_t addr16) { return SW128_DESC_BITS | (uint64_t)addr16; }
+
+// One operand chunk (128-byte rows) = four K slices 32 bytes apart: K = 16 per kind::f16 step, K = 32 per kind::f8f6f4 step.
+// `acc` = 0 overwrites the accumulator with the first slice (first chunk of a tile).
+template <bool CTA2, bool F8>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem_acc, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (CTA2) {
+    if (F8) {
+      tc2_mma_f8(tmem_acc, da, db, idesc, acc); tc2_mma_f8(tmem_acc, da + 2, db + 2, idesc, 1u);
+      tc2_mma_f8(tmem_acc, da + 4, db + 4, idesc, 1u); tc2_mma_f8(tmem_acc, da + 6, db + 6, idesc, 1u);
+    } else {
+      tc2_mma_bf16(tmem_acc, da, db, idesc, acc); tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+      tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u); tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+    }
+  } else {
+    if (F8) {
+      tc_mma_f8(tmem_acc, da, db, idesc, acc); tc_mma_f8(tmem_acc, da + 2, db + 2, idesc, 1u);
+      tc_mma_f8(tmem_acc, da + 4, db + 4, idesc, 1u); tc_mma_f8(tmem_acc, da + 6, db + 6, idesc, 1u);
+    } else {
+      tc_mma_bf16(tmem_acc, da, db, idesc, acc); tc_mma_bf16(tmem_acc, da + 2, db + 2, idesc, 1u);
+      tc_mma_bf16(tmem_acc, da + 4, db + 4, idesc, 1u); tc_mma_bf16(tmem_acc, da + 6, db + 6, idesc, 1u);
+    }
+  }
 }
 
 template <int CH> struct TmemLd;
@@ -436,6 +465,82 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
   q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.y_stride; tile = q;
   t.n0 = (int)tile * p.bn;
   return t;
+}
+
+// The MMA-issuing warp of the production kernel.  What the tensor core needs per K step is short (measured with
+// tools/experiments/mma_step_cost.cu on B200: 128 cycles at N = 256, 64 at N = 128, <= 48 at N <= 64, the same for
+// kind::f16 K = 16 and kind::f8f6f4 K = 32, single CTA or pair, no penalty for alternating kinds), while one lane
+// retires a dependent instruction only every ~8-10 cycles: the issue loop, not the MMA, set the ~110-cycle floor per
+// step of the narrow layers and the 166-200 cycles of the N = 256 ones.  So this loop is specialised at compile time
+// (MODE) instead of branching per chunk, keeps every parameter in registers (no constant-bank reloads) and walks the
+// ring with running pre-shifted descriptor counters.
+//   MODE 0  every chunk one step group with `idesc` (plain layers; fold 2 = packed first conv with N = 2*BN)
+//   MODE 1  mixed fp16 + fp8 operands: chunks [0, nf8) of the K range are kind::f8f6f4, the rest kind::f16
+//   MODE 2  fold 1, single CTA: type-0 chunks (kc == 0 or kc > T) are one N = 2*BN group, type-1 chunks one N = BN group
+//   MODE 3  fold 1, CTA pair: type-0 chunks are two N = BN groups (b_hi halves -> columns [0, BN), b_lo halves -> [BN, 2BN))
+template <bool CTA2, int MODE>
+__device__ __forceinline__ void mma_issuer_lean(const ConvTcParams& p, uint32_t smem_base, uint32_t bar0, uint32_t tmem_base,
+                                                uint32_t KC, uint32_t KS, uint32_t a_slot, uint32_t b_bytes, uint32_t b_half,
+                                                uint32_t tile0, uint32_t tile_step, uint32_t total_tiles) {
+  const uint32_t fmt = p.f16in ? 0u : ((1u << 7) | (1u << 10));
+  const uint32_t mbits = ((CTA2 ? 256u : 128u) >> 4) << 24;
+  uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 3) << 17) | mbits;
+  uint32_t idesc2 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 2) << 17) | mbits;          // N = 2*BN
+  if (MODE == 0 && p.fold == 2) idesc1 = idesc2;
+  uint32_t nstages = (uint32_t)p.num_stages, nf8 = (uint32_t)p.nf8, BN = (uint32_t)p.BN, splitk = (uint32_t)p.splitk;
+  const uint32_t T = KC >> 1;
+  uint32_t slotA16 = a_slot >> 4, slotB16 = b_bytes >> 4, bofs16 = (KS * a_slot) >> 4, bhalf16 = b_half >> 4;
+  uint32_t stage16 = (KS * (a_slot + b_bytes)) >> 4, base16 = smem_base >> 4;
+  // opaque copies: keep ptxas from re-reading the kernel parameters (constant bank) inside the loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(idesc1)); asm volatile("mov.u32 %0, %0;" : "+r"(idesc2));
+  asm volatile("mov.u32 %0, %0;" : "+r"(nstages)); asm volatile("mov.u32 %0, %0;" : "+r"(nf8));
+  asm volatile("mov.u32 %0, %0;" : "+r"(slotA16)); asm volatile("mov.u32 %0, %0;" : "+r"(slotB16));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bofs16)); asm volatile("mov.u32 %0, %0;" : "+r"(stage16));
+  asm volatile("mov.u32 %0, %0;" : "+r"(KS)); asm volatile("mov.u32 %0, %0;" : "+r"(KC));
+  uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+  uint32_t sa16 = base16, fb = bar0, eb = bar0 + 8u * 16u;
+  for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
+    mbar_wait(bar0 + 8u * (34u + as), aphase ^ 1u);                       // accumulator `as` drained by the epilogue
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + as * 256u;
+    const uint32_t tfull = bar0 + 8u * (32u + as);
+    // mixed operands under split-K: this work item's K range starts at chunk kbase of the whole K loop
+    uint32_t nf = 0;
+    if (MODE == 1) {
+      const uint32_t kbase = splitk > 1u ? (uint32_t)decode_tile(p, tile).split * KC : 0u;
+      nf = nf8 > kbase ? nf8 - kbase : 0u;                                // chunks [0, nf) of this item are fp8
+    }
+    for (uint32_t kc = 0; kc < KC; kc += KS) {
+      const uint32_t nsub = KC - kc < KS ? KC - kc : KS;
+      mbar_wait(fb, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        uint32_t a16 = sa16, b16 = sa16 + bofs16;
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < nsub; ++sub, a16 += slotA16, b16 += slotB16) {
+          const uint32_t kcs = kc + sub;
+          const uint64_t da = sw128_desc16(a16), db = sw128_desc16(b16);
+          const uint32_t acc = kcs ? 1u : 0u;
+          if (MODE == 0) issue_chunk<CTA2, false>(tmem_acc, da, db, idesc1, acc);
+          if (MODE == 1) {
+            if (kcs < nf) issue_chunk<CTA2, true>(tmem_acc, da, db, idesc1, acc);
+            else issue_chunk<CTA2, false>(tmem_acc, da, db, idesc1, acc);
+          }
+          if (MODE == 2) issue_chunk<CTA2, false>(tmem_acc, da, db, (kcs == 0u || kcs > T) ? idesc2 : idesc1, acc);
+          if (MODE == 3) {
+            issue_chunk<CTA2, false>(tmem_acc, da, db, idesc1, acc);
+            if (kcs == 0u || kcs > T) issue_chunk<CTA2, false>(tmem_acc + BN, da, db + (uint64_t)bhalf16, idesc1, acc);
+          }
+        }
+        if (CTA2) { tc2_commit_mc(eb); if (kc + KS >= KC) tc2_commit_mc(tfull); }
+        else { tc_commit(eb); if (kc + KS >= KC) tc_commit(tfull); }
+      }
+      __syncwarp();
+      ++stage; sa16 += stage16; fb += 8u; eb += 8u;
+      if (stage == nstages) { stage = 0; phase ^= 1u; sa16 = base16; fb = bar0; eb = bar0 + 8u * 16u; }
+    }
+    as ^= 1u; if (as == 0u) aphase ^= 1u;
+  }
 }
 
 // Epilogue for one accumulator tile, CH columns at a time.
@@ -933,6 +1038,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == TC_MMA_WARP && (!CTA2 || cta_rank == 0u)) {
     // ================================================================ MMA issuer (leader CTA of a pair)
+    if (!INSTR && p.lean) {
+      if (p.mix) mma_issuer_lean<CTA2, 1>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
+      else if (fold == 1u && CTA2) mma_issuer_lean<CTA2, 3>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
+      else if (fold == 1u) mma_issuer_lean<CTA2, 2>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
+      else mma_issuer_lean<CTA2, 0>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
+    } else {
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
     // (a/b format code 0 is F16 under kind::f16 and E4M3 under kind::f8f6f4: fp16 and mixed inputs use one descriptor for both)
     const uint32_t fmt = p.f16in ? 0u : ((1u << 7) | (1u << 10));
@@ -1035,6 +1146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.prof[blockIdx.x * 8 + 2] = pm0;                            // MMA: waiting for a free accumulator
       p.prof[blockIdx.x * 8 + 3] = pm1;                            // MMA: waiting for operands
       p.prof[blockIdx.x * 8 + 4] = clock64() - pstart;             // MMA: total
+    }
     }
   } else if (warp < TC_EPI_WARPS) {
     // ================================================================ epilogue warps (TMEM lanes by warp%4)
@@ -1402,6 +1514,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
         (!p.st256 || p.BN % 32 || views[i]->c_off % 32 || views[i]->c_buf % 32 || p.kxn))
       return EAMM_ERR_UNSUPPORTED;
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
+  static int lean_env = -1;
+  if (lean_env < 0) { const char* e = getenv("EAMM_TC_LEAN"); lean_env = e ? atoi(e) : 1; }
+  p.lean = (lean_env && !p.halo && !p.pf_wide) ? 1 : 0;
   p.mix64 = mix64 ? 1 : 0;
   p.nf8 = mix64 ? p.ntap : (mix ? p.ntap * p.cin_chunks : 0);
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
