@@ -181,7 +181,7 @@ def run_case(idx):
     plan = getattr(layer, "last_plan", ())
     if "kxw" in name and (not plan or plan[1] not in (3, 4)):
         status, worst = "BAD", float("nan")          # the scheme under test was not selected
-    if name.startswith("pfwide") and (not plan or plan[4] != 3):
+    if name.startswith("pfwide") and (not plan or (plan[4] & 0xff) != 3):
         status, worst = "BAD", float("nan")
     if "splitk" in name and planes != 4 and (not plan or (plan[4] >> 8) < 2):
         status, worst = "BAD", float("nan")
