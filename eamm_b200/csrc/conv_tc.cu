@@ -24,9 +24,12 @@
 //               split-K    layers with too few N = 256 tiles for the chip (hourglass 8x8 ... 2x2): partial tiles through
 //                          an fp32 workspace, the last-arriving CTA reduces in split order and runs the epilogue
 //               CTA pair   N tile 256 and folded layers: tcgen05.mma.cta_group::2, M = 256, half of B per CTA
+//               halo tile  3x3 / UP2 with fp16 or mixed operands on large maps: 8 x 16-pixel tiles, ONE 10 x 18 halo tile per
+//                          128-byte K chunk in shared memory, the filter taps are shifted descriptor views of it (every conv
+//                          of the step was bound by the ~12 TB/s L2 -> SM rate of re-staging the A tile per tap); weights
+//                          stream through their own ring; UP2 keeps the four parity classes of a tile in one work item
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
-//               pairs, 4 narrow unfolded pairs, 8 folded pairs with one wide N = 2*BN step (measured no faster: a pair MMA
-//               costs about twice a single-CTA one of the same N, those layers are not A-fetch bound) -- default 19; bit 4 = 16: pairs for mixed fp16+fp8 layers with N < 256),
+//               pairs, 4 narrow unfolded pairs -- default 19; bit 4 = 16: pairs for mixed fp16+fp8 layers with N < 256),
 //               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4, bit 2: compact scheme-3 epilogue buffer; default 7), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
 //               split-K / the 32-byte epilogue stores off, EAMM_TC_SPLITK_DIST = 1 selects the distributed split-K reduction
 //               (opt-in), EAMM_TC_SPLITK_MAX caps the split factor (9), EAMM_TC_BNCOST = 0 restores the older N-tile rule,
@@ -92,9 +95,6 @@ struct ConvTcParams {
                        // (packed `first` conv: both activation planes already sit in one K window).
   int b_rows_total;    // rows of one weight plane block (classes * cout): the lo block starts there
   int cta2;            // CTA pairs with cta_group::2 MMAs (tiles 2i, 2i+1 = adjacent M tiles of one class / N tile)
-  int pf_wide;         // folded pairs: a type-0 chunk is ONE N = 2*BN step.  CTA 0 stages all BN rows of b_hi, CTA 1 all
-                       // BN rows of b_lo (a pair MMA takes B rows [0, N/2) from CTA 0 and [N/2, N) from CTA 1), so the
-                       // accumulator columns are [hi | lo] as in the single-CTA kernel and A is fetched once, not twice
   int ksub;            // 64-channel K chunks per pipeline stage (1..4)
   int chunk_shift;     // log2(cin_chunks) (cin/64 is a power of two for every layer of the path)
   int debug;           // EAMM_TC_DEBUG: 1 = no TMA (MMA side alone), 2 = no MMA (TMA side alone); timing only
@@ -106,13 +106,22 @@ struct ConvTcParams {
   const float* bias; const float* scale2; const float* shift2;
   float* out_nchw; int out_nchw_c; float* out_nhwc; unsigned char* out_u8;
   long long total_tiles;
-  int lean;            // the specialised MMA issue loop (mma_issuer_lean); 0 = the generic loop (EAMM_TC_LEAN=0, halo, pf_wide, INSTR)
+  int lean;            // the specialised MMA issue loop (mma_issuer_lean); 0 = the generic loop (EAMM_TC_LEAN=0, halo, INSTR)
   int f16in;           // the A/B operands are fp16 (EAMM_F16 input): tensor-map coordinates are BYTES (uint8 maps)
   int mix;             // EAMM_F16 two-plane input: K loop = [a_hi8 x w_lo8 | a_lo8 x w_hi8] as kind::f8f6f4 steps over 128-channel
                        // chunks (n8 = ntap * cin/128 chunks each), then a_hi x w_hi as kind::f16 steps over 64-channel chunks
   int nf8;             // mix: fp8 chunks at the head of the K loop (2 * ntap * cin/128, or ntap for mix64)
   int mix64;           // mix with cin == c_buf == 64: plane 1 of a pixel, [lo8 x 64 | hi8 x 64], is ONE 128-byte K chunk that
                        // meets the weight row [w_hi8 x 64 | w_lo8 x 64]: both cross terms in one fp8 chunk per tap
+  int ah;              // halo-tile scheme (see the header): A ring of `ah_na` slots (one 10 x 18-pixel halo tile of a 128-byte K
+                       // chunk each) + weight ring of `num_stages` stages (`ksub` taps each); tap (ty, tx) reads the view
+                       // slot + (ty * 10 + tx) * 128 B with 8-row groups (= image rows of the 8 x 16 tile) 1280 B apart
+  int ah_g;            // UP2: parity classes per work item (accumulator columns cls * BN); 1 otherwise
+  int cls_groups;      // class groups per M tile (classes / ah_g)
+  int ah_na;           // A ring slots
+  int ah_spc;          // weight stages per K chunk (= ah_g * ntap / ksub)
+  int ah_nsec;         // K sections of a tile, each {first A byte column, 128-byte chunks, kind::f8f6f4?, first weight byte column}
+  int ah_cbase[3], ah_nch[3], ah_f8[3], ah_bcol[3];
   const float* acc_scale;   // [cout] accumulator multiplier (undoes the operand pre-scales), or null
   float* amax_out; float* amax_out2;   // running max |value| of out / out2 (calibration statistic), or null
 };
@@ -170,8 +179,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) { 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Relaxed: the arrive only tells the leader's MMA warp that this warp's tcgen05.ld reads of the accumulator have completed
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it); no generic-proxy data is handed over.  A release at
+// cluster scope made the lane wait for all of its outstanding global stores first (ERRBAR + membar: 13-21 % of the warp
+// samples of down0 / up1 in profiles/r2_ncu_summary.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster,
                                              int c0, int c1, int c2, int c3) {
@@ -459,7 +472,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
   const uint32_t rank = p.cta2 ? (tile & 1u) : 0u;
   if (p.cta2) tile >>= 1;
   uint32_t q = tile / (uint32_t)p.n_tiles; t.nt = (int)(tile - q * p.n_tiles); tile = q;
-  q = tile / (uint32_t)p.classes; t.cls = (int)(tile - q * p.classes); tile = q;
+  q = tile / (uint32_t)p.cls_groups; t.cls = (int)(tile - q * p.cls_groups) * p.ah_g; tile = q;
   if (p.cta2) tile = 2u * tile + rank;
   q = tile / (uint32_t)p.tiles_x; t.x0 = (int)(tile - q * p.tiles_x) * p.x_stride; tile = q;
   q = tile / (uint32_t)p.tiles_y; t.y0 = (int)(tile - q * p.tiles_y) * p.y_stride; tile = q;
@@ -540,6 +553,164 @@ __device__ __forceinline__ void mma_issuer_lean(const ConvTcParams& p, uint32_t 
       if (stage == nstages) { stage = 0; phase ^= 1u; sa16 = base16; fb = bar0; eb = bar0 + 8u * 16u; }
     }
     as ^= 1u; if (as == 0u) aphase ^= 1u;
+  }
+}
+
+
+// ------------------------------------------------------------------------------ halo-tile scheme (ConvTcParams::ah)
+// Barriers: weight ring full/empty = bars[0..15] / [16..31] as in the plain scheme, A ring full = bars[36..39], empty = bars[40..43].
+constexpr uint32_t AH_PITCH = 10, AH_ROWS = 18, AH_A_BYTES = AH_PITCH * AH_ROWS * 128;     // 180 pixel rows of 128 bytes
+// K-major SWIZZLE_128B descriptor of a halo view: 8-row groups AH_PITCH * 128 bytes apart (tools/experiments/halo_desc.cu:
+// the swizzle is a function of the absolute shared-memory address, so neither the start nor the group stride needs 1024-byte alignment)
+constexpr uint64_t AH_DESC_BITS = ((uint64_t)1 << 16) | ((uint64_t)((AH_PITCH * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+
+// All TC_PRODUCERS warps walk every weight stage of every tile (cheap counters) and issue the ones whose running index is
+// theirs; the producer that owns the first weight stage of a K chunk also stages that chunk's halo tile.
+template <bool CTA2>
+__device__ __forceinline__ void producer_ah(const ConvTcParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                            uint32_t smem_base, uint32_t bar0, uint32_t w, uint32_t cta_rank,
+                                            uint32_t tile0, uint32_t tile_step, uint32_t total_tiles) {
+  const uint32_t KS = (uint32_t)p.ksub, NB = (uint32_t)p.num_stages, NA = (uint32_t)p.ah_na, SPC = (uint32_t)p.ah_spc;
+  const uint32_t ntap = (uint32_t)p.ntap, a_slot = (uint32_t)p.a_slot_bytes;
+  const uint32_t b_bytes = (uint32_t)p.BN * (CTA2 ? 64u : 128u);
+  const uint32_t b_base = smem_base + NA * a_slot, stage_bytes = KS * b_bytes;
+  const uint32_t a_tx = AH_A_BYTES * (CTA2 ? 2u : 1u), b_tx = stage_bytes * (CTA2 ? 2u : 1u);
+  const int nsec = p.ah_nsec, cout = p.cout;
+  uint32_t bslot = 0, bphase = 0, aslot = 0, aphase = 0, turn = 0;
+  for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
+    const TileCoord tc = decode_tile(p, tile);
+    const int brow0 = tc.nt * p.BN + (CTA2 ? (int)cta_rank * (p.BN >> 1) : 0);
+    for (int sec = 0; sec < nsec; ++sec) {
+      const uint32_t nch = (uint32_t)p.ah_nch[sec];
+      for (uint32_t cc = 0; cc < nch; ++cc) {
+        uint32_t cls_l = 0, t0 = 0;
+        for (uint32_t r = 0; r < SPC; ++r) {
+          if (turn == w) {
+            mbar_wait(bar0 + 8u * (16u + bslot), bphase ^ 1u);
+            if (r == 0u) mbar_wait(bar0 + 8u * (40u + aslot), aphase ^ 1u);
+            if (elect_one()) {
+              const uint32_t fbl = bar0 + 8u * bslot, afl = bar0 + 8u * (36u + aslot);
+              const uint32_t fb = CTA2 ? mapa_shared(fbl, 0u) : fbl, af = CTA2 ? mapa_shared(afl, 0u) : afl;
+              if (r == 0u) {
+                if (!CTA2 || cta_rank == 0u) mbar_expect_tx(afl, a_tx);
+                const int cbase = p.ah_cbase[sec] + (int)cc * 128;
+                if (CTA2) tma2_load_4d(smem_base + aslot * a_slot, tmA, af, cbase, tc.x0 - 1, tc.y0 - 1, tc.n0);
+                else tma_load_4d(smem_base + aslot * a_slot, tmA, af, cbase, tc.x0 - 1, tc.y0 - 1, tc.n0);
+              }
+              if (!CTA2 || cta_rank == 0u) mbar_expect_tx(fbl, b_tx);
+              const int brow = (tc.cls + (int)cls_l) * cout + brow0;
+              const uint32_t sB = b_base + bslot * stage_bytes;
+              for (uint32_t sub = 0; sub < KS; ++sub) {
+                const int bcol = p.ah_bcol[sec] + (int)(((t0 + sub) * nch + cc) * 128u);
+                if (CTA2) tma2_load_2d(sB + sub * b_bytes, tmB, fb, bcol, brow);
+                else tma_load_2d(sB + sub * b_bytes, tmB, fb, bcol, brow);
+              }
+            }
+            __syncwarp();
+          }
+          turn = turn + 1u == (uint32_t)TC_PRODUCERS ? 0u : turn + 1u;
+          if (++bslot == NB) { bslot = 0; bphase ^= 1u; }
+          t0 += KS;
+          if (t0 == ntap) { t0 = 0; ++cls_l; }
+        }
+        if (++aslot == NA) { aslot = 0; aphase ^= 1u; }
+      }
+    }
+  }
+}
+
+// One weight stage of the halo-tile issuer: KS taps of one parity class, fully unrolled.  KIND 0 = 3x3 (KS 3: stage = filter
+// row, KS 1: stage = tap), 1 = UP2 (KS 4: stage = class, 2: class row, 1: tap).  Every descriptor is the stage's base plus a
+// compile-time offset, so the elected lane's instructions are independent of each other (a lone lane retires a DEPENDENT
+// instruction only every ~8-10 cycles: see mma_issuer_lean).  `a16` = halo view of the stage's first tap, in 16-byte units.
+template <bool CTA2, bool F8, int KIND, int KS>
+__device__ __forceinline__ void ah_issue_stage(uint32_t acc_col, uint32_t a16, uint32_t b16, uint32_t slotB16, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int sub = 0; sub < KS; ++sub) {
+    // tap offsets inside a stage: x-adjacent taps are one pixel row (8 units) apart; UP2 KS 4 walks (0,0) (0,1) (1,0) (1,1)
+    const uint32_t toff = (KIND == 1 && KS == 4) ? (uint32_t)((sub >> 1) * (int)AH_PITCH * 8 + (sub & 1) * 8) : (uint32_t)(sub * 8);
+    const uint64_t da = AH_DESC_BITS | (uint64_t)(a16 + toff), db = sw128_desc16(b16 + (uint32_t)sub * slotB16);
+    issue_chunk<CTA2, F8>(acc_col, da, db, idesc, sub == 0 ? acc0 : 1u);
+  }
+}
+
+template <bool CTA2, int KIND, int KS>
+__device__ __forceinline__ void mma_issuer_ah(const ConvTcParams& p, uint32_t smem_base, uint32_t bar0, uint32_t tmem_base,
+                                              uint32_t tile0, uint32_t tile_step, uint32_t total_tiles) {
+  uint32_t idesc = (1u << 4) | ((uint32_t)(p.BN >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);   // fp16 / e4m3 operands: format 0
+  uint32_t NB = (uint32_t)p.num_stages, NA = (uint32_t)p.ah_na, SPC = (uint32_t)p.ah_spc, BN = (uint32_t)p.BN;
+  const uint32_t b_bytes = BN * (CTA2 ? 64u : 128u);
+  uint32_t slotA16 = (uint32_t)p.a_slot_bytes >> 4, slotB16 = b_bytes >> 4, stage16 = ((uint32_t)KS * b_bytes) >> 4;
+  uint32_t base16 = smem_base >> 4, bbase16 = (smem_base + NA * (uint32_t)p.a_slot_bytes) >> 4;
+  uint32_t nsec = (uint32_t)p.ah_nsec;
+  // per-section chunk counts and kinds packed into registers (no constant-bank reads inside the loops)
+  uint32_t nch0 = (uint32_t)p.ah_nch[0], nch1 = nsec > 1u ? (uint32_t)p.ah_nch[1] : 0u, nch2 = nsec > 2u ? (uint32_t)p.ah_nch[2] : 0u;
+  uint32_t f8mask = (p.ah_f8[0] ? 1u : 0u) | ((nsec > 1u && p.ah_f8[1]) ? 2u : 0u) | ((nsec > 2u && p.ah_f8[2]) ? 4u : 0u);
+  const uint32_t grp = (uint32_t)p.ah_g;
+  asm volatile("mov.u32 %0, %0;" : "+r"(idesc)); asm volatile("mov.u32 %0, %0;" : "+r"(NB));
+  asm volatile("mov.u32 %0, %0;" : "+r"(NA)); asm volatile("mov.u32 %0, %0;" : "+r"(SPC));
+  asm volatile("mov.u32 %0, %0;" : "+r"(slotA16)); asm volatile("mov.u32 %0, %0;" : "+r"(slotB16));
+  asm volatile("mov.u32 %0, %0;" : "+r"(stage16)); asm volatile("mov.u32 %0, %0;" : "+r"(BN));
+  asm volatile("mov.u32 %0, %0;" : "+r"(nch0)); asm volatile("mov.u32 %0, %0;" : "+r"(nch1));
+  asm volatile("mov.u32 %0, %0;" : "+r"(nch2)); asm volatile("mov.u32 %0, %0;" : "+r"(f8mask));
+  asm volatile("mov.u32 %0, %0;" : "+r"(nsec));
+  uint32_t bslot = 0, bphase = 0, aslot = 0, aphase = 0, as = 0, aphase_t = 0;
+  uint32_t a16 = base16, b16 = bbase16;
+  uint32_t fb = bar0, eb = bar0 + 8u * 16u, afb = bar0 + 8u * 36u, aeb = bar0 + 8u * 40u;
+  for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
+    // UP2: halo offset of the item's first class (classes cls0 .. cls0 + grp - 1; grp 4 -> 0, grp 2 -> class row, grp 1 -> class)
+    uint32_t cls0 = 0;
+    if (KIND == 1 && grp < 4u) cls0 = (uint32_t)decode_tile(p, tile).cls;
+    mbar_wait(bar0 + 8u * (34u + as), aphase_t ^ 1u);                       // accumulator `as` drained by the epilogue
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + as * 256u;
+    const uint32_t tfull = bar0 + 8u * (32u + as);
+    uint32_t fresh = 0u;                                                    // 0 on the first K chunk: a class's first tap overwrites
+    for (uint32_t sec = 0; sec < nsec; ++sec) {
+      const uint32_t nch = sec == 0u ? nch0 : (sec == 1u ? nch1 : nch2);
+      const bool f8 = (f8mask >> sec) & 1u;
+      const bool last_sec = sec + 1u == nsec;
+      for (uint32_t cc = 0; cc < nch; ++cc) {
+        const bool last_chunk = last_sec && cc + 1u == nch;
+        // stage walk state: 3x3 -> (row offset, x) ; UP2 -> (class, tap)
+        uint32_t soff = 0, sx = 0, cls_l = 0;
+        for (uint32_t r = 0; r < SPC; ++r) {
+          // this stage's first-tap view and accumulate flag, computed before the waits
+          uint32_t va16, acc0, acc_col;
+          if (KIND == 0) { va16 = a16 + soff; acc0 = fresh | r; acc_col = tmem_acc; }
+          else {
+            const uint32_t c = cls0 + cls_l;
+            va16 = a16 + ((c >> 1) * AH_PITCH + (c & 1u)) * 8u + soff;
+            acc0 = fresh | sx; acc_col = tmem_acc + cls_l * BN;
+          }
+          mbar_wait(fb, bphase);
+          if (r == 0u) mbar_wait(afb, aphase);
+          tc_fence_after();
+          if (elect_one()) {
+            if (f8) ah_issue_stage<CTA2, true, KIND, KS>(acc_col, va16, b16, slotB16, idesc, acc0);
+            else ah_issue_stage<CTA2, false, KIND, KS>(acc_col, va16, b16, slotB16, idesc, acc0);
+            const bool last_r = r + 1u == SPC;
+            if (CTA2) { tc2_commit_mc(eb); if (last_r) { tc2_commit_mc(aeb); if (last_chunk) tc2_commit_mc(tfull); } }
+            else { tc_commit(eb); if (last_r) { tc_commit(aeb); if (last_chunk) tc_commit(tfull); } }
+          }
+          __syncwarp();
+          b16 += stage16; fb += 8u; eb += 8u;
+          if (++bslot == NB) { bslot = 0; bphase ^= 1u; b16 = bbase16; fb = bar0; eb = bar0 + 8u * 16u; }
+          if (KIND == 0) {
+            if (KS == 3) soff += AH_PITCH * 8u;                                  // next filter row
+            else { soff += 8u; if (++sx == 3u) { sx = 0; soff += (AH_PITCH - 3u) * 8u; } }
+          } else {
+            if (KS == 4) ++cls_l;                                                // next class
+            else if (KS == 2) { if (++sx == 2u) { sx = 0; soff = 0; ++cls_l; } else soff = AH_PITCH * 8u; }
+            else { ++sx; if (sx == 4u) { sx = 0; soff = 0; ++cls_l; } else soff = (sx >> 1) * AH_PITCH * 8u + (sx & 1u) * 8u; }
+          }
+        }
+        fresh = 1u;
+        a16 += slotA16; afb += 8u; aeb += 8u;
+        if (++aslot == NA) { aslot = 0; aphase ^= 1u; a16 = base16; afb = bar0 + 8u * 36u; aeb = bar0 + 8u * 40u; }
+      }
+    }
+    as ^= 1u; if (as == 0u) aphase_t ^= 1u;
   }
 }
 
@@ -862,7 +1033,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * 16 + 4];
+  __shared__ __align__(8) uint64_t bars[2 * 16 + 4 + 8];      // + halo-tile scheme: A ring full [36..39] / empty [40..43]
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t sk_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -890,6 +1061,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int a = 0; a < 8; ++a) mbar_init(bar0 + 8u * (36 + a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -926,6 +1098,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // is congruent to w.  A lone warp retires a dependent scalar instruction every ~8-10 cycles, so
     // one producer could not feed short-K layers (measured 600-800 cycles per 64-channel chunk).
     const uint32_t w = (uint32_t)(warp - TC_EPI_WARPS);
+    if (!INSTR && p.ah) producer_ah<CTA2>(p, &tmA, &tmB, smem_base, bar0, w, cta_rank, tile0, tile_step, total_tiles);
+    else {
     const uint32_t ntap = (uint32_t)p.ntap;
     const uint32_t chunk_shift = (uint32_t)p.chunk_shift, chunk_mask = (1u << chunk_shift) - 1u;
     const int passes = p.passes, kind = p.kind;
@@ -1010,15 +1184,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t sB = sa + KS * a_slot + sub * b_bytes;
               if (CTA2) {
                 tma2_load_4d(sa + sub * a_slot, &tmA, fb, cbase, tc.x0 + dx, tc.y0 + dy, tc.n0);
-                if (fold && !type1 && p.pf_wide) {
-                  // wide step: this CTA stages every row of ONE weight plane of the N tile (rank 0: hi, rank 1: lo)
-                  const int prow = tc.cls * p.cout + tc.nt * p.BN + (int)cta_rank * p.b_rows_total;
-                  tma2_load_2d(sB, &tmB, fb, bcol, prow);
-                  tma2_load_2d(sB + b_half, &tmB, fb, bcol, prow + (p.BN >> 1));
-                } else {
-                  tma2_load_2d(sB, &tmB, fb, bcol, brow);
-                  if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
-                }
+                tma2_load_2d(sB, &tmB, fb, bcol, brow);
+                if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
               } else {
                 tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase, tc.x0 + dx, tc.y0 + dy, tc.n0);
                 tma_load_2d(sB, &tmB, fb, bcol, brow);
@@ -1036,9 +1203,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       p.prof[blockIdx.x * 8 + 0] = pw;                             // producer 0: cycles waiting for a free slot
       p.prof[blockIdx.x * 8 + 1] = clock64() - pstart;             // producer 0: total
     }
+    }
   } else if (warp == TC_MMA_WARP && (!CTA2 || cta_rank == 0u)) {
     // ================================================================ MMA issuer (leader CTA of a pair)
-    if (!INSTR && p.lean) {
+    if (!INSTR && p.ah) {
+      const int ks = p.ksub;
+      if (p.kind == EAMM_CONV_3X3) {
+        if (ks == 3) mma_issuer_ah<CTA2, 0, 3>(p, smem_base, bar0, tmem_base, tile0, tile_step, total_tiles);
+        else mma_issuer_ah<CTA2, 0, 1>(p, smem_base, bar0, tmem_base, tile0, tile_step, total_tiles);
+      } else {
+        if (ks == 4) mma_issuer_ah<CTA2, 1, 4>(p, smem_base, bar0, tmem_base, tile0, tile_step, total_tiles);
+        else if (ks == 2) mma_issuer_ah<CTA2, 1, 2>(p, smem_base, bar0, tmem_base, tile0, tile_step, total_tiles);
+        else mma_issuer_ah<CTA2, 1, 1>(p, smem_base, bar0, tmem_base, tile0, tile_step, total_tiles);
+      }
+    }
+    else if (!INSTR && p.lean) {
       if (p.mix) mma_issuer_lean<CTA2, 1>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
       else if (fold == 1u && CTA2) mma_issuer_lean<CTA2, 3>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
       else if (fold == 1u) mma_issuer_lean<CTA2, 2>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
@@ -1111,13 +1290,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // interleave the columns as [hi|lo|hi|lo], so the type-0 chunk runs as two N = BN steps instead
                 // (b_hi halves -> columns [0,BN), b_lo halves -> [BN,2BN)): same column layout and the same
                 // per-column accumulation order as the single-CTA kernel, i.e. bit-identical results
-                // (pf_wide: the producers staged plane-per-CTA instead, and the type-0 chunk is one N = 2*BN step)
-                const uint32_t idw = (fold == 1 && p.pf_wide) ? idesc : idesc1;
-                tc2_mma_bf16(tmem_acc, da, db, idw, first);
-                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idw, 1u);
-                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idw, 1u);
-                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idw, 1u);
-                if (fold == 1 && idesc == idesc2 && !p.pf_wide) {
+                tc2_mma_bf16(tmem_acc, da, db, idesc1, first);
+                tc2_mma_bf16(tmem_acc, da + 2, db + 2, idesc1, 1u);
+                tc2_mma_bf16(tmem_acc, da + 4, db + 4, idesc1, 1u);
+                tc2_mma_bf16(tmem_acc, da + 6, db + 6, idesc1, 1u);
+                if (fold == 1 && idesc == idesc2) {
                   const uint64_t dl = db + (uint64_t)(b_half >> 4);
                   const uint32_t acc2 = tmem_acc + (uint32_t)BN;
                   tc2_mma_bf16(acc2, da, dl, idesc1, first);
@@ -1174,6 +1351,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
           splitk_done(p, tc);
         } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
+      }
+      else if (p.ah_g > 1) {                       // halo-tile UP2: the item's parity classes sit side by side in the accumulator
+        for (int g = 0; g < p.ah_g; ++g) {
+          TileCoord tg = tc; tg.cls = tc.cls + g;
+          if (p.BN % 32 == 0) epilogue_tile<32>(p, tg, tmem_acc + (uint32_t)(g * p.BN), quadrant, lane, half, amax1, amax2);
+          else epilogue_tile<16>(p, tg, tmem_acc + (uint32_t)(g * p.BN), quadrant, lane, half, amax1, amax2);
+        }
       }
       else if (p.BN % 32 == 0) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
       else epilogue_tile<16>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
@@ -1264,7 +1448,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query);
 extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) { return conv_tc_run(a, stream, nullptr); }
 
 /* Dry run of eamm_conv_tc's planning: fills out[0..5] = {N tile, 7x7 scheme, fold, K chunks per stage,
- * CTA pairs (bit 0) / wide folded step (bit 1), pipeline stages} for these arguments (a->weight_fold is ignored) without launching anything. */
+ * CTA pairs (bit 0) / halo-tile scheme (bit 1) / distributed split-K (bit 2) / split factor (bits 8+), pipeline stages} for these arguments (a->weight_fold is ignored) without launching anything. */
 extern "C" int eamm_conv_tc_query(const eamm_conv_args* a, int* out) {
   if (!out) return EAMM_ERR_ARG;
   return conv_tc_run(a, nullptr, out);
@@ -1347,6 +1531,33 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
       cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
   }
+  static int prof_env = -1;
+  if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
+  const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA, plain scheme only
+  // mixed-format outputs are written 32 channels at a time (one 32-byte store per e4m3 plane): N tiles of 32+ columns
+  bool need32 = false;
+  for (int i = 0; i < 2; ++i)
+    if (views[i] && views[i]->dtype == EAMM_F16 && views[i]->planes == 2) need32 = true;
+  if (need32 && a->cout % 32) return EAMM_ERR_UNSUPPORTED;
+  // Halo-tile scheme (ConvTcParams::ah): 3x3 / UP2 layers with fp16 or mixed operands whose 8 x 16-pixel tiles fill the chip.
+  // EAMM_TC_AH=0 switches it off (A/B runs).
+  static int ah_env = -1;
+  if (ah_env < 0) { const char* e = getenv("EAMM_TC_AH"); ah_env = e ? atoi(e) : 1; }
+  p.ah = 0; p.ah_g = 1; p.cls_groups = p.classes; p.ah_na = 0; p.ah_spc = 0; p.ah_nsec = 0;
+  int ah_bn = 0;
+  if (ah_env && f16in && !row7 && !instr && (a->kind == EAMM_CONV_3X3 || a->kind == EAMM_CONV_UP2_3X3) &&
+      in->w % 8 == 0 && in->h % 16 == 0) {
+    const int bn = a->cout <= 256 ? a->cout : (a->cout % 256 == 0 ? 256 : 0);
+    if (bn && bn % 16 == 0 && !(need32 && bn % 32) && !(ah_env == 2 && bn == 256)) {      // EAMM_TC_AH=2: narrow N tiles only
+      const int g = a->kind == EAMM_CONV_UP2_3X3 ? (256 / bn >= 4 ? 4 : (256 / bn >= 2 ? 2 : 1)) : 1;
+      const long long items = (long long)(in->w / 8) * (in->h / 16) * in->n * (p.classes / g) * (a->cout / bn);
+      if (items >= num_sms) { p.ah = 1; p.ah_g = g; p.cls_groups = p.classes / g; ah_bn = bn; }
+    }
+  }
+  if (p.ah) {
+    p.bw = 8; p.bh = 16; p.bn = 1; p.bw_log2 = 3; p.bh_log2 = 4; p.x_stride = 8; p.y_stride = 16;
+    p.tiles_x = in->w / 8; p.tiles_y = in->h / 16; p.tiles_n = in->n;
+  }
   // N tile: the widest UMMA N (<= 256) dividing cout that still yields at least one tile per SM;
   // small maps (hourglass 8x8 ... 2x2) prefer narrow N tiles so that more SMs stream the weights.
   static int fold_env = -1;
@@ -1359,12 +1570,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     else if (!row7 && p.passes == 3) p.fold = 1;
   }
   if (!query && a->weight_fold != p.fold) return EAMM_ERR_ARG; // the caller packed the weights for the other scheme
-  // mixed-format outputs are written 32 channels at a time (one 32-byte store per e4m3 plane): N tiles of 32+ columns
-  bool need32 = false;
-  for (int i = 0; i < 2; ++i)
-    if (views[i] && views[i]->dtype == EAMM_F16 && views[i]->planes == 2) need32 = true;
-  if (need32 && a->cout % 32) return EAMM_ERR_UNSUPPORTED;
   if (p.kxn) p.BN = p.kxn == 1 ? 32 : KXW_COLS;
+  else if (p.ah) p.BN = ah_bn;
   else {
     const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes;
     p.BN = 0;
@@ -1407,7 +1614,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.splitk = 1; p.sk_dist = 0; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   static int splitk_env = -1;
   if (splitk_env < 0) { const char* e = getenv("EAMM_TC_SPLITK"); splitk_env = e ? atoi(e) : 1; }
-  if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && a->cout % 256 == 0 && (query || a->splitk_ws)) {
+  if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && !p.ah && a->cout % 256 == 0 && (query || a->splitk_ws)) {
     const long long t256 = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / 256);
     const int kc_all = p.taps * p.cin_chunks * p.passes;
     int S = 1;
@@ -1440,13 +1647,11 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     }
   }
   p.n_tiles = p.kxn ? 1 : a->cout / p.BN;
-  static int cta2_env = -1, prof_env = -1;
+  static int cta2_env = -1;
   if (cta2_env < 0) { const char* e = getenv("EAMM_TC_CTA2"); cta2_env = e ? atoi(e) : 19; }   // bit 0: pairs, bit 1: folded pairs, bit 2: unfolded pairs with N < 256 (measured slower in
                                                                                              // single-plane mode: the leader's one MMA warp issues for both CTAs; off by default)
-  if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
-  const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA only
   {
-    const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles;
+    const long long tiles_all = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.cls_groups * p.n_tiles;
     const bool common = cta2_env && !instr && !p.halo && !p.kxn && !row7 && p.splitk == 1 && (num_sms % 2) == 0;
     // (a) unfolded layers (3-pass cout > 128, every single-plane layer), (b) folded layers (split mode, cout <= 128); both
     // once they fill the chip and when a pair's two M tiles exist (even count).  The arithmetic (per-column
@@ -1457,7 +1662,6 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
                         ((cta2_env & 16) && p.mix && p.BN % 32 == 0);       // mixed operands: 8 steps per (tap, 64 ch) like a folded layer
     const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
     p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
-    p.pf_wide = (p.cta2 && p.fold == 1 && (cta2_env & 8)) ? 1 : 0;
   }
   p.b_rows_total = p.kxn ? p.BN : p.classes * a->cout;
   p.a_slot_bytes = p.halo ? 17 * 1024 : TC_A_BYTES;
@@ -1485,15 +1689,41 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (p.cta2) ksub = p.BN == 256 && !p.fold ? (cta2_ksub_env > 0 ? cta2_ksub_env : 1) : (kc_total >= 2 ? 2 : 1);
   if (ksub_env > 0) ksub = ksub_env;
   while (ksub > 1 && (uint32_t)ksub * chunk_bytes * 2u > ring_bytes) --ksub;      // keep at least two stages
-  p.ksub = ksub;
-  const uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
+  uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
   int stages = (int)(ring_bytes / stage_bytes);
+  if (p.ah) {
+    // weight stage = `ksub` taps of one parity class (a whole filter row / a whole 2x2 class when the tile is narrow)
+    const uint32_t b_bytes = (uint32_t)p.BN * (p.cta2 ? 64u : 128u);
+    if (a->kind == EAMM_CONV_3X3) ksub = 3u * b_bytes <= 24u * 1024u ? 3 : 1;
+    else ksub = 4u * b_bytes <= 32u * 1024u ? 4 : (2u * b_bytes <= 32u * 1024u ? 2 : 1);
+    p.a_slot_bytes = 23 * 1024;                       // 180 pixel rows of 128 bytes, slots 1024-byte aligned
+    p.ah_na = 3;
+    p.ah_spc = p.ah_g * p.ntap / ksub;
+    stage_bytes = (uint32_t)ksub * b_bytes;
+    stages = (int)((ring_bytes - (uint32_t)p.ah_na * (uint32_t)p.a_slot_bytes) / stage_bytes);
+    // K sections (byte columns of the uint8 tensor maps; see the plain producer for the operand layout)
+    const int nc8 = a->cin / 128, nc16 = a->cin / 64;
+    if (mix64) {
+      p.ah_nsec = 2;
+      p.ah_cbase[0] = 2 * in->c_buf; p.ah_nch[0] = 1; p.ah_f8[0] = 1; p.ah_bcol[0] = 0;
+      p.ah_cbase[1] = 0; p.ah_nch[1] = 1; p.ah_f8[1] = 0; p.ah_bcol[1] = p.ntap * 128;
+    } else if (mix) {
+      p.ah_nsec = 3;
+      p.ah_cbase[0] = 3 * in->c_buf + in->c_off; p.ah_nch[0] = nc8; p.ah_f8[0] = 1; p.ah_bcol[0] = 0;
+      p.ah_cbase[1] = 2 * in->c_buf + in->c_off; p.ah_nch[1] = nc8; p.ah_f8[1] = 1; p.ah_bcol[1] = p.ntap * nc8 * 128;
+      p.ah_cbase[2] = 2 * in->c_off; p.ah_nch[2] = nc16; p.ah_f8[2] = 0; p.ah_bcol[2] = 2 * p.ntap * nc8 * 128;
+    } else {
+      p.ah_nsec = 1;
+      p.ah_cbase[0] = 2 * in->c_off; p.ah_nch[0] = nc16; p.ah_f8[0] = 0; p.ah_bcol[0] = 0;
+    }
+  }
+  p.ksub = ksub;
   if (stages > 8) stages = 8;
   if (stages < 2) return EAMM_ERR_UNSUPPORTED;
   p.num_stages = stages;
   if (query) {
     query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub;
-    query[4] = p.cta2 | (p.pf_wide << 1) | (p.sk_dist << 2) | (p.splitk << 8); query[5] = p.num_stages;
+    query[4] = p.cta2 | (p.ah << 1) | (p.sk_dist << 2) | (p.splitk << 8); query[5] = p.num_stages;
     return 0;
   }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
@@ -1516,12 +1746,12 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
   static int lean_env = -1;
   if (lean_env < 0) { const char* e = getenv("EAMM_TC_LEAN"); lean_env = e ? atoi(e) : 1; }
-  p.lean = (lean_env && !p.halo && !p.pf_wide) ? 1 : 0;
+  p.lean = (lean_env && !p.halo) ? 1 : 0;
   p.mix64 = mix64 ? 1 : 0;
   p.nf8 = mix64 ? p.ntap : (mix ? p.ntap * p.cin_chunks : 0);
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * p.n_tiles * p.splitk;
+  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.cls_groups * p.n_tiles * p.splitk;
   if (p.total_tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
 
   EncodeTiledFn encode = get_encode_fn();
@@ -1546,6 +1776,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     }
     cuuint32_t es[4] = {1, 1, 1, 1};
     if (f16in) { dims[0] *= 2; box[0] = 128; }            // byte units: fp16 and e4m3 planes are addressed through one uint8 map
+    if (p.ah) { box[1] = AH_PITCH; box[2] = AH_ROWS; box[3] = 1; }      // the 10 x 18-pixel halo of an 8 x 16 tile
     CUresult r = encode(&tmA, f16in ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in->data, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1571,7 +1802,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem + (p.ah ? (size_t)p.ah_na * p.a_slot_bytes : 0);
   // the attribute is per device: a process that drives several GPUs (nn.DataParallel replicas, train.py:53-60) must set it on each
   static size_t smem_set_dev[64] = {0};
   int cur_dev = 0;

@@ -463,6 +463,7 @@ class ConvLayer:
             # fp16 + 2 x e4m3 operands: one byte matrix and one power-of-two exponent per output channel
             self.weight, self.w_exp = pack_tc_weights_mix(full, 4 if kind == L.CONV_UP2_3X3 else 1)
             self.acc_scales = {}             # input exponent -> [cout] fp32 accumulator multipliers 2^-(e_in + e_w)
+            self.plans = {}
         else:
             raise ValueError(impl)
         self.scale2 = self.shift2 = None
@@ -496,6 +497,13 @@ class ConvLayer:
             ws = splitk_workspace(self.bias.device, stream)
             a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel()
             a.acc_scale = self.acc_scale(inp.scale_exp).data_ptr()
+            key = (inp.n, inp.h, inp.w)
+            if key not in self.plans:                # (N tile, 0, 0, chunks/stage, pair / halo-tile bits, stages): tools, tests
+                q = (C.c_int * 6)()
+                L.check(lib.eamm_conv_tc_query(C.byref(a), q), "conv %s (plan)" % self.name)
+                L.LAUNCHES -= 1
+                self.plans[key] = tuple(q)
+            self.last_plan = self.plans[key]
         elif self.impl != "simt":
             ws = splitk_workspace(self.bias.device, stream)
             a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel()

@@ -288,7 +288,7 @@ def test_cabi_conv_tc_matches_conv_simt_on_layer_shapes(dev):
     for idx in (1, 3, 5, 7, 8, 9, 10, 12, 13, 15, 17, 18, 19, 21, 22):
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]
     # 112-column kx-in-N schemes and split-K: the case fails unless the planner really chose the scheme under test
-    new = [i for i, c in enumerate(mod.CASES) if c[0].startswith(("kxw", "splitk", "f16", "mix"))]
+    new = [i for i, c in enumerate(mod.CASES) if c[0].startswith(("kxw", "splitk", "f16", "mix", "ah "))]
     assert len(new) >= 32
     for idx in new:
         assert mod.run_case(idx) == 0, mod.CASES[idx][0]

@@ -52,12 +52,6 @@ CASES = [
     ("kxw 7x7 64->16 256x256 N=2 sigmoid x3", "7x7", "s", 64, 16, 2, 256, 256, 2, 0, 0, "nchw"),
     ("kxw 7x7 64->16 256x256 N=3 sigmoid", "7x7", "s", 64, 16, 3, 256, 256, 1, 0, 0, "nchw"),
     ("kxw 7x7 128->16 128x128 N=2 sigmoid x3", "7x7", "s", 128, 16, 2, 128, 128, 2, 0, 0, "nchw"),
-    # EAMM_TC_CTA2=11 (name prefix pfwide): folded pairs with one N = 2*BN step per type-0 chunk
-    ("pfwide 3x3 64->128 256x256 N=2 pool x3", "3x3", "rp", 64, 128, 2, 256, 256, 2, 0, 0, ""),
-    ("pfwide up2 128->64 128x128 N=2 x3", "up2", "r", 128, 64, 2, 128, 128, 2, 0, 0, ""),
-    ("pfwide 3x3 128->128 32x32 N=8 r+o2 x3", "3x3", "", 128, 128, 8, 32, 32, 2, 1, 1, ""),
-    ("pfwide up2 256->128 64x64 N=5 x3", "up2", "r", 256, 128, 5, 64, 64, 2, 0, 0, ""),
-    ("pfwide 3x3 64->32 64x64 N=8 pool x3", "3x3", "rp", 64, 32, 8, 64, 64, 2, 0, 0, ""),
     # name prefix splitk: split-K must be planned (small hourglass maps); launched three times (counter self-reset)
     ("splitk 3x3 1024->1024 4x4 N=32 pool x3", "3x3", "rp", 1024, 1024, 32, 4, 4, 2, 0, 0, ""),
     ("splitk up2 1024->1024 2x2 N=32 x3", "up2", "r", 1024, 1024, 32, 2, 2, 2, 0, 0, ""),
@@ -89,6 +83,19 @@ CASES = [
     ("mix64 3x3 64->128 64x64 N=3 pool", "3x3", "rp", 64, 128, 3, 64, 64, 4, 0, 0, ""),
     ("mix64 cta2 3x3 64->128 256x256 N=2 pool", "3x3", "rp", 64, 128, 2, 256, 256, 4, 0, 0, ""),
     ("mix64 up2 64->64 32x32 N=2 relu", "up2", "r", 64, 64, 2, 32, 32, 4, 0, 0, ""),
+    # name prefix ah: the halo-tile scheme (8 x 16 tiles, one halo tile per K chunk, taps as descriptor views) must be planned
+    ("ah mix cta2 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 4, 1, 1, ""),
+    ("ah mix 3x3 128->256 128x128 N=2 pool", "3x3", "rp", 128, 256, 2, 128, 128, 4, 0, 0, ""),
+    ("ah mix64 3x3 64->128 256x256 N=2 pool", "3x3", "rp", 64, 128, 2, 256, 256, 4, 0, 0, ""),
+    ("ah mix up2 128->64 128x128 N=2 relu", "up2", "r", 128, 64, 2, 128, 128, 4, 0, 0, ""),
+    ("ah mix up2 256->128 64x64 N=5 relu", "up2", "r", 256, 128, 5, 64, 64, 4, 0, 0, ""),
+    ("ah mix 3x3 256->512 32x32 N=16 pool", "3x3", "rp", 256, 512, 16, 32, 32, 4, 0, 0, ""),
+    ("ah mix 3x3 128->128 64x64 N=5 relu (odd pairs)", "3x3", "r", 128, 128, 5, 64, 64, 4, 0, 0, ""),
+    ("ah f16 3x3 64->64 64x64 N=8 pool", "3x3", "rp", 64, 64, 8, 64, 64, 3, 0, 0, ""),
+    ("ah f16 3x3 256->256 64x64 N=8 res+out2", "3x3", "", 256, 256, 8, 64, 64, 3, 1, 1, ""),
+    ("ah f16 up2 128->64 64x64 N=5", "up2", "r", 128, 64, 5, 64, 64, 3, 0, 0, ""),
+    ("ah f16 up2 256->128 64x64 N=3", "up2", "r", 256, 128, 3, 64, 64, 3, 0, 0, ""),
+    ("ah f16 3x3 64->48 32x32 N=40 relu", "3x3", "r", 64, 48, 40, 32, 32, 3, 0, 0, ""),
 ]
 
 
@@ -97,8 +104,6 @@ def run_case(idx):
     from eamm_b200 import _lib as L
     from eamm_b200.engine import ActBuf, ConvLayer, current_stream_ptr
     name, kind, fl, cin, cout, N, H, W, planes, has_res, has_out2, special = CASES[idx]
-    if name.startswith("pfwide"):                  # opt-in variant; kxw / splitk cases run on the defaults
-        os.environ["EAMM_TC_CTA2"] = "11"
     dev = torch.device("cuda:0")
     lib = L.load()
     g = torch.Generator().manual_seed(100 + idx)
@@ -181,8 +186,8 @@ def run_case(idx):
     plan = getattr(layer, "last_plan", ())
     if "kxw" in name and (not plan or plan[1] not in (3, 4)):
         status, worst = "BAD", float("nan")          # the scheme under test was not selected
-    if name.startswith("pfwide") and (not plan or (plan[4] & 0xff) != 3):
-        status, worst = "BAD", float("nan")
+    if name.startswith("ah ") and (not plan or not (plan[4] & 2)):
+        status, worst = "BAD", float("nan")          # the halo-tile scheme was not selected
     if "splitk" in name and planes != 4 and (not plan or (plan[4] >> 8) < 2):
         status, worst = "BAD", float("nan")
     print("%s case %2d %-38s rel_err %.3e plan %s" % (status, idx, name, worst, plan), flush=True)
