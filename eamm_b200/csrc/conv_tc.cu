@@ -118,6 +118,7 @@ struct ConvTcParams {
                        // slot + (ty * 10 + tx) * 128 B with 8-row groups (= image rows of the 8 x 16 tile) 1280 B apart
   int ah_g;            // UP2: parity classes per work item (accumulator columns cls * BN); 1 otherwise
   int cls_groups;      // class groups per M tile (classes / ah_g)
+  int dec_shift;       // >= 0: decode_tile by shifts, log2 of (n_tiles, cls_groups, tiles_x, tiles_y) in 5-bit fields; -1: divisions
   int ah_na;           // A ring slots
   int ah_spc;          // weight stages per K chunk (= ah_g * ntap / ksub)
   int ah_nsec;         // K sections of a tile, each {first A byte column, 128-byte chunks, kind::f8f6f4?, first weight byte column}
@@ -326,6 +327,54 @@ __device__ __forceinline__ void ldg256_cg(const void* p, float* v) {
 
 // EAMM_F16 views (one fp16 plane, or fp16 + e4m3 lo8 + e4m3 hi8): stored = value * v.mul, saturating packs.
 // The mixed format needs the 32-byte path with CH == 32 (one 32-byte store per e4m3 plane and chunk).
+// e4m3(hi / 64) of four fp16 values straight from their f16x2 pairs (the product by 2^-6 is exact in fp16 wherever the
+// e4m3 result is non-zero, so this equals rounding hi * 2^-6 from fp32)
+__device__ __forceinline__ uint32_t f16x4_to_hi8x4(uint32_t h01, uint32_t h23) {
+  uint32_t s01, s23;
+  uint16_t lo, hi;
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(s01) : "r"(h01), "r"(0x24002400u));       // 0x2400 = 2^-6
+  asm("mul.f16x2 %0, %1, %2;" : "=r"(s23) : "r"(h23), "r"(0x24002400u));
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(lo) : "r"(s01));
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(hi) : "r"(s23));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+// Eight consecutive channels of one pixel (the pooled epilogue: a lane owns an 8-channel slice).  `off` = element offset
+// of channel `ch` of the view (act_offset), 8-element aligned.
+__device__ __forceinline__ void store8(const ActView& v, long long off, int ch, const float* f) {
+  if (v.dtype == EAMM_F16) {
+    __half* p = static_cast<__half*>(v.data) + off;
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = f32x2_to_f16x2_sat(f[2 * j] * v.mul, f[2 * j + 1] * v.mul);
+    *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (v.planes == 2) {
+      uint32_t lo8[2], hi8[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 a = f16x2_to_f32x2(h[2 * j]), b = f16x2_to_f32x2(h[2 * j + 1]);
+        lo8[j] = f32x4_to_e4m3x4_sat((f[4 * j] * v.mul - a.x) * MIX_LO_GAIN, (f[4 * j + 1] * v.mul - a.y) * MIX_LO_GAIN,
+                                     (f[4 * j + 2] * v.mul - b.x) * MIX_LO_GAIN, (f[4 * j + 3] * v.mul - b.y) * MIX_LO_GAIN);
+        hi8[j] = f16x4_to_hi8x4(h[2 * j], h[2 * j + 1]);
+      }
+      uint8_t* q = reinterpret_cast<uint8_t*>(p) + 2 * v.c_buf - (v.c_off + ch);
+      *reinterpret_cast<uint2*>(q) = make_uint2(lo8[0], lo8[1]);
+      *reinterpret_cast<uint2*>(q + v.c_buf) = make_uint2(hi8[0], hi8[1]);
+    }
+    return;
+  }
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(v.data) + off;
+  const uint2 a = float4_to_bf16x4(make_float4(f[0], f[1], f[2], f[3]));
+  const uint2 b = float4_to_bf16x4(make_float4(f[4], f[5], f[6], f[7]));
+  *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b.x, b.y);
+  if (v.planes == 2) {
+    const float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+    const uint2 la = float4_to_bf16x4(make_float4(f[0] - ha.x, f[1] - ha.y, f[2] - ha.z, f[3] - ha.w));
+    const uint2 lb = float4_to_bf16x4(make_float4(f[4] - hb.x, f[5] - hb.y, f[6] - hb.z, f[7] - hb.w));
+    *reinterpret_cast<uint4*>(p + v.c_buf) = make_uint4(la.x, la.y, lb.x, lb.y);
+  }
+}
+
 template <int CH>
 __device__ __forceinline__ void store_chunk_f16(const ActView& v, long long off, int ch, const float* f, bool wide) {
   __half* p = static_cast<__half*>(v.data) + off;
@@ -349,7 +398,7 @@ __device__ __forceinline__ void store_chunk_f16(const ActView& v, long long off,
       const float2 a = f16x2_to_f32x2(h[2 * j]), b = f16x2_to_f32x2(h[2 * j + 1]);
       lo8[j] = f32x4_to_e4m3x4_sat((f[4 * j] * v.mul - a.x) * MIX_LO_GAIN, (f[4 * j + 1] * v.mul - a.y) * MIX_LO_GAIN,
                                    (f[4 * j + 2] * v.mul - b.x) * MIX_LO_GAIN, (f[4 * j + 3] * v.mul - b.y) * MIX_LO_GAIN);
-      hi8[j] = f32x4_to_e4m3x4_sat(a.x * MIX_HI_GAIN, a.y * MIX_HI_GAIN, b.x * MIX_HI_GAIN, b.y * MIX_HI_GAIN);
+      hi8[j] = f16x4_to_hi8x4(h[2 * j], h[2 * j + 1]);
     }
     // plane 1 of the pixel starts 2*c_buf bytes after plane 0 and holds [c_buf lo8 bytes | c_buf hi8 bytes]:
     // p points at fp16 element (c_off + ch) of plane 0, i.e. 2*(c_off + ch) bytes into the pixel
@@ -471,7 +520,21 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
   // CTA pairs: tiles 2i and 2i+1 are adjacent M tiles of the same (class, N tile) -- they share the weights
   const uint32_t rank = p.cta2 ? (tile & 1u) : 0u;
   if (p.cta2) tile >>= 1;
-  uint32_t q = tile / (uint32_t)p.n_tiles; t.nt = (int)(tile - q * p.n_tiles); tile = q;
+  uint32_t q;
+  if (p.dec_shift >= 0) {
+    // every divisor is a power of two (all power-of-two maps with plain tiles): shifts instead of four ~20-instruction
+    // divisions per warp and tile (6 % of the instructions of the narrow layers)
+    const uint32_t sh = (uint32_t)p.dec_shift;
+    const uint32_t s_nt = sh & 31u, s_cg = (sh >> 5) & 31u, s_tx = (sh >> 10) & 31u, s_ty = (sh >> 15) & 31u;
+    t.nt = (int)(tile & ((1u << s_nt) - 1u)); tile >>= s_nt;
+    t.cls = (int)(tile & ((1u << s_cg) - 1u)) * p.ah_g; tile >>= s_cg;
+    if (p.cta2) tile = 2u * tile + rank;
+    t.x0 = (int)(tile & ((1u << s_tx) - 1u)) * p.x_stride; tile >>= s_tx;
+    t.y0 = (int)(tile & ((1u << s_ty) - 1u)) * p.y_stride; tile >>= s_ty;
+    t.n0 = (int)tile * p.bn;
+    return t;
+  }
+  q = tile / (uint32_t)p.n_tiles; t.nt = (int)(tile - q * p.n_tiles); tile = q;
   q = tile / (uint32_t)p.cls_groups; t.cls = (int)(tile - q * p.cls_groups) * p.ah_g; tile = q;
   if (p.cta2) tile = 2u * tile + rank;
   q = tile / (uint32_t)p.tiles_x; t.x0 = (int)(tile - q * p.tiles_x) * p.x_stride; tile = q;
@@ -725,6 +788,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   const int x = tc.x0 + xl, y = tc.y0 + yl, n = tc.n0 + nl;
   bool valid = (y < p.H) && (n < p.N);
   const bool pool = p.flags & EAMM_EPI_POOL2;
+  // pooled layers that only write an activation view: the reduce-scatter variant below
+  const bool pool_rs = pool && p.has_out && !p.has_res && !p.has_out2 && p.out_nhwc == nullptr && p.out_nchw == nullptr &&
+                       p.out.dtype != EAMM_F32 && (p.out.c_off % 8) == 0 && (p.out.c_buf % 8) == 0;
   int oy = y, ox = x, OH = p.H, OW = p.W;
   if (pool) { oy = y >> 1; ox = x >> 1; OH = p.H >> 1; OW = p.W >> 1; valid = valid && !(xl & 1) && !(yl & 1); }
   else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); OH = 2 * p.H; OW = 2 * p.W; }
@@ -787,6 +853,32 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
     if (p.flags & EAMM_EPI_RELU) {
 #pragma unroll
       for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (pool && CH == 32 && pool_rs) {
+      // 2x2 average as a reduce-scatter over the window's four lanes (x partner = lane ^ 1, y partner = lane ^ bw): each
+      // lane ends up with 8 of the chunk's 32 channels of the pooled pixel, so the conversions and stores that follow run
+      // on a quarter of the values (the butterfly left all four lanes with identical copies of all 32).
+      const bool hx = lane & 1, hy = lane & p.bw;
+      float g[16], h8[8];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float send = hx ? f[j] : f[j + 16], keep = hx ? f[j + 16] : f[j];
+        g[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float send = hy ? g[j] : g[j + 8], keep = hy ? g[j + 8] : g[j];
+        h8[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, p.bw));
+      }
+      if ((y < p.H) && (n < p.N)) {
+        const int c8 = co + (hx ? 16 : 0) + (hy ? 8 : 0);
+        store8(p.out, act_offset(p.out, n, oy, ox, c8), c8, h8);
+        if (p.amax_out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) amax1 = fmaxf(amax1, fabsf(h8[j]));
+        }
+      }
+      continue;
     }
     if (pool) {
 #pragma unroll
@@ -1752,6 +1844,10 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.bias = a->bias; p.scale2 = a->scale2; p.shift2 = a->shift2;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c; p.out_nhwc = a->out_nhwc_f32; p.out_u8 = a->out_u8_nhwc;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.cls_groups * p.n_tiles * p.splitk;
+  {
+    const int l0 = ilog2_exact(p.n_tiles), l1 = ilog2_exact(p.cls_groups), l2 = ilog2_exact(p.tiles_x), l3 = ilog2_exact(p.tiles_y);
+    p.dec_shift = (l0 >= 0 && l1 >= 0 && l2 >= 0 && l3 >= 0) ? (l0 | (l1 << 5) | (l2 << 10) | (l3 << 15)) : -1;
+  }
   if (p.total_tiles > 0x7fffffffLL) return EAMM_ERR_UNSUPPORTED;
 
   EncodeTiledFn encode = get_encode_fn();
