@@ -118,6 +118,7 @@ struct ConvTcParams {
                        // slot + (ty * 10 + tx) * 128 B with 8-row groups (= image rows of the 8 x 16 tile) 1280 B apart
   int ah_g;            // UP2: parity classes per work item (accumulator columns cls * BN); 1 otherwise
   int cls_groups;      // class groups per M tile (classes / ah_g)
+  int epi_fast;        // fast epilogue variant (epilogue_fast): 0 = generic, 1 = plain, 2 = pooled, 3 = residual, 4 = residual + out2, 5 / 6 = plain / pooled with folded weight planes
   int dec_shift;       // >= 0: decode_tile by shifts, log2 of (n_tiles, cls_groups, tiles_x, tiles_y) in 5-bit fields; -1: divisions
   int ah_na;           // A ring slots
   int ah_spc;          // weight stages per K chunk (= ah_g * ntap / ksub)
@@ -640,6 +641,9 @@ __device__ __forceinline__ void producer_ah(const ConvTcParams& p, const CUtenso
   const uint32_t a_tx = AH_A_BYTES * (CTA2 ? 2u : 1u), b_tx = stage_bytes * (CTA2 ? 2u : 1u);
   const int nsec = p.ah_nsec, cout = p.cout;
   uint32_t bslot = 0, bphase = 0, aslot = 0, aphase = 0, turn = 0;
+  const bool prof = p.prof != nullptr;
+  long long pw = 0, pstart = 0;
+  if (prof) pstart = clock64();
   for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
     const TileCoord tc = decode_tile(p, tile);
     const int brow0 = tc.nt * p.BN + (CTA2 ? (int)cta_rank * (p.BN >> 1) : 0);
@@ -649,8 +653,11 @@ __device__ __forceinline__ void producer_ah(const ConvTcParams& p, const CUtenso
         uint32_t cls_l = 0, t0 = 0;
         for (uint32_t r = 0; r < SPC; ++r) {
           if (turn == w) {
+            long long tw = 0;
+            if (prof) tw = clock64();
             mbar_wait(bar0 + 8u * (16u + bslot), bphase ^ 1u);
             if (r == 0u) mbar_wait(bar0 + 8u * (40u + aslot), aphase ^ 1u);
+            if (prof) pw += clock64() - tw;
             if (elect_one()) {
               const uint32_t fbl = bar0 + 8u * bslot, afl = bar0 + 8u * (36u + aslot);
               const uint32_t fb = CTA2 ? mapa_shared(fbl, 0u) : fbl, af = CTA2 ? mapa_shared(afl, 0u) : afl;
@@ -679,6 +686,10 @@ __device__ __forceinline__ void producer_ah(const ConvTcParams& p, const CUtenso
         if (++aslot == NA) { aslot = 0; aphase ^= 1u; }
       }
     }
+  }
+  if (prof && w == 0 && (threadIdx.x & 31) == 0) {
+    p.prof[blockIdx.x * 8 + 0] = pw;                             // producer 0: cycles waiting for free slots
+    p.prof[blockIdx.x * 8 + 1] = clock64() - pstart;             // producer 0: total
   }
 }
 
@@ -720,11 +731,17 @@ __device__ __forceinline__ void mma_issuer_ah(const ConvTcParams& p, uint32_t sm
   uint32_t bslot = 0, bphase = 0, aslot = 0, aphase = 0, as = 0, aphase_t = 0;
   uint32_t a16 = base16, b16 = bbase16;
   uint32_t fb = bar0, eb = bar0 + 8u * 16u, afb = bar0 + 8u * 36u, aeb = bar0 + 8u * 40u;
+  const bool prof = p.prof != nullptr;
+  long long pm0 = 0, pm1 = 0, pstart = 0;
+  if (prof) pstart = clock64();
   for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
     // UP2: halo offset of the item's first class (classes cls0 .. cls0 + grp - 1; grp 4 -> 0, grp 2 -> class row, grp 1 -> class)
     uint32_t cls0 = 0;
     if (KIND == 1 && grp < 4u) cls0 = (uint32_t)decode_tile(p, tile).cls;
+    long long t0 = 0;
+    if (prof) t0 = clock64();
     mbar_wait(bar0 + 8u * (34u + as), aphase_t ^ 1u);                       // accumulator `as` drained by the epilogue
+    if (prof) pm0 += clock64() - t0;
     tc_fence_after();
     const uint32_t tmem_acc = tmem_base + as * 256u;
     const uint32_t tfull = bar0 + 8u * (32u + as);
@@ -746,8 +763,10 @@ __device__ __forceinline__ void mma_issuer_ah(const ConvTcParams& p, uint32_t sm
             va16 = a16 + ((c >> 1) * AH_PITCH + (c & 1u)) * 8u + soff;
             acc0 = fresh | sx; acc_col = tmem_acc + cls_l * BN;
           }
+          if (prof) t0 = clock64();
           mbar_wait(fb, bphase);
           if (r == 0u) mbar_wait(afb, aphase);
+          if (prof) pm1 += clock64() - t0;
           tc_fence_after();
           if (elect_one()) {
             if (f8) ah_issue_stage<CTA2, true, KIND, KS>(acc_col, va16, b16, slotB16, idesc, acc0);
@@ -774,6 +793,264 @@ __device__ __forceinline__ void mma_issuer_ah(const ConvTcParams& p, uint32_t sm
       }
     }
     as ^= 1u; if (as == 0u) aphase_t ^= 1u;
+  }
+  if (prof && (threadIdx.x & 31) == 0) {
+    p.prof[blockIdx.x * 8 + 2] = pm0;                            // MMA: waiting for a free accumulator
+    p.prof[blockIdx.x * 8 + 3] = pm1;                            // MMA: waiting for operands
+    p.prof[blockIdx.x * 8 + 4] = clock64() - pstart;             // MMA: total
+  }
+}
+
+// ------------------------------------------------------------------------------ fast epilogue (ConvTcParams::epi_fast)
+// The hot layers of the path (activation-view outputs, N tile a multiple of 32, no split-K) take this variant of
+// epilogue_tile: same arithmetic in the same order, but (a) everything that depends only on the tile -- pixel addresses of
+// the views, flags, vector bases -- is computed once per tile instead of per 32-column chunk (the generic code re-read ~40
+// kernel parameters from the constant bank per chunk: LDCU results sit on the long scoreboard), (b) the residual / second
+// output / pooling variants are compile-time, (c) the TMEM load of the next chunk is issued as soon as the current chunk
+// has left its registers, so its latency hides behind the conversions and stores.
+// View format codes: 0 = bf16, 1 = bf16 hi/lo planes, 2 = fp16, 3 = fp16 + e4m3 lo8 + e4m3 hi8 (mixed).
+struct EpiView {
+  char* p0;          // byte address of plane 0 at (pixel, first channel of the N tile)
+  char* p1;          // second plane at the same channel: bf16 lo plane, or the e4m3 lo8 bytes of the mixed format
+  int fmt, c_buf;
+  float mul, inv_mul;
+};
+__device__ __forceinline__ EpiView epi_view(const ActView& v, int n, int y, int x, int co0) {
+  EpiView e;
+  const long long off = act_offset(v, n, y, x, co0);                       // elements (2 bytes each in every non-f32 format)
+  e.p0 = static_cast<char*>(v.data) + 2 * off;
+  e.fmt = (v.dtype == EAMM_F16 ? 2 : 0) + (v.planes == 2 ? 1 : 0);
+  e.c_buf = v.c_buf;
+  // mixed: plane 1 of the pixel starts 2*c_buf bytes after plane 0 and holds [c_buf lo8 | c_buf hi8]
+  e.p1 = e.fmt == 3 ? e.p0 - 2 * (v.c_off + co0) + 2 * v.c_buf + (v.c_off + co0) : e.p0 + 2 * v.c_buf;
+  e.mul = v.mul; e.inv_mul = v.inv_mul;
+  return e;
+}
+
+// NCH consecutive channels (8 or 32) of one pixel, starting `c` channels into the N tile
+template <int NCH>
+__device__ __forceinline__ void epi_store(const EpiView& e, int c, const float* f) {
+  char* q0 = e.p0 + 2 * c;
+  if (e.fmt >= 2) {
+    uint32_t h[NCH / 2];
+#pragma unroll
+    for (int j = 0; j < NCH / 2; ++j) h[j] = f32x2_to_f16x2_sat(f[2 * j] * e.mul, f[2 * j + 1] * e.mul);
+    if (NCH == 32) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        stg256(q0 + 32 * g, make_uint4(h[8 * g], h[8 * g + 1], h[8 * g + 2], h[8 * g + 3]),
+               make_uint4(h[8 * g + 4], h[8 * g + 5], h[8 * g + 6], h[8 * g + 7]));
+    } else {
+      *reinterpret_cast<uint4*>(q0) = make_uint4(h[0], h[1], h[2], h[3]);
+    }
+    if (e.fmt == 3) {
+      uint32_t lo8[NCH / 4], hi8[NCH / 4];
+#pragma unroll
+      for (int j = 0; j < NCH / 4; ++j) {
+        const float2 a = f16x2_to_f32x2(h[2 * j]), b = f16x2_to_f32x2(h[2 * j + 1]);
+        lo8[j] = f32x4_to_e4m3x4_sat((f[4 * j] * e.mul - a.x) * MIX_LO_GAIN, (f[4 * j + 1] * e.mul - a.y) * MIX_LO_GAIN,
+                                     (f[4 * j + 2] * e.mul - b.x) * MIX_LO_GAIN, (f[4 * j + 3] * e.mul - b.y) * MIX_LO_GAIN);
+        hi8[j] = f16x4_to_hi8x4(h[2 * j], h[2 * j + 1]);
+      }
+      char* q1 = e.p1 + c;
+      if (NCH == 32) {
+        stg256(q1, make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]), make_uint4(lo8[4], lo8[5], lo8[6], lo8[7]));
+        stg256(q1 + e.c_buf, make_uint4(hi8[0], hi8[1], hi8[2], hi8[3]), make_uint4(hi8[4], hi8[5], hi8[6], hi8[7]));
+      } else {
+        *reinterpret_cast<uint2*>(q1) = make_uint2(lo8[0], lo8[1]);
+        *reinterpret_cast<uint2*>(q1 + e.c_buf) = make_uint2(hi8[0], hi8[1]);
+      }
+    }
+    return;
+  }
+  char* q1 = e.p1 + 2 * c;
+#pragma unroll
+  for (int g = 0; g < NCH / 16; ++g) {
+    uint2 q[4];
+    float4 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[i] = float4_to_bf16x4(make_float4(f[16 * g + 4 * i], f[16 * g + 4 * i + 1], f[16 * g + 4 * i + 2], f[16 * g + 4 * i + 3]));
+      h[i] = bf16x4_to_float4(q[i]);
+    }
+    stg256(q0 + 32 * g, make_uint4(q[0].x, q[0].y, q[1].x, q[1].y), make_uint4(q[2].x, q[2].y, q[3].x, q[3].y));
+    if (e.fmt == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        q[i] = float4_to_bf16x4(make_float4(f[16 * g + 4 * i] - h[i].x, f[16 * g + 4 * i + 1] - h[i].y,
+                                            f[16 * g + 4 * i + 2] - h[i].z, f[16 * g + 4 * i + 3] - h[i].w));
+      stg256(q1 + 32 * g, make_uint4(q[0].x, q[0].y, q[1].x, q[1].y), make_uint4(q[2].x, q[2].y, q[3].x, q[3].y));
+    }
+  }
+  if (NCH == 8) {
+    const uint2 a = float4_to_bf16x4(make_float4(f[0], f[1], f[2], f[3]));
+    const uint2 b = float4_to_bf16x4(make_float4(f[4], f[5], f[6], f[7]));
+    *reinterpret_cast<uint4*>(q0) = make_uint4(a.x, a.y, b.x, b.y);
+    if (e.fmt == 1) {
+      const float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+      const uint2 la = float4_to_bf16x4(make_float4(f[0] - ha.x, f[1] - ha.y, f[2] - ha.z, f[3] - ha.w));
+      const uint2 lb = float4_to_bf16x4(make_float4(f[4] - hb.x, f[5] - hb.y, f[6] - hb.z, f[7] - hb.w));
+      *reinterpret_cast<uint4*>(q1) = make_uint4(la.x, la.y, lb.x, lb.y);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_add16_bf16(const uint4 a, const uint4 b, float* o) {
+  const float4 x0 = bf16x4_to_float4(make_uint2(a.x, a.y)), x1 = bf16x4_to_float4(make_uint2(a.z, a.w));
+  const float4 x2 = bf16x4_to_float4(make_uint2(b.x, b.y)), x3 = bf16x4_to_float4(make_uint2(b.z, b.w));
+  o[0] += x0.x; o[1] += x0.y; o[2] += x0.z; o[3] += x0.w; o[4] += x1.x; o[5] += x1.y; o[6] += x1.z; o[7] += x1.w;
+  o[8] += x2.x; o[9] += x2.y; o[10] += x2.z; o[11] += x2.w; o[12] += x3.x; o[13] += x3.y; o[14] += x3.z; o[15] += x3.w;
+}
+// residual of one 32-channel chunk: the loads are issued ahead of use (all of them back to back -- a loop over the planes
+// with a load -> use dependence per iteration serialised four DRAM round trips per chunk: 17 k cycles per conv2 tile),
+// epi_res_add then adds plane by plane in add_chunk's order.  rr = [16-channel group][plane] x 32 bytes.
+__device__ __forceinline__ void epi_res_load(const EpiView& e, int c, uint4* rr) {
+  const char* q0 = e.p0 + 2 * c;
+  const char* q1 = e.p1 + 2 * c;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    ldg256(q0 + 32 * g, rr[4 * g], rr[4 * g + 1]);
+    if (e.fmt == 1) ldg256(q1 + 32 * g, rr[4 * g + 2], rr[4 * g + 3]);
+  }
+}
+__device__ __forceinline__ void epi_res_add(const EpiView& e, const uint4* rr, float* f) {
+  if (e.fmt == 2) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t w[8] = {rr[4 * g].x, rr[4 * g].y, rr[4 * g].z, rr[4 * g].w, rr[4 * g + 1].x, rr[4 * g + 1].y, rr[4 * g + 1].z, rr[4 * g + 1].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 x = f16x2_to_f32x2(w[j]);
+        f[16 * g + 2 * j] += x.x * e.inv_mul; f[16 * g + 2 * j + 1] += x.y * e.inv_mul;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    epi_add16_bf16(rr[4 * g], rr[4 * g + 1], f + 16 * g);
+    if (e.fmt == 1) epi_add16_bf16(rr[4 * g + 2], rr[4 * g + 3], f + 16 * g);
+  }
+}
+
+template <bool POOL, bool RES, bool OUT2, bool FOLD>
+__device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
+                                              int quadrant, int lane, int half, float& amax1, float& amax2) {
+  const int r = quadrant * 32 + lane;
+  const int xl = r & (p.bw - 1);
+  const int yl = (r >> p.bw_log2) & (p.bh - 1);
+  const int nl = r >> (p.bw_log2 + p.bh_log2);
+  const int x = tc.x0 + xl, y = tc.y0 + yl, n = tc.n0 + nl;
+  const bool valid = (y < p.H) && (n < p.N);
+  int oy = y, ox = x;
+  if (POOL) { oy = y >> 1; ox = x >> 1; }
+  else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); }
+  const int BN = p.BN, co0 = tc.nt * BN, bw = p.bw;
+  const bool relu = (p.flags & EAMM_EPI_RELU) != 0;
+  const bool track1 = p.amax_out != nullptr, track2 = OUT2 && p.amax_out2 != nullptr;
+  const float* bias = p.bias + co0;
+  const float* asc = p.acc_scale != nullptr ? p.acc_scale + co0 : nullptr;
+  const float* sc2 = OUT2 ? p.scale2 + co0 : nullptr;
+  const float* sh2 = OUT2 ? p.shift2 + co0 : nullptr;
+  // out-of-range rows of a partial tile compute on garbage and store nothing: their addresses are never formed
+  const EpiView vo = epi_view(p.out, valid ? n : 0, valid ? oy : 0, valid ? ox : 0, co0);
+  EpiView vr = vo, v2 = vo;
+  if (RES) vr = epi_view(p.res, valid ? n : 0, valid ? oy : 0, valid ? ox : 0, co0);
+  if (OUT2) v2 = epi_view(p.out2, valid ? n : 0, valid ? oy : 0, valid ? ox : 0, co0);
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
+  const int cstep = (TC_EPI_WARPS / 4) * 32;
+  int c0 = half * 32;
+  if (c0 >= BN) return;
+  uint32_t raw[32], raw2[FOLD ? 32 : 1];
+  uint4 rr[RES ? 8 : 1];
+  TmemLd<32>::ld(taddr + c0, raw);
+  if (FOLD) TmemLd<32>::ld(taddr + BN + c0, raw2);
+  for (; c0 < BN; c0 += cstep) {
+    if (RES && c0 != half * 32) TmemLd<32>::ld(taddr + c0, raw);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float f[32];
+    if (FOLD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[FOLD ? j : 0]));
+    }
+    if (asc != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + g);
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(asc + c0) + g);
+        f[4 * g] = fmaf(__uint_as_float(raw[4 * g]), sv.x, b.x);
+        f[4 * g + 1] = fmaf(__uint_as_float(raw[4 * g + 1]), sv.y, b.y);
+        f[4 * g + 2] = fmaf(__uint_as_float(raw[4 * g + 2]), sv.z, b.z);
+        f[4 * g + 3] = fmaf(__uint_as_float(raw[4 * g + 3]), sv.w, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + g);
+        f[4 * g] = __uint_as_float(raw[4 * g]) + b.x;
+        f[4 * g + 1] = __uint_as_float(raw[4 * g + 1]) + b.y;
+        f[4 * g + 2] = __uint_as_float(raw[4 * g + 2]) + b.z;
+        f[4 * g + 3] = __uint_as_float(raw[4 * g + 3]) + b.w;
+      }
+    }
+    // the accumulator columns of this chunk are in f: fetch the next chunk while this one is converted and stored
+    // (the residual variants prefetch the residual instead: registers)
+    if (!RES && c0 + cstep < BN) {
+      TmemLd<32>::ld(taddr + c0 + cstep, raw);
+      if (FOLD) TmemLd<32>::ld(taddr + BN + c0 + cstep, raw2);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (POOL) {
+      // 2x2 average as a reduce-scatter over the window's four lanes (see epilogue_tile)
+      const bool hx = lane & 1, hy = lane & bw;
+      float g[16], h8[8];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float send = hx ? f[j] : f[j + 16], keep = hx ? f[j + 16] : f[j];
+        g[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float send = hy ? g[j] : g[j + 8], keep = hy ? g[j + 8] : g[j];
+        h8[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, bw));
+      }
+      if (valid) {
+        epi_store<8>(vo, c0 + (hx ? 16 : 0) + (hy ? 8 : 0), h8);
+        if (track1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) amax1 = fmaxf(amax1, fabsf(h8[j]));
+        }
+      }
+      continue;
+    }
+    if (valid) {
+      if (RES) { epi_res_load(vr, c0, rr); epi_res_add(vr, rr, f); }      // all planes' loads first, then the adds
+      epi_store<32>(vo, c0, f);
+      if (track1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) amax1 = fmaxf(amax1, fabsf(f[j]));
+      }
+      if (OUT2) {
+        // second output in place (f is dead after the first store)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(sc2 + c0) + g);
+          const float4 tv = __ldg(reinterpret_cast<const float4*>(sh2 + c0) + g);
+          f[4 * g] = fmaxf(fmaf(f[4 * g], sv.x, tv.x), 0.f);
+          f[4 * g + 1] = fmaxf(fmaf(f[4 * g + 1], sv.y, tv.y), 0.f);
+          f[4 * g + 2] = fmaxf(fmaf(f[4 * g + 2], sv.z, tv.z), 0.f);
+          f[4 * g + 3] = fmaxf(fmaf(f[4 * g + 3], sv.w, tv.w), 0.f);
+        }
+        epi_store<32>(v2, c0, f);
+        if (track2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax2 = fmaxf(amax2, f[j]);          // post-ReLU: non-negative
+        }
+      }
+    }
   }
 }
 
@@ -1423,15 +1700,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0; uint32_t aphase = 0;
     long long pe = 0, pstart = 0;
     float amax1 = 0.f, amax2 = 0.f;              // running max |out|, |out2| of this thread (calibration statistic)
-    if (INSTR) pstart = clock64();
+    const bool eprof = p.prof != nullptr;
+    if (eprof) pstart = clock64();
     float* kxn_smem = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
                                                (size_t)p.num_stages * stage_bytes);
     for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(p, tile);
       long long t0 = 0;
-      if (INSTR) t0 = clock64();
+      if (eprof) t0 = clock64();
       mbar_wait(tfull_bar(as), aphase);
-      if (INSTR) pe += clock64() - t0;
+      if (eprof) pe += clock64() - t0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * 256);
       if (INSTR && dbg >= 5) {                     // 5: protocol only, 6: real main loop, no epilogue work
@@ -1443,6 +1721,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
           splitk_done(p, tc);
         } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
+      }
+      else if (p.epi_fast) {
+        for (int g = 0; g < p.ah_g; ++g) {          // halo-tile UP2: the item's parity classes sit side by side in the accumulator
+          TileCoord tg = tc; tg.cls = tc.cls + g;
+          const uint32_t ta = tmem_acc + (uint32_t)(g * p.BN);
+          if (p.epi_fast == 1) epilogue_fast<false, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          else if (p.epi_fast == 2) epilogue_fast<true, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          else if (p.epi_fast == 3) epilogue_fast<false, true, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          else if (p.epi_fast == 4) epilogue_fast<false, true, true, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          else if (p.epi_fast == 5) epilogue_fast<false, false, false, true>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          else epilogue_fast<true, false, false, true>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+        }
       }
       else if (p.ah_g > 1) {                       // halo-tile UP2: the item's parity classes sit side by side in the accumulator
         for (int g = 0; g < p.ah_g; ++g) {
@@ -1473,7 +1763,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.amax_out2 != nullptr) atomicMax(reinterpret_cast<int*>(p.amax_out2), __float_as_int(amax2));
       }
     }
-    if (INSTR && p.prof && warp == 0 && lane == 0) {
+    if (eprof && warp == 0 && lane == 0) {
       p.prof[blockIdx.x * 8 + 5] = pe;                             // epilogue warp 0: waiting for an accumulator
       p.prof[blockIdx.x * 8 + 6] = clock64() - pstart;             // epilogue: total
     }
@@ -1625,7 +1915,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   }
   static int prof_env = -1;
   if (prof_env < 0) { const char* e = getenv("EAMM_TC_PROF"); prof_env = e ? atoi(e) : 0; }
-  const bool instr = prof_env || p.debug;            // the instrumented instantiation is single-CTA, plain scheme only
+  const bool instr = prof_env == 1 || p.debug;       // the instrumented instantiation is single-CTA, plain scheme only
+                                                     // (EAMM_TC_PROF=2: role counters of the production kernels, halo-tile scheme)
   // mixed-format outputs are written 32 channels at a time (one 32-byte store per e4m3 plane): N tiles of 32+ columns
   bool need32 = false;
   for (int i = 0; i < 2; ++i)
@@ -1835,6 +2126,18 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (views[i] && views[i]->dtype == EAMM_F16 && views[i]->planes == 2 &&
         (!p.st256 || p.BN % 32 || views[i]->c_off % 32 || views[i]->c_buf % 32 || p.kxn))
       return EAMM_ERR_UNSUPPORTED;
+  {
+    // fast epilogue: activation-view outputs only, 32-column chunks, 32-byte accesses, no split-K / kx-in-N
+    static int fast_env = -1;
+    if (fast_env < 0) { const char* e = getenv("EAMM_TC_EPIFAST"); fast_env = e ? atoi(e) : 1; }
+    const bool pool = (a->flags & EAMM_EPI_POOL2) != 0;
+    bool ok = fast_env && !instr && !p.kxn && p.splitk == 1 && p.BN % 32 == 0 && p.st256 && a->out && !a->out_nhwc_f32 && !a->out_nchw &&
+              !(a->flags & EAMM_EPI_SIGMOID);
+    if (ok && pool && (a->residual || a->out2 || a->out->c_off % 8 || a->out->c_buf % 8)) ok = false;
+    if (ok && a->out2 && !a->residual) ok = false;
+    if (ok && p.fold && (a->residual || a->out2)) ok = false;
+    p.epi_fast = !ok ? 0 : (p.fold ? (pool ? 6 : 5) : (pool ? 2 : (a->residual ? (a->out2 ? 4 : 3) : 1)));
+  }
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
   static int lean_env = -1;
   if (lean_env < 0) { const char* e = getenv("EAMM_TC_LEAN"); lean_env = e ? atoi(e) : 1; }
@@ -1952,12 +2255,13 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     for (long long b = 0; b < grid; ++b) for (int j = 0; j < 8; ++j) acc[j] += (double)host[b * 8 + j];
     const double tiles_per_cta = (double)p.total_tiles / (double)grid;
     const int KCh = kc_total;
-    fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%dx%d KC=%d tiles/cta=%.1f | per tile (cycles): "
+    const double mg = p.cta2 ? grid / 2.0 : (double)grid;          // the MMA counters exist in the leader CTA of a pair only
+    fprintf(stderr, "[tc_prof] kind=%d %dx%dx%d cin=%d cout=%d BN=%d stages=%dx%d KC=%d ah=%d(g%d) cta2=%d epi=%d tiles/cta=%.1f | per tile (cycles): "
             "total=%.0f prod_wait_empty=%.0f mma_wait_acc=%.0f mma_wait_full=%.0f epi_wait_full=%.0f epi_busy=%.0f | per stage=%.0f\n",
-            p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, p.ksub, KCh, tiles_per_cta,
-            acc[4] / grid / tiles_per_cta, acc[0] / grid / tiles_per_cta, acc[2] / grid / tiles_per_cta,
-            acc[3] / grid / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
-            acc[4] / grid / tiles_per_cta / KCh);
+            p.kind, p.N, p.H, p.W, a->cin, a->cout, p.BN, p.num_stages, p.ksub, KCh, p.ah, p.ah_g, p.cta2, p.epi_fast, tiles_per_cta,
+            acc[4] / mg / tiles_per_cta, acc[0] / grid / tiles_per_cta, acc[2] / mg / tiles_per_cta,
+            acc[3] / mg / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
+            acc[4] / mg / tiles_per_cta / KCh);
   }
   return 0;
 }
