@@ -95,9 +95,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIBPATH
-    if not os.path.exists(path) or not _build.is_fresh():
-        path = _build.build()
+    path = os.environ.get("EAMM_B200_LIB")       # tooling: a diagnostic build of the same sources (tools/experiments/bin)
+    if not path:
+        path = _build.LIBPATH
+        if not os.path.exists(path) or not _build.is_fresh():
+            path = _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly

@@ -31,8 +31,7 @@
 //   switches    EAMM_TC_HALO / _FOLD / _CTA2 = 0 disable a variant (_CTA2 is a bit mask: 1 pairs, 2 folded
 //               pairs, 4 narrow unfolded pairs -- default 19; bit 4 = 16: pairs for mixed fp16+fp8 layers with N < 256),
 //               EAMM_TC_KXW (bit 0: 7x7 scheme 3, bit 1: scheme 4, bit 2: compact scheme-3 epilogue buffer; default 7), EAMM_TC_SPLITK = 0 / EAMM_TC_ST256 = 0 switch
-//               split-K / the 32-byte epilogue stores off, EAMM_TC_SPLITK_DIST = 1 selects the distributed split-K reduction
-//               (opt-in), EAMM_TC_SPLITK_MAX caps the split factor (9), EAMM_TC_BNCOST = 0 restores the older N-tile rule,
+//               split-K / the 32-byte epilogue stores off, EAMM_TC_SPLITK_MAX caps the split factor (9), EAMM_TC_BNCOST = 0 restores the older N-tile rule,
 //               EAMM_TC_NUM_SMS lets eamm_conv_tc_query plan on a host without a GPU, EAMM_TC_KSUB / _CTA2_KSUB force the
 //               chunks per stage, EAMM_TC_PROF = 1 prints per-role cycle counters, EAMM_TC_DEBUG = 1..6
 //               switches TMA / MMA / epilogue off (timing experiments; results are garbage).
@@ -82,12 +81,8 @@ struct ConvTcParams {
                        // (deterministic) and runs the normal epilogue.  For the 8x8 ... 2x2 hourglass layers, which
                        // otherwise need N tiles of 32 columns to occupy the chip and then pay the per-MMA A-slab cost
                        // 8x more often than an N = 256 tile would.
-  int sk_dist;         // distributed reduction: every CTA of a tile waits for all S partials (arrival counter spin; the S CTAs
-                       // are co-resident: cooperative launch, one item per CTA) and then reduces + finishes the
-                       // 32-column chunks j = split, split + S, ... of the tile, instead of the last arriver doing all 8
   float* sk_ws;        // [out tile][split][128][BN] fp32 partials
-  unsigned int* sk_cnt;// [out tile] arrival counters (+512: completion counters of the distributed mode), zero before and
-                       // after every launch
+  unsigned int* sk_cnt;// [out tile] arrival counters, zero before and after every launch
   int fold;            // split mode with 2*BN <= 256: the weight planes are stacked along N.  Chunk type 0 =
                        // a_hi x [b_hi; b_lo] (N = 2*BN), type 1 = a_lo x b_hi (N = BN); the epilogue adds
                        // accumulator columns [BN, 2BN) (the a_hi*b_lo cross term) to [0, BN).  2 A loads and
@@ -118,6 +113,9 @@ struct ConvTcParams {
                        // slot + (ty * 10 + tx) * 128 B with 8-row groups (= image rows of the 8 x 16 tile) 1280 B apart
   int ah_g;            // UP2: parity classes per work item (accumulator columns cls * BN); 1 otherwise
   int cls_groups;      // class groups per M tile (classes / ah_g)
+  int b_res;           // the whole weight matrix of the CTA stays in shared memory (packed first conv: 7 chunks = 112 KB, loaded
+                       // once; the ring then carries A only -- that layer ran at the L2 -> SM cap re-staging 16 KB of weights per
+                       // 16 KB of pixels); barrier bars[44]
   int epi_fast;        // fast epilogue variant (epilogue_fast): 0 = generic, 1 = plain, 2 = pooled, 3 = residual, 4 = residual + out2, 5 / 6 = plain / pooled with folded weight planes
   int dec_shift;       // >= 0: decode_tile by shifts, log2 of (n_tiles, cls_groups, tiles_x, tiles_y) in 5-bit fields; -1: divisions
   int ah_na;           // A ring slots
@@ -558,7 +556,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, uint32_t
 template <bool CTA2, int MODE>
 __device__ __forceinline__ void mma_issuer_lean(const ConvTcParams& p, uint32_t smem_base, uint32_t bar0, uint32_t tmem_base,
                                                 uint32_t KC, uint32_t KS, uint32_t a_slot, uint32_t b_bytes, uint32_t b_half,
-                                                uint32_t tile0, uint32_t tile_step, uint32_t total_tiles) {
+                                                uint32_t tile0, uint32_t tile_step, uint32_t total_tiles, uint32_t bres_base = 0u) {
   const uint32_t fmt = p.f16in ? 0u : ((1u << 7) | (1u << 10));
   const uint32_t mbits = ((CTA2 ? 256u : 128u) >> 4) << 24;
   uint32_t idesc1 = (1u << 4) | fmt | ((uint32_t)(p.BN >> 3) << 17) | mbits;
@@ -567,7 +565,9 @@ __device__ __forceinline__ void mma_issuer_lean(const ConvTcParams& p, uint32_t 
   uint32_t nstages = (uint32_t)p.num_stages, nf8 = (uint32_t)p.nf8, BN = (uint32_t)p.BN, splitk = (uint32_t)p.splitk;
   const uint32_t T = KC >> 1;
   uint32_t slotA16 = a_slot >> 4, slotB16 = b_bytes >> 4, bofs16 = (KS * a_slot) >> 4, bhalf16 = b_half >> 4;
-  uint32_t stage16 = (KS * (a_slot + b_bytes)) >> 4, base16 = smem_base >> 4;
+  uint32_t stage16 = (KS * (a_slot + (bres_base ? 0u : b_bytes))) >> 4, base16 = smem_base >> 4;
+  uint32_t bres16 = bres_base >> 4;                   // MODE 0 only: resident weights, chunk kc at bres16 + kc * slotB16
+  if (bres_base) { mbar_wait(bar0 + 8u * 44u, 0u); tc_fence_after(); }
   // opaque copies: keep ptxas from re-reading the kernel parameters (constant bank) inside the loops
   asm volatile("mov.u32 %0, %0;" : "+r"(idesc1)); asm volatile("mov.u32 %0, %0;" : "+r"(idesc2));
   asm volatile("mov.u32 %0, %0;" : "+r"(nstages)); asm volatile("mov.u32 %0, %0;" : "+r"(nf8));
@@ -592,7 +592,7 @@ __device__ __forceinline__ void mma_issuer_lean(const ConvTcParams& p, uint32_t 
       mbar_wait(fb, phase);
       tc_fence_after();
       if (elect_one()) {
-        uint32_t a16 = sa16, b16 = sa16 + bofs16;
+        uint32_t a16 = sa16, b16 = (MODE == 0 && bres16) ? bres16 + kc * slotB16 : sa16 + bofs16;
 #pragma unroll 1
         for (uint32_t sub = 0; sub < nsub; ++sub, a16 += slotA16, b16 += slotB16) {
           const uint32_t kcs = kc + sub;
@@ -687,10 +687,12 @@ __device__ __forceinline__ void producer_ah(const ConvTcParams& p, const CUtenso
       }
     }
   }
+#ifndef EAMM_EPI_PHASES
   if (prof && w == 0 && (threadIdx.x & 31) == 0) {
     p.prof[blockIdx.x * 8 + 0] = pw;                             // producer 0: cycles waiting for free slots
     p.prof[blockIdx.x * 8 + 1] = clock64() - pstart;             // producer 0: total
   }
+#endif
 }
 
 // One weight stage of the halo-tile issuer: KS taps of one parity class, fully unrolled.  KIND 0 = 3x3 (KS 3: stage = filter
@@ -967,7 +969,13 @@ __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileC
   if (FOLD) TmemLd<32>::ld(taddr + BN + c0, raw2);
   for (; c0 < BN; c0 += cstep) {
     if (RES && c0 != half * 32) TmemLd<32>::ld(taddr + c0, raw);
+#ifdef EAMM_EPI_PHASES
+    long long ph0 = clock64();
+#endif
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef EAMM_EPI_PHASES
+    long long ph1 = clock64();
+#endif
     float f[32];
     if (FOLD) {
 #pragma unroll
@@ -1003,6 +1011,19 @@ __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileC
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
     }
+#ifdef EAMM_EPI_PHASES
+    {
+      float keep = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) keep += f[j];
+      asm volatile("" :: "f"(keep));
+    }
+    long long ph2 = clock64();
+    if (p.prof != nullptr && quadrant == 0 && half == 0 && lane == 0) {
+      atomicAdd(p.prof + blockIdx.x * 8 + 0, (unsigned long long)(ph1 - ph0));
+      atomicAdd(p.prof + blockIdx.x * 8 + 1, (unsigned long long)(ph2 - ph1));
+    }
+#endif
     if (POOL) {
       // 2x2 average as a reduce-scatter over the window's four lanes (see epilogue_tile)
       const bool hx = lane & 1, hy = lane & bw;
@@ -1072,11 +1093,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
   if (pool) { oy = y >> 1; ox = x >> 1; OH = p.H >> 1; OW = p.W >> 1; valid = valid && !(xl & 1) && !(yl & 1); }
   else if (p.kind == EAMM_CONV_UP2_3X3) { oy = 2 * y + (tc.cls >> 1); ox = 2 * x + (tc.cls & 1); OH = 2 * p.H; OW = 2 * p.W; }
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
-  // chunk walk: the two warps of a quadrant alternate over the CH-column chunks; in the distributed split-K mode a
-  // CTA owns the chunks j = split, split + S, ... only
-  const int dist = (p.splitk > 1 && p.sk_dist) ? 1 : 0;
-  const int cfirst = dist ? (tc.split + half * p.splitk) * CH : half * CH;
-  const int cstep = (dist ? p.splitk : 1) * (TC_EPI_WARPS / 4) * CH;
+  // chunk walk: the two warps of a quadrant alternate over the CH-column chunks
+  const int cfirst = half * CH;
+  const int cstep = (TC_EPI_WARPS / 4) * CH;
   for (int c0 = cfirst; c0 < p.BN; c0 += cstep) {
     uint32_t raw[CH];
     if (p.splitk > 1) {                             // reducer of a split-K tile: partials summed in split order
@@ -1241,43 +1260,6 @@ __device__ __forceinline__ bool splitk_publish(const ConvTcParams& p, const Tile
   return last;
 }
 
-// Distributed variant: publish, arrive, then wait until all S partial tiles of the output tile are visible.  Safe because
-// the S CTAs run at the same time (cooperative launch, at most one work item per CTA); the wait is bounded and traps.
-__device__ __forceinline__ void splitk_publish_wait(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
-                                                    int quadrant, int lane, int half) {
-  const int r = quadrant * 32 + lane;
-  const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
-  float* dst = p.sk_ws + (((size_t)tc.out_tile * p.splitk + tc.split) * 128 + r) * p.BN;
-  for (int c0 = half * 32; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * 32) {
-    uint32_t raw[32];
-    TmemLd<32>::ld(taddr + (uint32_t)c0, raw);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int g = 0; g < 4; ++g) stg256_cg(dst + c0 + 8 * g, raw + 8 * g);
-  }
-  __threadfence();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (threadIdx.x == 0) {
-    unsigned int* cnt = p.sk_cnt + tc.out_tile;
-    atomicAdd(cnt, 1u);
-    unsigned int seen = 0, it = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
-      if (++it > (1u << 24)) __trap();
-    } while (seen < (unsigned int)p.splitk);
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  __threadfence();
-}
-// ... and after the CTA's share of the epilogue: the CTA that finishes last zeroes both counters for the next launch
-__device__ __forceinline__ void splitk_done(const ConvTcParams& p, const TileCoord& tc) {
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (threadIdx.x == 0) {
-    const unsigned int old = atomicAdd(p.sk_cnt + 512 + tc.out_tile, 1u);
-    if (old == (unsigned int)(p.splitk - 1)) { p.sk_cnt[tc.out_tile] = 0u; p.sk_cnt[512 + tc.out_tile] = 0u; }
-  }
-}
-
 // kx-in-N epilogue (7x7 -> <=4 channels, sigmoid, NCHW fp32): accumulator row p holds, for the input
 // column x0-3+p, the partial sums D[p][kx*4+co] over (ky, channels).  out[x0+j][co] = bias +
 // sum_kx D[j+kx][kx*4+co]; the shifted rows are exchanged through shared memory (S, stride 29).
@@ -1402,7 +1384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * 16 + 4 + 8];      // + halo-tile scheme: A ring full [36..39] / empty [40..43]
+  __shared__ __align__(8) uint64_t bars[2 * 16 + 4 + 8 + 1];      // + halo-tile scheme: A ring full [36..39] / empty [40..43]
   __shared__ uint32_t tmem_base_smem;
   __shared__ uint32_t sk_flag;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1418,8 +1400,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_bytes = CTA2 ? (uint32_t)p.BN * (fold ? 128u : 64u)
                                 : (uint32_t)p.BN * 128u * (p.halo ? 7u : (fold ? 2u : 1u));
   const uint32_t KS = (uint32_t)p.ksub;                         // 64-channel sub-chunks per pipeline stage
-  const uint32_t stage_bytes = KS * (a_slot + b_bytes);
-  const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + b_bytes;   // bytes of a type-0 chunk
+  const uint32_t b_res = (uint32_t)p.b_res;
+  const uint32_t stage_bytes = KS * (a_slot + (b_res ? 0u : b_bytes));
+  const uint32_t sub_tx = (p.halo ? 134u * 128u : (uint32_t)TC_A_BYTES) + (b_res ? 0u : b_bytes);   // bytes of a type-0 chunk
+  const uint32_t bres_base = smem_base + (uint32_t)p.num_stages * stage_bytes;      // resident weights behind the ring
   const uint32_t b_half = (uint32_t)p.BN * (CTA2 ? 64u : 128u);        // fold: offset of the b_lo rows inside a B slot
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (16 + s); };
@@ -1431,6 +1415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     for (int a = 0; a < 8; ++a) mbar_init(bar0 + 8u * (36 + a), 1);
+    mbar_init(bar0 + 8u * 44u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -1478,6 +1463,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool haloish = p.halo || p.kxn;
     uint32_t slot = 0, phase = 0, si = w;
     for (uint32_t i = 0; i < w; ++i) { if (++slot == nstages) { slot = 0; phase ^= 1u; } }
+    if (b_res && w == 0u && tile0 < total_tiles && elect_one()) {
+      // resident weights (single CTA, fold 2, one N tile): chunk kc = [hi rows | lo rows] x 64 K elements
+      mbar_expect_tx(bar0 + 8u * 44u, (uint32_t)KC * b_bytes);
+      for (int kc = 0; kc < KC; ++kc) {
+        tma_load_2d(bres_base + (uint32_t)kc * b_bytes, &tmB, bar0 + 8u * 44u, kc * 64, 0);
+        tma_load_2d(bres_base + (uint32_t)kc * b_bytes + b_half, &tmB, bar0 + 8u * 44u, kc * 64, p.b_rows_total);
+      }
+    }
+    __syncwarp();
     long long pw = 0, pstart = 0;
     if (INSTR) pstart = clock64();
     for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
@@ -1557,8 +1551,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (fold && !type1) tma2_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
               } else {
                 tma_load_4d(sa + sub * a_slot, &tmA, fb, cbase, tc.x0 + dx, tc.y0 + dy, tc.n0);
-                tma_load_2d(sB, &tmB, fb, bcol, brow);
-                if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
+                if (!b_res) {
+                  tma_load_2d(sB, &tmB, fb, bcol, brow);
+                  if (fold && !type1) tma_load_2d(sB + b_half, &tmB, fb, bcol, brow + p.b_rows_total);
+                }
               }
             }
           }
@@ -1590,7 +1586,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.mix) mma_issuer_lean<CTA2, 1>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
       else if (fold == 1u && CTA2) mma_issuer_lean<CTA2, 3>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
       else if (fold == 1u) mma_issuer_lean<CTA2, 2>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
-      else mma_issuer_lean<CTA2, 0>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles);
+      else mma_issuer_lean<CTA2, 0>(p, smem_base, bar0, tmem_base, (uint32_t)KC, KS, a_slot, b_bytes, b_half, tile0, tile_step, total_tiles,
+                                    b_res ? bres_base : 0u);
     } else {
     // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A/B, N>>3 at 17, M>>4 at 24
     // (a/b format code 0 is F16 under kind::f16 and E4M3 under kind::f8f6f4: fp16 and mixed inputs use one descriptor for both)
@@ -1716,11 +1713,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (p.kxn == 1) { if (half == 0) epilogue_kxn(p, tc, tmem_acc, quadrant, lane, kxn_smem + as * (128 * 29)); }
       else if (p.kxn) epilogue_kxn_wide(p, tc, tmem_acc, quadrant, lane, half, kxn_smem);
       else if (p.splitk > 1) {
-        if (p.sk_dist) {
-          splitk_publish_wait(p, tc, tmem_acc, quadrant, lane, half);
-          epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
-          splitk_done(p, tc);
-        } else if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
+        if (splitk_publish(p, tc, tmem_acc, quadrant, lane, half, &sk_flag)) epilogue_tile<32>(p, tc, tmem_acc, quadrant, lane, half, amax1, amax2);
       }
       else if (p.epi_fast) {
         for (int g = 0; g < p.ah_g; ++g) {          // halo-tile UP2: the item's parity classes sit side by side in the accumulator
@@ -1830,7 +1823,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query);
 extern "C" int eamm_conv_tc(const eamm_conv_args* a, void* stream) { return conv_tc_run(a, stream, nullptr); }
 
 /* Dry run of eamm_conv_tc's planning: fills out[0..5] = {N tile, 7x7 scheme, fold, K chunks per stage,
- * CTA pairs (bit 0) / halo-tile scheme (bit 1) / distributed split-K (bit 2) / split factor (bits 8+), pipeline stages} for these arguments (a->weight_fold is ignored) without launching anything. */
+ * CTA pairs (bit 0) / halo-tile scheme (bit 1) / split factor (bits 8+), pipeline stages} for these arguments (a->weight_fold is ignored) without launching anything. */
 extern "C" int eamm_conv_tc_query(const eamm_conv_args* a, int* out) {
   if (!out) return EAMM_ERR_ARG;
   return conv_tc_run(a, nullptr, out);
@@ -1994,7 +1987,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   // S = the largest divisor of the K-chunk count that keeps tiles * S within the SM count (>= 8 chunks per item).
   // The partial sums are added in split order, so a result is reproducible for a given batch size, but its last
   // bits depend on S and hence on how many frames share the launch.
-  p.splitk = 1; p.sk_dist = 0; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.splitk = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   static int splitk_env = -1;
   if (splitk_env < 0) { const char* e = getenv("EAMM_TC_SPLITK"); splitk_env = e ? atoi(e) : 1; }
   if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && !p.ah && a->cout % 256 == 0 && (query || a->splitk_ws)) {
@@ -2020,9 +2013,6 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && cost_split * 100 < cost_plain * 85 &&
         (query || a->splitk_ws_bytes >= need) && (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
       p.BN = 256; p.splitk = S;
-      static int dist_env = -1;
-      if (dist_env < 0) { const char* e = getenv("EAMM_TC_SPLITK_DIST"); dist_env = e ? atoi(e) : 0; }
-      p.sk_dist = (dist_env && t256 <= 512) ? 1 : 0;
       if (!query) {
         p.sk_cnt = reinterpret_cast<unsigned int*>(a->splitk_ws);
         p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(a->splitk_ws) + 4096);
@@ -2074,6 +2064,21 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   while (ksub > 1 && (uint32_t)ksub * chunk_bytes * 2u > ring_bytes) --ksub;      // keep at least two stages
   uint32_t stage_bytes = (uint32_t)ksub * chunk_bytes;
   int stages = (int)(ring_bytes / stage_bytes);
+  // resident weights (ConvTcParams::b_res): packed first conv in split mode -- one N tile, 7 chunks of [hi | lo] rows
+  static int lean_env = -1, bres_env = -1;
+  if (lean_env < 0) { const char* e = getenv("EAMM_TC_LEAN"); lean_env = e ? atoi(e) : 1; }
+  if (bres_env < 0) { const char* e = getenv("EAMM_TC_BRES"); bres_env = e ? atoi(e) : 1; }
+  p.b_res = 0;
+  size_t bres_bytes = 0;
+  if (bres_env && lean_env && !instr && row7 && p.fold == 2 && !p.cta2 && p.n_tiles == 1 && p.splitk == 1) {
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u * 2u;
+    if ((size_t)kc_total * b_bytes + 4u * (uint32_t)p.a_slot_bytes <= ring_bytes) {
+      p.b_res = 1; bres_bytes = (size_t)kc_total * b_bytes;
+      ksub = ksub_env > 0 ? ksub_env : 1;
+      stage_bytes = (uint32_t)ksub * (uint32_t)p.a_slot_bytes;
+      stages = (int)((ring_bytes - bres_bytes) / stage_bytes);
+    }
+  }
   if (p.ah) {
     // weight stage = `ksub` taps of one parity class (a whole filter row / a whole 2x2 class when the tile is narrow)
     const uint32_t b_bytes = (uint32_t)p.BN * (p.cta2 ? 64u : 128u);
@@ -2106,7 +2111,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   p.num_stages = stages;
   if (query) {
     query[0] = p.BN; query[1] = mode7; query[2] = p.fold; query[3] = p.ksub;
-    query[4] = p.cta2 | (p.ah << 1) | (p.sk_dist << 2) | (p.splitk << 8); query[5] = p.num_stages;
+    query[4] = p.cta2 | (p.ah << 1) | (p.splitk << 8); query[5] = p.num_stages;
     return 0;
   }
   p.has_out = a->out != nullptr; p.has_out2 = a->out2 != nullptr; p.has_res = a->residual != nullptr;
@@ -2139,8 +2144,6 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     p.epi_fast = !ok ? 0 : (p.fold ? (pool ? 6 : 5) : (pool ? 2 : (a->residual ? (a->out2 ? 4 : 3) : 1)));
   }
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
-  static int lean_env = -1;
-  if (lean_env < 0) { const char* e = getenv("EAMM_TC_LEAN"); lean_env = e ? atoi(e) : 1; }
   p.lean = (lean_env && !p.halo) ? 1 : 0;
   p.mix64 = mix64 ? 1 : 0;
   p.nf8 = mix64 ? p.ntap : (mix ? p.ntap * p.cin_chunks : 0);
@@ -2201,7 +2204,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem + (p.ah ? (size_t)p.ah_na * p.a_slot_bytes : 0);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem + (p.ah ? (size_t)p.ah_na * p.a_slot_bytes : 0) + bres_bytes;
   // the attribute is per device: a process that drives several GPUs (nn.DataParallel replicas, train.py:53-60) must set it on each
   static size_t smem_set_dev[64] = {0};
   int cur_dev = 0;
@@ -2232,18 +2235,6 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, p);
     if (e != cudaSuccess) return (int)e;
-  } else if (p.splitk > 1 && p.sk_dist && !instr) {
-    // the CTAs of a tile wait for each other: ask the runtime to guarantee that the whole grid is resident
-    if (grid != p.total_tiles) return EAMM_ERR_UNSUPPORTED;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, p);
-    if (e != cudaSuccess) return (int)e;
   } else if (instr) conv_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   else conv_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   EAMM_LAUNCH_CHECK();
@@ -2262,6 +2253,10 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
             acc[4] / mg / tiles_per_cta, acc[0] / grid / tiles_per_cta, acc[2] / mg / tiles_per_cta,
             acc[3] / mg / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
             acc[4] / mg / tiles_per_cta / KCh);
+#ifdef EAMM_EPI_PHASES
+    fprintf(stderr, "[epi_phases] per chunk of warp 0 (cycles): tmem wait %.0f, bias/scale + relu %.0f (chunks per tile %d)\n",
+            acc[0] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), acc[1] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), p.BN / 64 * p.ah_g);
+#endif
   }
   return 0;
 }
