@@ -41,6 +41,7 @@
 // dense_motion.py:98,110.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <stdio.h>
 #include "common.cuh"
 
@@ -116,6 +117,13 @@ struct ConvTcParams {
   int b_res;           // the whole weight matrix of the CTA stays in shared memory (packed first conv: 7 chunks = 112 KB, loaded
                        // once; the ring then carries A only -- that layer ran at the L2 -> SM cap re-staging 16 KB of weights per
                        // 16 KB of pixels); barrier bars[44]
+  int tma_st;          // fast epilogue stores through shared memory + TMA (cp.async.bulk.tensor store): a lane owns a pixel, so its
+                       // 32-byte global stores touched 32 different lines per warp instruction and kept the LSU busy for ~50 % of a
+                       // narrow layer's time, with the next chunk's bias loads queued behind them.  Each epilogue warp stages its
+                       // 32 pixels x 32 channels (4 KB, swizzled: conflict-free 16-byte shared stores) and one lane issues the bulk
+                       // stores.  st_base = offset of the staging area (8 warps x 2 x 4 KB) from the ring base.
+  int st_base;
+  int st_stride;       // bytes of staging per epilogue warp: 4 KB (out) or 8 KB (out + out2)
   int epi_fast;        // fast epilogue variant (epilogue_fast): 0 = generic, 1 = plain, 2 = pooled, 3 = residual, 4 = residual + out2, 5 / 6 = plain / pooled with folded weight planes
   int dec_shift;       // >= 0: decode_tile by shifts, log2 of (n_tiles, cls_groups, tiles_x, tiles_y) in 5-bit fields; -1: divisions
   int ah_na;           // A ring slots
@@ -238,6 +246,21 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
+// Output tensor maps of the TMA-store epilogue: 5-D byte maps {pixel bytes, column parity, x, row parity, image * H + y} of `out`
+// and `out2` (parities = the UP2 scatter; 1 otherwise), one with 64-byte boxes (fp16 / bf16 planes, SWIZZLE_64B) and one with
+// 32-byte boxes (the e4m3 planes of the mixed format, SWIZZLE_32B).
+struct StoreMaps { CUtensorMap o64, o32, p64, p32; };
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // K-major SWIZZLE_128B smem matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 |
 // SBO(=1024B>>4)<<32 | version 1 <<46 | layout SWIZZLE_128B(2) <<61.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
@@ -815,6 +838,7 @@ struct EpiView {
   char* p0;          // byte address of plane 0 at (pixel, first channel of the N tile)
   char* p1;          // second plane at the same channel: bf16 lo plane, or the e4m3 lo8 bytes of the mixed format
   int fmt, c_buf;
+  int col0, col1;    // byte columns of p0 / p1 inside the pixel record (TMA-store coordinates)
   float mul, inv_mul;
 };
 __device__ __forceinline__ EpiView epi_view(const ActView& v, int n, int y, int x, int co0) {
@@ -825,6 +849,8 @@ __device__ __forceinline__ EpiView epi_view(const ActView& v, int n, int y, int 
   e.c_buf = v.c_buf;
   // mixed: plane 1 of the pixel starts 2*c_buf bytes after plane 0 and holds [c_buf lo8 | c_buf hi8]
   e.p1 = e.fmt == 3 ? e.p0 - 2 * (v.c_off + co0) + 2 * v.c_buf + (v.c_off + co0) : e.p0 + 2 * v.c_buf;
+  e.col0 = 2 * (v.c_off + co0);
+  e.col1 = e.fmt == 3 ? 2 * v.c_buf + v.c_off + co0 : 2 * v.c_buf + 2 * (v.c_off + co0);
   e.mul = v.mul; e.inv_mul = v.inv_mul;
   return e;
 }
@@ -903,6 +929,63 @@ __device__ __forceinline__ void epi_add16_bf16(const uint4 a, const uint4 b, flo
   o[0] += x0.x; o[1] += x0.y; o[2] += x0.z; o[3] += x0.w; o[4] += x1.x; o[5] += x1.y; o[6] += x1.z; o[7] += x1.w;
   o[8] += x2.x; o[9] += x2.y; o[10] += x2.z; o[11] += x2.w; o[12] += x3.x; o[13] += x3.y; o[14] += x3.z; o[15] += x3.w;
 }
+// TMA-store variant of epi_store<32> (ConvTcParams::tma_st): the lane's 32 channels go to the warp's staging area (row = lane,
+// 16-byte pieces XOR-swizzled as the tensor maps expect: conflict-free st.shared.v4), lane 0 issues the bulk stores.
+struct EpiTma { const CUtensorMap* m64; const CUtensorMap* m32; uint32_t area; int px, x, py, yr; };
+__device__ __forceinline__ void epi_store_tma(const EpiView& e, const EpiTma& t, int lane, int c, const float* f) {
+  if (lane == 0) bulk_wait_read0();               // earlier bulk stores of this warp have finished reading the staging areas
+  __syncwarp();
+  const uint32_t row64 = t.area + (uint32_t)lane * 64u, sw64 = ((uint32_t)lane >> 1) & 3u;
+  const uint32_t row32 = t.area + 2048u + (uint32_t)lane * 32u, sw32 = ((uint32_t)lane >> 2) & 1u;
+  if (e.fmt >= 2) {
+    uint32_t h[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h[j] = f32x2_to_f16x2_sat(f[2 * j] * e.mul, f[2 * j + 1] * e.mul);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sts128(row64 + (((uint32_t)k ^ sw64) << 4), h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+    if (e.fmt == 3) {
+      uint32_t lo8[8], hi8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 a = f16x2_to_f32x2(h[2 * j]), b = f16x2_to_f32x2(h[2 * j + 1]);
+        lo8[j] = f32x4_to_e4m3x4_sat((f[4 * j] * e.mul - a.x) * MIX_LO_GAIN, (f[4 * j + 1] * e.mul - a.y) * MIX_LO_GAIN,
+                                     (f[4 * j + 2] * e.mul - b.x) * MIX_LO_GAIN, (f[4 * j + 3] * e.mul - b.y) * MIX_LO_GAIN);
+        hi8[j] = f16x4_to_hi8x4(h[2 * j], h[2 * j + 1]);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        sts128(row32 + (((uint32_t)k ^ sw32) << 4), lo8[4 * k], lo8[4 * k + 1], lo8[4 * k + 2], lo8[4 * k + 3]);
+        sts128(row32 + 1024u + (((uint32_t)k ^ sw32) << 4), hi8[4 * k], hi8[4 * k + 1], hi8[4 * k + 2], hi8[4 * k + 3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint2 a = float4_to_bf16x4(make_float4(f[8 * k], f[8 * k + 1], f[8 * k + 2], f[8 * k + 3]));
+      const uint2 b = float4_to_bf16x4(make_float4(f[8 * k + 4], f[8 * k + 5], f[8 * k + 6], f[8 * k + 7]));
+      sts128(row64 + (((uint32_t)k ^ sw64) << 4), a.x, a.y, b.x, b.y);
+      if (e.fmt == 1) {
+        const float4 ha = bf16x4_to_float4(a), hb = bf16x4_to_float4(b);
+        const uint2 la = float4_to_bf16x4(make_float4(f[8 * k] - ha.x, f[8 * k + 1] - ha.y, f[8 * k + 2] - ha.z, f[8 * k + 3] - ha.w));
+        const uint2 lb = float4_to_bf16x4(make_float4(f[8 * k + 4] - hb.x, f[8 * k + 5] - hb.y, f[8 * k + 6] - hb.z, f[8 * k + 7] - hb.w));
+        sts128(row64 + 2048u + (((uint32_t)k ^ sw64) << 4), la.x, la.y, lb.x, lb.y);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_5d(t.m64, t.area, e.col0 + 2 * c, t.px, t.x, t.py, t.yr);
+    if (e.fmt == 3) {
+      tma_store_5d(t.m32, t.area + 2048u, e.col1 + c, t.px, t.x, t.py, t.yr);
+      tma_store_5d(t.m32, t.area + 3072u, e.col1 + e.c_buf + c, t.px, t.x, t.py, t.yr);
+    } else if (e.fmt == 1) {
+      tma_store_5d(t.m64, t.area + 2048u, e.col1 + 2 * c, t.px, t.x, t.py, t.yr);
+    }
+    bulk_commit();
+  }
+}
+
 // residual of one 32-channel chunk: the loads are issued ahead of use (all of them back to back -- a loop over the planes
 // with a load -> use dependence per iteration serialised four DRAM round trips per chunk: 17 k cycles per conv2 tile),
 // epi_res_add then adds plane by plane in add_chunk's order.  rr = [16-channel group][plane] x 32 bytes.
@@ -935,9 +1018,10 @@ __device__ __forceinline__ void epi_res_add(const EpiView& e, const uint4* rr, f
   }
 }
 
-template <bool POOL, bool RES, bool OUT2, bool FOLD>
+template <bool POOL, bool RES, bool OUT2, bool FOLD, bool TMA>
 __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileCoord& tc, uint32_t tmem_acc,
-                                              int quadrant, int lane, int half, float& amax1, float& amax2) {
+                                              int quadrant, int lane, int half, float& amax1, float& amax2,
+                                              const StoreMaps* maps, uint32_t st_area) {
   const int r = quadrant * 32 + lane;
   const int xl = r & (p.bw - 1);
   const int yl = (r >> p.bw_log2) & (p.bh - 1);
@@ -959,6 +1043,17 @@ __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileC
   EpiView vr = vo, v2 = vo;
   if (RES) vr = epi_view(p.res, valid ? n : 0, valid ? oy : 0, valid ? ox : 0, co0);
   if (OUT2) v2 = epi_view(p.out2, valid ? n : 0, valid ? oy : 0, valid ? ox : 0, co0);
+  // TMA-store coordinates of the warp's 32 pixels (tiles lie inside one image: bn == 1, H a multiple of the tile height)
+  constexpr bool tma = TMA;          // compile-time: the residual / pooled variants never carry the staging code (registers)
+  EpiTma t1, t2;
+  if (tma) {
+    const int q32 = quadrant * 32;
+    const bool up2 = p.kind == EAMM_CONV_UP2_3X3;
+    t1.m64 = &maps->o64; t1.m32 = &maps->o32; t1.area = st_area;
+    t1.px = up2 ? (tc.cls & 1) : 0; t1.py = up2 ? (tc.cls >> 1) : 0;
+    t1.x = tc.x0 + (q32 & (p.bw - 1)); t1.yr = tc.n0 * p.H + tc.y0 + (q32 >> p.bw_log2);
+    t2 = t1; t2.m64 = &maps->p64; t2.m32 = &maps->p32; t2.area = st_area + 4096u;
+  }
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
   const int cstep = (TC_EPI_WARPS / 4) * 32;
   int c0 = half * 32;
@@ -1049,7 +1144,12 @@ __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileC
     }
     if (valid) {
       if (RES) { epi_res_load(vr, c0, rr); epi_res_add(vr, rr, f); }      // all planes' loads first, then the adds
-      epi_store<32>(vo, c0, f);
+      if (tma) epi_store_tma(vo, t1, lane, c0, f);
+      else epi_store<32>(vo, c0, f);
+#ifdef EAMM_EPI_PHASES
+      if (p.prof != nullptr && quadrant == 0 && half == 0 && lane == 0)
+        atomicAdd(p.prof + blockIdx.x * 8 + 7, (unsigned long long)(clock64() - ph2));
+#endif
       if (track1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) amax1 = fmaxf(amax1, fabsf(f[j]));
@@ -1065,7 +1165,8 @@ __device__ __forceinline__ void epilogue_fast(const ConvTcParams& p, const TileC
           f[4 * g + 2] = fmaxf(fmaf(f[4 * g + 2], sv.z, tv.z), 0.f);
           f[4 * g + 3] = fmaxf(fmaf(f[4 * g + 3], sv.w, tv.w), 0.f);
         }
-        epi_store<32>(v2, c0, f);
+        if (tma) epi_store_tma(v2, t2, lane, c0, f);
+        else epi_store<32>(v2, c0, f);
         if (track2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) amax2 = fmaxf(amax2, f[j]);          // post-ReLU: non-negative
@@ -1382,7 +1483,7 @@ __device__ __forceinline__ void epilogue_kxn_wide(const ConvTcParams& p, const T
 template <bool INSTR, bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvTcParams p) {
+               const __grid_constant__ StoreMaps tmS, const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * 16 + 4 + 8 + 1];      // + halo-tile scheme: A ring full [36..39] / empty [40..43]
   __shared__ uint32_t tmem_base_smem;
@@ -1701,6 +1802,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (eprof) pstart = clock64();
     float* kxn_smem = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
                                                (size_t)p.num_stages * stage_bytes);
+    const uint32_t st_area = smem_base + (uint32_t)p.st_base + (uint32_t)(warp * p.st_stride);     // TMA-store staging of this warp
     for (uint32_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(p, tile);
       long long t0 = 0;
@@ -1719,12 +1821,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int g = 0; g < p.ah_g; ++g) {          // halo-tile UP2: the item's parity classes sit side by side in the accumulator
           TileCoord tg = tc; tg.cls = tc.cls + g;
           const uint32_t ta = tmem_acc + (uint32_t)(g * p.BN);
-          if (p.epi_fast == 1) epilogue_fast<false, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
-          else if (p.epi_fast == 2) epilogue_fast<true, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
-          else if (p.epi_fast == 3) epilogue_fast<false, true, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
-          else if (p.epi_fast == 4) epilogue_fast<false, true, true, false>(p, tg, ta, quadrant, lane, half, amax1, amax2);
-          else if (p.epi_fast == 5) epilogue_fast<false, false, false, true>(p, tg, ta, quadrant, lane, half, amax1, amax2);
-          else epilogue_fast<true, false, false, true>(p, tg, ta, quadrant, lane, half, amax1, amax2);
+          if (p.epi_fast == 1) {
+            if (p.tma_st) epilogue_fast<false, false, false, false, true>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+            else epilogue_fast<false, false, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+          }
+          else if (p.epi_fast == 2) epilogue_fast<true, false, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+          else if (p.epi_fast == 3) epilogue_fast<false, true, false, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+          else if (p.epi_fast == 4) epilogue_fast<false, true, true, false, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+          else if (p.epi_fast == 5) {
+            if (p.tma_st) epilogue_fast<false, false, false, true, true>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+            else epilogue_fast<false, false, false, true, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
+          }
+          else epilogue_fast<true, false, false, true, false>(p, tg, ta, quadrant, lane, half, amax1, amax2, &tmS, st_area);
         }
       }
       else if (p.ah_g > 1) {                       // halo-tile UP2: the item's parity classes sit side by side in the accumulator
@@ -1744,6 +1852,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (p.tma_st && lane == 0) bulk_wait0();       // this warp's bulk stores have landed
     if (p.amax_out != nullptr || p.amax_out2 != nullptr) {
       // values are non-negative: the integer order of their bit patterns is the float order
 #pragma unroll
@@ -2045,7 +2154,24 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
                             : p.kxn == 2 ? 128u * (28u * (uint32_t)p.s_nc + 1u) * 4u
                             : (p.kxn ? 128u * (uint32_t)KXW_LD * 4u : 0u);
   // (scheme 3 takes everything the SM has: with <= 3 NCHW channels that is a fourth 44 KB stage)
-  const uint32_t ring_bytes = (p.kxn == 2 ? 225u * 1024u : 200u * 1024u) - extra_smem;
+  // TMA-store epilogue (ConvTcParams::tma_st): plain (no residual / second output / pooling) activation-view outputs of layers
+  // whose tiles lie inside one image and whose 32-pixel warp groups are whole rows / row segments; dense NHWC views.  By default
+  // only where the epilogue is the critical path, N tiles of <= 64 columns (packed first conv, up1: measured -5 % / -8 % per tile);
+  // wider layers are MMA- or L2-bound and need the shared memory for their weight ring.  EAMM_TC_TMAST=0: off, 2: every plain layer.
+  static int tmast_env = -1;
+  if (tmast_env < 0) { const char* e = getenv("EAMM_TC_TMAST"); tmast_env = e ? atoi(e) : 1; }
+  auto tma_view_ok = [&](const eamm_act* v, int up) {
+    return v && v->dtype != EAMM_F32 && v->n_stride == (int64_t)v->h * v->w * v->planes * v->c_buf && (uintptr_t)v->data % 128 == 0 &&
+           (v->planes * v->c_buf) % 64 == 0 && v->c_off % 32 == 0 && v->c_buf % 32 == 0 && v->h == in->h * up && v->w == in->w * up &&
+           v->n == in->n;
+  };
+  const int st_up = a->kind == EAMM_CONV_UP2_3X3 ? 2 : 1;
+  p.tma_st = (tmast_env && !instr && !p.kxn && p.splitk == 1 && p.BN % 32 == 0 && !(a->flags & (EAMM_EPI_POOL2 | EAMM_EPI_SIGMOID)) &&
+              !a->out_nhwc_f32 && !a->out_nchw && p.bn == 1 && p.bw >= 8 && in->h % p.bh == 0 && in->w % p.bw == 0 &&
+              tma_view_ok(a->out, st_up) && !a->out2 && !a->residual && (p.BN <= 64 || tmast_env == 2))
+                 ? 1 : 0;
+  const uint32_t st_bytes = p.tma_st ? 32u * 1024u : 0u;      // 8 warps x 4 KB
+  const uint32_t ring_bytes = (p.tma_st ? 226u * 1024u - st_bytes : (p.kxn == 2 ? 225u * 1024u : 200u * 1024u)) - extra_smem;
   // K chunks per stage: as many as keep >= 4 stages in the ring (>= 3 for the widest tiles); short
   // single-warp issue loops are latency-bound, so fewer, fatter stages win until smem runs out.
   static int ksub_env = -1;
@@ -2142,6 +2268,7 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     if (ok && a->out2 && !a->residual) ok = false;
     if (ok && p.fold && (a->residual || a->out2)) ok = false;
     p.epi_fast = !ok ? 0 : (p.fold ? (pool ? 6 : 5) : (pool ? 2 : (a->residual ? (a->out2 ? 4 : 3) : 1)));
+    if (!p.epi_fast || pool) p.tma_st = 0;
   }
   p.acc_scale = a->acc_scale; p.amax_out = a->out ? a->amax_out : nullptr; p.amax_out2 = a->out2 ? a->amax_out2 : nullptr;
   p.lean = (lean_env && !p.halo) ? 1 : 0;
@@ -2204,7 +2331,30 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return EAMM_ERR_UNSUPPORTED - 200 - (int)r;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem + (p.ah ? (size_t)p.ah_na * p.a_slot_bytes : 0) + bres_bytes;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + extra_smem + (p.ah ? (size_t)p.ah_na * p.a_slot_bytes : 0) + bres_bytes;
+  StoreMaps tmS;
+  memset(&tmS, 0, sizeof(tmS));
+  p.st_base = 0; p.st_stride = 0;
+  if (p.tma_st) {
+    p.st_base = (int)((smem - 1024 + 1023) / 1024 * 1024);      // staging areas: 1024-byte aligned, behind everything else
+    smem = (size_t)p.st_base + st_bytes + 1024;
+    p.st_stride = (int)(st_bytes / TC_EPI_WARPS);
+    const int bx = p.bw < 32 ? p.bw : 32, by = 32 / bx;
+    auto enc = [&](CUtensorMap* m, const eamm_act* v, int box_bytes) -> bool {
+      // {pixel bytes, column parity, x, row parity, image * H_in + y}: output pixel (up*y + py, up*x + px)
+      const cuuint64_t pixb = (cuuint64_t)v->planes * v->c_buf * 2, wout = (cuuint64_t)v->w;
+      cuuint64_t dims[5] = {pixb, (cuuint64_t)st_up, (cuuint64_t)in->w, (cuuint64_t)st_up, (cuuint64_t)in->n * in->h};
+      cuuint64_t strides[4] = {pixb, (cuuint64_t)st_up * pixb, wout * pixb, (cuuint64_t)st_up * wout * pixb};
+      cuuint32_t box[5] = {(cuuint32_t)box_bytes, 1, (cuuint32_t)bx, 1, (cuuint32_t)by};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, v->data, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool okm = enc(&tmS.o64, a->out, 64) && enc(&tmS.o32, a->out, 32);
+    if (okm && a->out2) okm = enc(&tmS.p64, a->out2, 64) && enc(&tmS.p32, a->out2, 32);
+    if (!okm) return EAMM_ERR_UNSUPPORTED - 300;
+  }
   // the attribute is per device: a process that drives several GPUs (nn.DataParallel replicas, train.py:53-60) must set it on each
   static size_t smem_set_dev[64] = {0};
   int cur_dev = 0;
@@ -2233,10 +2383,10 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmS, p);
     if (e != cudaSuccess) return (int)e;
-  } else if (instr) conv_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
-  else conv_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  } else if (instr) conv_tc_kernel<true, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, tmS, p);
+  else conv_tc_kernel<false, false><<<(unsigned)grid, TC_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, tmS, p);
   EAMM_LAUNCH_CHECK();
   if (prof_env) {        // bring-up instrumentation only: synchronous read-back and print
     static unsigned long long host[1024 * 8];
@@ -2254,8 +2404,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
             acc[3] / mg / tiles_per_cta, acc[5] / grid / tiles_per_cta, (acc[6] - acc[5]) / grid / tiles_per_cta,
             acc[4] / mg / tiles_per_cta / KCh);
 #ifdef EAMM_EPI_PHASES
-    fprintf(stderr, "[epi_phases] per chunk of warp 0 (cycles): tmem wait %.0f, bias/scale + relu %.0f (chunks per tile %d)\n",
-            acc[0] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), acc[1] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), p.BN / 64 * p.ah_g);
+    fprintf(stderr, "[epi_phases] per chunk of warp 0 (cycles): tmem wait %.0f, bias/scale + relu %.0f, first store %.0f (chunks per tile %d, tma_st %d)\n",
+            acc[0] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), acc[1] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g),
+            acc[7] / grid / tiles_per_cta / (p.BN / 64.0 * p.ah_g), p.BN / 64 * p.ah_g, p.tma_st);
 #endif
   }
   return 0;
