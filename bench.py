@@ -35,7 +35,9 @@ from eamm_b200 import get_config, synth, sharding           # noqa: E402
 
 ALG_GFLOP_PER_FRAME = 107.286       # 30 convs, 2*MAC, per (source, kp) frame
 # ncu --set full DRAM traffic (read + write bytes) of ONE bottleneck-conv launch at B=32: (bytes, source file)
-TRAFFIC = {"fp32_bf16x3": (138.35e6 + 95.15e6, "profiles/r1b_ncu_summary.md")}
+TRAFFIC = {"fp32_bf16x3": (138.35e6 + 95.15e6, "profiles/r1b_ncu_summary.md"),
+           # mixed fp16 + 2 x e4m3 operands: mean of conv1 (136.7 + 89.4 MB) and conv2 (276.1 + 220.0 MB: residual read, two outputs)
+           "mix": (0.5 * (136.74e6 + 89.44e6 + 276.12e6 + 219.98e6), "profiles/r2_ncu_summary.md")}
 METRIC = "256x256 frames/sec (DenseMotionNetwork + OcclusionAwareGenerator forward, 10 kp)"
 
 
@@ -477,7 +479,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": {"fp32": "fp32-equivalent split operands: fp16 + 2 x e4m3 (bottleneck) / bf16 hi+lo (other layers), fp32 accumulate"
+        "dtype": {"fp32": "fp32-equivalent split operands: fp16 + 2 x e4m3 (generator 3x3 / UP2 convs) / bf16 hi+lo (7x7 convs, hourglass), fp32 accumulate"
                   if mixed else "bf16x3 split (fp32-equivalent, fp32 accumulate)",
                   "fp32_bf16x3": "bf16x3 split (fp32-equivalent, fp32 accumulate)",
                   "fp16": "fp16 (fp32 accumulate, fp32 warp)", "bf16": "bf16 (fp32 accumulate, fp32 warp)",
