@@ -1565,11 +1565,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t slot = 0, phase = 0, si = w;
     for (uint32_t i = 0; i < w; ++i) { if (++slot == nstages) { slot = 0; phase ^= 1u; } }
     if (b_res && w == 0u && tile0 < total_tiles && elect_one()) {
-      // resident weights (single CTA, fold 2, one N tile): chunk kc = [hi rows | lo rows] x 64 K elements
+      // resident weights (single CTA, one N tile): chunk kc = 64 K elements of every row ([hi rows | lo rows] when folded)
       mbar_expect_tx(bar0 + 8u * 44u, (uint32_t)KC * b_bytes);
       for (int kc = 0; kc < KC; ++kc) {
-        tma_load_2d(bres_base + (uint32_t)kc * b_bytes, &tmB, bar0 + 8u * 44u, kc * 64, 0);
-        tma_load_2d(bres_base + (uint32_t)kc * b_bytes + b_half, &tmB, bar0 + 8u * 44u, kc * 64, p.b_rows_total);
+        const int bcol = kc * (p.f16in ? 128 : 64);                  // fp16 maps are addressed in bytes
+        tma_load_2d(bres_base + (uint32_t)kc * b_bytes, &tmB, bar0 + 8u * 44u, bcol, 0);
+        if (fold) tma_load_2d(bres_base + (uint32_t)kc * b_bytes + b_half, &tmB, bar0 + 8u * 44u, bcol, p.b_rows_total);
       }
     }
     __syncwarp();
@@ -2141,7 +2142,9 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     const long long m_tiles_pc = (long long)p.tiles_x * p.tiles_y * p.tiles_n;     // M tiles per (class, N tile)
     const bool pair_a = !p.fold && (p.BN == 256 || ((cta2_env & 4) && p.BN % 32 == 0));
     const bool pair_b = ((cta2_env & 2) && p.fold == 1 && p.BN % 32 == 0) ||
-                        ((cta2_env & 16) && p.mix && p.BN % 32 == 0);       // mixed operands: 8 steps per (tap, 64 ch) like a folded layer
+                        ((cta2_env & 16) && p.mix && p.BN % 32 == 0) ||     // mixed operands: 8 steps per (tap, 64 ch) like a folded layer
+                        ((cta2_env & 16) && p.ah && p.BN % 32 == 0);        // halo tiles, one-plane fp16: the weight stream is what is left of
+                                                                            // the L2 traffic, a pair halves it per SM (down0 fp16 mode: L2-bound alone)
     const bool fills = m_tiles_pc % 2 == 0 && tiles_all >= num_sms;
     p.cta2 = (common && fills && (pair_a || pair_b)) ? 1 : 0;
   }
@@ -2196,8 +2199,8 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (bres_env < 0) { const char* e = getenv("EAMM_TC_BRES"); bres_env = e ? atoi(e) : 1; }
   p.b_res = 0;
   size_t bres_bytes = 0;
-  if (bres_env && lean_env && !instr && row7 && p.fold == 2 && !p.cta2 && p.n_tiles == 1 && p.splitk == 1) {
-    const uint32_t b_bytes = (uint32_t)p.BN * 128u * 2u;
+  if (bres_env && lean_env && !instr && row7 && (p.fold == 2 || p.passes == 1) && !p.cta2 && p.n_tiles == 1 && p.splitk == 1) {
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u * (p.fold ? 2u : 1u);
     if ((size_t)kc_total * b_bytes + 4u * (uint32_t)p.a_slot_bytes <= ring_bytes) {
       p.b_res = 1; bres_bytes = (size_t)kc_total * b_bytes;
       ksub = ksub_env > 0 ? ksub_env : 1;
