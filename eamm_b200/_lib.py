@@ -79,6 +79,7 @@ _PROTOS = {
     "eamm_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "eamm_maxpool": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "eamm_act_copy": (C.c_int, [C.POINTER(Act), C.POINTER(Act), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_lstm_layer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eamm_pack_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

@@ -7,10 +7,21 @@ The whole clip is processed as one batch of B*T frames (the reference loops over
   audio FC, pose MLP                        eamm_linear (ReLU, x`weight` fused)
   3-layer LSTM                              eamm_linear (input projections for all t) + eamm_lstm_layer
   decon: ConvTranspose 1x1->4x4             eamm_linear (the 16 output pixels are 16 column blocks)
-         4 x ConvTranspose(k4, s2, p1)      eamm_conv_simt UP2 kind with parity-class weights, NCHW fp32 out
-Everything is fp32 on CUDA cores: this stage runs once per clip and feeds the keypoint softmax
-(temperature 0.1), so it is kept at full fp32 accuracy in every precision mode of the frame path.
+         4 x ConvTranspose(k4, s2, p1)      UP2 kind with parity-class weights, NCHW fp32 out: eamm_conv_tc on bf16 hi/lo
+                                            planes (three tensor-core passes, fp32-equivalent: the maps are powers of two),
+                                            or eamm_conv_simt with EAMM_B200_AT_DECON=simt
+This stage runs once per clip and feeds the keypoint softmax (temperature 0.1), so it is kept at fp32(-equivalent)
+accuracy in every precision mode of the frame path.  The MFCC convs stay on fp32 CUDA cores by default: they sit in front
+of FC1 -> LSTM -> decon -> softmax(T = 0.1) and the chain amplifies their rounding ~100x.  Opt-in (EAMM_B200_AT_AUDIO=tc):
+audio1 / 3 / 4 / 5 (28x12 and 26x5 maps, 93 % of the encoder's FLOPs) on tensor cores over maps padded to 32x16 / 32x8
+(bf16 hi/lo planes, three passes; eamm_act_copy moves the activations into and out of the padded buffers and re-zeroes the
+padding a convolution has written, so every layer still sees the reference's zero padding; the two max-pools and audio0
+work on the exact maps).  Measured on B200, 300-frame LRW clip: AT_net2 10.2 -> 4.6 ms per clip, AT_net2 output still
+within 1e-4 of the reference, but the normalised keypoints move by more than the 1e-3 the clip test states (worst frame
+PSNR 57.3 -> 51.4 dB): 16 significant bits per operand are not enough in front of that chain.
 """
+import os
+
 import ctypes as C
 
 import torch
@@ -69,10 +80,13 @@ class ATNet2Engine:
                                       _round_up(w.shape[1], 4), 4, "simt"))
         # MFCC encoder (util.py:540-548)
         self.aud = {}
+        self.aud_tc = os.environ.get("EAMM_B200_AT_AUDIO", "simt") == "tc"
         for i in (0, 1, 3, 4, 5):
             conv, norm = m.audio_eocder[i][0], m.audio_eocder[i][1]
             w, b = fold_bn(f(conv.weight), torch.zeros(conv.out_channels, device=dev), _bn(norm))
-            self.aud[i] = ConvLayer("at.audio%d" % i, L.CONV_3X3, L.EPI_RELU, w, b, _round_up(w.shape[1], 4), 4, "simt")
+            tc = self.aud_tc and i != 0
+            self.aud[i] = ConvLayer("at.audio%d" % i, L.CONV_3X3, L.EPI_RELU, w, b, _round_up(w.shape[1], 64 if tc else 4),
+                                    16 if tc else 4, "tc3" if tc else "simt")
         # audio FC: the encoder output is flattened (c, h, w) in the reference, (h, w, c) here
         w1 = f(m.audio_eocder_fc[0].weight)
         hw = w1.shape[1] // 512
@@ -97,7 +111,13 @@ class ATNet2Engine:
         s, t = bn_affine(_bn(d[1]))
         w0 = f(d[0].weight)[:, :, 1:5, 1:5] * s.view(1, -1, 1, 1)                 # 1x1 input: out(y,x) uses tap (y+1,x+1)
         b0 = f(d[0].bias) * s + t
-        self.dec0 = Linear("at.decon0", w0.permute(2, 3, 1, 0).reshape(16 * 256, 256), b0.repeat(16), True, dev)
+        # decon stack on tensor cores: the 1x1 -> 4x4 layer then writes NCHW (columns (c, y, x)) and eamm_nchw_to_act
+        # splits it into the bf16 hi/lo planes the convolutions read
+        self.dec_tc = os.environ.get("EAMM_B200_AT_DECON", "tc") != "simt"
+        if self.dec_tc:
+            self.dec0 = Linear("at.decon0", w0.permute(1, 2, 3, 0).reshape(256 * 16, 256), b0.repeat_interleave(16), True, dev)
+        else:
+            self.dec0 = Linear("at.decon0", w0.permute(2, 3, 1, 0).reshape(16 * 256, 256), b0.repeat(16), True, dev)
         self.dec = []
         for i in (3, 6, 9, 12):
             w, b = f(d[i].weight), f(d[i].bias)                                   # [cin][cout][4][4]
@@ -105,7 +125,8 @@ class ATNet2Engine:
                 s, t = bn_affine(_bn(d[i + 1]))
                 w, b = w * s.view(1, -1, 1, 1), b * s + t
             lay = ConvLayer("at.decon%d" % i, L.CONV_UP2_3X3, L.EPI_RELU if i != 12 else 0,
-                            w.permute(1, 0, 2, 3), b, w.shape[0], 4, "simt", parity=convT_parity_weights(w))
+                            w.permute(1, 0, 2, 3), b, w.shape[0], 16 if self.dec_tc else 4, "tc3" if self.dec_tc else "simt",
+                            parity=convT_parity_weights(w))
             lay.flops_per_in_pixel = 2.0 * w.shape[0] * w.shape[1] * 16
             self.dec.append(lay)
         self.ws = WorkspaceCache()
@@ -130,11 +151,17 @@ class ATNet2Engine:
         ws.a4 = ActBuf(M, 26, 5, 256, "f32", dev)
         ws.a5 = ActBuf(M, 26, 5, 512, "f32", dev)
         ws.p2 = ActBuf(M, 12, 2, 512, "f32", dev)
+        if self.aud_tc:
+            # padded twins of the conv operands (zero-initialised; the padding is kept zero by eamm_act_copy)
+            pb = lambda h, w, c: ActBuf(M, h, w, c, "bf16x2", dev)
+            ws.a0p, ws.a1p = pb(32, 16, 64), pb(32, 16, 128)
+            ws.p1p, ws.a3p, ws.a4p, ws.a5p = pb(32, 8, 128), pb(32, 8, 256), pb(32, 8, 256), pb(32, 8, 512)
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         ws.f1, ws.pose_h, ws.x2 = e(M, 2048), e(M, 128), e(M, 512)
         ws.img_proj, ws.gates = e(B, 4 * self.HID), e(M, 4 * self.HID)
         ws.h = [e(M, self.HID) for _ in range(3)]
-        ws.d = [ActBuf(M, 4 << i, 4 << i, c, "f32", dev) for i, c in enumerate((256, 128, 128, 128))]
+        ws.d = [ActBuf(M, 4 << i, 4 << i, c, "bf16x2" if self.dec_tc else "f32", dev) for i, c in enumerate((256, 128, 128, 128))]
+        ws.d0_nchw = e(M, 256 * 16) if self.dec_tc else None
         self.ws[key] = ws
         return ws
 
@@ -156,11 +183,24 @@ class ATNet2Engine:
         _launch("at.mfcc_to_act", lambda: L.check(lib.eamm_nchw_to_act(audio.data_ptr(), M, 1, 28, 12, C.byref(a), st),
                                                   "nchw_to_act"), nbytes=M * 28 * 12 * 4)
         self.aud[0].launch(lib, st, ws.a_in.act(), out=ws.a0.act())
-        self.aud[1].launch(lib, st, ws.a0.act(), out=ws.a1.act())
-        self._pool(ws.a1, ws.p1, 1, 2)
-        self.aud[3].launch(lib, st, ws.p1.act(), out=ws.a3.act())
-        self.aud[4].launch(lib, st, ws.a3.act(), out=ws.a4.act())
-        self.aud[5].launch(lib, st, ws.a4.act(), out=ws.a5.act())
+        if self.aud_tc:
+            self._copy(ws.a0, ws.a0p, 28, 12)                       # exact fp32 -> padded bf16 hi/lo
+            self.aud[1].launch(lib, st, ws.a0p.act(), out=ws.a1p.act())
+            self._copy(ws.a1p, ws.a1, 28, 12)                       # valid region -> exact fp32 for the max-pool
+            self._pool(ws.a1, ws.p1, 1, 2)
+            self._copy(ws.p1, ws.p1p, 26, 5)
+            self.aud[3].launch(lib, st, ws.p1p.act(), out=ws.a3p.act())
+            self._copy(ws.a3p, ws.a3p, 26, 5, zero_rest=True)       # the conv wrote its padding: zero it again
+            self.aud[4].launch(lib, st, ws.a3p.act(), out=ws.a4p.act())
+            self._copy(ws.a4p, ws.a4p, 26, 5, zero_rest=True)
+            self.aud[5].launch(lib, st, ws.a4p.act(), out=ws.a5p.act())
+            self._copy(ws.a5p, ws.a5, 26, 5)
+        else:
+            self.aud[1].launch(lib, st, ws.a0.act(), out=ws.a1.act())
+            self._pool(ws.a1, ws.p1, 1, 2)
+            self.aud[3].launch(lib, st, ws.p1.act(), out=ws.a3.act())
+            self.aud[4].launch(lib, st, ws.a3.act(), out=ws.a4.act())
+            self.aud[5].launch(lib, st, ws.a4.act(), out=ws.a5.act())
         self._pool(ws.a5, ws.p2, 2, 2)
         # ---- audio FC (x weight) and pose MLP write the two halves of the LSTM input (util.py:592-594)
         self.fc1.launch(lib, st, ws.p2.t.data_ptr(), self.fc1.K, ws.f1.data_ptr(), 2048, M)
@@ -181,7 +221,13 @@ class ATNet2Engine:
                     flops=2.0 * M * 4 * self.HID * self.HID)
             x, ldx = hout, self.HID
         # ---- decon (util.py:600-606)
-        self.dec0.launch(lib, st, x.data_ptr(), self.HID, ws.d[0].t.data_ptr(), 16 * 256, M)
+        if self.dec_tc:
+            self.dec0.launch(lib, st, x.data_ptr(), self.HID, ws.d0_nchw.data_ptr(), 16 * 256, M)
+            a0 = ws.d[0].act()
+            _launch("at.decon0_to_act", lambda: L.check(lib.eamm_nchw_to_act(ws.d0_nchw.data_ptr(), M, 256, 4, 4, C.byref(a0), st),
+                                                        "nchw_to_act"), nbytes=M * 4096 * 8)
+        else:
+            self.dec0.launch(lib, st, x.data_ptr(), self.HID, ws.d[0].t.data_ptr(), 16 * 256, M)
         out = torch.empty(B, T, 35, 64, 64, dtype=torch.float32, device=dev)
         for i, lay in enumerate(self.dec):
             if i < 3:
@@ -189,6 +235,12 @@ class ATNet2Engine:
             else:
                 lay.launch(lib, st, ws.d[i].act(), out_nchw=out, out_nchw_c=35)
         return out
+
+    def _copy(self, src, dst, h, w, zero_rest=False):
+        a, b = src.act(), dst.act()
+        _launch("at.act_copy", lambda: L.check(self.lib.eamm_act_copy(C.byref(a), C.byref(b), h, w, 1 if zero_rest else 0,
+                                                                     current_stream_ptr()), "act_copy"),
+                nbytes=src.n * h * w * src.c_buf * 8)
 
     def _pool(self, src, dst, sy, sx):
         a, b = src.act(), dst.act()

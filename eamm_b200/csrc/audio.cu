@@ -112,6 +112,30 @@ maxpool_kernel(ActView in, ActView out, int k, int sy, int sx, long long total) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// region copy between two views of different map sizes / storage formats: dst(n, y < h, x < w, :) = src(n, y, x, :);
+// zero_rest also clears dst's other pixels (src == dst: only that).  The MFCC convs run on tensor cores over maps padded
+// to powers of two (28x12 -> 32x16, 26x5 -> 32x8): this moves data into / out of the padded buffers and re-zeroes the
+// padding a convolution has written, so that the next layer still sees the reference's zero padding.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+act_copy_kernel(ActView src, ActView dst, int h, int w, int zero_rest, int in_place, long long total) {
+  const int c4 = dst.c >> 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(idx % c4);
+    long long pix = idx / c4;
+    int x = (int)(pix % dst.w);
+    int y = (int)((pix / dst.w) % dst.h);
+    int n = (int)(pix / ((long long)dst.w * dst.h));
+    if (y < h && x < w) {
+      if (!in_place) act_store4(dst, act_offset(dst, n, y, x, 4 * g), act_load4(src, act_offset(src, n, y, x, 4 * g)));
+    } else if (zero_rest) {
+      act_store4(dst, act_offset(dst, n, y, x, 4 * g), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LSTM layer recurrence (gate order i, f, g, o as nn.LSTM; zero initial state, util.py:581-582).
 // gates_x [B][T][4H] already holds W_ih x_t + b_ih + b_hh (eamm_linear).  Cluster of 8 CTAs per
 // sequence; CTA r owns hidden units [32r, 32r+32) = 128 gate rows; thread (row, half) keeps half a row
@@ -217,6 +241,23 @@ extern "C" int eamm_maxpool(const eamm_act* in, const eamm_act* out, int k, int 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   maxpool_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(vi, vo, k, stride_y, stride_x, total);
+  EAMM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int eamm_act_copy(const eamm_act* src, const eamm_act* dst, int h, int w, int zero_rest, void* stream) {
+  int rc = check_view(src); if (rc) return rc;
+  rc = check_view(dst); if (rc) return rc;
+  if (h <= 0 || w <= 0 || h > src->h || w > src->w || h > dst->h || w > dst->w) return EAMM_ERR_ARG;
+  if (src->n != dst->n || src->c != dst->c || dst->c % 4) return EAMM_ERR_SHAPE;
+  const int in_place = src->data == dst->data && src->c_off == dst->c_off;
+  if (in_place && (src->h != dst->h || src->w != dst->w || src->dtype != dst->dtype || src->planes != dst->planes)) return EAMM_ERR_ARG;
+  if (in_place && !zero_rest) return 0;
+  ActView vs = make_view(src), vd = make_view(dst);
+  long long total = (long long)dst->n * dst->h * dst->w * (dst->c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  act_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(vs, vd, h, w, zero_rest, in_place, total);
   EAMM_LAUNCH_CHECK();
   return 0;
 }

@@ -274,6 +274,12 @@ int eamm_linear(const float* x, int ldx, const float* w, const float* bias, cons
 /* eamm_maxpool: nn.MaxPool2d(k, stride=(stride_y, stride_x)), no padding, floor mode (util.py:543,547). */
 int eamm_maxpool(const eamm_act* in, const eamm_act* out, int k, int stride_y, int stride_x, void* stream);
 
+/* eamm_act_copy: dst(n, y < h, x < w, :) = src(n, y, x, :) between two views of any map size / storage format (same n and c);
+ * zero_rest != 0 also clears every other pixel of dst (src == dst: only that).  No reference counterpart: AT_net2's MFCC
+ * convolutions (util.py:541-546, 28x12 and 26x5 maps) run on tensor cores over maps padded to powers of two; this moves
+ * activations into / out of the padded buffers and restores the zero padding between layers. */
+int eamm_act_copy(const eamm_act* src, const eamm_act* dst, int h, int w, int zero_rest, void* stream);
+
 /* eamm_lstm_layer: the recurrence of one nn.LSTM layer (util.py:557,597; gate order i,f,g,o; zero initial state)
  * over whole sequences.  gates_x [B][T][4*hidden] = W_ih x_t + b_ih + b_hh (eamm_linear), w_hh [4*hidden][hidden]
  * (nn.LSTM.weight_hh_l*, as stored), h_out [B][T][hidden].  hidden must be 256.  One 8-CTA cluster per sequence. */

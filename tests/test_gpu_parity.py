@@ -619,6 +619,34 @@ def test_at_net2_matches_reference_golden(dev, name):
     assert np.abs(lstm - blob["lstm_out"]).max() <= 2e-5
 
 
+def test_cabi_act_copy_moves_regions_between_formats_and_rezeroes_padding(dev):
+    """eamm_act_copy (no reference counterpart: the padded-map plumbing of AT_net2's tensor-core MFCC convs)."""
+    from eamm_b200 import _lib as L
+    from eamm_b200.engine import ActBuf, current_stream_ptr
+    lib = L.load()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 28, 12, 64, generator=g).to(dev)
+    src = ActBuf(3, 28, 12, 64, "f32", dev)
+    src.store_float(x)
+    pad = ActBuf(3, 32, 16, 64, "bf16x2", dev)
+    a, b = src.act(), pad.act()
+    L.check(lib.eamm_act_copy(C.byref(a), C.byref(b), 28, 12, 0, current_stream_ptr()), "act_copy")
+    got = pad.to_float()                                               # NCHW fp32
+    assert (got[:, :, :28, :12] - x.permute(0, 3, 1, 2)).abs().max() <= 2e-5
+    assert got[:, :, 28:].abs().max() == 0 and got[:, :, :, 12:].abs().max() == 0
+    pad.t.fill_(1.0)                                                   # dirty everything, then restore the zero padding
+    L.check(lib.eamm_act_copy(C.byref(b), C.byref(b), 26, 5, 1, current_stream_ptr()), "act_copy")
+    t = pad.to_float()
+    assert t[:, :, 26:].abs().max() == 0 and t[:, :, :, 5:].abs().max() == 0 and (t[:, :, :26, :5] != 0).all()
+    back = ActBuf(3, 28, 12, 64, "f32", dev)
+    pad.store_float(F.pad(x, (0, 0, 0, 4, 0, 4)))
+    c = back.act()
+    L.check(lib.eamm_act_copy(C.byref(b), C.byref(c), 28, 12, 0, current_stream_ptr()), "act_copy")
+    torch.cuda.synchronize()
+    assert (back.to_float() - x.permute(0, 3, 1, 2)).abs().max() <= 2e-5
+    assert lib.eamm_act_copy(C.byref(a), C.byref(b), 40, 12, 0, current_stream_ptr()) == -1        # EAMM_ERR_ARG: region > source
+
+
 def test_at_net2_long_clip_is_causal_and_batch_consistent(dev):
     """Size-independent properties at a clip length the oracle would take minutes for: frame t depends only on windows
     <= t (LSTM causality), and sequences of a batch do not interact."""
@@ -719,4 +747,6 @@ def test_config4_real_mfcc_clip_300_frames_psnr(dev):
     k_src, k_drv = det(s), det_a(deco[0])
     k_init = {k: k_drv[k][:1] for k in ("value", "jacobian")}
     k_norm = clip.smooth_and_normalize(k_drv, k_src, k_init, relative=True, scale=clip.movement_scale(k_src, k_init))
-    assert np.abs(k_norm["value"].cpu().numpy() - blob["kp_value"]).max() <= 1e-3
+    kerr = float(np.abs(k_norm["value"].cpu().numpy() - blob["kp_value"]).max())
+    print("configs[4] clip: normalised keypoints max-abs %.3e (tol 1.0e-03)" % kerr)
+    assert kerr <= 1e-3

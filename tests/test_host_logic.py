@@ -565,7 +565,8 @@ def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
             hs.append(hh)
         h = torch.stack(hs, 1).view(B * T, 256)
     assert torch.allclose(h, taps["lstm_out"].view(B * T, 256), atol=1e-5)
-    d = lin(eng.dec0, h).view(B * T, 4, 4, 256).permute(0, 3, 1, 2)
+    # (tensor-core decon stack: the 1x1 -> 4x4 GEMM writes NCHW, (c, y, x) columns; the SIMT variant writes NHWC)
+    d = lin(eng.dec0, h).view(B * T, 256, 4, 4) if eng.dec_tc else lin(eng.dec0, h).view(B * T, 4, 4, 256).permute(0, 3, 1, 2)
     for lay in eng.dec:
         d = _emulate_up2(lay, d)
     got = d[:, :35].view(B, T, 35, 64, 64)
