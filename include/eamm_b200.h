@@ -249,8 +249,10 @@ int eamm_conv_tc_fold(int kind, int split, int cout, int halo_scheme);
 
 /* Planning dry run of eamm_conv_tc for `args` (weight_fold ignored, nothing launched):
  * out[0] = N tile, out[1] = 7x7 scheme (eamm_conv_tc_uses_halo), out[2] = fold (eamm_conv_tc_fold),
- * out[3] = K chunks per pipeline stage, out[4] = bit 0 CTA pairs (cta_group::2), bit 1 wide folded step, bits 8.. =
- * split-K factor (1 = none; planned as if a workspace were given),
+ * out[3] = K chunks (halo-tile scheme: filter taps) per pipeline stage, out[4] = bit 0 CTA pairs (cta_group::2), bit 1
+ * halo-tile scheme (3x3 / UP2 with EAMM_F16 inputs on maps whose 8 x 16-pixel tiles fill the chip: one 10 x 18 halo tile per
+ * K chunk in shared memory, the taps are descriptor views of it), bits 8.. = split-K factor (1 = none; planned as if a
+ * workspace were given),
  * out[5] = pipeline stages (`out` has room for 6 ints).  The host packs the weights for out[1]/out[2]. */
 int eamm_conv_tc_query(const eamm_conv_args* args, int* out);
 

@@ -162,7 +162,8 @@ def _plan(lib, L, kind, cin, cout, n, h, w, planes, flags=0, nhwc=False, nchw_c=
     a.splitk_ws, a.splitk_ws_bytes = 4096, L.SPLITK_WS_BYTES
     q = (ctypes.c_int * 6)()
     assert lib.eamm_conv_tc_query(ctypes.byref(a), q) == 0
-    return {"bn": q[0], "scheme": q[1], "fold": q[2], "ksub": q[3], "pair": q[4] & 1, "splitk": q[4] >> 8, "stages": q[5]}
+    return {"bn": q[0], "scheme": q[1], "fold": q[2], "ksub": q[3], "pair": q[4] & 1, "halo_tile": (q[4] >> 1) & 1,
+            "splitk": q[4] >> 8, "stages": q[5]}
 
 
 def test_conv_tc_planner_decisions_for_the_path_layers():
@@ -193,6 +194,9 @@ for B in (1, 32):
     out["res_mix_%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 2, f16=True)
     out["res_f16_%%d" %% B] = P(L.CONV_3X3, 256, 256, B, 64, 64, 1, f16=True)
     out["final_f16_%%d" %% B] = P(L.CONV_7X7, 64, 16, B, 256, 256, 1, flags=4, nchw_c=3, f16=True)
+    out["down0_mix_%%d" %% B] = P(L.CONV_3X3, 64, 128, B, 256, 256, 2, flags=3, f16=True)
+    out["up1_mix_%%d" %% B] = P(L.CONV_UP2_3X3, 128, 64, B, 128, 128, 2, flags=1, f16=True)
+    out["up0_f16_%%d" %% B] = P(L.CONV_UP2_3X3, 256, 128, B, 64, 64, 1, flags=1, f16=True)
 print(json.dumps(out))
 """ % (ROOT, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
@@ -218,6 +222,15 @@ print(json.dumps(out))
     # mixed fp16 + fp8 bottleneck convs: N = 256 CTA pairs like the bf16 hi/lo scheme, never folded, no split at B = 32
     assert (p["res_mix_32"]["bn"], p["res_mix_32"]["pair"], p["res_mix_32"]["fold"], p["res_mix_32"]["splitk"]) == (256, 1, 0, 1)
     assert p["res_mix_1"]["fold"] == 0 and p["res_f16_32"]["bn"] == 256 and p["res_f16_32"]["pair"] == 1
+    # halo-tile scheme (one 10x18 halo tile per K chunk, taps as descriptor views): every 3x3 / UP2 layer with fp16 or mixed
+    # operands whose 8x16 tiles fill the chip -- the B=32 generator layers, not the batch-1 calls, never the bf16 hi/lo layers
+    for k in ("res_mix_32", "res_f16_32", "down0_mix_32", "up1_mix_32", "up0_f16_32", "down0_mix_1"):
+        assert p[k]["halo_tile"] == 1 and p[k]["pair"] == 1 and p[k]["fold"] == 0 and p[k]["splitk"] == 1, (k, p[k])
+    for k in ("res_mix_1", "res_f16_1", "up1_mix_1", "res32", "res1", "down0_32", "enc4_32", "mask32", "final32"):
+        assert p[k]["halo_tile"] == 0, (k, p[k])
+    # weight stage = a filter row for the narrow N tiles (3 taps), one tap at N = 256; UP2: a whole 2x2 class
+    assert (p["down0_mix_32"]["bn"], p["down0_mix_32"]["ksub"]) == (128, 3) and p["res_mix_32"]["ksub"] == 1
+    assert (p["up1_mix_32"]["bn"], p["up1_mix_32"]["ksub"]) == (64, 4) and (p["up0_f16_32"]["bn"], p["up0_f16_32"]["ksub"]) == (128, 4)
 
 
 def _decode_mix_act(buf):
