@@ -2033,11 +2033,25 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   int ah_bn = 0;
   if (ah_env && f16in && !row7 && !instr && (a->kind == EAMM_CONV_3X3 || a->kind == EAMM_CONV_UP2_3X3) &&
       in->w % 8 == 0 && in->h % 16 == 0) {
-    const int bn = a->cout <= 256 ? a->cout : (a->cout % 256 == 0 ? 256 : 0);
-    if (bn && bn % 16 == 0 && !(need32 && bn % 32) && !(ah_env == 2 && bn == 256)) {      // EAMM_TC_AH=2: narrow N tiles only
+    // N tile: the widest of {cout (<= 256) or 256, 128, 64} whose work items fill the chip; failing that the narrowest one if
+    // it still occupies 60 % of the SMs (batch-1 calls: a 64x64 bottleneck conv is 32 tiles x 4 N tiles = 128 items, and the
+    // per-tap scheme kept each of those SMs on its own L2 -> SM limit: 1.7 MB per item against 0.76 MB with a halo tile)
+    const int first = a->cout <= 256 ? a->cout : (a->cout % 256 == 0 ? 256 : 0);
+    const int cand[3] = {first, 128, 64};
+    int last_ok = 0, last_g = 1;
+    for (int i = 0; i < 3 && !p.ah; ++i) {
+      const int bn = cand[i];
+      if (bn <= 0 || bn > first || (i > 0 && bn == cand[i - 1]) || a->cout % bn || bn % 16 || (need32 && bn % 32) ||
+          (ah_env == 2 && bn == 256))
+        continue;
       const int g = a->kind == EAMM_CONV_UP2_3X3 ? (256 / bn >= 4 ? 4 : (256 / bn >= 2 ? 2 : 1)) : 1;
       const long long items = (long long)(in->w / 8) * (in->h / 16) * in->n * (p.classes / g) * (a->cout / bn);
+      last_ok = bn; last_g = g;
       if (items >= num_sms) { p.ah = 1; p.ah_g = g; p.cls_groups = p.classes / g; ah_bn = bn; }
+    }
+    if (!p.ah && last_ok) {
+      const long long items = (long long)(in->w / 8) * (in->h / 16) * in->n * (p.classes / last_g) * (a->cout / last_ok);
+      if (items * 10 >= (long long)num_sms * 6) { p.ah = 1; p.ah_g = last_g; p.cls_groups = p.classes / last_g; ah_bn = last_ok; }
     }
   }
   if (p.ah) {

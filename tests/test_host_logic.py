@@ -226,7 +226,11 @@ print(json.dumps(out))
     # operands whose 8x16 tiles fill the chip -- the B=32 generator layers, not the batch-1 calls, never the bf16 hi/lo layers
     for k in ("res_mix_32", "res_f16_32", "down0_mix_32", "up1_mix_32", "up0_f16_32", "down0_mix_1"):
         assert p[k]["halo_tile"] == 1 and p[k]["pair"] == 1 and p[k]["fold"] == 0 and p[k]["splitk"] == 1, (k, p[k])
-    for k in ("res_mix_1", "res_f16_1", "up1_mix_1", "res32", "res1", "down0_32", "enc4_32", "mask32", "final32"):
+    # batch 1: the narrowest N tile when it still occupies >= 60 % of the SMs (single CTAs: pairs need a full chip)
+    for k in ("res_mix_1", "res_f16_1", "up1_mix_1"):
+        assert (p[k]["halo_tile"], p[k]["bn"], p[k]["pair"], p[k]["splitk"]) == (1, 64, 0, 1), (k, p[k])
+    assert p["up0_f16_1"]["halo_tile"] == 0                     # 64 items for 148 SMs: the per-tap scheme with its own N tile
+    for k in ("res32", "res1", "down0_32", "enc4_32", "mask32", "final32"):
         assert p[k]["halo_tile"] == 0, (k, p[k])
     # weight stage = a filter row for the narrow N tiles (3 taps), one tap at N = 256; UP2: a whole 2x2 class
     assert (p["down0_mix_32"]["bn"], p["down0_mix_32"]["ksub"]) == (128, 3) and p["res_mix_32"]["ksub"] == 1
