@@ -1203,14 +1203,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcParams& p, const TileC
       const float* src = p.sk_ws + (((size_t)tc.out_tile * p.splitk) * 128 + r) * p.BN + c0;
       float acc[CH];
 #pragma unroll
-      for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, acc + 8 * g);
-      for (int s2 = 1; s2 < p.splitk; ++s2) {
-        src += 128 * p.BN;
-        float v[CH];
+      for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+      if ((y < p.H) && (n < p.N)) {                 // (dead rows were not published: splitk_publish)
 #pragma unroll
-        for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, v + 8 * g);
+        for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, acc + 8 * g);
+        for (int s2 = 1; s2 < p.splitk; ++s2) {
+          src += 128 * p.BN;
+          float v[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) acc[j] += v[j];
+          for (int g = 0; g < CH / 8; ++g) ldg256_cg(src + 8 * g, v + 8 * g);
+#pragma unroll
+          for (int j = 0; j < CH; ++j) acc[j] += v[j];
+        }
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(acc[j]);
@@ -1340,12 +1344,16 @@ __device__ __forceinline__ bool splitk_publish(const ConvTcParams& p, const Tile
   const int r = quadrant * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(quadrant * 32) << 16);
   float* dst = p.sk_ws + (((size_t)tc.out_tile * p.splitk + tc.split) * 128 + r) * p.BN;
+  // rows outside the batch / the map carry nothing (a batch-1 call on a 4x4 map has 16 live rows of 128): not published
+  const bool live = (tc.y0 + ((r >> p.bw_log2) & (p.bh - 1)) < p.H) && (tc.n0 + (r >> (p.bw_log2 + p.bh_log2)) < p.N);
   for (int c0 = half * 32; c0 < p.BN; c0 += (TC_EPI_WARPS / 4) * 32) {
     uint32_t raw[32];
     TmemLd<32>::ld(taddr + (uint32_t)c0, raw);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (live) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) stg256_cg(dst + c0 + 8 * g, raw + 8 * g);
+      for (int g = 0; g < 4; ++g) stg256_cg(dst + c0 + 8 * g, raw + 8 * g);
+    }
   }
   __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -2117,12 +2125,24 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
   if (splitk_env && !p.kxn && !p.halo && !row7 && !p.fold && !p.ah && a->cout % 256 == 0 && (query || a->splitk_ws)) {
     const long long t256 = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / 256);
     const int kc_all = p.taps * p.cin_chunks * p.passes;
-    int S = 1;
-    static int splitk_max = -1;
+    static int splitk_max = -1, sk_narrow_env = -1;
     if (splitk_max < 0) { const char* e = getenv("EAMM_TC_SPLITK_MAX"); splitk_max = e ? atoi(e) : 9; }
-    for (int d = 2; d <= splitk_max && t256 * d <= num_sms; ++d)
-      if (kc_all % d == 0 && kc_all / d >= 8) S = d;
-    const long long need = 4096 + t256 * S * 128ll * 256 * 4;
+    if (sk_narrow_env < 0) { const char* e = getenv("EAMM_TC_SPLITK_NARROW"); sk_narrow_env = e ? atoi(e) : 1; }
+    // N tile of the split layer: 256, or -- when 256-column tiles x splits still leave more than half of the SMs without
+    // work (batch-1 calls: one M tile, a handful of N tiles) -- 128 / 64 columns, so that the weight matrix, which is what
+    // these layers stream, is pulled through the L2 -> SM ports of (nearly) every SM instead of 36 of them
+    int sk_bn = 256, S = 1;
+    long long best_ctas = 0;
+    for (int bn = 256; bn >= 64; bn >>= 1) {
+      const long long t = t256 * (256 / bn);
+      int s_ = 1;
+      for (int d = 2; d <= splitk_max && t * d <= num_sms; ++d)
+        if (kc_all % d == 0 && kc_all / d >= 8) s_ = d;
+      if (t * s_ > best_ctas) { best_ctas = t * s_; sk_bn = bn; S = s_; }
+      if (t * s_ * 2 > num_sms || !sk_narrow_env) break;
+    }
+    const long long tsk = t256 * (256 / sk_bn);
+    const long long need = 4096 + tsk * S * 128ll * sk_bn * 4;
     // Worth it?  Measured cycle model (EAMM_TC_PROF role counters, B200): one K=16 MMA step costs ~110 cycles up to
     // N = 64, 124 at N = 128, 192 at N = 256 (the 128-row A slab is re-fetched per step whatever N is); publishing
     // a partial tile and electing costs ~20k cycles, the reducer's reload + epilogue ~10k + 3k per split (the
@@ -2132,11 +2152,12 @@ static int conv_tc_run(const eamm_conv_args* a, void* stream, int* query) {
     const long long tiles_plain = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.classes * (a->cout / p.BN);
     const long long waves = (tiles_plain + num_sms - 1) / num_sms;
     const long long step_plain = p.BN >= 256 ? 192 : (p.BN >= 128 ? 124 : (p.BN >= 64 ? 114 : 110));
+    const long long step_split = sk_bn >= 256 ? 192 : (sk_bn >= 128 ? 124 : 114);
     const long long cost_plain = waves * (4ll * kc_all * step_plain + 2000 + 14000ll * p.BN / 256);
-    const long long cost_split = 4ll * (kc_all / S) * 192 + 30000 + 3000ll * S;
-    if (t256 * 2 <= num_sms && t256 <= 1024 && S > 1 && cost_split * 100 < cost_plain * 85 &&
+    const long long cost_split = 4ll * (kc_all / S) * step_split + (30000ll * sk_bn) / 256 + 3000ll * S;
+    if (t256 * 2 <= num_sms && tsk <= 1024 && S > 1 && cost_split * 100 < cost_plain * 85 &&
         (query || a->splitk_ws_bytes >= need) && (query || (uintptr_t)a->splitk_ws % 16 == 0)) {
-      p.BN = 256; p.splitk = S;
+      p.BN = sk_bn; p.splitk = S;
       if (!query) {
         p.sk_cnt = reinterpret_cast<unsigned int*>(a->splitk_ws);
         p.sk_ws = reinterpret_cast<float*>(static_cast<char*>(a->splitk_ws) + 4096);

@@ -210,7 +210,8 @@ print(json.dumps(out))
     # cout <= 128 in split mode: weight planes folded into N, CTA pairs once the chip is filled
     assert (p["down0_32"]["bn"], p["down0_32"]["fold"], p["down0_32"]["pair"]) == (128, 1, 1)
     # small hourglass maps: N = 256 tiles with split-K (<= 9 splits, tiles * splits <= 148 SMs)
-    assert (p["enc4_32"]["bn"], p["enc4_32"]["splitk"]) == (256, 9) and (p["enc4_1"]["bn"], p["enc4_1"]["splitk"]) == (256, 9)
+    # (batch 1: one M tile -- 64-column tiles so that 16 N tiles x 9 splits stream the weights through 144 SMs, not 36)
+    assert (p["enc4_32"]["bn"], p["enc4_32"]["splitk"]) == (256, 9) and (p["enc4_1"]["bn"], p["enc4_1"]["splitk"]) == (64, 9)
     assert (p["dec1_32"]["bn"], p["dec1_32"]["splitk"]) == (256, 4)
     # 7x7 layers: 112-column kx-in-N schemes (4 = full-width mask+occlusion, 3 = four output rows for `final`), folded
     for B in (1, 32):
