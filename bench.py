@@ -36,8 +36,8 @@ from eamm_b200 import get_config, synth, sharding           # noqa: E402
 ALG_GFLOP_PER_FRAME = 107.286       # 30 convs, 2*MAC, per (source, kp) frame
 # ncu --set full DRAM traffic (read + write bytes) of ONE bottleneck-conv launch at B=32: (bytes, source file)
 TRAFFIC = {"fp32_bf16x3": (138.35e6 + 95.15e6, "profiles/r1b_ncu_summary.md"),
-           # mixed fp16 + 2 x e4m3 operands: mean of conv1 (136.7 + 89.4 MB) and conv2 (276.1 + 220.0 MB: residual read, two outputs)
-           "mix": (0.5 * (136.74e6 + 89.44e6 + 276.12e6 + 219.98e6), "profiles/r2_ncu_summary.md")}
+           # mixed fp16 + 2 x e4m3 operands: mean of conv1 (136.7 + 91.6 MB) and conv2 (278.0 + 227.6 MB: residual read, two outputs)
+           "mix": (0.5 * (136.70e6 + 91.59e6 + 278.02e6 + 227.63e6), "profiles/r2_ncu_final.md (res_conv1 + res_conv2, mean)")}
 METRIC = "256x256 frames/sec (DenseMotionNetwork + OcclusionAwareGenerator forward, 10 kp)"
 
 
