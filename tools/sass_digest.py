@@ -33,7 +33,7 @@ def main():
             continue
         if cur is None or "/*" not in line:
             continue
-        cur["instructions"] += 1 if re.search(r"/\*[0-9a-f]{4}\*/", line) else 0
+        cur["instructions"] += 1 if re.search(r"/\*[0-9a-f]{4,}\*/", line) else 0
         for name, pat in PATTERNS:
             if re.search(pat, line):
                 cur[name] += 1
@@ -47,7 +47,27 @@ def main():
         print("%-72s %6d  %s" % (nice[:72], cnt["instructions"], cols))
         total.update(cnt)
     print("# total: " + "  ".join("%s=%d" % (n, total[n]) for n, _ in PATTERNS if total[n]))
+    ptxas_resources()
     return 0
+
+
+def ptxas_resources():
+    """Registers / spills / static shared memory per kernel from the `-Xptxas -v` logs build.py keeps next to the objects."""
+    libdir = os.path.dirname(LIB)
+    logs = sorted(f for f in os.listdir(libdir) if f.endswith(".ptxas.log"))
+    if not logs:
+        return
+    print("#\n# ptxas -v resource usage (eamm_b200/lib/*.ptxas.log): registers, barriers, static smem, stack, spill stores / loads")
+    for f in logs:
+        text = open(os.path.join(libdir, f)).read()
+        entries = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                             r"(\d+) bytes spill loads\n.*?Used (\d+) registers, used (\d+) barriers(?:, \d+ bytes cumulative stack size)?"
+                             r"(?:, (\d+) bytes smem)?", text)
+        names = subprocess.run(["c++filt"], input="\n".join(e[0] for e in entries), capture_output=True, text=True).stdout.splitlines()
+        for e, nice in zip(entries, names):
+            nice = re.sub(r"\(.*", "", nice)
+            print("%-72s regs=%-3s barriers=%s smem=%-6s stack=%-4s spill_st=%-4s spill_ld=%s"
+                  % (nice[:72], e[4], e[5], e[6] or 0, e[1], e[2], e[3]))
 
 
 if __name__ == "__main__":
