@@ -238,6 +238,63 @@ print(json.dumps(out))
     assert (p["up1_mix_32"]["bn"], p["up1_mix_32"]["ksub"]) == (64, 4) and (p["up0_f16_32"]["bn"], p["up0_f16_32"]["ksub"]) == (128, 4)
 
 
+def test_conv_tc_planner_accepts_every_path_layer_at_every_bench_batch():
+    """Sweep of the planning dry run over every tensor-core conv of the full-config path (generator + dense-motion
+    hourglass, all four operand formats) at the frame counts the BASELINE configs and the sharded job produce (1 ... 512
+    per GPU, odd and ragged ones included): the planner must accept each call and return a launchable plan."""
+    code = r"""
+import ctypes, json, os, sys
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+os.environ["EAMM_TC_NUM_SMS"] = "148"
+for k in list(os.environ):
+    if k.startswith("EAMM_TC_") and k != "EAMM_TC_NUM_SMS":
+        del os.environ[k]
+from eamm_b200 import _lib as L
+from test_host_logic import _plan
+lib = L.load()
+C3, UP, C7 = L.CONV_3X3, L.CONV_UP2_3X3, L.CONV_7X7
+layers = [("down0", C3, 64, 128, 256, dict(flags=3)), ("down1", C3, 128, 256, 128, dict(flags=3)),
+          ("res", C3, 256, 256, 64, dict(flags=1)), ("up0", UP, 256, 128, 64, dict(flags=1)),
+          ("up1", UP, 128, 64, 128, dict(flags=1)), ("final", C7, 64, 16, 256, dict(flags=4, nchw_c=3)),
+          ("enc0", C3, 64, 128, 64, dict(flags=3)), ("enc1", C3, 128, 256, 32, dict(flags=3)),
+          ("enc2", C3, 256, 512, 16, dict(flags=3)), ("enc3", C3, 512, 1024, 8, dict(flags=3)),
+          ("enc4", C3, 1024, 1024, 4, dict(flags=3)), ("dec0", UP, 1024, 1024, 2, dict(flags=1)),
+          ("dec1", UP, 2048, 512, 4, dict(flags=1)), ("dec2", UP, 1024, 256, 8, dict(flags=1)),
+          ("dec3", UP, 512, 128, 16, dict(flags=1)), ("dec4", UP, 256, 64, 32, dict(flags=1)),
+          ("mask", C7, 128, 16, 64, dict(nhwc=True))]
+out = []
+for B in (1, 2, 3, 5, 8, 16, 31, 32, 33, 64, 128, 256, 512):
+    for name, kind, cin, cout, hw, kw in layers:
+        for planes, f16 in ((2, False), (1, False), (1, True), (2, True)):
+            if kind == C7 and f16 and planes == 2:
+                continue                       # the 7x7 layers never take mixed operands (engine.py)
+            q = _plan(lib, L, kind, cin, cout, B, hw, hw, planes, f16=f16, **kw)
+            out.append([name, B, planes, int(f16), q])
+print(json.dumps(out))
+""" % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    plans = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(plans) == 13 * (17 * 4 - 2)
+    for name, B, planes, f16, q in plans:
+        tag = (name, B, planes, f16, q)
+        assert 16 <= q["bn"] <= 256 and q["bn"] % 16 == 0, tag
+        assert q["stages"] >= 2 and q["ksub"] >= 1, tag
+        assert 1 <= q["splitk"] <= 9, tag
+        if q["halo_tile"]:                      # fp16 / mixed operands only, never split, never folded
+            assert f16 and name not in ("final", "mask") and q["splitk"] == 1 and q["fold"] == 0, tag
+        if q["splitk"] > 1:                     # split-K is for the maps whose tiles cannot fill the chip
+            assert name.startswith(("enc", "dec", "res", "up", "down")) and not q["pair"], tag
+        if name in ("final", "mask"):
+            assert q["bn"] == 112 and q["scheme"] in (3, 4), tag
+    # the plan is a function of (layer, frames in the launch): equal inputs, equal plans (bit-reproducible results)
+    seen = {}
+    for name, B, planes, f16, q in plans:
+        assert seen.setdefault((name, B, planes, f16), q) == q
+
+
 def _decode_mix_act(buf):
     """ActBuf in "mix" mode -> (hi, lo8, hi8) fp32 NHWC tensors in the stored (pre-scaled) domain, straight from the bytes."""
     c = buf.c_buf
