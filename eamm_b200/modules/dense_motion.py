@@ -25,6 +25,12 @@ class _EngineMixin:
             if isinstance(child, _EngineMixin):
                 child._invalidate()
 
+    def refresh_weights(self):
+        """Drop the packed weights (and calibration state); the next forward repacks from the current parameters.
+        `load_state_dict`, `.to()` / `.cuda()` and a `precision` change do this by themselves; call it after editing
+        parameters or BatchNorm statistics IN PLACE (`p.data.copy_(...)`), which nothing can observe cheaply."""
+        self._invalidate()
+
     @property
     def precision(self):
         return self._precision

@@ -435,6 +435,14 @@ def test_dropin_modules_keep_reference_state_dict_layout_and_refuse_cpu():
         gen(src, kp_driving=kpd, kp_source=kps)
     with pytest.raises(ValueError):
         gen.precision = "fp64"
+    # the packed-weight engine is dropped (parent and dense-motion child) by everything that may change the parameters
+    # (the child's own engine only exists when DenseMotionNetwork is called stand-alone; it has its own `precision`)
+    for change, child_too in ((lambda: gen.load_state_dict(sd), True), (lambda: gen.float(), True),
+                              (lambda: gen.refresh_weights(), True), (lambda: setattr(gen, "precision", "fp16"), False)):
+        gen._eng = gen.dense_motion_network._eng = object()
+        change()
+        assert gen._eng is None
+        assert (gen.dense_motion_network._eng is None) == child_too
 
 
 def test_conv_layer_table_matches_reference_flop_count():
