@@ -47,6 +47,16 @@ def build(force=False, verbose=False):
     if not force and is_fresh():
         return LIBPATH
     os.makedirs(LIBDIR, exist_ok=True)
+    # one builder at a time: the ranks of a torchrun job that all find the library stale must not write the same objects
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_fresh():          # another process built it while this one waited
+            return LIBPATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objs = []
 
