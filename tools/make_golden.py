@@ -9,6 +9,8 @@ CPU fp32 and
      float64 checksums for the full 256x256 config (kept small on purpose).
 
 Usage:  python tools/make_golden.py            (needs /root/reference; never runs on the GPU box)
+        python tools/make_golden.py --verify   regenerate every fixture into a scratch directory (same oracle == reference
+                                               assertions) and check that the committed tests/golden/*.npz hold the same arrays
 """
 import os
 import sys
@@ -30,6 +32,7 @@ from eamm_b200.config import get_kp_config     # noqa: E402
 from modules.generator import OcclusionAwareGenerator  # noqa: E402  (the reference)
 from modules.keypoint_detector import KPDetector, KPDetector_a  # noqa: E402  (the reference)
 
+OUT = os.path.join(ROOT, "tests", "golden")        # --verify regenerates into a scratch directory instead
 KEYS = ["mask", "sparse_deformed", "occlusion_map", "deformed", "prediction"]
 STRIDES = {"mask": 4, "sparse_deformed": 4, "occlusion_map": 4, "deformed": 8, "prediction": 8, "deformation": 4}
 
@@ -66,7 +69,7 @@ def run_case(name, cfg_name, batch, size, with_jacobian=True, shared_source=Fals
         else:
             s = STRIDES[k]
             blob[k] = a[..., ::s, ::s].copy() if k != "deformation" else a[:, ::s, ::s, :].copy()
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **blob)
     stats = {k: (float(v.min()), float(v.max()), float(v.mean())) for k, v in want.items()}
     print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB")
@@ -106,7 +109,7 @@ def run_natural_case(name):
         blob["sum_" + k] = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
         s = NATURAL_STRIDES[k]                                         # denser than the synthetic cases: 4 frames only
         blob[k] = a[..., ::s, ::s].copy() if k != "deformation" else a[:, ::s, ::s, :].copy()
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **blob)
     print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB")
 
@@ -132,7 +135,7 @@ def run_kp_case(name, cfg_name, batch, size, audio):
         a = want[k].numpy()
         blob["sum_" + k] = np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
         blob[k] = a[..., ::2, ::2].copy() if (k == "heatmap" and cfg_name == "full") else a
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **blob)
     print(name, "ok ->", path, os.path.getsize(path) // 1024, "KiB", "value absmax %.3f" % want["value"].abs().max())
 
@@ -180,7 +183,7 @@ def run_glue_case(name, T, with_emo):
     ov, oj = kp_glue.clip_glue(drv["value"], drv["jacobian"], emo["value"] if with_emo else None,
                                emo["jacobian"] if with_emo else None, src, init, movement_scale=scale, relative=True)
     assert torch.equal(ov, rv) and torch.equal(oj, rj), name + ": oracle != reference"
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, meta=np.array([T, int(with_emo)]), scale=np.array([scale]), value=rv.numpy(), jacobian=rj.numpy())
     print(name, "ok ->", path, "scale %.6f" % scale)
 
@@ -201,7 +204,7 @@ def run_at_case(name, B, T):
     got = oracle.at_net2_forward(sd, img, mfcc, pose, 1.6, taps)
     assert torch.equal(want, got), name + ": oracle != reference"
     a = want.numpy()
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, meta=np.array([B, T]), out=a[..., ::4, ::4].copy(), lstm_out=taps["lstm_out"].numpy(),
                         in_checksum=np.array([img.double().sum(), mfcc.double().sum(), pose.double().sum()]),
                         sum_out=np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()]))
@@ -271,7 +274,7 @@ def run_clip_case(name, T=300):
     scale = float(np.sqrt(ConvexHull(o_src["value"][0].numpy()).volume) / np.sqrt(ConvexHull(o_init["value"][0].numpy()).volume))
     ov, oj = kp_glue.clip_glue(o_drv["value"], o_drv["jacobian"], None, None, o_src, o_init, movement_scale=scale)
     assert np.abs(ov.numpy() - nv).max() <= 1e-6 and np.abs(oj.numpy() - nj).max() <= 1e-5, "oracle chain != reference chain"
-    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, meta=np.array([T]), mfcc13=mfcc13.astype(np.float32), pose7=pose7.astype(np.float32),
                         pixels_u8=px, kp_value=nv, kp_jacobian=nj, frames_u8_s8=np.stack(frames),
                         frame_sums=np.array(sums), scale=np.array([scale]),
@@ -280,8 +283,31 @@ def run_clip_case(name, T=300):
           float(nv.std(axis=0).mean()))
 
 
+def verify_committed(scratch):
+    """Compare the freshly generated fixtures in `scratch` with the committed ones, array by array (bit-exact)."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    names = sorted(f for f in os.listdir(gold) if f.endswith(".npz"))
+    bad = [f for f in names if not os.path.exists(os.path.join(scratch, f))]
+    for f in names:
+        if f in bad:
+            continue
+        a, b = np.load(os.path.join(gold, f), allow_pickle=True), np.load(os.path.join(scratch, f), allow_pickle=True)
+        same = set(a.files) == set(b.files) and all(
+            a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes() for k in a.files)
+        if not same:
+            bad.append(f)
+    print("verify: %d committed fixtures, %d regenerate bit-identically from the reference%s"
+          % (len(names), len(names) - len(bad), "" if not bad else "; DIFFERENT: " + ", ".join(bad)))
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    verify = "--verify" in sys.argv[1:]
+    if verify:
+        import tempfile
+        sys.argv.remove("--verify")
+        OUT = tempfile.mkdtemp(prefix="eamm_golden_")
     only = sys.argv[1:]
     if only:                                   # python tools/make_golden.py natural_b4 ...  (regenerate selected fixtures)
         table = {"natural_b4": lambda: run_natural_case("natural_b4"), "clip_lrw_t300": lambda: run_clip_case("clip_lrw_t300"),
@@ -311,3 +337,5 @@ if __name__ == "__main__":
     run_glue_case("kp_glue_plain_t40", 40, False)
     run_at_case("at_b2_t3", 2, 3)
     run_at_case("at_b1_t6", 1, 6)
+    if verify:
+        sys.exit(verify_committed(OUT))
