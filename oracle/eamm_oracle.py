@@ -21,8 +21,9 @@ seeded state dict into the real ``OcclusionAwareGenerator`` and checks this orac
 bit-for-bit, then writes ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` re-checks the
 oracle against those fixtures everywhere else.
 
-Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
-legs may import this module.  The product path (``eamm_b200``) never does.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s baseline legs (cpu_baseline, ``--impl reference``,
+and cudnn_baseline = these same functions on CUDA tensors as the eager-PyTorch bar; none of them is the thing
+measured as ours) may import this module.  The product path (``eamm_b200``) never does.
 """
 import torch
 import torch.nn.functional as F
