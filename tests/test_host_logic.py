@@ -271,13 +271,33 @@ for B in (1, 2, 3, 5, 8, 16, 31, 32, 33, 64, 128, 256, 512):
                 continue                       # the 7x7 layers never take mixed operands (engine.py)
             q = _plan(lib, L, kind, cin, cout, B, hw, hw, planes, f16=f16, **kw)
             out.append([name, B, planes, int(f16), q])
-print(json.dumps(out))
+# `first` (generator.py:25) as engine.FirstConvTC launches it: packed 16-byte pixels, 7 K chunks, hi/lo or one plane
+first = []
+for B in (1, 2, 3, 5, 8, 16, 31, 32, 33, 64, 128, 256, 512):
+    for H in (64, 256, 512):
+        for passes, f16, mix_out in ((2, False, False), (2, False, True), (1, False, False), (1, True, False)):
+            inp = L.Act(data=4096, dtype=L.EAMM_F16 if f16 else L.EAMM_BF16, n=B, h=H, w=H, c=8, c_off=0, c_buf=8, planes=1,
+                        n_stride=(H + 6) * (H + 8) * 8)
+            pl = 2 if passes == 2 else 1
+            o = L.Act(data=4096, dtype=L.EAMM_F16 if (f16 or mix_out) else L.EAMM_BF16, n=B, h=H, w=H, c=64, c_off=0,
+                      c_buf=64, planes=pl, n_stride=H * H * 64 * pl)
+            a = L.ConvArgs()
+            a.kind, a.flags, a.cin, a.cout = L.CONV_ROW7_PACKED, L.EPI_RELU, 8, 64
+            a.inp, a.out, a.bias, a.weight, a.pack_passes = ctypes.pointer(inp), ctypes.pointer(o), 4096, 4096, passes
+            q = (ctypes.c_int * 6)()
+            first.append([B, H, passes, lib.eamm_conv_tc_query(ctypes.byref(a), q), list(q)])
+print(json.dumps({"layers": out, "first": first}))
 """ % (ROOT, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     import json
-    plans = json.loads(r.stdout.strip().splitlines()[-1])
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    plans = res["layers"]
     assert len(plans) == 13 * (17 * 4 - 2)
+    assert len(res["first"]) == 13 * 3 * 4
+    for B, H, passes, rc, q in res["first"]:
+        assert rc == 0 and 16 <= q[0] <= 64 and q[5] >= 2, (B, H, passes, rc, q)
+        assert q[2] == (2 if passes == 2 else 0), (B, H, passes, q)       # hi/lo planes: fold scheme 2 (include/eamm_b200.h)
     for name, B, planes, f16, q in plans:
         tag = (name, B, planes, f16, q)
         assert 16 <= q["bn"] <= 256 and q["bn"] % 16 == 0, tag
