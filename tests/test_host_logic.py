@@ -74,6 +74,73 @@ def test_tc_weight_packing_order_and_split():
     assert up.shape == (4 * 8, 4 * 64)
 
 
+def test_row7_packed_first_conv_and_fold_packings_reproduce_the_conv():
+    """`first` (generator.py:25) as EAMM_CONV_ROW7_PACKED: the source packed to 16-byte pixels [hi0,hi1,hi2,0,lo0,lo1,lo2,0] with a
+    3-row / 3-column zero border, one 64-wide K window per filter row = 8 consecutive packed pixels (kx = 7 is padding); the
+    weight matrices of engine.pack_tc_weights_row7 (one plane, hi/lo in two passes, hi/lo folded along N) times those windows
+    equal the 7x7 / pad-3 convolution of the split operands.  Likewise fold scheme 1 (pack_tc_weights_fold) for a 3x3 layer."""
+    g = torch.Generator().manual_seed(11)
+    H, W, cout = 6, 9, 8
+    x = torch.rand(3, H, W, generator=g)
+    w = torch.randn(cout, 3, 7, 7, generator=g) * 0.1
+    a_hi = x.bfloat16().float()
+    a_lo = (x - a_hi).bfloat16().float()
+    w_hi = w.bfloat16().float()
+    w_lo = (w - w_hi).bfloat16().float()
+    conv = lambda a, b: F.conv2d(a[None].double(), b.double(), padding=3)[0]
+    packed = torch.zeros(H + 6, W + 8, 8, dtype=torch.float64)
+    packed[3:3 + H, 3:3 + W, 0:3] = a_hi.permute(1, 2, 0).double()
+
+    def windows():                                        # A [H*W][7 ky][64]: pixel (y, x), filter row ky -> packed[y+ky, x:x+8]
+        return torch.stack([torch.stack([packed[y + ky, xx:xx + 8].reshape(64) for ky in range(7)])
+                            for y in range(H) for xx in range(W)])
+
+    # one plane (bf16 / fp16 modes): K = (ky, kx, channel)
+    w1 = engine.pack_tc_weights_row7(w, 16, 1).double()
+    assert w1.shape == (16, 7 * 64)
+    D = windows().reshape(H * W, -1) @ w1.T
+    got = D[:, :cout].T.reshape(cout, H, W)
+    assert torch.allclose(got, conv(a_hi, w_hi), atol=1e-12) and D[:, cout:].abs().max() == 0
+    # hi/lo planes, two passes: pass 0 = w_lo against the hi channels, pass 1 = w_hi against hi and lo channels
+    packed[3:3 + H, 3:3 + W, 4:7] = a_lo.permute(1, 2, 0).double()
+    want = conv(a_hi, w_lo) + conv(a_hi + a_lo, w_hi)
+    assert (want - conv(x, w)).abs().max() <= 2e-5 * conv(x, w).abs().max()        # 16 mantissa bits per operand
+    A = windows()
+    w2 = engine.pack_tc_weights_row7(w, 16, 2).double().view(16, 2, 7 * 64)
+    D = A.reshape(H * W, -1) @ w2[:, 0].T + A.reshape(H * W, -1) @ w2[:, 1].T
+    assert torch.allclose(D[:, :cout].T.reshape(cout, H, W), want, atol=1e-12)
+    # folded along N: rows [w_hi vs (a_hi, a_lo) | w_lo vs a_hi]; the epilogue adds the two halves
+    wf = engine.pack_tc_weights_row7(w, 16, 2, fold=2).double()
+    assert wf.shape == (32, 7 * 64)
+    D = A.reshape(H * W, -1) @ wf.T
+    assert torch.allclose((D[:, :16] + D[:, 16:])[:, :cout].T.reshape(cout, H, W), want, atol=1e-12)
+
+    # fold scheme 1, 3x3: per tap a_lo x b_hi (N = bn) and a_hi x [b_hi; b_lo] (N = 2 bn), halves added in the epilogue
+    cin, co, hh = 64, 16, 5
+    xa = torch.randn(cin, hh, hh, generator=g)
+    wa = torch.randn(co, cin, 3, 3, generator=g) * 0.05
+    full = wa.permute(2, 3, 0, 1).reshape(9, co, cin)
+    pf = engine.pack_tc_weights_fold(full, 1).double()                             # [2*co][9*cin]
+    assert pf.shape == (2 * co, 9 * cin)
+    xh = xa.bfloat16().float(); xl = (xa - xh).bfloat16().float()
+    wh = wa.bfloat16().float(); wl = (wa - wh).bfloat16().float()
+    c3 = lambda a, b: F.conv2d(a[None].double(), b.double(), padding=1)[0]
+    want3 = c3(xl, wh) + c3(xh, wh) + c3(xh, wl)
+    pad = lambda t: F.pad(t.double(), (1, 1, 1, 1))
+    ph, pl = pad(xh), pad(xl)
+    got3 = torch.zeros(co, hh, hh, dtype=torch.float64)
+    for y in range(hh):
+        for xx in range(hh):
+            acc = torch.zeros(2 * co, dtype=torch.float64)
+            for t in range(9):
+                ky, kx = divmod(t, 3)
+                blk = pf[:, t * cin:(t + 1) * cin]
+                acc[:co] += blk[:co] @ pl[:, y + ky, xx + kx]                       # a_lo x b_hi
+                acc += blk @ ph[:, y + ky, xx + kx]                                 # a_hi x [b_hi; b_lo]
+            got3[:, y, xx] = acc[:co] + acc[co:]
+    assert torch.allclose(got3, want3, atol=1e-10)
+
+
 # ------------------------------------------------------------------ sampler pins (index selection)
 def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
     """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
