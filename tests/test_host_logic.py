@@ -141,6 +141,42 @@ def test_row7_packed_first_conv_and_fold_packings_reproduce_the_conv():
     assert torch.allclose(got3, want3, atol=1e-10)
 
 
+def test_mix_calibration_exponents_centre_the_maxima_with_hysteresis():
+    """engine.MixCalib (fp16 + 2 x e4m3 activations): the pre-scale exponent puts a tensor's maximum at 2^11.5 (+-0.5 octave:
+    4x below the e4m3 lo8 saturation, 22x below fp16 overflow); later forwards only move a tensor whose stored maximum left
+    [2^9, 2^13.2]; tensors that were never written (0) or overflowed (inf / nan) keep their exponent."""
+    import math
+    cal = engine.MixCalib()
+    for nm in ("a", "b", "c", "d", "e"):
+        cal.register(nm)
+    assert cal.register("a") == "a" and len(cal.slots) == 5          # idempotent
+    cal.alloc(torch.device("cpu"))
+    cal.begin(True)
+    assert cal.track and cal.ptr("b") == cal.amax.data_ptr() + 4
+    cal.amax.copy_(torch.tensor([3.7, 1e-3, 900.0, 0.0, float("nan")]))
+    new = cal.proposal(force=True)
+    for nm, v in (("a", 3.7), ("b", 1e-3), ("c", 900.0)):
+        stored = math.log2(v) + new[nm]
+        assert abs(stored - engine.ACT_TOP) <= 0.5 + 1e-9, (nm, stored)
+    assert new["d"] == 0 and new["e"] == 0
+    cal.exps = new
+    # drift inside the window: nothing moves; outside: only that tensor is re-centred
+    cal.amax.copy_(torch.tensor([3.7 * 2.0, 1e-3 / 3.0, 900.0 * 3.5, 0.0, 1.0]))
+    again = cal.proposal(force=False)
+    assert again["a"] == new["a"] and again["b"] == new["b"]
+    assert again["c"] != new["c"] and abs(math.log2(900.0 * 3.5) + again["c"] - engine.ACT_TOP) <= 0.5 + 1e-9
+    assert again["e"] != 0                                             # first real value of a late tensor
+    cal.begin(False)
+    assert not cal.track and cal.ptr("a") is None                      # untracked forwards pass no statistics pointer
+    # weight side: one exponent per output channel puts the row maximum just below 2^13.4, lo8 within the e4m3 range
+    g = torch.Generator().manual_seed(4)
+    full = torch.randn(9, 32, 128, generator=g) * torch.logspace(-3, 1, 32).view(1, 32, 1)
+    packed, e = engine.pack_tc_weights_mix(full, 1)
+    assert packed.shape == (32, 9 * 128 * 4) and packed.dtype == torch.uint8 and e.dtype == torch.int32
+    top = torch.log2(full.abs().amax(dim=(0, 2))) + e.float()
+    assert (top <= engine.MIX_TOP).all() and (top > engine.MIX_TOP - 1.0).all()
+
+
 # ------------------------------------------------------------------ sampler pins (index selection)
 def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
     """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
