@@ -17,6 +17,22 @@ KP_FILTER = (0.05, 8.0, 1.0, 100.0, 10.0)                 # mincutoff, beta, dcu
 EMO_FILTER = (1.0, 0.2, 1.0, 100.0, 100.0)                # demo.py:231-236
 
 
+def mfcc_windows(mfcc):
+    """The audio windows `test_auido` cuts from a whole utterance (demo.py:318-333): `mfcc` [n,13] is
+    python_speech_features.mfcc(speech, 16000, winstep=0.01) of the zero-padded waveform; frame `ind` (3 <= ind <=
+    n // 4 - 4) sees rows (ind-3)*4 .. (ind+4)*4 without cepstral coefficient 0.  Returns [T,28,12] fp32, T = n // 4 - 6:
+    one strided view instead of the reference's Python loop, same rows."""
+    mfcc = np.ascontiguousarray(np.asarray(mfcc, dtype=np.float32))
+    if mfcc.ndim != 2 or mfcc.shape[1] < 2:
+        raise ValueError("eamm_b200: mfcc must be [n, n_cep >= 2]")
+    T = mfcc.shape[0] // 4 - 6
+    if T <= 0:
+        return np.zeros((0, 28, mfcc.shape[1] - 1), dtype=np.float32)
+    s0, s1 = mfcc.strides
+    win = np.lib.stride_tricks.as_strided(mfcc, shape=(T, 28, mfcc.shape[1]), strides=(4 * s0, s0, s1), writeable=False)
+    return np.ascontiguousarray(win[:, :, 1:])
+
+
 def clip_inputs_from_windows(mfcc13, pose7, T=None):
     """Host-side input preparation of `test_auido` (demo.py:286-343) for pre-windowed MFCC such as the LRW samples
     (/root/reference/dataset/LRW/MFCC/*/*.npy, [n,28,13]): drop cepstral coefficient 0 (`[:, :, 1:]`, demo.py:329),

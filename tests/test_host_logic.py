@@ -177,6 +177,53 @@ def test_mix_calibration_exponents_centre_the_maxima_with_hysteresis():
     assert (top <= engine.MIX_TOP).all() and (top > engine.MIX_TOP - 1.0).all()
 
 
+def test_clip_input_preparation_matches_the_reference_loops():
+    """eamm_b200.clip host-side input preparation against a literal restatement of demo.py:296-340 (`test_auido`): the MFCC
+    window loop (:321-328) and the pose mirroring / tiling / cut (:297-299, :334-340), for utterance and pose lengths on
+    both sides of every branch.  Index work: bit-exact."""
+    from eamm_b200 import clip
+    rng = np.random.default_rng(0)
+
+    def ref_windows(mfcc):                                   # demo.py:321-328
+        ind, out = 3, []
+        while ind <= int(mfcc.shape[0] / 4) - 4:
+            out.append(mfcc[(ind - 3) * 4: (ind + 4) * 4, 1:])
+            ind += 1
+        return out
+
+    def ref_pose(all_pose, n_frames):                        # demo.py:297-299, 334-340
+        pose = all_pose[:, :6]
+        if len(pose) == 1:
+            pose = np.repeat(pose, 100, 0)
+        if len(pose) < n_frames:
+            gap = n_frames - len(pose)
+            n = int((gap / len(pose) / 2)) + 2
+            pose = np.concatenate((pose, pose[::-1, :]), axis=0)
+            pose = np.tile(pose, (n, 1))
+        if len(pose) > n_frames:
+            pose = pose[:n_frames, :]
+        return pose
+
+    for n in (0, 23, 27, 28, 31, 32, 100, 401, 1203):
+        mfcc = rng.standard_normal((n, 13)).astype(np.float32)
+        want = ref_windows(mfcc)
+        got = clip.mfcc_windows(mfcc)
+        assert got.shape == (len(want), 28, 12) and got.dtype == np.float32
+        assert len(want) == max(0, n // 4 - 6)
+        if want:
+            assert np.array_equal(got, np.stack(want))
+    with pytest.raises(ValueError):
+        clip.mfcc_windows(np.zeros((40,), dtype=np.float32))
+    for n_win, n_pose, T in ((30, 30, 300), (30, 1, 300), (30, 7, 64), (30, 90, 40), (12, 299, 300), (5, 300, 300), (9, 3, 9)):
+        win13 = rng.standard_normal((n_win, 28, 13)).astype(np.float32)
+        pose7 = rng.standard_normal((n_pose, 7)).astype(np.float32)
+        m, p = clip.clip_inputs_from_windows(win13, pose7, T=T)
+        assert tuple(m.shape) == (1, T, 28, 12) and tuple(p.shape) == (1, T, 6)
+        assert np.array_equal(p[0].numpy(), ref_pose(pose7, T).astype(np.float32))
+        for t in (0, T // 2, T - 1):
+            assert np.array_equal(m[0, t].numpy(), win13[t % n_win, :, 1:])
+
+
 # ------------------------------------------------------------------ sampler pins (index selection)
 def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
     """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
