@@ -224,6 +224,41 @@ def test_clip_input_preparation_matches_the_reference_loops():
             assert np.array_equal(m[0, t].numpy(), win13[t % n_win, :, 1:])
 
 
+def test_workspace_cache_lru_and_keypoint_struct_rules():
+    """Host plumbing of engine.py that needs no GPU: the bounded per-shape workspace cache (least recently USED shape is
+    dropped) and the eamm_kp struct built from the caller's dicts (dense_motion.py:55: 'jacobian' is optional; a leading
+    dimension of 1 or an expanded stride-0 batch broadcasts; anything else is refused with the reference's shapes named)."""
+    ws = engine.WorkspaceCache(limit=2)
+    ws[(1, 256, 256)] = "a"
+    ws[(32, 256, 256)] = "b"
+    assert ws.get((1, 256, 256)) == "a"                      # touch: (32, ...) is now the oldest
+    ws[(8, 256, 256)] = "c"
+    assert (32, 256, 256) not in ws and (1, 256, 256) in ws and len(ws) == 2 and list(ws.values()) == ["a", "c"]
+    assert ws.get((5, 5, 5)) is None
+    ws.clear()
+    assert len(ws) == 0
+
+    cpu = torch.device("cpu")
+    B, K = 4, 10
+    kp = {"value": torch.rand(B, K, 2), "jacobian": torch.rand(B, K, 2, 2), "heatmap": torch.rand(B, K, 58, 58)}   # extra key ignored
+    s, keep = engine._kp_struct(kp, B, K, cpu)
+    assert (s.value, s.jacobian) == (kp["value"].data_ptr(), kp["jacobian"].data_ptr())
+    assert (s.value_stride, s.jacobian_stride) == (K * 2, K * 4) and len(keep) == 2
+    s, _ = engine._kp_struct({"value": kp["value"]}, B, K, cpu)                       # no Jacobians
+    assert s.jacobian is None
+    one = {"value": torch.rand(1, K, 2), "jacobian": torch.rand(1, K, 2, 2)}
+    for d in (one, {k: v.expand(B, *v.shape[1:]) for k, v in one.items()}):             # batch 1 / expanded: broadcast
+        s, keep = engine._kp_struct(d, B, K, cpu)
+        assert (s.value_stride, s.jacobian_stride) == (0, 0) and keep[0].shape[0] == 1
+    nc = kp["value"].transpose(1, 2).contiguous().transpose(1, 2)                        # right shape, wrong strides: copied
+    s, keep = engine._kp_struct({"value": nc}, B, K, cpu)
+    assert keep[0].is_contiguous() and torch.equal(keep[0], nc)
+    for bad in ({"value": torch.rand(B, K, 3)}, {"value": torch.rand(3, K, 2)}, {"value": torch.rand(B, K, 2).double()},
+                {"value": kp["value"], "jacobian": torch.rand(B, K, 4)}, {"value": kp["value"].numpy()}):
+        with pytest.raises(RuntimeError):
+            engine._kp_struct(bad, B, K, cpu)
+
+
 # ------------------------------------------------------------------ sampler pins (index selection)
 def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
     """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
