@@ -650,6 +650,38 @@ def test_dropin_modules_keep_reference_state_dict_layout_and_refuse_cpu():
         assert (gen.dense_motion_network._eng is None) == child_too
 
 
+def test_kp_detector_and_at_net2_dropins_keep_the_reference_parameter_layout():
+    """the drop-ins load, strictly, the seeded state dicts that tools/make_golden.py loaded
+    strictly into the REAL KPDetector / KPDetector_a / AT_net2 (that is what pins the key names and shapes); AT_net2 also
+    swallows the unused StyleGAN2 `generator.*` entries of a reference checkpoint; all of them refuse to run on the CPU."""
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    from eamm_b200.modules.util import AT_net2
+    for audio, cls in ((False, KPDetector), (True, KPDetector_a)):
+        cfg = get_kp_config("full", audio=audio)
+        det = cls(**cfg).eval()
+        sd = synth.make_kp_state_dict(cfg)
+        res = det.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert set(det.state_dict()) == set(sd)
+        x = synth.make_kp_inputs(cfg, 1, 256, audio)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            det(x)
+    at = AT_net2().eval()
+    sd = synth.make_at_state_dict()
+    sd["generator.style.1.weight"] = torch.zeros(4, 4)               # a reference checkpoint carries the StyleGAN2 decoder
+    res = at.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert not any(k.startswith("generator.") for k in at.state_dict())
+    img, mfcc, pose = synth.make_at_inputs(1, 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        at(img, mfcc, pose, "cnn", 1.6)
+    with pytest.raises(NotImplementedError):
+        at(img, mfcc, pose, "gan", 1.6)
+    with pytest.raises(Exception, match="jaco_net type wrong"):       # util.py:611
+        at(img, mfcc, pose, "other", 1.6)
+
+
 def test_conv_layer_table_matches_reference_flop_count():
     cfg = get_config("full")
     flops = 0.0
