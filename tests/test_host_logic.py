@@ -723,6 +723,51 @@ def test_shared_library_exports_every_declared_symbol():
     assert lib.eamm_warp_image(null, 0, null, null, 1, 3, 8, 8, 2, 2, null) == -1      # EAMM_ERR_ARG, no launch
 
 
+def test_every_entry_point_rejects_null_arguments_without_touching_a_device():
+    """Error convention of the boundary (include/eamm_b200.h: < 0 = EAMM_ERR_*, rejected before anything is launched): every
+    launching entry point returns EAMM_ERR_ARG on null buffers / zeroed structs, on a host with or without a GPU; the pure
+    planning helpers answer from the layer shape alone."""
+    from eamm_b200 import _lib as L
+    lib = L.load()
+    C = ctypes
+    act, kp, ca = L.Act(), L.Kp(), L.ConvArgs()
+    n = None
+    calls = {
+        "eamm_aa_downsample": lambda: lib.eamm_aa_downsample(n, 0, n, 1, 256, 256, 4, n, 13, n),
+        "eamm_aa_downsample_act": lambda: lib.eamm_aa_downsample_act(n, 0, 1, 256, 256, 4, n, 13, C.byref(act), n),
+        "eamm_kp_head": lambda: lib.eamm_kp_head(n, 16, 1, 64, 64, 10, 10, 3, 0.1, n, n, n, n),
+        "eamm_kp_clip": lambda: lib.eamm_kp_clip(n, n, n, n, 4, 10, 0, n, n, n, n, 0, n, n, n, n, 1.0, 1, n, n, n, n),
+        "eamm_kp_stage": lambda: lib.eamm_kp_stage(n, 0, C.byref(kp), C.byref(kp), 10, 0.01, C.byref(act), n, n, n),
+        "eamm_flow_combine": lambda: lib.eamm_flow_combine(n, 16, C.byref(kp), C.byref(kp), 10, 1, 1, 64, 64, n, n, n, n),
+        "eamm_warp_occlude": lambda: lib.eamm_warp_occlude(C.byref(act), n, n, 0, 0, C.byref(act), None, n, n, n, n),
+        "eamm_warp_image": lambda: lib.eamm_warp_image(n, 0, n, n, 1, 3, 8, 8, 2, 2, n),
+        "eamm_nchw_to_act": lambda: lib.eamm_nchw_to_act(n, 1, 3, 8, 8, C.byref(act), n),
+        "eamm_conv_simt": lambda: lib.eamm_conv_simt(C.byref(ca), n),
+        "eamm_conv_tc": lambda: lib.eamm_conv_tc(C.byref(ca), n),
+        "eamm_conv_tc_query": lambda: lib.eamm_conv_tc_query(C.byref(ca), (C.c_int * 6)()),
+        "eamm_pack_image": lambda: lib.eamm_pack_image(n, 1, 3, 8, 8, 0, n, n),
+        "eamm_linear": lambda: lib.eamm_linear(n, 4, n, n, n, 1, n, 4, 1, 4, 4, 0, 1.0, n),
+        "eamm_maxpool": lambda: lib.eamm_maxpool(C.byref(act), C.byref(act), 3, 1, 2, n),
+        "eamm_act_copy": lambda: lib.eamm_act_copy(C.byref(act), C.byref(act), 8, 8, 0, n),
+        "eamm_lstm_layer": lambda: lib.eamm_lstm_layer(n, n, n, 1, 1, 256, n),
+    }
+    helpers = {"eamm_abi_version", "eamm_device_ok", "eamm_conv_tc_uses_halo", "eamm_conv_tc_fold"}
+    assert set(calls) | helpers == set(L.exported_symbols())          # a new entry point must be added here
+    before = L.LAUNCHES
+    for name, fn in calls.items():
+        assert fn() == -1, name                                         # EAMM_ERR_ARG
+        with pytest.raises(RuntimeError, match="EAMM_ERR_ARG"):
+            L.check(fn(), name)
+    assert L.LAUNCHES == before                                         # rejected calls are not counted as launches
+    # weight-packing helpers (include/eamm_b200.h): hi/lo layers with cout <= 128 stack the weight planes along N (fold 1),
+    # cout = 256 keeps K = (pass, tap, channel); the packed first conv folds as scheme 2; one-plane layers never fold
+    assert [lib.eamm_conv_tc_fold(L.CONV_3X3, 1, c, 0) for c in (64, 128, 256)] == [1, 1, 0]
+    assert [lib.eamm_conv_tc_fold(L.CONV_3X3, 0, c, 0) for c in (64, 128, 256)] == [0, 0, 0]
+    assert (lib.eamm_conv_tc_fold(L.CONV_ROW7_PACKED, 1, 64, 0), lib.eamm_conv_tc_fold(L.CONV_ROW7_PACKED, 0, 64, 0)) == (2, 0)
+    assert lib.eamm_conv_tc_uses_halo(L.CONV_3X3, 64, 256, 0) == 0      # 7x7 schemes only
+    assert lib.eamm_conv_tc_uses_halo(L.CONV_7X7, 256, 16, 3) == 2      # `final`: kx in N (the query may widen it to scheme 3)
+
+
 def test_epilogue_chunk_walk_covers_every_column_chunk_once():
     """Epilogue of conv_tc.cu (epilogue_tile / the fast variants): the two epilogue warps of a TMEM lane quadrant start at
     chunk `half` and step by two chunks; every accumulator column chunk is read exactly once, for every N tile the planner
