@@ -768,6 +768,42 @@ def test_every_entry_point_rejects_null_arguments_without_touching_a_device():
     assert lib.eamm_conv_tc_uses_halo(L.CONV_7X7, 256, 16, 3) == 2      # `final`: kx in N (the query may widen it to scheme 3)
 
 
+def test_conv_tc_argument_validation_codes():
+    """eamm_conv_tc validates before it plans (the query runs the same checks and launches nothing): each class of bad call
+    maps to its EAMM_ERR_* code, so a binding can tell a caller error from a device error (> 0 = cudaError_t)."""
+    code = r"""
+import ctypes as C, json, os, sys
+sys.path.insert(0, %r)
+os.environ["EAMM_TC_NUM_SMS"] = "148"
+from eamm_b200 import _lib as L
+lib = L.load()
+def q(kind=L.CONV_3X3, cin=64, cout=64, n=2, h=16, w=16, planes=1, dt=L.EAMM_BF16, data=4096, wptr=4096, oh=None, c_buf=None):
+    a = L.ConvArgs(); a.kind, a.flags, a.cin, a.cout = kind, 0, cin, cout
+    cb = c_buf or cin
+    act = L.Act(data=data, dtype=dt, n=n, h=h, w=w, c=cin, c_off=0, c_buf=cb, planes=planes, n_stride=h * w * planes * cb)
+    o = oh or h
+    out = L.Act(data=4096, dtype=dt, n=n, h=o, w=o, c=cout, c_off=0, c_buf=cout, planes=planes, n_stride=o * o * planes * cout)
+    a.inp, a.weight, a.bias, a.out = C.pointer(act), wptr, 4096, C.pointer(out)
+    a.splitk_ws, a.splitk_ws_bytes = 4096, L.SPLITK_WS_BYTES
+    return lib.eamm_conv_tc_query(C.byref(a), (C.c_int * 6)())
+print(json.dumps({"ok": q(), "map6": q(h=6, w=6), "kind": q(kind=9), "cin32": q(cin=32), "cin96": q(cin=96, c_buf=128),
+                  "act_align": q(data=4100), "w_align": q(wptr=4100), "f32": q(dt=L.EAMM_F32), "planes3": q(planes=3),
+                  "out_size": q(oh=8), "cout20": q(cout=20), "n0": q(n=0)}))
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    rc = json.loads(r.stdout.strip().splitlines()[-1])
+    ARG, SHAPE, DTYPE, ALIGN, UNSUPPORTED = -1, -2, -3, -4, -5
+    assert rc["ok"] == 0
+    assert rc["map6"] == UNSUPPORTED and rc["kind"] == UNSUPPORTED      # non power-of-two maps, unknown conv kind
+    assert rc["cin32"] == ALIGN and rc["cin96"] == ALIGN                 # K chunks are 64 channels = one 128-byte swizzled row
+    assert rc["act_align"] == ALIGN and rc["w_align"] == ALIGN           # TMA needs 16-byte aligned bases
+    assert rc["f32"] == DTYPE and rc["planes3"] == DTYPE                 # tensor-core operands: bf16 / fp16, one or two planes
+    assert rc["out_size"] == SHAPE and rc["cout20"] == SHAPE             # output view must match the layer
+    assert rc["n0"] == ARG
+
+
 def test_epilogue_chunk_walk_covers_every_column_chunk_once():
     """Epilogue of conv_tc.cu (epilogue_tile / the fast variants): the two epilogue warps of a TMEM lane quadrant start at
     chunk `half` and step by two chunks; every accumulator column chunk is read exactly once, for every N tile the planner
