@@ -856,10 +856,10 @@ import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
 from eamm_b200 import sharding
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"],
-                        rank=int(os.environ["RANK"]), world_size=2)
-rank = dist.get_rank()
-total = 7
-a, b = sharding.partition(total, 2, rank)
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+total = int(os.environ["TOTAL"])
+a, b = sharding.partition(total, world, rank)
 frames = torch.arange(a, b, dtype=torch.float32).view(-1, 1) * 10.0       # "generated frames" of this rank
 allf = sharding.gather_frames(frames, total, dst=0)
 mx = sharding.reduce_max(1.0 + rank)
@@ -867,24 +867,25 @@ sm = sharding.reduce_sum(float(b - a))
 if rank == 0:
     assert allf.view(-1).tolist() == [10.0 * i for i in range(total)], allf
     print("OK", mx, sm)
-assert mx == 2.0 and sm == total
+assert mx == float(world) and sm == total
 dist.destroy_process_group()
 """
 
 
-def test_gloo_two_rank_gather_and_max_reduce(tmp_path):
+@pytest.mark.parametrize("world,total", [(2, 7), (4, 1026), (3, 2)])     # uneven blocks; a rank that owns no frame at all
+def test_gloo_multi_rank_gather_and_max_reduce(tmp_path, world, total):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), PORT=str(port))
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), PORT=str(port), WORLD=str(world), TOTAL=str(total))
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert "OK 2.0 7.0" in outs[0]
+    assert "OK %.1f %.1f" % (world, total) in outs[0]
 
 
 # ------------------------------------------------------------------ AT_net2 packing (SURVEY 8(f) rank 4)
