@@ -259,6 +259,32 @@ def test_workspace_cache_lru_and_keypoint_struct_rules():
             engine._kp_struct(bad, B, K, cpu)
 
 
+def test_anti_alias_kernel_is_separable_and_the_subsample_phase_is_zero():
+    """a3 (util.py:1005-1052): the engines hand eamm_aa_downsample the 1-D factor g1 = rowsum(k2) / sum of the reference's
+    13x13 Gaussian buffer (engine.py DenseMotionEngine._pack, kp_engine.py) and the kernel filters rows, then columns.  Pins
+    the two facts that rewrite rests on: k2 is exactly the outer product of that factor, and pad 6 -> depthwise conv -> `::4`
+    keeps output pixel (i, j) centred on input pixel (4i, 4j) -- phase 0, integer-exact."""
+    w = synth.aa_kernel(3)                                   # [3,1,13,13], the buffer `down.weight` of the reference
+    k2 = w[0, 0].double()
+    assert w.shape == (3, 1, 13, 13) and abs(k2.sum().item() - 1.0) < 1e-6 and torch.equal(w[0], w[1]) and torch.equal(w[1], w[2])
+    g1 = k2.sum(1)
+    g1 = g1 / g1.sum()
+    assert (torch.outer(g1, g1) - k2).abs().max().item() < 1e-8
+    assert torch.allclose(g1, g1.flip(0), atol=1e-12)        # symmetric: correlation == convolution
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 3, 64, 64, generator=g, dtype=torch.float64)
+    want = F.conv2d(F.pad(x, (6, 6, 6, 6)), w.double(), groups=3)[:, :, ::4, ::4]        # util.py:1048-1050
+    xp = F.pad(x, (6, 6, 6, 6))
+    rows = sum(g1[t] * xp[:, :, :, t:t + 64] for t in range(13))                          # filter along x, all padded rows
+    got = sum(g1[t] * rows[:, :, t:t + 64, :] for t in range(13))[:, :, ::4, ::4]         # then along y, subsample
+    assert got.shape == (1, 3, 16, 16) and (got - want).abs().max().item() < 5e-8      # k2 is the fp32 rounding of the outer product
+    # phase: an impulse at input (4i, 4j) lands with the kernel's centre weight on output (i, j) and nowhere stronger
+    imp = torch.zeros(1, 3, 64, 64, dtype=torch.float64)
+    imp[0, :, 20, 36] = 1.0
+    out = F.conv2d(F.pad(imp, (6, 6, 6, 6)), w.double(), groups=3)[:, :, ::4, ::4]
+    assert out[0, 0].argmax().item() == 5 * 16 + 9 and abs(out[0, 0, 5, 9].item() - k2[6, 6].item()) < 1e-15
+
+
 # ------------------------------------------------------------------ sampler pins (index selection)
 def _emulate_kxn_tile_gemm(xpad, pad, y_rows, x_cols, B, cin, ntap):
     """D[128, 112] of one conv_tc tile: K loop over `ntap` input-row taps; A rows = the listed (y, x) pixels."""
