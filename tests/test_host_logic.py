@@ -940,6 +940,102 @@ def _emulate_conv3(layer, x):
     return F.avg_pool2d(y, 2) if layer.flags & 2 else y
 
 
+def _emulate_conv7(layer, x):
+    w = layer.w_ref.view(7, 7, layer.cout, -1).permute(2, 3, 0, 1)
+    y = F.conv2d(F.pad(x, (0, 0, 0, 0, 0, w.shape[1] - x.shape[1])), w, layer.bias, padding=3)
+    y = F.relu(y) if layer.flags & 1 else y
+    return torch.sigmoid(y) if layer.flags & 4 else y
+
+
+def _emulate_hourglass(hg, x):
+    """HourglassPlan.run with torch: level-L buffer = [up-block slot | skip slot]; producers write their slot, consumers read
+    a slot (encoder) or the whole buffer (decoder, head).  Returns cat[0] = [decoder output | input] (padded slots)."""
+    nb, ca = hg.nb, hg.calign
+    ru = lambda c: (c + ca - 1) // ca * ca
+    B, _, h, w = x.shape
+    s_up = [ru(hg.dec_ch[nb - 1 - l]) for l in range(nb)]
+    s_sk = [ru(hg.enc_ch[l]) for l in range(nb)]
+    cat = [torch.zeros(B, s_up[l] + s_sk[l], h >> l, w >> l) for l in range(nb)]
+    bott = torch.zeros(B, ru(hg.enc_ch[nb]), h >> nb, w >> nb)
+    cat[0][:, s_up[0]:s_up[0] + x.shape[1]] = x
+    for i, layer in enumerate(hg.enc_layers):
+        assert layer.cin == s_sk[i]
+        y = _emulate_conv3(layer, cat[i][:, s_up[i]:s_up[i] + s_sk[i]])
+        if i + 1 < nb:
+            cat[i + 1][:, s_up[i + 1]:s_up[i + 1] + layer.cout] = y
+        else:
+            bott[:, :layer.cout] = y
+    for j, layer in enumerate(hg.dec_layers):
+        src = bott if j == 0 else cat[nb - j]
+        assert layer.cin == src.shape[1]
+        cat[nb - 1 - j][:, :layer.cout] = _emulate_up2(layer, src)
+    return cat[0], s_up[0]
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_sf1"])
+def test_generator_engine_packing_reproduces_the_oracle_on_cpu(cfg_name):
+    """Re-executes the PACKED generator (engine.GeneratorEngine / DenseMotionEngine / HourglassPlan built on the CPU: folded
+    BatchNorm, pre-activation affines moved into the producers' epilogues, merged mask + occlusion conv, UP2 parity weights,
+    channel-slot buffers instead of torch.cat, the 1-D anti-alias factor) with plain torch ops in the order engine._forward
+    launches the kernels, and compares with the oracle: every host-side rewrite of generator.py:59-97 / dense_motion.py:81-113
+    is pinned without a GPU.  The kernels' own arithmetic (heatmaps, sampling, softmax) is taken from the oracle here."""
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    cfg = get_config(cfg_name)
+    sd = synth.make_state_dict(cfg, seed=0)
+    m = OcclusionAwareGenerator(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        eng = engine.GeneratorEngine(m, "fp32_simt")
+        assert not eng.mixed and eng.dm is not None and not eng.first_packed
+        B, size = 2, 64
+        src, kpd, kps = synth.make_inputs(B, cfg, size=size, seed=1)
+        want = oracle.generator_forward(sd, cfg, src, kpd, kps)
+        # encoder
+        x = _emulate_conv7(eng.first, src)
+        for layer in eng.down:
+            x = _emulate_conv3(layer, x)
+        feat = x
+        # dense motion
+        dm = eng.dm
+        small = src
+        if dm.step != 1:
+            k2 = torch.outer(dm.g1, dm.g1).expand(3, 1, dm.taps, dm.taps)
+            pad = dm.taps // 2
+            small = F.conv2d(F.pad(src, (pad,) * 4), k2, groups=3)[:, :, ::dm.step, ::dm.step]
+        h, w = small.shape[2:]
+        dmp = cfg["dense_motion_params"]
+        hm = oracle.heatmap_representation(kpd, kps, h, w, dmp.get("kp_variance", 0.01))
+        sm = oracle.sparse_motions(kpd, kps, h, w)
+        ds = oracle.deformed_source(small, sm)
+        hg_in = torch.cat([hm, ds], dim=2).view(B, -1, h, w)                     # [hm_k, R_k, G_k, B_k] per keypoint
+        cat0, s_up0 = _emulate_hourglass(dm.hg, hg_in)
+        assert dm.head.cin == cat0.shape[1]
+        logits = _emulate_conv7(dm.head, cat0)                                     # merged mask (K+1) + occlusion (1) conv
+        K1 = cfg["num_kp"] + 1
+        mask = F.softmax(logits[:, :K1], dim=1)
+        occ = torch.sigmoid(logits[:, K1:K1 + 1])
+        deformation = (sm.permute(0, 1, 4, 2, 3) * mask.unsqueeze(2)).sum(dim=1).permute(0, 2, 3, 1)
+        assert (mask - want["mask"]).abs().max() <= 2e-5 and (occ - want["occlusion_map"]).abs().max() <= 2e-5
+        # warp x occlusion, then the bottleneck with every BatchNorm living in a neighbouring epilogue
+        x = oracle.deform_input(feat, deformation)
+        o = occ if occ.shape[2:] == x.shape[2:] else F.interpolate(occ, size=x.shape[2:], mode="bilinear", align_corners=False)
+        x = x * o
+        c = x.shape[1]
+        a = F.relu(x * eng.pre[0][:c].view(1, -1, 1, 1) + eng.pre[1][:c].view(1, -1, 1, 1))      # norm1 / ReLU of block 0
+        for i, (l1, l2) in enumerate(eng.res):
+            t = _emulate_conv3(l1, a)                                              # conv1 + folded norm2 + ReLU
+            x = _emulate_conv3(l2, t) + x                                          # conv2 + residual
+            if l2.scale2 is not None:                                              # next block's norm1 / ReLU (second output)
+                a = F.relu(x * l2.scale2.view(1, -1, 1, 1) + l2.shift2.view(1, -1, 1, 1))
+        assert eng.res[-1][1].scale2 is None
+        for layer in eng.up:
+            x = _emulate_up2(layer, x)
+        pred = _emulate_conv7(eng.final, x)[:, :3]
+        err = (pred - want["prediction"]).abs().max().item()
+        assert err <= 2e-5, err
+
+
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
     """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
     the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
