@@ -1036,6 +1036,47 @@ def test_generator_engine_packing_reproduces_the_oracle_on_cpu(cfg_name):
         assert err <= 2e-5, err
 
 
+@pytest.mark.parametrize("audio", [False, True])
+def test_kp_detector_engine_packing_reproduces_the_oracle_on_cpu(audio):
+    """SURVEY 8(f) rank 1, host side: KPDetectorEngine built on the CPU (Hourglass predictor in slot buffers, keypoint and
+    Jacobian 7x7 convs merged into ONE same-padded conv whose interior is the reference's valid conv,
+    keypoint_detector.py:82-103 / :183-203) re-executed with torch ops equals the oracle's value / jacobian / heatmap."""
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.kp_engine import KPDetectorEngine
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    cfg = get_kp_config("tiny", audio=audio)
+    sd = synth.make_kp_state_dict(cfg)
+    m = (KPDetector_a if audio else KPDetector)(**cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    B, size = 2, 64
+    x = synth.make_kp_inputs(cfg, B, size, audio)
+    with torch.no_grad():
+        eng = KPDetectorEngine(m, "fp32_simt")
+        want = (oracle.kp_detector_a_forward if audio else oracle.kp_detector_forward)(sd, cfg, x)
+        if eng.hg is not None:
+            small = x
+            if eng.step != 1:
+                k2 = torch.outer(eng.g1, eng.g1).expand(3, 1, eng.taps, eng.taps)
+                small = F.conv2d(F.pad(x, (eng.taps // 2,) * 4), k2, groups=3)[:, :, ::eng.step, ::eng.step]
+            feat, _ = _emulate_hourglass(eng.hg, small)
+        else:
+            feat = x
+        logits = _emulate_conv7(eng.head, feat)                 # same-padded: [B, K + 4J (padded), h, w]
+        off = 3 - m.pad
+        if off:
+            logits = logits[:, :, off:-off, off:-off]           # the valid conv of the reference
+        K, J = m.num_kp, m.num_jacobian_maps
+        shape = (B, K) + tuple(logits.shape[2:])
+        heat = F.softmax(logits[:, :K].reshape(B, K, -1) / m.temperature, dim=2).view(*shape)
+        assert heat.shape == want["heatmap"].shape and (heat - want["heatmap"]).abs().max() <= 1e-5
+        assert (oracle.gaussian2kp(heat) - want["value"]).abs().max() <= 1e-5
+        if J:
+            jm = logits[:, K:K + 4 * J].reshape(B, J, 4, *shape[2:])
+            jac = (heat.unsqueeze(2) * jm).view(B, K, 4, -1).sum(dim=-1).view(B, K, 2, 2)
+            assert (jac - want["jacobian"]).abs().max() <= 1e-4
+
+
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
     """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
     the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
