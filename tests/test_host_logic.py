@@ -1077,6 +1077,51 @@ def test_kp_detector_engine_packing_reproduces_the_oracle_on_cpu(audio):
             assert (jac - want["jacobian"]).abs().max() <= 1e-4
 
 
+def test_operand_format_plan_of_the_full_config(monkeypatch):
+    """Which layers run which operand scheme in each precision mode, read off engines built on the
+    CPU for the BASELINE configuration: fp32 mode = fp16 + 2 x e4m3 on every 3x3 / UP2 conv of the generator (down0/1, the 12
+    bottleneck convs, up0/1), bf16 hi/lo on the 7x7 convs and the dense-motion Hourglass; 17 calibrated tensors; the switches
+    documented in INTEGRATION.md change exactly what they say."""
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    for k in ("EAMM_B200_MIX", "EAMM_B200_MIX_HG", "EAMM_B200_MIX_SKIP", "EAMM_B200_MIX64", "EAMM_B200_CONV", "EAMM_TC_ROW7"):
+        monkeypatch.delenv(k, raising=False)
+    cfg = get_config("full")
+    m = OcclusionAwareGenerator(**cfg).eval()
+    m.load_state_dict(synth.make_state_dict(cfg, seed=0))
+
+    def plan(precision):
+        with torch.no_grad():
+            e = engine.GeneratorEngine(m, precision)
+        gen = [l.impl for l in e.down] + [l.impl for pair in e.res for l in pair] + [l.impl for l in e.up]
+        hg = [l.impl for l in e.dm.hg.enc_layers + e.dm.hg.dec_layers]
+        return e, gen, hg
+
+    e, gen, hg = plan("fp32")
+    assert e.mixed and e.first_packed and gen == ["mix"] * 16 and hg == ["tc3"] * 10
+    assert (e.final.impl, e.dm.head.impl, e.first.split, e.first.f16) == ("tc3", "tc3", True, False)
+    assert (e.enc_mix, e.res_mix, e.xf_mix, e.dec_mix) == ([True, True, True], True, True, [True, False])
+    assert sorted(e.calib.slots) == sorted(["enc0", "enc1", "enc2", "xf", "dec0"] + ["a%d" % i for i in range(6)] +
+                                           ["t%d" % i for i in range(6)])
+    assert all(l.w_exp.shape == (l.cout,) and l.weight.dtype == torch.uint8 for l in e.down + e.up)
+    for precision, impl, mode in (("fp32_bf16x3", "tc3", "bf16x2"), ("fp16", "tc16", "f16"), ("bf16", "tc", "bf16"),
+                                  ("fp32_simt", "simt", "f32")):
+        e, gen, hg = plan(precision)
+        assert not e.mixed and e.calib is None and (e.impl, e.mode) == (impl, mode)
+        assert gen == [impl] * 16 and hg == [impl] * 10 and e.final.impl == impl
+        assert e.first_packed == (impl != "simt")
+    monkeypatch.setenv("EAMM_B200_MIX", "0")                      # identical to fp32_bf16x3
+    e, gen, hg = plan("fp32")
+    assert not e.mixed and gen == ["tc3"] * 16
+    monkeypatch.setenv("EAMM_B200_MIX", "res")                    # the bottleneck only (the first cut of the scheme)
+    e, gen, hg = plan("fp32")
+    assert gen == ["tc3"] * 2 + ["mix"] * 12 + ["tc3"] * 2 and sorted(e.calib.slots) == sorted(
+        ["a%d" % i for i in range(6)] + ["t%d" % i for i in range(6)])
+    monkeypatch.setenv("EAMM_B200_MIX", "1")
+    monkeypatch.setenv("EAMM_B200_MIX_HG", "1")                   # opt-in: eligible Hourglass layers too (error table in profiles/)
+    e, gen, hg = plan("fp32")
+    assert gen == ["mix"] * 16 and "mix" in hg and hg[0] == "tc3"   # enc0 reads the 44-channel input: never mixed
+
+
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
     """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
     the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
