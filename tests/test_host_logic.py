@@ -20,6 +20,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ------------------------------------------------------------------ weight packing
+L_UP2 = 2          # _lib.CONV_UP2_3X3
+
+
 def test_fold_bn_matches_conv_then_bn():
     g = torch.Generator().manual_seed(0)
     w, b = torch.randn(8, 4, 3, 3, generator=g), torch.randn(8, generator=g)
@@ -1120,6 +1123,67 @@ def test_operand_format_plan_of_the_full_config(monkeypatch):
     monkeypatch.setenv("EAMM_B200_MIX_HG", "1")                   # opt-in: eligible Hourglass layers too (error table in profiles/)
     e, gen, hg = plan("fp32")
     assert gen == ["mix"] * 16 and "mix" in hg and hg[0] == "tc3"   # enc0 reads the 44-channel input: never mixed
+
+
+def test_every_tensor_core_weight_matrix_of_an_engine_decodes_to_its_fp32_weights():
+    """Every eamm_conv_tc weight matrix a GeneratorEngine holds (modes fp32_bf16x3 / fp16 / bf16 and the mixed fp16 + e4m3
+    layers of fp32 mode), decoded from its documented layout (include/eamm_b200.h: rows = (class, cout), K = (pass, tap,
+    channel) with planes lo, hi, hi; mixed: e4m3 lo8 | e4m3 hi8 | fp16 hi, one exponent per cout), gives back the layer's fp32
+    weights to the precision of the format -- for 3x3 and UP2 layers, padded couts / channel slots included."""
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    cfg = get_config("tiny")
+    m = OcclusionAwareGenerator(**cfg).eval()
+    m.load_state_dict(synth.make_state_dict(cfg, seed=0))
+
+    def layers(e):
+        out = list(e.down) + [l for pair in e.res for l in pair] + list(e.up)
+        return out + e.dm.hg.enc_layers + e.dm.hg.dec_layers
+
+    for precision, passes, rel in (("fp32_bf16x3", 3, 2.0 ** -15), ("fp16", 1, 2.0 ** -10), ("bf16", 1, 2.0 ** -7)):
+        with torch.no_grad():
+            e = engine.GeneratorEngine(m, precision)
+        seen = 0
+        for l in layers(e):
+            classes = 4 if l.kind == L_UP2 else 1
+            taps = l.w_ref.shape[0] // classes
+            ref = l.w_ref.view(classes, taps, l.cout, l.cin).permute(0, 2, 1, 3)                 # [cls][cout][tap][cin]
+            W = l.weight.float().view(classes, l.cout, passes, taps, l.cin)
+            if passes == 3:
+                assert torch.equal(W[:, :, 1], W[:, :, 2])                                         # hi plane twice (a_lo, a_hi passes)
+                dec = W[:, :, 0] + W[:, :, 1]
+            else:
+                dec = W[:, :, 0]
+            scale = ref.abs().amax().item()
+            assert (dec - ref).abs().max().item() <= rel * scale, (precision, l.name)
+            seen += 1
+        assert seen == len(e.down) + 2 * len(e.res) + len(e.up) + 2 * e.dm.hg.nb
+    # mixed layers of fp32 mode (tiny config: whichever layers are eligible; the full config's are pinned by the plan test)
+    cfgf = get_config("full")
+    mf = OcclusionAwareGenerator(**cfgf).eval()
+    mf.load_state_dict(synth.make_state_dict(cfgf, seed=0))
+    with torch.no_grad():
+        e = engine.GeneratorEngine(mf, "fp32")
+    mixed = [l for l in layers(e) if l.impl == "mix"]
+    assert len(mixed) == 16
+    for l in (mixed[0], mixed[1], mixed[2], mixed[-2], mixed[-1]):                                 # down0 (cin 64), down1, res, up0, up1
+        classes = 4 if l.kind == L_UP2 else 1
+        taps = l.w_ref.shape[0] // classes
+        rows, kk = classes * l.cout, taps * l.cin
+        ref = l.w_ref.view(classes, taps, l.cout, l.cin).permute(0, 2, 1, 3).reshape(rows, taps, l.cin)
+        raw = l.weight
+        assert raw.shape == (rows, 4 * kk)
+        hi = raw[:, 2 * kk:].contiguous().view(torch.float16).float().view(rows, taps, l.cin)
+        if l.cin == 64:                                   # per tap one 128-byte fp8 chunk [hi8 x 64 | lo8 x 64]
+            x8 = raw[:, :2 * kk].contiguous().view(torch.float8_e4m3fn).float().view(rows, taps, 128)
+            hi8, lo8 = x8[..., :64], x8[..., 64:]
+        else:
+            lo8 = raw[:, :kk].contiguous().view(torch.float8_e4m3fn).float().view(rows, taps, l.cin)
+            hi8 = raw[:, kk:2 * kk].contiguous().view(torch.float8_e4m3fn).float().view(rows, taps, l.cin)
+        sc = torch.exp2(-l.w_exp.float()).repeat(classes).view(rows, 1, 1)
+        dec = (hi + lo8 / 64.0) * sc
+        scale = ref.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-30)
+        assert ((dec - ref).abs() / scale).max().item() <= 2.0 ** -13, l.name                     # 11 + 4 bits, per-row scale
+        assert ((hi8 * 64.0 - hi).abs() / hi.abs().amax(dim=(1, 2), keepdim=True)).max().item() <= 2.0 ** -4   # hi8 = e4m3(hi / 64)
 
 
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
