@@ -1186,6 +1186,114 @@ def test_every_tensor_core_weight_matrix_of_an_engine_decodes_to_its_fp32_weight
         assert ((hi8 * 64.0 - hi).abs() / hi.abs().amax(dim=(1, 2), keepdim=True)).max().item() <= 2.0 ** -4   # hi8 = e4m3(hi / 64)
 
 
+class _DryLib:
+    """The C ABI with every launch replaced by its argument check: eamm_conv_tc -> eamm_conv_tc_query (the same validation and
+    planning code, nothing launched), every other kernel entry point -> a recorder that returns 0."""
+
+    def __init__(self, real, log):
+        self._real, self._log = real, log
+
+    def __getattr__(self, name):
+        real, log = self._real, self._log
+        if name == "eamm_conv_tc":
+            def conv_tc(args, stream):
+                q = (ctypes.c_int * 6)()
+                rc = real.eamm_conv_tc_query(args, q)
+                log.append(("conv_tc", rc, args._obj.inp.contents.n))
+                return rc
+            return conv_tc
+        if name in ("eamm_conv_tc_query", "eamm_conv_tc_fold", "eamm_conv_tc_uses_halo", "eamm_abi_version"):
+            return getattr(real, name)
+
+        def stub(*a):
+            log.append((name[5:], 0, None))
+            return 0
+        return stub
+
+
+FRAME_LAUNCHES = (["pack_image", "conv_tc", "conv_tc", "conv_tc", "aa_downsample", "kp_stage"] + ["conv_tc"] * 11 +
+                  ["flow_combine", "warp_occlude", "warp_image"] + ["conv_tc"] * 15)
+
+
+def test_host_program_dry_run_launch_sequence_and_argument_checks(monkeypatch):
+    """engine._forward end to end on the CPU with the launches stubbed out (_DryLib): the host program of
+    generator.py:59-97 / dense_motion.py:81-113 issues the 35 launches DESIGN.md lists, in that order, and all 29 eamm_conv_tc
+    argument structs it builds -- real buffers, slot views, operand formats, pre-scale exponents, weight packings chosen from the
+    planner's answer -- pass the library's own validation in every tensor-core precision mode; a shared (stride-0) source runs
+    the encoder once; the source cache drops the encoder launches; u8 frames and the no-dense-motion constructor corner work."""
+    from eamm_b200 import _lib as L
+    from eamm_b200.modules.generator import OcclusionAwareGenerator
+    monkeypatch.setenv("EAMM_TC_NUM_SMS", "148")
+    for k in ("EAMM_B200_MIX", "EAMM_B200_MIX_HG", "EAMM_B200_MIX_SKIP", "EAMM_B200_MIX64", "EAMM_B200_CONV", "EAMM_TC_ROW7"):
+        monkeypatch.delenv(k, raising=False)
+    ws = torch.zeros(L.SPLITK_WS_BYTES, dtype=torch.uint8)
+    monkeypatch.setattr(engine, "current_stream_ptr", lambda: None)
+    monkeypatch.setattr(engine, "splitk_workspace", lambda device, stream: ws)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)       # (asks the driver: none on this host)
+    real, log = L.load(), []
+    launches0 = L.LAUNCHES
+
+    def build(cfg_name, precision):
+        cfg = get_config(cfg_name)
+        m = OcclusionAwareGenerator(**cfg).eval()
+        m.load_state_dict(synth.make_state_dict(cfg, seed=0))
+        e = engine.GeneratorEngine(m, precision)
+        e.lib = _DryLib(real, log)
+        if e.dm is not None:
+            e.dm.lib = e.lib
+        return m, e, cfg
+
+    with torch.no_grad():
+        for precision in ("fp32", "fp32_bf16x3", "fp16", "bf16"):
+            m, e, cfg = build("full", precision)
+            src, kpd, kps = synth.make_inputs(2, cfg, size=256, seed=1)
+            del log[:]
+            out = e.run(src, kpd, kps)
+            assert [n for n, _, _ in log] == FRAME_LAUNCHES, precision
+            assert all(rc == 0 for _, rc, _ in log), (precision, [x for x in log if x[1]])
+            assert {k: tuple(v.shape) for k, v in out.items()} == {
+                "mask": (2, 11, 64, 64), "sparse_deformed": (2, 11, 3, 64, 64), "occlusion_map": (2, 1, 64, 64),
+                "deformed": (2, 3, 256, 256), "prediction": (2, 3, 256, 256)}
+            assert list(out) == ["mask", "sparse_deformed", "occlusion_map", "deformed", "prediction"]    # generator.py:66-95 order
+        # fp32 mode again (mixed formats): one shared source for 3 frames -> the encoder (3 convs) sees one image
+        m, e, cfg = build("full", "fp32")
+        src, kpd, kps = synth.make_inputs(3, cfg, size=256, seed=1, shared_source=True)
+        del log[:]
+        e.run(src[:1].expand(3, -1, -1, -1), kpd, kps)
+        convs = [n for name, rc, n in log if name == "conv_tc"]
+        assert convs[:3] == [1, 1, 1] and set(convs[3:]) == {3} and all(rc == 0 for _, rc, _ in log)
+        # source cache: the same source tensor again -> per-frame kernels only (no pack / first / down0 / down1 / anti-alias)
+        m.cache_source = True
+        one = src[:1].expand(3, -1, -1, -1)
+        e.run(one, kpd, kps)
+        del log[:]
+        e.run(one, kpd, kps)
+        assert [n for n, _, _ in log] == FRAME_LAUNCHES[5:] and len(log) == 30
+        one2 = src[:1].clone().expand(3, -1, -1, -1)                    # another tensor: recomputed
+        del log[:]
+        e.run(one2, kpd, kps)
+        assert len(log) == 35
+        m.cache_source = False
+        m.emit_u8 = True
+        out = e.run(one2, kpd, kps)
+        assert out["prediction_u8"].shape == (3, 256, 256, 3) and out["prediction_u8"].dtype == torch.uint8
+        # constructor corner: no dense-motion network (generator.py:67) -> encoder, copy + norm1, bottleneck, decoder
+        m, e, cfg = build("tiny_nodm", "fp32")
+        src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=1)
+        del log[:]
+        out = e.run(src, kpd, kps)
+        names = [n for n, _, _ in log]
+        assert set(out) == {"prediction"} and "kp_stage" not in names and names.count("warp_occlude") == 1
+        assert all(rc == 0 for _, rc, _ in log)
+        # empty batch: nothing is launched, empty tensors of the reference's shapes come back
+        m, e, cfg = build("full", "fp16")
+        del log[:]
+        src, kpd, kps = synth.make_inputs(1, cfg, size=256, seed=1)
+        out = e.run(src[:0], {k: v[:0] for k, v in kpd.items()}, {k: v[:0] for k, v in kps.items()})
+        assert not log and out["prediction"].shape == (0, 3, 256, 256) and out["mask"].shape == (0, 11, 64, 64)
+    assert L.LAUNCHES > launches0                                        # (stubbed launches are counted like real ones)
+
+
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
     """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
     the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
