@@ -1294,6 +1294,56 @@ def test_host_program_dry_run_launch_sequence_and_argument_checks(monkeypatch):
     assert L.LAUNCHES > launches0                                        # (stubbed launches are counted like real ones)
 
 
+def test_kp_detector_and_at_net2_host_programs_dry_run(monkeypatch):
+    """The same dry run (launches stubbed, eamm_conv_tc -> its own argument check) for the SURVEY 8(f) engines: keypoint
+    detectors in tensor-core modes and AT_net2 with its default and opt-in conv back ends; launch counts as documented."""
+    from eamm_b200 import _lib as L, kp_engine, at_engine
+    from eamm_b200.config import get_kp_config
+    from eamm_b200.modules.keypoint_detector import KPDetector, KPDetector_a
+    from eamm_b200.modules.util import AT_net2
+    monkeypatch.setenv("EAMM_TC_NUM_SMS", "148")
+    ws = torch.zeros(L.SPLITK_WS_BYTES, dtype=torch.uint8)
+    for mod in (engine, kp_engine, at_engine):
+        monkeypatch.setattr(mod, "current_stream_ptr", lambda: None)
+    monkeypatch.setattr(engine, "splitk_workspace", lambda device, stream: ws)
+    real, log = L.load(), []
+    with torch.no_grad():
+        for audio, cls in ((False, KPDetector), (True, KPDetector_a)):
+            cfg = get_kp_config("full", audio=audio)
+            m = cls(**cfg).eval()
+            m.load_state_dict(synth.make_kp_state_dict(cfg))
+            x = synth.make_kp_inputs(cfg, 2, 256, audio)
+            for precision in ("fp32", "fp16", "bf16"):
+                e = kp_engine.KPDetectorEngine(m, precision)
+                e.lib = _DryLib(real, log)
+                del log[:]
+                out = e.run(x)
+                names = [n for n, _, _ in log]
+                assert all(rc == 0 for _, rc, _ in log), (audio, precision, [r for r in log if r[1]])
+                # KPDetector: anti-alias, 10 Hourglass convs, merged head conv, head kernel; KPDetector_a: layout, conv, head
+                assert names == (["nchw_to_act", "conv_tc", "kp_head"] if audio else
+                                 ["aa_downsample_act"] + ["conv_tc"] * 11 + ["kp_head"]), (audio, precision, names)
+                assert out["value"].shape == (2, 10, 2) and out["jacobian"].shape == (2, 10, 2, 2)
+                assert out["heatmap"].shape == (2, 10, 58, 58)                    # valid 7x7 conv on the 64 x 64 map
+        sd = synth.make_at_state_dict()
+        img, mfcc, pose = synth.make_at_inputs(1, 3)
+        for audio_tc, decon in (("simt", "tc"), ("tc", "tc"), ("simt", "simt")):
+            monkeypatch.setenv("EAMM_B200_AT_AUDIO", audio_tc)
+            monkeypatch.setenv("EAMM_B200_AT_DECON", decon)
+            m = AT_net2().eval()
+            m.load_state_dict(dict(sd), strict=True)
+            e = at_engine.ATNet2Engine(m)
+            e.lib = _DryLib(real, log)
+            del log[:]
+            out = e.run(img, mfcc, pose, 1.6)
+            names = [n for n, _, _ in log]
+            assert out.shape == (1, 3, 35, 64, 64) and all(rc == 0 for _, rc, _ in log), (audio_tc, decon)
+            n_tc = (4 if audio_tc == "tc" else 0) + (4 if decon == "tc" else 0)
+            assert names.count("conv_tc") == n_tc and names.count("conv_simt") == 8 + 5 + 4 - n_tc
+            assert names.count("lstm_layer") == 3 and names.count("maxpool") == 2 and names.count("linear") == 9
+            assert names.count("act_copy") == (6 if audio_tc == "tc" else 0)
+
+
 def test_at_net2_engine_packing_reproduces_the_oracle_on_cpu():
     """Re-executes every packed stage of ATNet2Engine with torch (the kernels' documented semantics) and compares with
     the oracle: pins BN folding, the (c,h,w)->(h,w,c) FC permutation, the LSTM layer-0 split, the 1x1 ConvTranspose as
