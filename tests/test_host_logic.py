@@ -1199,14 +1199,14 @@ class _DryLib:
             def conv_tc(args, stream):
                 q = (ctypes.c_int * 6)()
                 rc = real.eamm_conv_tc_query(args, q)
-                log.append(("conv_tc", rc, args._obj.inp.contents.n))
+                log.append(("conv_tc", rc, args._obj.inp.contents.n, tuple(q)))
                 return rc
             return conv_tc
         if name in ("eamm_conv_tc_query", "eamm_conv_tc_fold", "eamm_conv_tc_uses_halo", "eamm_abi_version"):
             return getattr(real, name)
 
         def stub(*a):
-            log.append((name[5:], 0, None))
+            log.append((name[5:], 0, None, None))
             return 0
         return stub
 
@@ -1249,26 +1249,43 @@ def test_host_program_dry_run_launch_sequence_and_argument_checks(monkeypatch):
             src, kpd, kps = synth.make_inputs(2, cfg, size=256, seed=1)
             del log[:]
             out = e.run(src, kpd, kps)
-            assert [n for n, _, _ in log] == FRAME_LAUNCHES, precision
-            assert all(rc == 0 for _, rc, _ in log), (precision, [x for x in log if x[1]])
+            assert [r[0] for r in log] == FRAME_LAUNCHES, precision
+            assert all(r[1] == 0 for r in log), (precision, [x for x in log if x[1]])
             assert {k: tuple(v.shape) for k, v in out.items()} == {
                 "mask": (2, 11, 64, 64), "sparse_deformed": (2, 11, 3, 64, 64), "occlusion_map": (2, 1, 64, 64),
                 "deformed": (2, 3, 256, 256), "prediction": (2, 3, 256, 256)}
             assert list(out) == ["mask", "sparse_deformed", "occlusion_map", "deformed", "prediction"]    # generator.py:66-95 order
+        # the bench configuration itself (BASELINE configs[1]: 32 frames, fp32 mode): the plans DESIGN.md section 4 describes
+        m, e, cfg = build("full", "fp32")
+        src, kpd, kps = synth.make_inputs(32, cfg, size=256, seed=1)
+        del log[:]
+        e.run(src, kpd, kps)
+        assert [r[0] for r in log] == FRAME_LAUNCHES and all(r[1] == 0 for r in log)
+        q = [r[3] for r in log if r[0] == "conv_tc"]            # (N tile, scheme, fold, chunks/stage, pair | halo<<1 | splitk<<8, stages)
+        pair, halo, splitk = (lambda x: x[4] & 1), (lambda x: (x[4] >> 1) & 1), (lambda x: x[4] >> 8)
+        first, down0, down1, hg, head, res, up0, up1, final = q[0], q[1], q[2], q[3:13], q[13], q[14:26], q[26], q[27], q[28]
+        assert first[0] == 64 and first[2] == 2                                   # packed row-7, hi/lo folded along N
+        assert (down0[0], pair(down0), halo(down0)) == (128, 1, 1) and (down1[0], pair(down1), halo(down1)) == (256, 1, 1)
+        assert all((x[0], pair(x), halo(x), splitk(x)) == (256, 1, 1, 1) for x in res)            # CTA pairs, halo tiles
+        assert (up0[0], halo(up0), up1[0], halo(up1)) == (128, 1, 64, 1)
+        assert (head[1], head[0], final[1], final[0]) == (4, 112, 3, 112)                             # kx-in-N 7x7 schemes
+        assert [splitk(x) for x in hg] == [1, 1, 1, 1, 9, 8, 4, 1, 1, 1]        # enc4 / dec0 / dec1: too few tiles for 148 SMs
+        assert all(halo(x) == 0 for x in hg)                                                           # bf16 hi/lo: per-tap tiles
+        del m, e, src
         # fp32 mode again (mixed formats): one shared source for 3 frames -> the encoder (3 convs) sees one image
         m, e, cfg = build("full", "fp32")
         src, kpd, kps = synth.make_inputs(3, cfg, size=256, seed=1, shared_source=True)
         del log[:]
         e.run(src[:1].expand(3, -1, -1, -1), kpd, kps)
-        convs = [n for name, rc, n in log if name == "conv_tc"]
-        assert convs[:3] == [1, 1, 1] and set(convs[3:]) == {3} and all(rc == 0 for _, rc, _ in log)
+        convs = [r[2] for r in log if r[0] == "conv_tc"]
+        assert convs[:3] == [1, 1, 1] and set(convs[3:]) == {3} and all(r[1] == 0 for r in log)
         # source cache: the same source tensor again -> per-frame kernels only (no pack / first / down0 / down1 / anti-alias)
         m.cache_source = True
         one = src[:1].expand(3, -1, -1, -1)
         e.run(one, kpd, kps)
         del log[:]
         e.run(one, kpd, kps)
-        assert [n for n, _, _ in log] == FRAME_LAUNCHES[5:] and len(log) == 30
+        assert [r[0] for r in log] == FRAME_LAUNCHES[5:] and len(log) == 30
         one2 = src[:1].clone().expand(3, -1, -1, -1)                    # another tensor: recomputed
         del log[:]
         e.run(one2, kpd, kps)
@@ -1282,9 +1299,9 @@ def test_host_program_dry_run_launch_sequence_and_argument_checks(monkeypatch):
         src, kpd, kps = synth.make_inputs(2, cfg, size=64, seed=1)
         del log[:]
         out = e.run(src, kpd, kps)
-        names = [n for n, _, _ in log]
+        names = [r[0] for r in log]
         assert set(out) == {"prediction"} and "kp_stage" not in names and names.count("warp_occlude") == 1
-        assert all(rc == 0 for _, rc, _ in log)
+        assert all(r[1] == 0 for r in log)
         # empty batch: nothing is launched, empty tensors of the reference's shapes come back
         m, e, cfg = build("full", "fp16")
         del log[:]
@@ -1318,8 +1335,8 @@ def test_kp_detector_and_at_net2_host_programs_dry_run(monkeypatch):
                 e.lib = _DryLib(real, log)
                 del log[:]
                 out = e.run(x)
-                names = [n for n, _, _ in log]
-                assert all(rc == 0 for _, rc, _ in log), (audio, precision, [r for r in log if r[1]])
+                names = [r[0] for r in log]
+                assert all(r[1] == 0 for r in log), (audio, precision, [r for r in log if r[1]])
                 # KPDetector: anti-alias, 10 Hourglass convs, merged head conv, head kernel; KPDetector_a: layout, conv, head
                 assert names == (["nchw_to_act", "conv_tc", "kp_head"] if audio else
                                  ["aa_downsample_act"] + ["conv_tc"] * 11 + ["kp_head"]), (audio, precision, names)
@@ -1336,8 +1353,8 @@ def test_kp_detector_and_at_net2_host_programs_dry_run(monkeypatch):
             e.lib = _DryLib(real, log)
             del log[:]
             out = e.run(img, mfcc, pose, 1.6)
-            names = [n for n, _, _ in log]
-            assert out.shape == (1, 3, 35, 64, 64) and all(rc == 0 for _, rc, _ in log), (audio_tc, decon)
+            names = [r[0] for r in log]
+            assert out.shape == (1, 3, 35, 64, 64) and all(r[1] == 0 for r in log), (audio_tc, decon)
             n_tc = (4 if audio_tc == "tc" else 0) + (4 if decon == "tc" else 0)
             assert names.count("conv_tc") == n_tc and names.count("conv_simt") == 8 + 5 + 4 - n_tc
             assert names.count("lstm_layer") == 3 and names.count("maxpool") == 2 and names.count("linear") == 9
